@@ -1,0 +1,252 @@
+/*
+ * vsb.h -- C-ABI of libvsb_b200.so: the B200 (sm_100a) implementation of the per-layer hot path
+ * of aaron1138/Voxel-Stack-Blender (Z-blend -> LUT -> XY filters).
+ *
+ * The reference has no FFI (it is pure Python over OpenCV/NumPy/SciPy/Numba wheels); the entry
+ * points below replace the third-party call sites of its hot path one for one.  Each declaration
+ * cites the reference lines it replaces (paths relative to the reference repository root).  The
+ * binding a maintainer adds on the reference side is a ctypes stub, shown in INTEGRATION.md and
+ * implemented in voxel-stack-blender_b200/vsb_native.py.
+ *
+ * Conventions
+ *   - all image pointers are DEVICE pointers, row-major uint8 [H][pitch], pitch in bytes;
+ *   - "bits" are bit-packed binary masks: uint32 words, `wpr` words per row (>= ceil(W/32),
+ *     a multiple of 4), pixel x of a row lives in word x>>5, bit x&31; bits at x >= W are 0;
+ *   - `stream` is a cudaStream_t passed as void* (0 = default stream);
+ *   - functions are asynchronous on `stream`, own no memory, are re-entrant per stream, and
+ *     return 0 on success or a negative vsb_status; vsb_last_error_string() describes the last
+ *     failure of the calling thread;
+ *   - there is no CPU fallback anywhere behind this interface.
+ */
+#ifndef VSB_H_
+#define VSB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VSB_MAX_PRIORS 16 /* prior masks one fused launch can take (more are pre-OR'ed with vsb_bits_or) */
+#define VSB_MAX_XY_OPS 16
+#define VSB_FAST_REACH 63 /* largest chamfer reach (ceil(F)-1) of the shared-memory tile path */
+
+typedef enum {
+    VSB_OK = 0,
+    VSB_ERR_ARG = -1,     /* bad argument (null pointer, size, alignment, unsupported parameter) */
+    VSB_ERR_CUDA = -2,    /* CUDA runtime error; see vsb_last_error_string() */
+    VSB_ERR_UNSUPPORTED = -3
+} vsb_status;
+
+typedef void *vsb_stream_t;
+
+const char *vsb_last_error_string(void);
+int vsb_version(void);
+/* number of kernel launches issued through this library by the calling process (bench.py's
+ * gpu_launches claim) */
+unsigned long long vsb_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * K1  threshold + bit-pack.      replaces cv2.threshold(img,127,255,THRESH_BINARY)
+ *     processing_core.py:44 (load_image).  bit = gray > thresh.
+ * ------------------------------------------------------------------------------------------- */
+int vsb_threshold_pack(const uint8_t *gray, size_t pitch, int W, int H, int thresh,
+                       uint32_t *bits, int wpr, vsb_stream_t stream);
+
+/* bits -> 0/255 bytes (the `binary_image` load_image returns).  processing_core.py:44-45 */
+int vsb_bits_unpack(const uint32_t *bits, int wpr, int W, int H, uint8_t *out, size_t pitch,
+                    vsb_stream_t stream);
+
+/* OR of n packed masks.          replaces the copy + cv2.bitwise_or loop
+ *     processing_core.py:61-65 (find_prior_combined_white_mask).  srcs = host array of device ptrs */
+int vsb_bits_or(const uint32_t *const *srcs, int n, int wpr, int H, uint32_t *dst,
+                vsb_stream_t stream);
+
+/* rec = OR(priors) & ~cur, optional population count (cv2.countNonZero) into *count_out (device
+ * uint64, must be zeroed by the caller).   processing_core.py:119,122,259-260,350-351 */
+int vsb_maskdiff(const uint32_t *cur, const uint32_t *const *priors, int n, int wpr, int H,
+                 uint32_t *rec_out, unsigned long long *count_out, vsb_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Chamfer table  T[(R+1)*(R+1)] float32 (host helper, no device work):  T[M][m] = the 5x5
+ * chamfer value (a=1, b=1.4, c=2.1969) of displacement (M,m) in canonical float32 summation
+ * order.  cv2.distanceTransform(src, DIST_L2, 5) == min over zero pixels of T[max|d|][min|d|].
+ * ------------------------------------------------------------------------------------------- */
+int vsb_chamfer_table(float *T_host, int R);
+
+/* K2  dense chamfer distance map, clipped: dist = min(D, clip) where D is the distance to the
+ *     nearest set bit of `seed_bits`, exact for D < R+1; pixels with no seed within Chebyshev
+ *     reach R get `clip`.     replaces cv2.distanceTransform(~cur, DIST_L2, 5)
+ *     processing_core.py:129,250,379.   T = device copy of vsb_chamfer_table(R), R <= 63. */
+int vsb_dt_chamfer5(const uint32_t *seed_bits, int wpr, int W, int H, int R, const float *T_dev,
+                    float clip, float *dist, size_t dist_pitch_elems, vsb_stream_t stream);
+
+/* same windowed tile kernel with the exact Euclidean metric: dist = min(sqrt(d2), clip), exact for
+ * d < R+1 (R <= 63). */
+int vsb_dt_exact_windowed(const uint32_t *seed_bits, int wpr, int W, int H, int R, float clip,
+                          float *dist, size_t dist_pitch_elems, vsb_stream_t stream);
+
+/* K2' exact Euclidean distance transform, unbounded reach (cv2.DIST_MASK_PRECISE analogue):
+ *     separable -- column pass (vertical distance to the nearest set bit, uint16 scratch
+ *     `colnear` [H][pitch_elems], 0xFFFF = none) then a row pass over the lower envelope of
+ *     parabolas.  d2_out (optional) = exact integer squared distance (INT32_MAX if no seed);
+ *     dist_out (optional) = sqrtf(d2). */
+int vsb_dt_exact(const uint32_t *seed_bits, int wpr, int W, int H, uint16_t *colnear,
+                 int32_t *d2_out, float *dist_out, size_t pitch_elems, vsb_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K3  fused Z-blend: rec mask, windowed chamfer distance, fade gradient, merge with the gray
+ *     layer, composed LUT gather.  One launch per layer.
+ *     replaces processing_core.py:107-153 (fixed fade), :222-284 (weighted stack), :442-460
+ *     (merge_to_output) and lut_manager.py:57-63 (apply_z_lut) for leading apply_lut ops.
+ * ------------------------------------------------------------------------------------------- */
+typedef enum {
+    VSB_Z_FIXED = 0,    /* g = trunc(255*(1 - min(d,F)/den)) on rec               :138-152 */
+    VSB_Z_WEIGHTED = 1, /* g = trunc(255*(sum_i rec_i ? (1-min(d,F_i)/den_i)*w_i : 0)/W)  :252-282 */
+    VSB_Z_CONST = 2,    /* g = const_val on rec (degenerate F <= 0)                 :138-140 */
+    VSB_Z_DIST = 3,     /* no image output: write min(d,F) at rec pixels into dist_out (Enhanced EDT
+                           stage 1, :379-381) */
+    VSB_Z_ENHANCED = 4  /* stack level only: VSB_Z_DIST + vsb_ccl8_max + vsb_enhanced_fade  :338-404 */
+} vsb_zmode;
+
+typedef enum {
+    VSB_METRIC_CHAMFER5 = 0, /* the reference's metric: cv2.distanceTransform(.., DIST_L2, 5) */
+    VSB_METRIC_EXACT = 1     /* exact Euclidean (sqrt of the integer squared distance)       */
+} vsb_metric;
+
+typedef struct {
+    int mode;      /* vsb_zmode */
+    int metric;    /* vsb_metric */
+    int n_priors;  /* <= VSB_MAX_PRIORS, newest first */
+    int reach;     /* R = ceil(max fade)-1, <= VSB_FAST_REACH */
+    int const_val; /* VSB_Z_CONST */
+    float fade;    /* F as float32 */
+    float den;     /* F > 0 ? F : 1 */
+    float total_weight;
+    float weights[VSB_MAX_PRIORS];
+    float fades[VSB_MAX_PRIORS];
+    float dens[VSB_MAX_PRIORS];
+    int enhanced_arith;  /* VSB_Z_ENHANCED: 0 = float32 (SciPy flavour), 1 = float64 (Numba flavour) */
+    double fade_limit;   /* VSB_Z_ENHANCED: F as the Python float the reference passes on */
+} vsb_zparams;
+
+int vsb_zblend_fused(const uint8_t *gray, size_t gray_pitch, int W, int H, const uint32_t *cur_bits,
+                     const uint32_t *const *prior_bits /* host array of device ptrs */, int wpr,
+                     const vsb_zparams *params /* host */, const float *T_dev,
+                     const uint8_t *lut256_dev /* may be NULL = identity */, uint8_t *out,
+                     size_t out_pitch, float *dist_out /* VSB_Z_DIST only */,
+                     size_t dist_pitch_elems, vsb_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K5  Enhanced EDT: 8-connected components of rec + per-component max of the clipped distance,
+ *     then the ROI-normalised fade.   replaces cv2.connectedComponents (processing_core.py:383),
+ *     ndimage.maximum / numba pass 1 (:291, :313-320) and the two fades (:295-302 float32,
+ *     :323-334 float64), merge (:458) and the leading LUT.
+ *     labels: int32 [H*W] scratch; at rec pixels it ends up holding the linear index y*W+x of the
+ *     component's root pixel (other entries are never touched);
+ *     compmax: uint32 [H*W] scratch holding the float bits of the maximum, indexed by root.
+ * ------------------------------------------------------------------------------------------- */
+int vsb_ccl8_max(const uint32_t *rec_bits, int wpr, int W, int H, const float *dist,
+                 size_t dist_pitch_elems, int32_t *labels, uint32_t *compmax, vsb_stream_t stream);
+
+int vsb_enhanced_fade(const uint8_t *gray, size_t gray_pitch, int W, int H, const uint32_t *rec_bits,
+                      int wpr, const float *dist, size_t dist_pitch_elems, const int32_t *labels,
+                      const uint32_t *compmax, double fade_limit, int arith /* 0 = float32 (SciPy), 1 = float64 (Numba) */,
+                      const uint8_t *lut256_dev, uint8_t *out, size_t out_pitch, vsb_stream_t stream);
+
+/* the two per-label fades exactly as the reference exposes them to its tests (dense, contiguous
+ * arrays; labels 1..num_labels-1 from any labelling, 0 = background):
+ *     arith 0 = _calculate_receding_gradient_field_enhanced_edt_scipy  processing_core.py:287-303
+ *     arith 1 = _calculate_receding_gradient_field_enhanced_edt_numba  processing_core.py:305-336
+ * cmax: uint32 [num_labels] scratch. */
+int vsb_enhanced_from_labels(const float *dist, const int32_t *labels, int W, int H, int num_labels,
+                             double fade_limit, int arith, uint32_t *cmax, uint8_t *out,
+                             vsb_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K4  XY operations.
+ * ------------------------------------------------------------------------------------------- */
+/* lut gather                         lut_manager.py:57-63 */
+int vsb_lut_apply(const uint8_t *in, size_t in_pitch, int W, int H, const uint8_t *lut256_dev,
+                  uint8_t *out, size_t out_pitch, vsb_stream_t stream);
+
+/* max(a,b)                           processing_core.py:458 (merge_to_output) */
+int vsb_merge_max(const uint8_t *a, size_t a_pitch, const uint8_t *b, size_t b_pitch, int W, int H,
+                  uint8_t *out, size_t out_pitch, vsb_stream_t stream);
+
+/* cv2.GaussianBlur on uint8: Q8.8 taps (host arrays, odd lengths <= 63, each summing to 256),
+ * (sum + 2^15) >> 16, BORDER_REFLECT_101.        xy_blend_processor.py:27-33 */
+int vsb_gaussian_q88(const uint8_t *in, size_t in_pitch, int W, int H, const int32_t *kx, int nkx,
+                     const int32_t *ky, int nky, uint8_t *out, size_t out_pitch, vsb_stream_t stream);
+
+/* cv2.bilateralFilter on uint8: taps (dy[k],dx[k]) in row-major order with float32 space weights
+ * sw[k], colour weights cw[256] (host arrays), float32 accumulate with FMA, round-half-even,
+ * BORDER_REFLECT_101.                              xy_blend_processor.py:35-40 */
+int vsb_bilateral(const uint8_t *in, size_t in_pitch, int W, int H, int radius, int ntaps,
+                  const int8_t *dy, const int8_t *dx, const float *sw, const float *cw256,
+                  uint8_t *out, size_t out_pitch, vsb_stream_t stream);
+
+/* cv2.medianBlur on uint8: exact k x k median, BORDER_REPLICATE.   xy_blend_processor.py:42-46 */
+int vsb_median(const uint8_t *in, size_t in_pitch, int W, int H, int ksize, uint8_t *out,
+               size_t out_pitch, vsb_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Host-buffer entry points (the plugin path measured as `e2e`): pinned or pageable HOST arrays
+ * in, HOST array out; device staging buffers are owned by an opaque stack context.
+ *     replaces ProcessingPipelineThread._process_single_image_task + the producer loop
+ *     processing_pipeline.py:74-113,188-223 for FIXED_FADE / WEIGHTED_STACK.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct vsb_stack vsb_stack;
+
+typedef struct {
+    int type;   /* 0 none, 1 lut, 2 gaussian, 3 bilateral, 4 median */
+    uint8_t lut[256];
+    int32_t kx[63], ky[63];
+    int nkx, nky;
+    int radius, ntaps;
+    int8_t tap_dy[1024], tap_dx[1024];
+    float tap_sw[1024];
+    float cw[256];
+    int median_ksize;
+} vsb_xy_op;
+
+int vsb_stack_create(int W, int H, int n_priors, const vsb_zparams *zp, const vsb_xy_op *ops,
+                     int n_ops, vsb_stack **out_stack);
+int vsb_stack_destroy(vsb_stack *s);
+/* forget the sliding window of prior masks (start of a new stack / Z-shard) */
+int vsb_stack_reset(vsb_stack *s);
+/* feed a halo layer: thresholded and pushed into the window, no output */
+int vsb_stack_push_halo(vsb_stack *s, const uint8_t *gray_host, size_t pitch);
+/* one layer, host in -> host out (H2D, kernels, D2H; synchronous on return) */
+int vsb_stack_process_host(vsb_stack *s, const uint8_t *gray_host, size_t in_pitch,
+                           uint8_t *out_host, size_t out_pitch);
+/* pipelined variant: H2D, kernels and D2H of consecutive layers overlap on three streams.
+ * submit returns a ticket (>= 0); the output is complete after vsb_stack_wait(ticket).  At most
+ * vsb_stack_slots() layers may be in flight; host buffers should be pinned. */
+int vsb_stack_submit_host(vsb_stack *s, const uint8_t *gray_host, size_t in_pitch,
+                          uint8_t *out_host, size_t out_pitch);
+int vsb_stack_wait(vsb_stack *s, int ticket);
+int vsb_stack_slots(vsb_stack *s);
+/* one layer, device in -> device out on the stack's stream (asynchronous) */
+int vsb_stack_process_device(vsb_stack *s, const uint8_t *gray_dev, size_t in_pitch,
+                             uint8_t *out_dev, size_t out_pitch);
+/* n consecutive device-resident layers (layer i at base + i*stride), one call */
+int vsb_stack_process_device_batch(vsb_stack *s, const uint8_t *gray_dev, size_t in_pitch,
+                                   size_t in_layer_stride, uint8_t *out_dev, size_t out_pitch,
+                                   size_t out_layer_stride, int n_layers);
+int vsb_stack_sync(vsb_stack *s);
+vsb_stream_t vsb_stack_stream(vsb_stack *s);
+
+/* ---------------------------------------------------------------------------------------------
+ * Synthetic stack rasteriser (measurement utility): layer z of a primitive
+ * table (x, y, r0, slope, z_start, z_end) float32[6] per disk, plus an optional raft rectangle.
+ * Pixel = 255 iff inside any primitive.
+ * ------------------------------------------------------------------------------------------- */
+int vsb_synth_layer(const float *prims_dev, int n_prims, const float *raft /* host: x0,y0,x1,y1,corner_r,z_end or NULL */,
+                    int z, int W, int H, uint8_t *out, size_t pitch, vsb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VSB_H_ */

@@ -1,0 +1,456 @@
+"""GPU (-m gpu): parity of the sm_100a kernels, called through the C-ABI, against the CPU oracle on the same
+seeded inputs and against the committed outputs of the unmodified reference (tests/golden).
+Bar: bit-exact for every integer / byte stage and for the chamfer5 Z-blend; +-1 LSB only where the
+reference's own library paths disagree with each other (bilateral d in {3,5}: IPP truncates)."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+import vsb_oracle as O
+from conftest import preset_ops
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def E():
+    import vsb_engine
+    vsb_engine.torch()
+    return vsb_engine
+
+
+def sha(a):
+    return hashlib.sha1(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def small_stack(W=500, H=300, L=8, seed=0, raft=False, **kw):
+    import vsb_synth as S
+    kw.setdefault("n_blobs", 10); kw.setdefault("grid", 80); kw.setdefault("r_range", (12.0, 70.0)); kw.setdefault("r_turn", 90.0)
+    table, rf = S.make_table(W, H, L, seed=seed, raft=raft, **kw)
+    return [S.raster_numpy(table, rf, z, W, H) for z in range(L)]
+
+
+def crop(slices, z, N, win):
+    y0, y1, x0, x1 = win
+    cur = np.ascontiguousarray(O.threshold(slices[z][y0:y1, x0:x1]))
+    pri = [np.ascontiguousarray(O.threshold(slices[k][y0:y1, x0:x1])) for k in range(max(0, z - N), z)]
+    return cur, list(reversed(pri))
+
+
+def make_cfg(**kw):
+    from config import Config, ProcessingMode
+    c = Config()
+    c.use_fixed_fade_receding = True
+    for k, v in kw.items():
+        setattr(c, k, ProcessingMode(v) if k == "blending_mode" else v)
+    return c
+
+
+# ---- K1 ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(1, 1), (7, 31), (33, 32), (50, 129), (64, 1000), (301, 517), (40, 4000)])
+def test_threshold_pack_unpack(E, shape):
+    rng = np.random.default_rng(shape[1])
+    g = rng.integers(0, 256, shape, dtype=np.uint8)
+    g[0, 0] = 127; g[-1, -1] = 128
+    assert np.array_equal(E.threshold_np(g), O.threshold(g))
+    for thr in (0, 200, 255):
+        assert np.array_equal(E.threshold_np(g, thr), O.threshold(g, thr))
+
+
+def test_mask_or_and_count(E):
+    import processing_core as core
+    rng = np.random.default_rng(1)
+    masks = [(rng.random((77, 203)) < 0.2).astype(np.uint8) * 255 for _ in range(20)]
+    assert core.find_prior_combined_white_mask([]) is None
+    for n in (1, 2, 5, 16, 17, 20):
+        assert np.array_equal(core.find_prior_combined_white_mask(masks[:n]), O.combine_priors(masks[:n]))
+    cur = E.pack(E.DevImage.from_numpy(masks[0]))
+    pri = [E.pack(E.DevImage.from_numpy(m)) for m in masks[1:4]]
+    want = int(((O.combine_priors(masks[1:4]) & ~masks[0]) > 0).sum())
+    assert E.count_receding(cur, pri) == want
+
+
+# ---- K2 / K2' ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("R", [0, 1, 9, 39, 63])
+def test_dense_chamfer_bit_exact(E, R):
+    rng = np.random.default_rng(R)
+    for shape, p in (((97, 203), 0.01), ((64, 257), 0.0005), ((130, 140), 0.2)):
+        seed = (rng.random(shape) < p).astype(np.uint8) * 255
+        want = np.minimum(O.chamfer5(seed, R), np.float32(R + 1))
+        got = E.distance_np(seed, R, R + 1, "chamfer5")
+        assert np.array_equal(got, want)
+
+
+def test_dense_chamfer_vs_library_golden(E, slices, ref_dist):
+    z, wins = ref_dist
+    for lz, win in wins.items():
+        cur, _ = crop(slices, int(lz), 0, win)
+        got = E.distance_np(cur, 63, 1e9, "chamfer5")
+        ref = z["d5_" + lz]
+        m = got < 64
+        assert m.sum() > 10000
+        assert np.abs(got[m] - ref[m]).max() < 1e-4
+        assert (ref[~m] > 63.9).all()
+
+
+def test_exact_edt(E, slices, ref_dist):
+    rng = np.random.default_rng(5)
+    for shape, p in (((90, 150), 0.01), ((64, 300), 0.001), ((33, 40), 0.3)):
+        seed = (rng.random(shape) < p).astype(np.uint8) * 255
+        seed[shape[0] // 3, shape[1] // 2] = 255
+        d2o = O.edt_exact_sq(seed)
+        d2, dist = E.edt_exact_np(seed)
+        assert np.array_equal(d2, d2o)
+        assert np.array_equal(dist, np.sqrt(d2o.astype(np.float32)))
+        for R in (5, 40, 63):
+            got = E.distance_np(seed, R, float(R + 1), "exact")
+            want = np.minimum(np.sqrt(d2o.astype(np.float32)), np.float32(R + 1))
+            assert np.array_equal(got, want)
+    z, wins = ref_dist
+    for lz, win in wins.items():                               # cv2.DIST_MASK_PRECISE, 1e-4 px (north_star)
+        cur, _ = crop(slices, int(lz), 0, win)
+        _, dist = E.edt_exact_np(cur)
+        assert np.abs(dist - z["dp_" + lz]).max() < 1e-4
+    d2, dist = E.edt_exact_np(np.zeros((20, 70), np.uint8))     # no seed at all
+    assert (d2 == 0x7fffffff).all()
+
+
+# ---- fused Z-blend ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("F,N", [(10.0, 3), (40.0, 4), (7.5, 2), (64.0, 4), (0.5, 1), (1.0, 3), (23.25, 6)])
+def test_fixed_fade_synthetic(E, F, N):
+    import processing_core as core
+    layers = small_stack(L=N + 3, seed=int(F))
+    cfg = make_cfg(fixed_fade_distance_receding=F, receding_layers=N)
+    for zi in range(1, len(layers)):
+        cur = O.threshold(layers[zi])
+        pri = [O.threshold(l) for l in reversed(layers[max(0, zi - N):zi])]
+        comb = O.combine_priors(pri)
+        got = core.process_z_blending(cur, core.find_prior_combined_white_mask(pri), cfg, [])
+        assert np.array_equal(got, O.fixed_fade(cur, comb, F, True)), (zi, F)
+
+
+def test_fixed_fade_edge_cases(E):
+    import processing_core as core
+    cur = np.zeros((40, 130), np.uint8); cur[10:20, 60:70] = 255
+    prior = np.zeros_like(cur); prior[5:30, 40:100] = 255
+    cfg = make_cfg(fixed_fade_distance_receding=6.0)
+    assert core.process_z_blending(cur, None, cfg, []).sum() == 0                        # no priors (:115)
+    assert core.process_z_blending(prior, cur, cfg, []).sum() == 0                       # nothing recedes (:122)
+    assert np.array_equal(core.process_z_blending(cur, prior, cfg, []), O.fixed_fade(cur, prior, 6.0))
+    cfg0 = make_cfg(fixed_fade_distance_receding=0.0)                                    # F <= 0 (:139)
+    assert np.array_equal(core.process_z_blending(cur, prior, cfg0, []), O.fixed_fade(cur, prior, 0.0))
+    empty = np.zeros_like(cur)                                                           # current layer has no white pixel
+    assert np.array_equal(core.process_z_blending(empty, prior, cfg, []), O.fixed_fade(empty, prior, 6.0))
+    full = np.full_like(cur, 255)
+    assert core.process_z_blending(full, prior, cfg, []).sum() == 0
+
+
+def test_modes_vs_reference_goldens(E, slices, ref_modes):
+    """every stored output of the reference's process_z_blending on real-slice crops"""
+    import processing_core as core
+    import vsb_params as P
+    z, wins = ref_modes
+    n = 0
+    for key in z.files:
+        if key == "wins":
+            continue
+        parts = key.split("_")
+        kind = parts[0]
+        if kind == "minmax":
+            continue                                    # SURVEY 8f rank 1, raises UnsupportedOnDevice (below)
+        if kind == "enh":
+            flavour, wn, lz, Fs = parts[1], parts[2], parts[3], parts[4]
+            cur, pri = crop(slices, int(lz), 4, wins[wn])
+            cfg = make_cfg(blending_mode="enhanced_edt", fixed_fade_distance_receding=float(Fs[1:]),
+                           use_numba_jit=(flavour == "numba"))
+            got = core.process_z_blending(cur, pri, cfg, [])
+        elif kind == "fixed":
+            wn, lz, Fs, Ns = parts[1], parts[2], parts[3], parts[4]
+            cur, pri = crop(slices, int(lz), 4, wins[wn])
+            cfg = make_cfg(fixed_fade_distance_receding=float(Fs[1:]))
+            got = core.process_z_blending(cur, core.find_prior_combined_white_mask(pri[:int(Ns[1:])]), cfg, [])
+        elif kind == "weighted":
+            wn, lz = parts[1], parts[2]
+            cur, pri = crop(slices, int(lz), 4, wins[wn])
+            cfg = make_cfg(blending_mode="weighted_stack", manual_weights=[100, 75, 50, 25],
+                           fade_distances_receding=[40.0, 30.0, 20.0, 10.0])
+            got = core.process_z_blending(cur, pri, cfg, [])
+        else:
+            wn, lz = parts[1], parts[2]
+            cur, pri = crop(slices, int(lz), 4, wins[wn])
+            cfg = make_cfg(blending_mode="weighted_stack", manual_weights=[10, 0, 30], fade_distances_receding=[12.5],
+                           fixed_fade_distance_receding=25.0)
+            got = core.process_z_blending(cur, pri, cfg, [])
+        assert np.array_equal(got, z[key]), key
+        n += 1
+    assert n > 140
+    with pytest.raises(P.UnsupportedOnDevice):
+        from config import Config
+        core.process_z_blending(cur, pri[0], Config(), [])
+
+
+def test_reference_unit_tests_on_device(E, ref_scenes):
+    """tests/test_processing.py of the reference, re-run against the device implementation."""
+    import cv2
+    import processing_core as core
+    s = ref_scenes
+    cfg = make_cfg(blending_mode="weighted_stack", fixed_fade_distance_receding=20.0, manual_weights=[100, 50],
+                   fade_distances_receding=[20.0, 10.0])
+    g = core._calculate_weighted_receding_gradient_field(s["weighted_cur"], [s["weighted_new"], s["weighted_old"]], cfg)
+    assert 200 < g[42, 50] < 210 and 20 < g[38, 50] < 30                    # :75-76
+    assert np.array_equal(g, s["weighted_out"])
+    cur = np.zeros((100, 100), np.uint8)
+    assert core._calculate_weighted_receding_gradient_field(cur, [], cfg).sum() == 0     # :83-84
+    cfg.manual_weights = []
+    assert core._calculate_weighted_receding_gradient_field(cur, [np.full_like(cur, 255)], cfg).sum() == 0
+    # test_enhanced_edt_max_fade_limit (:102-152): library setup exactly as edt_setup() does it
+    cur, prior = s["enh_cur"], s["enh_prior"]
+    rec = cv2.bitwise_and(prior, cv2.bitwise_not(cur))
+    dmap = cv2.distanceTransform(cv2.bitwise_not(cur), cv2.DIST_L2, 5)
+    rd = cv2.bitwise_and(dmap, dmap, mask=rec)
+    n, labels = cv2.connectedComponents(rec)
+    for name, fn in (("scipy", core._calculate_receding_gradient_field_enhanced_edt_scipy),
+                     ("numba", core._calculate_receding_gradient_field_enhanced_edt_numba)):
+        g = fn(rd, labels.astype(np.int32), n, 10.0)
+        g = cv2.bitwise_and(g, g, mask=rec)
+        assert g[50, 35] == 0 and g[50, 25] == 0
+        assert 180 < g[50, 57] < 185 and 108 < g[50, 59] < 112
+        assert np.array_equal(g, s["enh_out_" + name])
+        cfg = make_cfg(blending_mode="enhanced_edt", fixed_fade_distance_receding=10.0, use_numba_jit=(name == "numba"))
+        assert np.array_equal(core._calculate_receding_gradient_field_enhanced_edt(cur, [prior], cfg), s["enh_out_" + name])
+
+
+def test_enhanced_synthetic_both_flavours(E):
+    import processing_core as core
+    layers = small_stack(W=420, H=260, L=7, seed=11, n_blobs=14)
+    for F in (6.0, 20.0, 64.0):
+        for zi in (2, 4, 6):
+            cur = O.threshold(layers[zi])
+            pri = [O.threshold(l) for l in reversed(layers[max(0, zi - 4):zi])]
+            for flavour in ("scipy", "numba"):
+                cfg = make_cfg(blending_mode="enhanced_edt", fixed_fade_distance_receding=F, use_numba_jit=(flavour == "numba"))
+                assert np.array_equal(core.process_z_blending(cur, pri, cfg, []), O.enhanced_fade(cur, pri, F, flavour)), (F, zi, flavour)
+
+
+def test_ccl_against_oracle_labels(E):
+    """component partition of the device union-find == the oracle's 8-connected labelling"""
+    t = E.torch()
+    import vsb_native as N
+    rng = np.random.default_rng(7)
+    for shape, p in (((60, 130), 0.35), ((97, 300), 0.55), ((33, 64), 0.1)):
+        m = (rng.random(shape) < p).astype(np.uint8) * 255
+        n, lab = O.ccl8(m)
+        H, W = shape
+        rec = E.pack(E.DevImage.from_numpy(m))
+        dist = t.from_numpy(rng.random(shape).astype(np.float32)).cuda()
+        L = t.empty(shape, dtype=t.int32, device="cuda"); C = t.empty(shape, dtype=t.int32, device="cuda")
+        N.check(N.load().vsb_ccl8_max(rec.ptr, rec.wpr, W, H, dist.data_ptr(), W, L.data_ptr(), C.data_ptr(), 0))
+        t.cuda.synchronize()
+        Ld = L.cpu().numpy()[m > 0]
+        lo = lab[m > 0]
+        # same partition: a bijection between device roots and oracle labels
+        pairs = set(zip(Ld.tolist(), lo.tolist()))
+        assert len(pairs) == len({a for a, _ in pairs}) == len({b for _, b in pairs}) == n - 1
+        mx = O.label_max(np.where(m > 0, dist.cpu().numpy(), 0).astype(np.float32), lab, n)
+        Cd = C.cpu().numpy().view(np.float32).ravel()
+        for root, l in pairs:
+            assert Cd[root] == mx[l]
+
+
+def test_exact_metric_fused(E):
+    """metric='exact' in the fused kernel == oracle fade over the exact Euclidean distance"""
+    import processing_core as core
+    layers = small_stack(seed=21)
+    for F in (9.0, 33.0):
+        cfg = make_cfg(fixed_fade_distance_receding=F, distance_metric="exact")
+        cur = O.threshold(layers[5]); pri = [O.threshold(l) for l in reversed(layers[2:5])]
+        comb = O.combine_priors(pri)
+        assert np.array_equal(core.process_z_blending(cur, comb, cfg, []), O.fixed_fade(cur, comb, F, True, "exact"))
+
+
+# ---- XY ----------------------------------------------------------------------------------------------------------
+def _op(**kw):
+    from config import XYBlendOperation
+    return XYBlendOperation(**kw)
+
+
+def test_gaussian_bit_exact(E, ref_xy):
+    import xy_blend_processor as xy
+    z = ref_xy
+    for nm in ("noise", "smooth", "soft", "zblend"):
+        im = z["in_" + nm]
+        for kx, ky, sx, sy in json.loads(str(z["gauss_sets"])):
+            got = xy.apply_gaussian_blur(im, _op(type="gaussian_blur", gaussian_ksize_x=kx, gaussian_ksize_y=ky,
+                                                 gaussian_sigma_x=sx, gaussian_sigma_y=sy))
+            assert np.array_equal(got, z[f"gauss_{nm}_{kx}_{ky}_{sx:g}_{sy:g}"]), (nm, kx, ky, sx, sy)
+    rng = np.random.default_rng(2)
+    for shape in ((5, 7), (40, 129), (300, 500)):            # ragged + smaller than the kernel
+        im = rng.integers(0, 256, shape, dtype=np.uint8)
+        for k, s in ((3, 0.8), (9, 2.0), (31, 5.0)):
+            got = xy.apply_gaussian_blur(im, _op(type="gaussian_blur", gaussian_ksize_x=k, gaussian_ksize_y=k, gaussian_sigma_x=s))
+            assert np.array_equal(got, O.gaussian_blur(im, k, k, s, 0.0))
+
+
+def test_bilateral(E, ref_xy):
+    import xy_blend_processor as xy
+    z = ref_xy
+    for nm in ("noise", "smooth", "soft", "zblend"):
+        im = z["in_" + nm]
+        for d, sc, ss in json.loads(str(z["bil_sets"])):
+            got = xy.apply_bilateral_filter(im, _op(type="bilateral_filter", bilateral_d=d, bilateral_sigma_color=sc,
+                                                    bilateral_sigma_space=ss))
+            assert np.array_equal(got, O.bilateral(im, d, sc, ss)), (nm, d)          # bit-exact vs the oracle
+            diff = np.abs(got.astype(int) - z[f"bil_{nm}_{d}_{sc:g}_{ss:g}"].astype(int))
+            assert diff.max() <= 1                                                   # +-1 LSB vs the library
+            if d >= 7 or d <= 0:
+                assert (diff != 0).sum() <= 2
+    big = np.zeros((70, 300), np.uint8); big[:, 150:] = 200; big[30:40, 100:200] = 90
+    got = xy.apply_bilateral_filter(big, _op(type="bilateral_filter", bilateral_d=0, bilateral_sigma_color=40.0, bilateral_sigma_space=9.0))
+    assert np.array_equal(got, O.bilateral(big, 0, 40.0, 9.0))                       # radius 14: taps in global memory
+
+
+def test_median(E, ref_xy):
+    import xy_blend_processor as xy
+    z = ref_xy
+    for nm in ("noise", "smooth", "soft", "zblend"):
+        im = z["in_" + nm]
+        for k in json.loads(str(z["med_sets"])):
+            got = xy.apply_median_blur(im, _op(type="median_blur", median_ksize=k))
+            assert np.array_equal(got, z[f"med_{nm}_{k}"]), (nm, k)
+    im = z["in_noise"]
+    assert xy.apply_median_blur(im, _op(type="median_blur", median_ksize=1)) is im       # same object (:45)
+
+
+def test_lut_and_merge(E, ref_luts):
+    import lut_manager, processing_core as core
+    rng = np.random.default_rng(4)
+    img = rng.integers(0, 256, (123, 457), dtype=np.uint8)
+    img[:40] = 0; img[40:60] = 255
+    z, _ = ref_luts
+    for name in ("file_EXP(LUT)-upShifted", "lut_005", "lut_020"):
+        assert np.array_equal(lut_manager.apply_z_lut(img, z[name]), z[name][img])
+    other = rng.integers(0, 256, img.shape, dtype=np.uint8)
+    assert np.array_equal(core.merge_to_output(img, other), np.maximum(img, other))
+
+
+def test_xy_pipeline_preset_chain(E, ref_xy, lut_file):
+    import xy_blend_processor as xy
+    from config import Config
+    cfg = Config.from_dict({"xy_blend_pipeline": preset_ops(lut_file)})
+    for nm in ("zblend", "noise"):
+        got = xy.process_xy_pipeline(ref_xy["in_" + nm], cfg.xy_blend_pipeline)
+        assert np.array_equal(got, ref_xy[f"chain_{nm}_preset"])
+    src = ref_xy["in_noise"]
+    out = xy.process_xy_pipeline(src, [])
+    assert np.array_equal(out, src) and out is not src
+    out = xy.process_xy_pipeline(src, [_op(type="none"), _op(type="bogus")])
+    assert np.array_equal(out, src)
+
+
+# ---- whole stacks ------------------------------------------------------------------------------------------------------
+def stack_cfg(which, lut_file):
+    from config import Config
+    if which == "cfg1":
+        return Config.from_dict({"blending_mode": "fixed_fade", "receding_layers": 3, "use_fixed_fade_receding": True,
+                                 "fixed_fade_distance_receding": 10.0,
+                                 "xy_blend_pipeline": [{"type": "apply_lut", "lut_params": {"lut_source": "file", "fixed_lut_path": lut_file}}]})
+    return Config.from_dict({"blending_mode": "fixed_fade", "receding_layers": 4, "use_fixed_fade_receding": True,
+                             "fixed_fade_distance_receding": 40.0, "xy_blend_pipeline": preset_ops(lut_file)})
+
+
+def engine_for(E, cfg, W, H):
+    import lut_manager, vsb_params as P
+    ops = P.xy_ops_from_pipeline(cfg.xy_blend_pipeline, lambda op: lut_manager.lut_from_params(op.lut_params))
+    return E.StackEngine(W, H, cfg, ops)
+
+
+@pytest.mark.parametrize("which", ["cfg1", "preset"])
+def test_full_test_slices_stack_vs_reference(E, slices, ref_stack, lut_file, which):
+    """BASELINE config 1 (and the Preset-Double-LUT chain) over all 40 test slices through the stack engine:
+    every layer's SHA-1 equals the output of the reference's ProcessingPipelineThread.run()."""
+    H, W = slices[0].shape
+    eng = engine_for(E, stack_cfg(which, lut_file), W, H)
+    outs = [eng.process(g) for g in slices]
+    eng.close()
+    bad = [i for i, o in enumerate(outs) if sha(o) != str(ref_stack[which + "_sha1"][i])]
+    for zi in [int(k) for k in ref_stack["keep"]]:
+        d = np.abs(outs[zi].astype(int) - ref_stack[f"{which}_{zi:03d}"].astype(int))
+        assert d.max() == 0, (which, zi, int((d > 0).sum()), int(d.max()))
+    assert not bad, bad
+
+
+def test_pipeline_thread_end_to_end(E, slices, ref_stack, lut_file, tmp_path):
+    """ProcessingPipelineThread.run() on PNG files: same files out, same pixels as the reference."""
+    import cv2
+    import processing_pipeline as pp
+    src, dst = tmp_path / "in", tmp_path / "out"
+    src.mkdir(); dst.mkdir()
+    os.chdir(tmp_path)
+    zs = list(range(10, 18))
+    for zi in zs:
+        cv2.imwrite(str(src / f"layer{zi:03d}.png"), slices[zi])
+    (src / "layer099.png").write_bytes(b"not a png")
+    cfg = stack_cfg("cfg1", lut_file)
+    cfg.input_folder, cfg.output_folder, cfg.start_index, cfg.stop_index = str(src), str(dst), 0, None
+    th = pp.ProcessingPipelineThread(cfg, max_workers=3)
+    errors, finished, progress = [], [], []
+    th.error_signal.connect(errors.append); th.finished_signal.connect(lambda: finished.append(1))
+    th.progress_update.connect(progress.append)
+    th.run()
+    assert not errors and finished == [1] and not th.error_occurred and progress[-1] == 100
+    assert sorted(os.listdir(dst)) == [f"layer{zi:03d}.png" for zi in zs]
+    # a run that starts at layer 10 sees no priors for layer 10 (checkpoint caveat), so
+    # compare from the first layer whose whole window lies inside the run
+    for zi in zs[3:]:
+        out = cv2.imread(str(dst / f"layer{zi:03d}.png"), cv2.IMREAD_GRAYSCALE)
+        assert sha(out) == str(ref_stack["cfg1_sha1"][zi]), zi
+    th2 = pp.ProcessingPipelineThread(cfg, max_workers=1)
+    cfg.input_folder = str(tmp_path / "out")          # empty index range -> error signal, no exception
+    cfg.start_index = 1000
+    errs = []
+    th2.error_signal.connect(errs.append)
+    th2.run()
+    assert errs and "No images found" in errs[0]
+
+
+@pytest.mark.parametrize("mode", ["fixed_fade", "weighted_stack", "enhanced_edt"])
+def test_stack_engine_modes_and_zshard(E, mode):
+    """stack engine vs the oracle's stack loop for every mode, and Z-slab + halo == whole stack."""
+    layers = small_stack(W=448, H=272, L=12, seed=5, raft=True, n_blobs=9)
+    cfg = make_cfg(blending_mode=mode, receding_layers=3, fixed_fade_distance_receding=14.0,
+                   manual_weights=[5, 3, 1], fade_distances_receding=[14.0, 9.0, 5.0])
+    from config import XYBlendOperation
+    cfg.xy_blend_pipeline = [XYBlendOperation(type="gaussian_blur", gaussian_ksize_x=5, gaussian_ksize_y=3, gaussian_sigma_x=1.1),
+                             XYBlendOperation(type="median_blur", median_ksize=3)]
+    ocfg = {"blending_mode": mode, "receding_layers": 3, "use_fixed_fade_receding": True,
+            "fixed_fade_distance_receding": 14.0, "manual_weights": [5, 3, 1], "fade_distances_receding": [14.0, 9.0, 5.0],
+            "xy_blend_pipeline": [{"type": "gaussian_blur", "gaussian_ksize_x": 5, "gaussian_ksize_y": 3, "gaussian_sigma_x": 1.1},
+                                  {"type": "median_blur", "median_ksize": 3}]}
+    want = O.run_stack(layers, ocfg)
+    H, W = layers[0].shape
+    eng = engine_for(E, cfg, W, H)
+    got = [eng.process(g) for g in layers]
+    for zi, (a, b) in enumerate(zip(got, want)):
+        assert np.array_equal(a, b), (mode, zi)
+    for part in E.zshard_plan(len(layers), 3, 3):                 # slabs re-ingest a 3-layer halo
+        eng.reset()
+        for h in layers[part["halo0"]:part["z0"]]:
+            eng.push_halo(h)
+        for zi in range(part["z0"], part["z1"]):
+            assert np.array_equal(eng.process(layers[zi]), want[zi]), (mode, part, zi)
+    eng.close()
+
+
+def test_synth_raster_device_equals_numpy(E):
+    import vsb_synth as S
+    W, H, L = 700, 333, 14
+    table, raft = S.make_table(W, H, L, seed=9, n_blobs=12, grid=75, r_range=(10, 90), r_turn=120)
+    dev = S.DeviceStack(W, H, L, seed=9)
+    # same table parameters are needed for equality: rebuild with the defaults DeviceStack uses
+    table, raft = S.make_table(W, H, L, seed=9)
+    for z in (0, 5, 11, 12, 13):
+        got = dev.layers[z][:, :W].cpu().numpy()
+        assert np.array_equal(got, S.raster_numpy(table, raft, z, W, H)), z

@@ -1,0 +1,339 @@
+// vsb_stack.cu -- the per-stack runtime behind the host-buffer entry points: sliding window of packed
+// prior masks, device staging slots, three-stream H2D / compute / D2H pipeline, XY op chain.
+//
+// Replaces the producer loop + per-layer task of ProcessingPipelineThread
+// (processing_pipeline.py:74-113, :163, :188-223): deque(maxlen=receding_layers) of thresholded masks,
+// newest-first snapshot per layer, Z-blend -> merge -> XY chain.  PNG decode/encode stays with the caller.
+#include <vector>
+#include <new>
+#include <cstring>
+#include "vsb_common.cuh"
+
+#define STACK_SLOTS 3
+
+struct DevOp {
+    int type; // 1 lut, 2 gaussian, 3 bilateral, 4 median
+    uint8_t *lut_dev;
+    vsb_xy_op op; // host copy of the parameters
+};
+
+struct vsb_stack {
+    int W, H, wpr, n_priors;
+    size_t pitch; // device pitch of staging / temporaries (multiple of 128)
+    vsb_zparams zp;
+    std::vector<DevOp> ops;      // XY chain after LUT composition
+    uint8_t *lead_lut_dev;       // leading apply_lut ops composed, or nullptr
+    float *T_dev;
+    cudaStream_t s_h2d, s_comp, s_d2h;
+    cudaEvent_t ev_h2d[STACK_SLOTS], ev_comp[STACK_SLOTS], ev_d2h[STACK_SLOTS];
+    bool slot_used[STACK_SLOTS];
+    uint8_t *gray_dev[STACK_SLOTS], *out_dev[STACK_SLOTS];
+    uint8_t *tmp[2];
+    std::vector<uint32_t *> ring; // n_priors + 1 packed masks
+    int head, count;
+    long long submitted;
+    // Enhanced-EDT scratch (allocated on first use)
+    uint32_t *rec_bits;
+    float *dist;
+    int32_t *labels;
+    uint32_t *cmax;
+};
+
+static void compose(uint8_t *acc, const uint8_t *next)
+{
+    uint8_t t[256];
+    for (int i = 0; i < 256; ++i) t[i] = next[acc[i]]; // final = cur[final], pyside_xy_blend_tab.py:314-321
+    memcpy(acc, t, 256);
+}
+
+extern "C" int vsb_stack_destroy(vsb_stack *s)
+{
+    if (!s) return VSB_OK;
+    cudaStreamSynchronize(s->s_h2d); cudaStreamSynchronize(s->s_comp); cudaStreamSynchronize(s->s_d2h);
+    for (auto &o : s->ops) if (o.lut_dev) cudaFree(o.lut_dev);
+    if (s->lead_lut_dev) cudaFree(s->lead_lut_dev);
+    if (s->T_dev) cudaFree(s->T_dev);
+    for (int i = 0; i < STACK_SLOTS; ++i) {
+        if (s->gray_dev[i]) cudaFree(s->gray_dev[i]);
+        if (s->out_dev[i]) cudaFree(s->out_dev[i]);
+        if (s->ev_h2d[i]) cudaEventDestroy(s->ev_h2d[i]);
+        if (s->ev_comp[i]) cudaEventDestroy(s->ev_comp[i]);
+        if (s->ev_d2h[i]) cudaEventDestroy(s->ev_d2h[i]);
+    }
+    for (int i = 0; i < 2; ++i) if (s->tmp[i]) cudaFree(s->tmp[i]);
+    for (auto p : s->ring) if (p) cudaFree(p);
+    if (s->rec_bits) cudaFree(s->rec_bits);
+    if (s->dist) cudaFree(s->dist);
+    if (s->labels) cudaFree(s->labels);
+    if (s->cmax) cudaFree(s->cmax);
+    if (s->s_h2d) cudaStreamDestroy(s->s_h2d);
+    if (s->s_comp) cudaStreamDestroy(s->s_comp);
+    if (s->s_d2h) cudaStreamDestroy(s->s_d2h);
+    delete s;
+    return VSB_OK;
+}
+
+#define STACK_CUDA(call)                                                                                       \
+    do {                                                                                                       \
+        cudaError_t e__ = (call);                                                                              \
+        if (e__ != cudaSuccess) {                                                                              \
+            vsb_set_error("%s failed: %s", #call, cudaGetErrorString(e__));                                    \
+            vsb_stack_destroy(s);                                                                              \
+            return VSB_ERR_CUDA;                                                                               \
+        }                                                                                                      \
+    } while (0)
+
+extern "C" int vsb_stack_create(int W, int H, int n_priors, const vsb_zparams *zp, const vsb_xy_op *ops, int n_ops,
+                                vsb_stack **out_stack)
+{
+    VSB_REQUIRE(out_stack && zp, "vsb_stack_create: null pointer");
+    VSB_REQUIRE(W > 0 && H > 0 && n_priors >= 0 && n_priors <= VSB_MAX_PRIORS,
+                "vsb_stack_create: bad geometry or more than %d receding layers", VSB_MAX_PRIORS);
+    VSB_REQUIRE(n_ops >= 0 && n_ops <= VSB_MAX_XY_OPS && (n_ops == 0 || ops), "vsb_stack_create: bad op list");
+    VSB_REQUIRE(zp->reach >= 0 && zp->reach <= VSB_FAST_REACH, "vsb_stack_create: reach %d > %d", zp->reach,
+                VSB_FAST_REACH);
+    vsb_stack *s = new (std::nothrow) vsb_stack();
+    VSB_REQUIRE(s, "vsb_stack_create: out of memory");
+    s->W = W; s->H = H; s->wpr = ((W + 127) / 128) * 4; s->n_priors = n_priors;
+    s->pitch = ((size_t)W + 127) & ~(size_t)127;
+    s->zp = *zp;
+    s->lead_lut_dev = nullptr; s->T_dev = nullptr;
+    s->s_h2d = s->s_comp = s->s_d2h = nullptr;
+    for (int i = 0; i < STACK_SLOTS; ++i) {
+        s->ev_h2d[i] = s->ev_comp[i] = s->ev_d2h[i] = nullptr;
+        s->slot_used[i] = false; s->gray_dev[i] = s->out_dev[i] = nullptr;
+    }
+    s->tmp[0] = s->tmp[1] = nullptr;
+    s->head = 0; s->count = 0; s->submitted = 0;
+    s->rec_bits = nullptr; s->dist = nullptr; s->labels = nullptr; s->cmax = nullptr;
+
+    // XY chain: compose runs of apply_lut; a leading run is folded into the Z-blend epilogue
+    uint8_t lead[256];
+    bool have_lead = false, leading = true;
+    for (int i = 0; i < n_ops; ++i) {
+        const vsb_xy_op &op = ops[i];
+        if (op.type == 0) continue;
+        if (op.type == 1) {
+            if (leading) {
+                if (!have_lead) { memcpy(lead, op.lut, 256); have_lead = true; }
+                else compose(lead, op.lut);
+            } else if (!s->ops.empty() && s->ops.back().type == 1) {
+                compose(s->ops.back().op.lut, op.lut);
+            } else {
+                DevOp d; d.type = 1; d.lut_dev = nullptr; d.op = op; s->ops.push_back(d);
+            }
+            continue;
+        }
+        leading = false;
+        if (op.type == 4 && op.median_ksize <= 1) continue; // apply_median_blur no-op, xy_blend_processor.py:45
+        if (op.type < 1 || op.type > 4) { vsb_set_error("vsb_stack_create: unknown op type %d", op.type); delete s; return VSB_ERR_ARG; }
+        DevOp d; d.type = op.type; d.lut_dev = nullptr; d.op = op; s->ops.push_back(d);
+    }
+    STACK_CUDA(cudaStreamCreateWithFlags(&s->s_h2d, cudaStreamNonBlocking));
+    STACK_CUDA(cudaStreamCreateWithFlags(&s->s_comp, cudaStreamNonBlocking));
+    STACK_CUDA(cudaStreamCreateWithFlags(&s->s_d2h, cudaStreamNonBlocking));
+    for (int i = 0; i < STACK_SLOTS; ++i) {
+        STACK_CUDA(cudaEventCreateWithFlags(&s->ev_h2d[i], cudaEventDisableTiming));
+        STACK_CUDA(cudaEventCreateWithFlags(&s->ev_comp[i], cudaEventDisableTiming));
+        STACK_CUDA(cudaEventCreateWithFlags(&s->ev_d2h[i], cudaEventDisableTiming));
+        STACK_CUDA(cudaMalloc((void **)&s->gray_dev[i], s->pitch * H));
+        STACK_CUDA(cudaMalloc((void **)&s->out_dev[i], s->pitch * H));
+    }
+    if (!s->ops.empty()) {
+        STACK_CUDA(cudaMalloc((void **)&s->tmp[0], s->pitch * H));
+        if (s->ops.size() > 1) STACK_CUDA(cudaMalloc((void **)&s->tmp[1], s->pitch * H));
+    }
+    if (have_lead) {
+        STACK_CUDA(cudaMalloc((void **)&s->lead_lut_dev, 256));
+        STACK_CUDA(cudaMemcpy(s->lead_lut_dev, lead, 256, cudaMemcpyHostToDevice));
+    }
+    for (auto &o : s->ops)
+        if (o.type == 1) {
+            STACK_CUDA(cudaMalloc((void **)&o.lut_dev, 256));
+            STACK_CUDA(cudaMemcpy(o.lut_dev, o.op.lut, 256, cudaMemcpyHostToDevice));
+        }
+    {
+        const int n1 = zp->reach + 1;
+        std::vector<float> T((size_t)n1 * n1);
+        vsb_chamfer_table(T.data(), zp->reach);
+        STACK_CUDA(cudaMalloc((void **)&s->T_dev, T.size() * sizeof(float)));
+        STACK_CUDA(cudaMemcpy(s->T_dev, T.data(), T.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    s->ring.assign((size_t)n_priors + 1, nullptr);
+    for (auto &p : s->ring) STACK_CUDA(cudaMalloc((void **)&p, (size_t)s->wpr * H * sizeof(uint32_t)));
+    *out_stack = s;
+    return VSB_OK;
+}
+
+extern "C" int vsb_stack_reset(vsb_stack *s)
+{
+    VSB_REQUIRE(s, "vsb_stack_reset: null stack");
+    s->head = 0; s->count = 0;
+    return VSB_OK;
+}
+
+extern "C" int vsb_stack_slots(vsb_stack *s) { return s ? STACK_SLOTS : 0; }
+extern "C" vsb_stream_t vsb_stack_stream(vsb_stack *s) { return s ? (vsb_stream_t)s->s_comp : nullptr; }
+
+static int ensure_enhanced_scratch(vsb_stack *s)
+{
+    if (s->dist) return VSB_OK;
+    const size_t n = (size_t)s->W * s->H;
+    VSB_CUDA(cudaMalloc((void **)&s->rec_bits, (size_t)s->wpr * s->H * sizeof(uint32_t)));
+    VSB_CUDA(cudaMalloc((void **)&s->dist, n * sizeof(float)));
+    VSB_CUDA(cudaMalloc((void **)&s->labels, n * sizeof(int32_t)));
+    VSB_CUDA(cudaMalloc((void **)&s->cmax, n * sizeof(uint32_t)));
+    return VSB_OK;
+}
+
+// all kernels of one layer on the compute stream; gray/out are device pointers
+static int run_layer(vsb_stack *s, const uint8_t *gray, size_t gpitch, uint8_t *out, size_t opitch, bool emit)
+{
+    vsb_stream_t st = (vsb_stream_t)s->s_comp;
+    const int nring = s->n_priors + 1;
+    uint32_t *cur = s->ring[s->head];
+    int rc = vsb_threshold_pack(gray, gpitch, s->W, s->H, 127, cur, s->wpr, st);
+    if (rc) return rc;
+    if (emit) {
+        const uint32_t *pri[VSB_MAX_PRIORS];
+        const int np = s->count < s->n_priors ? s->count : s->n_priors;
+        for (int i = 0; i < np; ++i) pri[i] = s->ring[(s->head - 1 - i + 2 * nring) % nring]; // newest first
+        vsb_zparams zp = s->zp;
+        if (zp.mode == VSB_Z_WEIGHTED) {
+            // k = min(len(priors), len(weights)); total weight is over the k used weights (processing_core.py:231-238)
+            const int k = np < zp.n_priors ? np : zp.n_priors;
+            float tot = 0.0f;
+            double totd = 0.0;
+            for (int i = 0; i < k; ++i) totd += (double)zp.weights[i];
+            tot = (float)totd;
+            zp.n_priors = (totd > 0.0) ? k : 0;
+            zp.total_weight = tot;
+        } else {
+            zp.n_priors = np;
+        }
+        const size_t nops = s->ops.size();
+        uint8_t *zdst = nops ? s->tmp[0] : out;
+        const size_t zpitch = nops ? s->pitch : opitch;
+        if (zp.mode == VSB_Z_ENHANCED) {
+            rc = ensure_enhanced_scratch(s);
+            if (rc) return rc;
+            rc = vsb_maskdiff(cur, pri, np, s->wpr, s->H, s->rec_bits, nullptr, st);
+            if (rc) return rc;
+            vsb_zparams zd = zp; zd.mode = VSB_Z_DIST;
+            rc = vsb_zblend_fused(nullptr, 0, s->W, s->H, cur, pri, s->wpr, &zd, s->T_dev, nullptr, nullptr, 0, s->dist,
+                                  (size_t)s->W, st);
+            if (rc) return rc;
+            rc = vsb_ccl8_max(s->rec_bits, s->wpr, s->W, s->H, s->dist, (size_t)s->W, s->labels, s->cmax, st);
+            if (rc) return rc;
+            rc = vsb_enhanced_fade(gray, gpitch, s->W, s->H, s->rec_bits, s->wpr, s->dist, (size_t)s->W, s->labels,
+                                   s->cmax, zp.fade_limit, zp.enhanced_arith, s->lead_lut_dev, zdst, zpitch, st);
+            if (rc) return rc;
+        } else {
+            rc = vsb_zblend_fused(gray, gpitch, s->W, s->H, cur, pri, s->wpr, &zp, s->T_dev, s->lead_lut_dev, zdst, zpitch,
+                                  nullptr, 0, st);
+            if (rc) return rc;
+        }
+        const uint8_t *src = zdst;
+        size_t spitch = zpitch;
+        for (size_t i = 0; i < nops; ++i) {
+            const bool last = (i + 1 == nops);
+            uint8_t *dst = last ? out : s->tmp[(i + 1) & 1];
+            const size_t dpitch = last ? opitch : s->pitch;
+            const DevOp &o = s->ops[i];
+            switch (o.type) {
+            case 1: rc = vsb_lut_apply(src, spitch, s->W, s->H, o.lut_dev, dst, dpitch, st); break;
+            case 2: rc = vsb_gaussian_q88(src, spitch, s->W, s->H, o.op.kx, o.op.nkx, o.op.ky, o.op.nky, dst, dpitch, st); break;
+            case 3: rc = vsb_bilateral(src, spitch, s->W, s->H, o.op.radius, o.op.ntaps, o.op.tap_dy, o.op.tap_dx,
+                                       o.op.tap_sw, o.op.cw, dst, dpitch, st); break;
+            case 4: rc = vsb_median(src, spitch, s->W, s->H, o.op.median_ksize, dst, dpitch, st); break;
+            default: rc = VSB_ERR_ARG;
+            }
+            if (rc) return rc;
+            src = dst; spitch = dpitch;
+        }
+    }
+    s->head = (s->head + 1) % nring;
+    if (s->count < s->n_priors) ++s->count;
+    return VSB_OK;
+}
+
+extern "C" int vsb_stack_process_device(vsb_stack *s, const uint8_t *gray_dev, size_t in_pitch, uint8_t *out_dev,
+                                        size_t out_pitch)
+{
+    VSB_REQUIRE(s && gray_dev && out_dev, "vsb_stack_process_device: null pointer");
+    return run_layer(s, gray_dev, in_pitch, out_dev, out_pitch, true);
+}
+
+extern "C" int vsb_stack_process_device_batch(vsb_stack *s, const uint8_t *gray_dev, size_t in_pitch,
+                                              size_t in_layer_stride, uint8_t *out_dev, size_t out_pitch,
+                                              size_t out_layer_stride, int n_layers)
+{
+    VSB_REQUIRE(s && gray_dev && out_dev && n_layers >= 0, "vsb_stack_process_device_batch: bad arguments");
+    for (int i = 0; i < n_layers; ++i) {
+        int rc = run_layer(s, gray_dev + (size_t)i * in_layer_stride, in_pitch, out_dev + (size_t)i * out_layer_stride,
+                           out_pitch, true);
+        if (rc) return rc;
+    }
+    return VSB_OK;
+}
+
+extern "C" int vsb_stack_sync(vsb_stack *s)
+{
+    VSB_REQUIRE(s, "vsb_stack_sync: null stack");
+    VSB_CUDA(cudaStreamSynchronize(s->s_h2d));
+    VSB_CUDA(cudaStreamSynchronize(s->s_comp));
+    VSB_CUDA(cudaStreamSynchronize(s->s_d2h));
+    return VSB_OK;
+}
+
+static int submit(vsb_stack *s, const uint8_t *gray_host, size_t in_pitch, uint8_t *out_host, size_t out_pitch, bool emit)
+{
+    const int slot = (int)(s->submitted % STACK_SLOTS);
+    if (s->slot_used[slot]) VSB_CUDA(cudaEventSynchronize(s->ev_d2h[slot])); // slot's previous layer fully drained
+    VSB_CUDA(cudaMemcpy2DAsync(s->gray_dev[slot], s->pitch, gray_host, in_pitch, (size_t)s->W, (size_t)s->H,
+                               cudaMemcpyHostToDevice, s->s_h2d));
+    VSB_CUDA(cudaEventRecord(s->ev_h2d[slot], s->s_h2d));
+    VSB_CUDA(cudaStreamWaitEvent(s->s_comp, s->ev_h2d[slot], 0));
+    int rc = run_layer(s, s->gray_dev[slot], s->pitch, s->out_dev[slot], s->pitch, emit);
+    if (rc) return rc;
+    VSB_CUDA(cudaEventRecord(s->ev_comp[slot], s->s_comp));
+    VSB_CUDA(cudaStreamWaitEvent(s->s_d2h, s->ev_comp[slot], 0));
+    if (emit)
+        VSB_CUDA(cudaMemcpy2DAsync(out_host, out_pitch, s->out_dev[slot], s->pitch, (size_t)s->W, (size_t)s->H,
+                                   cudaMemcpyDeviceToHost, s->s_d2h));
+    VSB_CUDA(cudaEventRecord(s->ev_d2h[slot], s->s_d2h));
+    s->slot_used[slot] = true;
+    const long long ticket = s->submitted++;
+    return (int)(ticket & 0x3fffffff);
+}
+
+extern "C" int vsb_stack_submit_host(vsb_stack *s, const uint8_t *gray_host, size_t in_pitch, uint8_t *out_host,
+                                     size_t out_pitch)
+{
+    VSB_REQUIRE(s && gray_host && out_host, "vsb_stack_submit_host: null pointer");
+    VSB_REQUIRE(in_pitch >= (size_t)s->W && out_pitch >= (size_t)s->W, "vsb_stack_submit_host: pitch < width");
+    return submit(s, gray_host, in_pitch, out_host, out_pitch, true);
+}
+
+extern "C" int vsb_stack_wait(vsb_stack *s, int ticket)
+{
+    VSB_REQUIRE(s && ticket >= 0, "vsb_stack_wait: bad arguments");
+    VSB_CUDA(cudaEventSynchronize(s->ev_d2h[ticket % STACK_SLOTS]));
+    return VSB_OK;
+}
+
+extern "C" int vsb_stack_push_halo(vsb_stack *s, const uint8_t *gray_host, size_t pitch)
+{
+    VSB_REQUIRE(s && gray_host && pitch >= (size_t)s->W, "vsb_stack_push_halo: bad arguments");
+    int t = submit(s, gray_host, pitch, nullptr, 0, false);
+    if (t < 0) return t;
+    return vsb_stack_wait(s, t);
+}
+
+extern "C" int vsb_stack_process_host(vsb_stack *s, const uint8_t *gray_host, size_t in_pitch, uint8_t *out_host,
+                                      size_t out_pitch)
+{
+    int t = vsb_stack_submit_host(s, gray_host, in_pitch, out_host, out_pitch);
+    if (t < 0) return t;
+    return vsb_stack_wait(s, t);
+}

@@ -1,0 +1,53 @@
+// vsb_tile.cuh -- staged bit-mask tile (128x32 pixels + 64-bit / R-row halo) and the row probe
+// shared by the fused Z-blend kernel and the dense distance kernels.
+#pragma once
+#include "vsb_common.cuh"
+
+#define HALO_WORDS 2                       // 64 mask bits either side of the tile
+#define ROW_WORDS (4 + 2 * HALO_WORDS)     // 8 words = 256 bits per staged row
+#define MAX_ROWS (VSB_TH + 2 * VSB_FAST_REACH)
+
+// nearest set bit to bit position px in a staged 256-bit row, searched over px-63 .. px+63
+__device__ __forceinline__ int nearest_dx(const uint32_t *rowp, int px)
+{
+    const int wi = px >> 5, b = px & 31; // wi in [2,5]
+    const uint32_t w0 = rowp[wi - 2], w1 = rowp[wi - 1], w2 = rowp[wi], w3 = rowp[wi + 1], w4 = rowp[wi + 2];
+    const uint32_t rlo = __funnelshift_r(w2, w3, b), rhi = __funnelshift_r(w3, w4, b);
+    const uint32_t ltop = __funnelshift_l(w1, w2, 31 - b), lnext = __funnelshift_l(w0, w1, 31 - b);
+    const int dr = rlo ? (__ffs(rlo) - 1) : (rhi ? 31 + __ffs(rhi) : 64);
+    const int dl = ltop ? __clz(ltop) : (lnext ? 32 + __clz(lnext) : 64);
+    return min(dl, dr);
+}
+
+
+// stage rows y0-R .. y0+TH-1+R, words (x0>>5)-2 .. (x0>>5)+5 of a packed mask; outside the image = 0
+__device__ __forceinline__ void stage_mask_tile(uint32_t (*s_cur)[ROW_WORDS], const uint32_t *__restrict__ bits,
+                                                int wpr, int H, int x0, int y0, int R)
+{
+    const int nrows = VSB_TH + 2 * R;
+    const int wbase = (x0 >> 5) - HALO_WORDS;
+    for (int i = threadIdx.x; i < nrows * ROW_WORDS; i += VSB_THREADS) {
+        const int hr = i >> 3, hw = i & 7;
+        const int yy = y0 - R + hr, wx = wbase + hw;
+        uint32_t v = 0;
+        if (yy >= 0 && yy < H && wx >= 0 && wx < wpr) v = bits[(size_t)yy * wpr + wx];
+        s_cur[hr][hw] = v;
+    }
+}
+
+// one bit per staged row: does the row hold any set bit (call after a __syncthreads())
+__device__ __forceinline__ void stage_rowany(uint32_t *s_rowany, const uint32_t (*s_cur)[ROW_WORDS], int nrows)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nmask = (nrows + 31) / 32;
+    if (warp < nmask) {
+        const int hr = warp * 32 + lane;
+        uint32_t v = 0;
+        if (hr < nrows) {
+#pragma unroll
+            for (int k = 0; k < ROW_WORDS; ++k) v |= s_cur[hr][k];
+        }
+        const uint32_t m = __ballot_sync(0xffffffffu, v != 0);
+        if (lane == 0) s_rowany[warp] = m;
+    }
+}

@@ -1,0 +1,366 @@
+"""
+vsb_engine -- device-side plumbing above the C-ABI: PyTorch owns device buffers and streams, every
+arithmetic step is a kernel of libvsb_b200.so.  Two layers:
+
+  * per-call helpers (numpy in -> numpy out) used by the re-authored processing_core /
+    xy_blend_processor / lut_manager entry points -- one H2D, the kernels, one D2H;
+  * StackEngine: the stack-level engine (C++ runtime in csrc/vsb_stack.cu) that keeps the sliding window
+    of packed prior masks on the device and pipelines H2D / kernels / D2H -- what
+    ProcessingPipelineThread.run() and bench.py drive.
+
+No CPU fallback: without a CUDA device every entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import threading
+from ctypes import c_void_p
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+import vsb_native as N
+import vsb_params as P
+
+_torch = None
+_lock = threading.Lock()
+
+
+def torch():
+    global _torch
+    if _torch is None:
+        import torch as _t
+        if not _t.cuda.is_available():
+            raise N.VsbError("no CUDA device visible: the B200 path has no CPU fallback")
+        _torch = _t
+    return _torch
+
+
+def _stream() -> int:
+    return torch().cuda.current_stream().cuda_stream
+
+
+def wpr_for(W: int) -> int:
+    return ((W + 127) // 128) * 4
+
+
+def pitch_for(W: int) -> int:
+    return (W + 127) & ~127
+
+
+class DevImage:
+    """uint8 [H, pitch] device buffer (pitch multiple of 128 so every row is 16-byte aligned)."""
+
+    def __init__(self, H: int, W: int, zero: bool = False):
+        t = torch()
+        self.H, self.W, self.pitch = H, W, pitch_for(W)
+        self.t = (t.zeros if zero else t.empty)((H, self.pitch), dtype=t.uint8, device="cuda")
+
+    @property
+    def ptr(self) -> int:
+        return self.t.data_ptr()
+
+    @classmethod
+    def from_numpy(cls, a: np.ndarray) -> "DevImage":
+        a = np.ascontiguousarray(a)
+        if a.dtype != np.uint8 or a.ndim != 2:
+            raise TypeError("expected a 2-D uint8 array")
+        d = cls(a.shape[0], a.shape[1])
+        d.t[:, : d.W].copy_(torch().from_numpy(a))
+        return d
+
+    def numpy(self) -> np.ndarray:
+        return self.t[:, : self.W].contiguous().cpu().numpy()
+
+
+class DevBits:
+    """bit-packed mask: uint32 [H, wpr]."""
+
+    def __init__(self, H: int, W: int):
+        t = torch()
+        self.H, self.W, self.wpr = H, W, wpr_for(W)
+        self.t = t.empty((H, self.wpr), dtype=t.int32, device="cuda")
+
+    @property
+    def ptr(self) -> int:
+        return self.t.data_ptr()
+
+
+_tables = {}
+_luts = {}
+
+
+def table_dev(R: int):
+    key = (torch().cuda.current_device(), R)
+    if key not in _tables:
+        _tables[key] = torch().from_numpy(N.chamfer_table(R)).cuda()
+    return _tables[key]
+
+
+def lut_dev(lut: np.ndarray):
+    lut = np.ascontiguousarray(lut)
+    if lut.dtype != np.uint8 or lut.shape != (256,):
+        raise ValueError("Provided lut_array must be a 256-entry NumPy array of dtype uint8.")
+    return torch().from_numpy(lut.copy()).cuda()
+
+
+# ---- per-call helpers -------------------------------------------------------------------------------------
+def pack(img: DevImage, thresh: int = 127) -> DevBits:
+    b = DevBits(img.H, img.W)
+    N.check(N.load().vsb_threshold_pack(img.ptr, img.pitch, img.W, img.H, thresh, b.ptr, b.wpr, _stream()),
+            "vsb_threshold_pack")
+    return b
+
+
+def unpack(b: DevBits) -> DevImage:
+    o = DevImage(b.H, b.W)
+    N.check(N.load().vsb_bits_unpack(b.ptr, b.wpr, b.W, b.H, o.ptr, o.pitch, _stream()), "vsb_bits_unpack")
+    return o
+
+
+def threshold_np(gray: np.ndarray, thresh: int = 127) -> np.ndarray:
+    return unpack(pack(DevImage.from_numpy(gray), thresh)).numpy()
+
+
+def or_bits(masks: Sequence[DevBits]) -> DevBits:
+    out = DevBits(masks[0].H, masks[0].W)
+    cur = list(masks)
+    first = True
+    while cur:
+        chunk, cur = cur[: N.VSB_MAX_PRIORS - (0 if first else 1)], cur[N.VSB_MAX_PRIORS - (0 if first else 1):]
+        srcs = [m.ptr for m in chunk] + ([] if first else [out.ptr])
+        N.check(N.load().vsb_bits_or(N.ptr_array(srcs), len(srcs), out.wpr, out.H, out.ptr, _stream()), "vsb_bits_or")
+        first = False
+    return out
+
+
+def count_receding(cur: DevBits, priors: Sequence[DevBits]) -> int:
+    t = torch()
+    cnt = t.zeros(1, dtype=t.int64, device="cuda")
+    N.check(N.load().vsb_maskdiff(cur.ptr, N.ptr_array([p.ptr for p in priors]), len(priors), cur.wpr, cur.H, None,
+                                  cnt.data_ptr(), _stream()), "vsb_maskdiff")
+    return int(cnt.item())
+
+
+def zblend(gray: Optional[DevImage], cur: DevBits, priors: Sequence[DevBits], z: N.ZParams,
+           lut: Optional[np.ndarray] = None) -> DevImage:
+    """One fused Z-blend launch; gray=None -> the bare gradient (merge with zeros)."""
+    H, W = cur.H, cur.W
+    if gray is None:
+        gray = DevImage(H, W, zero=True)
+    out = DevImage(H, W)
+    zz = N.ZParams.from_buffer_copy(z)
+    zz.n_priors = min(len(priors), N.VSB_MAX_PRIORS) if z.mode != N.Z_WEIGHTED else z.n_priors
+    T = table_dev(zz.reach)
+    ld = lut_dev(lut) if lut is not None else None
+    N.check(N.load().vsb_zblend_fused(gray.ptr, gray.pitch, W, H, cur.ptr, N.ptr_array([p.ptr for p in priors]),
+                                      cur.wpr, ctypes.byref(zz), T.data_ptr(), ld.data_ptr() if ld is not None else None,
+                                      out.ptr, out.pitch, None, 0, _stream()), "vsb_zblend_fused")
+    return out
+
+
+def enhanced(gray: Optional[DevImage], cur: DevBits, priors: Sequence[DevBits], z: N.ZParams,
+             lut: Optional[np.ndarray] = None) -> DevImage:
+    """Enhanced EDT: rec mask -> clipped distance at rec pixels -> CCL + per-component max -> fade."""
+    t = torch()
+    H, W = cur.H, cur.W
+    if gray is None:
+        gray = DevImage(H, W, zero=True)
+    out = DevImage(H, W)
+    lib = N.load()
+    pri = N.ptr_array([p.ptr for p in priors])
+    rec = DevBits(H, W)
+    N.check(lib.vsb_maskdiff(cur.ptr, pri, len(priors), cur.wpr, H, rec.ptr, None, _stream()), "vsb_maskdiff")
+    dist = t.empty((H, W), dtype=t.float32, device="cuda")
+    labels = t.empty((H, W), dtype=t.int32, device="cuda")
+    cmax = t.empty((H, W), dtype=t.int32, device="cuda")
+    zd = N.ZParams.from_buffer_copy(z)
+    zd.mode, zd.n_priors = N.Z_DIST, len(priors)
+    T = table_dev(zd.reach)
+    N.check(lib.vsb_zblend_fused(None, 0, W, H, cur.ptr, pri, cur.wpr, ctypes.byref(zd), T.data_ptr(), None, None, 0,
+                                 dist.data_ptr(), W, _stream()), "vsb_zblend_fused(dist)")
+    N.check(lib.vsb_ccl8_max(rec.ptr, rec.wpr, W, H, dist.data_ptr(), W, labels.data_ptr(), cmax.data_ptr(), _stream()),
+            "vsb_ccl8_max")
+    ld = lut_dev(lut) if lut is not None else None
+    N.check(lib.vsb_enhanced_fade(gray.ptr, gray.pitch, W, H, rec.ptr, rec.wpr, dist.data_ptr(), W, labels.data_ptr(),
+                                  cmax.data_ptr(), float(z.fade_limit), int(z.enhanced_arith),
+                                  ld.data_ptr() if ld is not None else None, out.ptr, out.pitch, _stream()),
+            "vsb_enhanced_fade")
+    return out
+
+
+def enhanced_from_labels_np(rd: np.ndarray, labels: np.ndarray, num_labels: int, F: float, arith: int) -> np.ndarray:
+    t = torch()
+    rd = np.ascontiguousarray(rd, np.float32)
+    labels = np.ascontiguousarray(labels, np.int32)
+    H, W = rd.shape
+    d = t.from_numpy(rd).cuda()
+    l = t.from_numpy(labels).cuda()
+    cmax = t.empty(max(1, int(num_labels)), dtype=t.int32, device="cuda")
+    out = t.empty((H, W), dtype=t.uint8, device="cuda")
+    N.check(N.load().vsb_enhanced_from_labels(d.data_ptr(), l.data_ptr(), W, H, int(num_labels), float(F), int(arith),
+                                              cmax.data_ptr(), out.data_ptr(), _stream()), "vsb_enhanced_from_labels")
+    return out.cpu().numpy()
+
+
+def distance_np(cur_white: np.ndarray, R: int, clip: float, metric: str = "chamfer5") -> np.ndarray:
+    """Dense clipped distance map to the nearest cur_white>127 pixel (K2)."""
+    t = torch()
+    img = DevImage.from_numpy(cur_white)
+    b = pack(img)
+    H, W = img.H, img.W
+    dist = t.empty((H, W), dtype=t.float32, device="cuda")
+    if metric == "chamfer5":
+        N.check(N.load().vsb_dt_chamfer5(b.ptr, b.wpr, W, H, R, table_dev(R).data_ptr(), float(clip), dist.data_ptr(), W,
+                                         _stream()), "vsb_dt_chamfer5")
+    else:
+        N.check(N.load().vsb_dt_exact_windowed(b.ptr, b.wpr, W, H, R, float(clip), dist.data_ptr(), W, _stream()),
+                "vsb_dt_exact_windowed")
+    return dist.cpu().numpy()
+
+
+def edt_exact_np(cur_white: np.ndarray):
+    """Unbounded exact EDT: (squared distances int32, distances float32)."""
+    t = torch()
+    img = DevImage.from_numpy(cur_white)
+    b = pack(img)
+    H, W = img.H, img.W
+    col = t.empty((H, W), dtype=t.int16, device="cuda")
+    d2 = t.empty((H, W), dtype=t.int32, device="cuda")
+    dist = t.empty((H, W), dtype=t.float32, device="cuda")
+    N.check(N.load().vsb_dt_exact(b.ptr, b.wpr, W, H, col.data_ptr(), d2.data_ptr(), dist.data_ptr(), W, _stream()),
+            "vsb_dt_exact")
+    return d2.cpu().numpy(), dist.cpu().numpy()
+
+
+def merge_np(a: np.ndarray, b: np.ndarray) -> np.ndarray:
+    da, db = DevImage.from_numpy(a), DevImage.from_numpy(b)
+    o = DevImage(da.H, da.W)
+    N.check(N.load().vsb_merge_max(da.ptr, da.pitch, db.ptr, db.pitch, da.W, da.H, o.ptr, o.pitch, _stream()),
+            "vsb_merge_max")
+    return o.numpy()
+
+
+def lut_apply(img: DevImage, lut: np.ndarray) -> DevImage:
+    o = DevImage(img.H, img.W)
+    ld = lut_dev(lut)
+    N.check(N.load().vsb_lut_apply(img.ptr, img.pitch, img.W, img.H, ld.data_ptr(), o.ptr, o.pitch, _stream()),
+            "vsb_lut_apply")
+    return o
+
+
+def gaussian(img: DevImage, qx: np.ndarray, qy: np.ndarray) -> DevImage:
+    o = DevImage(img.H, img.W)
+    qx, qy = np.ascontiguousarray(qx, np.int32), np.ascontiguousarray(qy, np.int32)
+    N.check(N.load().vsb_gaussian_q88(img.ptr, img.pitch, img.W, img.H, qx.ctypes.data_as(c_void_p), len(qx),
+                                      qy.ctypes.data_as(c_void_p), len(qy), o.ptr, o.pitch, _stream()), "vsb_gaussian_q88")
+    return o
+
+
+def bilateral(img: DevImage, d: int, sigma_color: float, sigma_space: float) -> DevImage:
+    radius, dy, dx, sw, cw = P.bilateral_tables(d, sigma_color, sigma_space)
+    o = DevImage(img.H, img.W)
+    N.check(N.load().vsb_bilateral(img.ptr, img.pitch, img.W, img.H, radius, len(sw), dy.ctypes.data_as(c_void_p),
+                                   dx.ctypes.data_as(c_void_p), sw.ctypes.data_as(c_void_p), cw.ctypes.data_as(c_void_p),
+                                   o.ptr, o.pitch, _stream()), "vsb_bilateral")
+    return o
+
+
+def median(img: DevImage, ksize: int) -> DevImage:
+    o = DevImage(img.H, img.W)
+    N.check(N.load().vsb_median(img.ptr, img.pitch, img.W, img.H, int(ksize), o.ptr, o.pitch, _stream()), "vsb_median")
+    return o
+
+
+# ---- synthetic stacks (measurement utility) -----------------------------------------------------------------
+def synth_layer(prims_dev, n_prims: int, raft: Optional[np.ndarray], z: int, W: int, H: int, out_ptr: int, pitch: int):
+    r = np.ascontiguousarray(raft, np.float32) if raft is not None else None
+    N.check(N.load().vsb_synth_layer(prims_dev.data_ptr() if n_prims else None, n_prims,
+                                     r.ctypes.data_as(c_void_p) if r is not None else None, int(z), W, H, out_ptr, pitch,
+                                     _stream()), "vsb_synth_layer")
+
+
+# ---- the stack-level engine -------------------------------------------------------------------------------------
+class StackEngine:
+    """Device-resident per-stack engine (csrc/vsb_stack.cu).  Layers must be fed in Z order; the window of
+    the last `receding_layers` thresholded masks lives on the device (processing_pipeline.py:163,216-223)."""
+
+    def __init__(self, W: int, H: int, cfg, xy_ops: Optional[List[N.XYOp]] = None, metric: str = "chamfer5",
+                 device: Optional[int] = None):
+        t = torch()
+        if device is not None:
+            t.cuda.set_device(device)
+        self.device = t.cuda.current_device()
+        self.W, self.H = int(W), int(H)
+        self.pitch = pitch_for(W)
+        z = P.zparams_from_config(cfg, metric)
+        n_priors = max(0, int(cfg.receding_layers))
+        if n_priors > N.VSB_MAX_PRIORS:
+            raise P.UnsupportedOnDevice(f"more than {N.VSB_MAX_PRIORS} receding layers")
+        ops = list(xy_ops or [])
+        if len(ops) > N.VSB_MAX_XY_OPS:
+            raise P.UnsupportedOnDevice(f"more than {N.VSB_MAX_XY_OPS} XY operations")
+        arr = (N.XYOp * max(1, len(ops)))(*ops)
+        h = c_void_p()
+        N.check(N.load().vsb_stack_create(self.W, self.H, n_priors, ctypes.byref(z), arr, len(ops), ctypes.byref(h)),
+                "vsb_stack_create")
+        self._h = h
+        self.slots = N.load().vsb_stack_slots(h)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            N.load().vsb_stack_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def reset(self):
+        N.check(N.load().vsb_stack_reset(self._h), "vsb_stack_reset")
+
+    def push_halo(self, gray: np.ndarray):
+        gray = np.ascontiguousarray(gray, np.uint8)
+        N.check(N.load().vsb_stack_push_halo(self._h, gray.ctypes.data_as(c_void_p), gray.strides[0]), "vsb_stack_push_halo")
+
+    def process(self, gray: np.ndarray) -> np.ndarray:
+        gray = np.ascontiguousarray(gray, np.uint8)
+        if gray.shape != (self.H, self.W):
+            raise ValueError(f"layer shape {gray.shape} != engine shape {(self.H, self.W)}")
+        out = np.empty_like(gray)
+        N.check(N.load().vsb_stack_process_host(self._h, gray.ctypes.data_as(c_void_p), gray.strides[0],
+                                                out.ctypes.data_as(c_void_p), out.strides[0]), "vsb_stack_process_host")
+        return out
+
+    def submit(self, gray_ptr: int, in_pitch: int, out_ptr: int, out_pitch: int) -> int:
+        """Pipelined host path on raw (ideally pinned) host pointers; returns a ticket for wait()."""
+        return N.check(N.load().vsb_stack_submit_host(self._h, gray_ptr, in_pitch, out_ptr, out_pitch),
+                       "vsb_stack_submit_host")
+
+    def wait(self, ticket: int):
+        N.check(N.load().vsb_stack_wait(self._h, ticket), "vsb_stack_wait")
+
+    def process_device(self, gray_ptr: int, in_pitch: int, out_ptr: int, out_pitch: int):
+        N.check(N.load().vsb_stack_process_device(self._h, gray_ptr, in_pitch, out_ptr, out_pitch),
+                "vsb_stack_process_device")
+
+    def process_device_batch(self, gray_ptr: int, in_pitch: int, in_stride: int, out_ptr: int, out_pitch: int,
+                             out_stride: int, n: int):
+        N.check(N.load().vsb_stack_process_device_batch(self._h, gray_ptr, in_pitch, in_stride, out_ptr, out_pitch,
+                                                        out_stride, n), "vsb_stack_process_device_batch")
+
+    def sync(self):
+        N.check(N.load().vsb_stack_sync(self._h), "vsb_stack_sync")
+
+    @property
+    def stream(self) -> int:
+        return N.load().vsb_stack_stream(self._h) or 0
+
+
+def zshard_plan(n_layers: int, world: int, halo: int):
+    """Contiguous Z-slabs [z0,z1) per rank plus the read-only halo [max(0,z0-halo), z0) each slab re-ingests
+    (masks only).  No data-path collective."""
+    per = -(-n_layers // world)
+    plan = []
+    for r in range(world):
+        z0, z1 = min(n_layers, r * per), min(n_layers, (r + 1) * per)
+        plan.append({"rank": r, "z0": z0, "z1": z1, "halo0": max(0, z0 - halo)})
+    return plan
