@@ -231,11 +231,17 @@ int vsb_stack_slots(vsb_stack *s);
 /* one layer, device in -> device out on the stack's stream (asynchronous) */
 int vsb_stack_process_device(vsb_stack *s, const uint8_t *gray_dev, size_t in_pitch,
                              uint8_t *out_dev, size_t out_pitch);
-/* n consecutive device-resident layers (layer i at base + i*stride), one call */
+/* n device-resident layers in one call: layer i is read at gray_dev + i*in_layer_stride (the stride may
+ * be negative to walk a slab downwards) and written to out_dev + (i % out_ring)*out_layer_stride */
 int vsb_stack_process_device_batch(vsb_stack *s, const uint8_t *gray_dev, size_t in_pitch,
-                                   size_t in_layer_stride, uint8_t *out_dev, size_t out_pitch,
-                                   size_t out_layer_stride, int n_layers);
+                                   long long in_layer_stride, uint8_t *out_dev, size_t out_pitch,
+                                   long long out_layer_stride, int out_ring, int n_layers);
 int vsb_stack_sync(vsb_stack *s);
+/* per-stage CUDA-event timing of the layer kernels on the stack's compute stream (measurement aid):
+ * enable(1) starts recording an event pair around every stage; read() synchronises, returns the number of
+ * stages and fills the summed milliseconds, kernel-launch counts and 32-byte stage names, then clears. */
+int vsb_stack_profile_enable(vsb_stack *s, int on);
+int vsb_stack_profile_read(vsb_stack *s, int max_stages, float *ms_sum, int *launches, char *names);
 vsb_stream_t vsb_stack_stream(vsb_stack *s);
 
 /* ---------------------------------------------------------------------------------------------

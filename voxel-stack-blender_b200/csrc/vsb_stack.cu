@@ -37,6 +37,28 @@ struct vsb_stack {
     float *dist;
     int32_t *labels;
     uint32_t *cmax;
+    // optional per-stage CUDA-event profiling (bench.py roofline leg)
+    bool prof_on;
+    struct ProfRec { int stage; int launches; cudaEvent_t a, b; };
+    std::vector<ProfRec> prof;
+};
+
+enum { ST_PACK = 0, ST_ZBLEND, ST_MASKDIFF, ST_ZDIST, ST_CCL, ST_EFADE, ST_OP0 };
+static const char *kStageNames[] = {"threshold_pack", "zblend_fused", "maskdiff", "zblend_dist", "ccl8_max", "enhanced_fade"};
+static const char *kOpNames[] = {"none", "lut_apply", "gaussian_q88", "bilateral", "median"};
+
+struct ProfScope {
+    vsb_stack *s; size_t idx; bool on;
+    ProfScope(vsb_stack *st, int stage, int launches) : s(st), idx(0), on(st->prof_on)
+    {
+        if (!on) return;
+        vsb_stack::ProfRec r; r.stage = stage; r.launches = launches; r.a = r.b = nullptr;
+        if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) { on = false; return; }
+        cudaEventRecord(r.a, s->s_comp);
+        idx = s->prof.size();
+        s->prof.push_back(r);
+    }
+    ~ProfScope() { if (on) cudaEventRecord(s->prof[idx].b, s->s_comp); }
 };
 
 static void compose(uint8_t *acc, const uint8_t *next)
@@ -62,6 +84,7 @@ extern "C" int vsb_stack_destroy(vsb_stack *s)
     }
     for (int i = 0; i < 2; ++i) if (s->tmp[i]) cudaFree(s->tmp[i]);
     for (auto p : s->ring) if (p) cudaFree(p);
+    for (auto &r : s->prof) { if (r.a) cudaEventDestroy(r.a); if (r.b) cudaEventDestroy(r.b); }
     if (s->rec_bits) cudaFree(s->rec_bits);
     if (s->dist) cudaFree(s->dist);
     if (s->labels) cudaFree(s->labels);
@@ -106,6 +129,7 @@ extern "C" int vsb_stack_create(int W, int H, int n_priors, const vsb_zparams *z
     s->tmp[0] = s->tmp[1] = nullptr;
     s->head = 0; s->count = 0; s->submitted = 0;
     s->rec_bits = nullptr; s->dist = nullptr; s->labels = nullptr; s->cmax = nullptr;
+    s->prof_on = false;
 
     // XY chain: compose runs of apply_lut; a leading run is folded into the Z-blend epilogue
     uint8_t lead[256];
@@ -192,7 +216,8 @@ static int run_layer(vsb_stack *s, const uint8_t *gray, size_t gpitch, uint8_t *
     vsb_stream_t st = (vsb_stream_t)s->s_comp;
     const int nring = s->n_priors + 1;
     uint32_t *cur = s->ring[s->head];
-    int rc = vsb_threshold_pack(gray, gpitch, s->W, s->H, 127, cur, s->wpr, st);
+    int rc;
+    { ProfScope ps(s, ST_PACK, 1); rc = vsb_threshold_pack(gray, gpitch, s->W, s->H, 127, cur, s->wpr, st); }
     if (rc) return rc;
     if (emit) {
         const uint32_t *pri[VSB_MAX_PRIORS];
@@ -217,20 +242,23 @@ static int run_layer(vsb_stack *s, const uint8_t *gray, size_t gpitch, uint8_t *
         if (zp.mode == VSB_Z_ENHANCED) {
             rc = ensure_enhanced_scratch(s);
             if (rc) return rc;
-            rc = vsb_maskdiff(cur, pri, np, s->wpr, s->H, s->rec_bits, nullptr, st);
+            { ProfScope ps(s, ST_MASKDIFF, 1); rc = vsb_maskdiff(cur, pri, np, s->wpr, s->H, s->rec_bits, nullptr, st); }
             if (rc) return rc;
             vsb_zparams zd = zp; zd.mode = VSB_Z_DIST;
-            rc = vsb_zblend_fused(nullptr, 0, s->W, s->H, cur, pri, s->wpr, &zd, s->T_dev, nullptr, nullptr, 0, s->dist,
-                                  (size_t)s->W, st);
+            { ProfScope ps(s, ST_ZDIST, 1);
+              rc = vsb_zblend_fused(nullptr, 0, s->W, s->H, cur, pri, s->wpr, &zd, s->T_dev, nullptr, nullptr, 0, s->dist,
+                                    (size_t)s->W, st); }
             if (rc) return rc;
-            rc = vsb_ccl8_max(s->rec_bits, s->wpr, s->W, s->H, s->dist, (size_t)s->W, s->labels, s->cmax, st);
+            { ProfScope ps(s, ST_CCL, 3); rc = vsb_ccl8_max(s->rec_bits, s->wpr, s->W, s->H, s->dist, (size_t)s->W, s->labels, s->cmax, st); }
             if (rc) return rc;
-            rc = vsb_enhanced_fade(gray, gpitch, s->W, s->H, s->rec_bits, s->wpr, s->dist, (size_t)s->W, s->labels,
-                                   s->cmax, zp.fade_limit, zp.enhanced_arith, s->lead_lut_dev, zdst, zpitch, st);
+            { ProfScope ps(s, ST_EFADE, 1);
+              rc = vsb_enhanced_fade(gray, gpitch, s->W, s->H, s->rec_bits, s->wpr, s->dist, (size_t)s->W, s->labels,
+                                     s->cmax, zp.fade_limit, zp.enhanced_arith, s->lead_lut_dev, zdst, zpitch, st); }
             if (rc) return rc;
         } else {
-            rc = vsb_zblend_fused(gray, gpitch, s->W, s->H, cur, pri, s->wpr, &zp, s->T_dev, s->lead_lut_dev, zdst, zpitch,
-                                  nullptr, 0, st);
+            { ProfScope ps(s, ST_ZBLEND, 1);
+              rc = vsb_zblend_fused(gray, gpitch, s->W, s->H, cur, pri, s->wpr, &zp, s->T_dev, s->lead_lut_dev, zdst, zpitch,
+                                    nullptr, 0, st); }
             if (rc) return rc;
         }
         const uint8_t *src = zdst;
@@ -240,6 +268,7 @@ static int run_layer(vsb_stack *s, const uint8_t *gray, size_t gpitch, uint8_t *
             uint8_t *dst = last ? out : s->tmp[(i + 1) & 1];
             const size_t dpitch = last ? opitch : s->pitch;
             const DevOp &o = s->ops[i];
+            ProfScope ps(s, ST_OP0 + (int)i, 1);
             switch (o.type) {
             case 1: rc = vsb_lut_apply(src, spitch, s->W, s->H, o.lut_dev, dst, dpitch, st); break;
             case 2: rc = vsb_gaussian_q88(src, spitch, s->W, s->H, o.op.kx, o.op.nkx, o.op.ky, o.op.nky, dst, dpitch, st); break;
@@ -265,13 +294,13 @@ extern "C" int vsb_stack_process_device(vsb_stack *s, const uint8_t *gray_dev, s
 }
 
 extern "C" int vsb_stack_process_device_batch(vsb_stack *s, const uint8_t *gray_dev, size_t in_pitch,
-                                              size_t in_layer_stride, uint8_t *out_dev, size_t out_pitch,
-                                              size_t out_layer_stride, int n_layers)
+                                              long long in_layer_stride, uint8_t *out_dev, size_t out_pitch,
+                                              long long out_layer_stride, int out_ring, int n_layers)
 {
-    VSB_REQUIRE(s && gray_dev && out_dev && n_layers >= 0, "vsb_stack_process_device_batch: bad arguments");
+    VSB_REQUIRE(s && gray_dev && out_dev && n_layers >= 0 && out_ring >= 1, "vsb_stack_process_device_batch: bad arguments");
     for (int i = 0; i < n_layers; ++i) {
-        int rc = run_layer(s, gray_dev + (size_t)i * in_layer_stride, in_pitch, out_dev + (size_t)i * out_layer_stride,
-                           out_pitch, true);
+        int rc = run_layer(s, gray_dev + (long long)i * in_layer_stride, in_pitch,
+                           out_dev + (long long)(i % out_ring) * out_layer_stride, out_pitch, true);
         if (rc) return rc;
     }
     return VSB_OK;
@@ -336,4 +365,43 @@ extern "C" int vsb_stack_process_host(vsb_stack *s, const uint8_t *gray_host, si
     int t = vsb_stack_submit_host(s, gray_host, in_pitch, out_host, out_pitch);
     if (t < 0) return t;
     return vsb_stack_wait(s, t);
+}
+
+// ---- per-stage profiling ---------------------------------------------------------------------------------
+static void prof_clear(vsb_stack *s)
+{
+    for (auto &r : s->prof) { if (r.a) cudaEventDestroy(r.a); if (r.b) cudaEventDestroy(r.b); }
+    s->prof.clear();
+}
+
+extern "C" int vsb_stack_profile_enable(vsb_stack *s, int on)
+{
+    VSB_REQUIRE(s, "vsb_stack_profile_enable: null stack");
+    cudaStreamSynchronize(s->s_comp);
+    prof_clear(s);
+    s->prof_on = on != 0;
+    return VSB_OK;
+}
+
+extern "C" int vsb_stack_profile_read(vsb_stack *s, int max_stages, float *ms_sum, int *launches, char *names /* max_stages x 32 */)
+{
+    VSB_REQUIRE(s && ms_sum && launches && names && max_stages > 0, "vsb_stack_profile_read: bad arguments");
+    VSB_CUDA(cudaStreamSynchronize(s->s_comp));
+    int nst = 0;
+    for (int i = 0; i < max_stages; ++i) { ms_sum[i] = 0.0f; launches[i] = 0; names[i * 32] = 0; }
+    for (auto &r : s->prof) {
+        if (r.stage >= max_stages) continue;
+        float ms = 0.0f;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) != cudaSuccess) continue;
+        ms_sum[r.stage] += ms;
+        launches[r.stage] += r.launches;
+        if (r.stage + 1 > nst) nst = r.stage + 1;
+    }
+    for (int i = 0; i < nst; ++i) {
+        const char *nm = i < ST_OP0 ? kStageNames[i]
+                                    : ((size_t)(i - ST_OP0) < s->ops.size() ? kOpNames[s->ops[i - ST_OP0].type] : "?");
+        snprintf(names + i * 32, 32, "%s", nm);
+    }
+    prof_clear(s);
+    return nst;
 }

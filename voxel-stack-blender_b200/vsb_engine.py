@@ -343,12 +343,24 @@ class StackEngine:
                 "vsb_stack_process_device")
 
     def process_device_batch(self, gray_ptr: int, in_pitch: int, in_stride: int, out_ptr: int, out_pitch: int,
-                             out_stride: int, n: int):
+                             out_stride: int, out_ring: int, n: int):
         N.check(N.load().vsb_stack_process_device_batch(self._h, gray_ptr, in_pitch, in_stride, out_ptr, out_pitch,
-                                                        out_stride, n), "vsb_stack_process_device_batch")
+                                                        out_stride, out_ring, n), "vsb_stack_process_device_batch")
 
     def sync(self):
         N.check(N.load().vsb_stack_sync(self._h), "vsb_stack_sync")
+
+    def profile(self, on: bool):
+        N.check(N.load().vsb_stack_profile_enable(self._h, 1 if on else 0), "vsb_stack_profile_enable")
+
+    def profile_read(self):
+        """[(stage name, summed ms, kernel launches)] since profile(True)."""
+        ms = (ctypes.c_float * 32)()
+        ln = (ctypes.c_int * 32)()
+        names = ctypes.create_string_buffer(32 * 32)
+        n = N.check(N.load().vsb_stack_profile_read(self._h, 32, ms, ln, names), "vsb_stack_profile_read")
+        return [(names.raw[i * 32:(i + 1) * 32].split(b"\0")[0].decode(), float(ms[i]), int(ln[i])) for i in range(n)
+                if ln[i] > 0]
 
     @property
     def stream(self) -> int:

@@ -80,9 +80,11 @@ _SIGS = {
     "vsb_stack_wait": (c_int, [c_void_p, c_int]),
     "vsb_stack_slots": (c_int, [c_void_p]),
     "vsb_stack_process_device": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_size_t]),
-    "vsb_stack_process_device_batch": (c_int, [c_void_p, c_void_p, c_size_t, c_size_t, c_void_p, c_size_t, c_size_t,
-                                               c_int]),
+    "vsb_stack_process_device_batch": (c_int, [c_void_p, c_void_p, c_size_t, ctypes.c_longlong, c_void_p, c_size_t,
+                                               ctypes.c_longlong, c_int, c_int]),
     "vsb_stack_sync": (c_int, [c_void_p]),
+    "vsb_stack_profile_enable": (c_int, [c_void_p, c_int]),
+    "vsb_stack_profile_read": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "vsb_stack_stream": (c_void_p, [c_void_p]),
     "vsb_synth_layer": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
 }
