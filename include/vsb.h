@@ -107,7 +107,8 @@ typedef enum {
     VSB_Z_CONST = 2,    /* g = const_val on rec (degenerate F <= 0)                 :138-140 */
     VSB_Z_DIST = 3,     /* no image output: write min(d,F) at rec pixels into dist_out (Enhanced EDT
                            stage 1, :379-381) */
-    VSB_Z_ENHANCED = 4  /* stack level only: VSB_Z_DIST + vsb_ccl8_max + vsb_enhanced_fade  :338-404 */
+    VSB_Z_ENHANCED = 4, /* stack level only: VSB_Z_DIST + vsb_ccl8_max + vsb_enhanced_fade  :338-404 */
+    VSB_Z_NONE = 5      /* vsb_layer_fused only: no Z-blend, the input already is the stage-1 image */
 } vsb_zmode;
 
 typedef enum {
@@ -190,6 +191,35 @@ int vsb_bilateral(const uint8_t *in, size_t in_pitch, int W, int H, int radius, 
 /* cv2.medianBlur on uint8: exact k x k median, BORDER_REPLICATE.   xy_blend_processor.py:42-46 */
 int vsb_median(const uint8_t *in, size_t in_pitch, int W, int H, int ksize, uint8_t *out,
                size_t out_pitch, vsb_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * The fused per-layer path (two launches per layer).
+ *   vsb_pack_flags : K1 plus one uint16 per 128x32 tile: the tile's single gray value, or 0x100 = mixed.
+ *                    flags: uint16 [ceil(H/32)][ceil(W/128)];  wpr must be 4*ceil(W/128).
+ *   vsb_layer_fused: Z-blend (FIXED / WEIGHTED / CONST, or NONE) -> lut1 -> [bilateral] -> [Gaussian] -> lut2
+ *                    in ONE kernel, intermediates in shared memory.  Same arithmetic, bit for bit, as the
+ *                    separate entry points above.  cur_flags / prior_flags (optional, from vsb_pack_flags)
+ *                    let tiles that are one uniform value with no receding pixel skip all work.
+ *     replaces processing_pipeline.py:98-107 (process_z_blending, merge_to_output, process_xy_pipeline)
+ *     for XY chains of the shape [apply_lut*] [bilateral_filter d<=9] [gaussian_blur k<=7] [apply_lut*].
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    int has_bilateral, radius, ntaps; /* radius <= 4, ntaps <= 96 */
+    int8_t tap_dy[96], tap_dx[96];
+    float tap_sw[96];
+    float cw[256];
+    int nkx, nky;                     /* 0 = no Gaussian; odd, <= 7 */
+    int32_t kx[7], ky[7];
+} vsb_xy_fused;
+
+int vsb_pack_flags(const uint8_t *gray, size_t pitch, int W, int H, int thresh, uint32_t *bits, int wpr,
+                   uint16_t *flags, vsb_stream_t stream);
+
+int vsb_layer_fused(const uint8_t *in, size_t in_pitch, int W, int H, const uint32_t *cur_bits,
+                    const uint32_t *const *prior_bits, const uint16_t *cur_flags,
+                    const uint16_t *const *prior_flags, int wpr, const vsb_zparams *params, const float *T_dev,
+                    const uint8_t *lut1_dev, const vsb_xy_fused *xy /* host, may be NULL */,
+                    const uint8_t *lut2_dev, uint8_t *out, size_t out_pitch, vsb_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Host-buffer entry points (the plugin path measured as `e2e`): pinned or pageable HOST arrays

@@ -454,3 +454,78 @@ def test_synth_raster_device_equals_numpy(E):
     for z in (0, 5, 11, 12, 13):
         got = dev.layers[z][:, :W].cpu().numpy()
         assert np.array_equal(got, S.raster_numpy(table, raft, z, W, H)), z
+
+
+# ---- the fused per-layer kernel (vsb_pack_flags + vsb_layer_fused) --------------------------------------------------
+FUSED_CHAINS = {
+    "lut_bil7_g3_lut": [{"type": "apply_lut", "lut_params": {"lut_generation_type": "gamma", "gamma_value": 2.2}},
+                        {"type": "bilateral_filter", "bilateral_d": 7, "bilateral_sigma_color": 60.0, "bilateral_sigma_space": 60.0},
+                        {"type": "gaussian_blur", "gaussian_ksize_x": 3, "gaussian_ksize_y": 3, "gaussian_sigma_x": 0.8},
+                        {"type": "apply_lut", "lut_params": {"lut_generation_type": "exp", "input_min": 200, "input_max": 255,
+                                                             "output_min": 200, "output_max": 255}}],
+    "bil9": [{"type": "bilateral_filter", "bilateral_d": 9, "bilateral_sigma_color": 75.0, "bilateral_sigma_space": 75.0}],
+    "g7x5_lut_lut": [{"type": "gaussian_blur", "gaussian_ksize_x": 7, "gaussian_ksize_y": 5, "gaussian_sigma_x": 1.5, "gaussian_sigma_y": 0.9},
+                     {"type": "apply_lut", "lut_params": {"lut_generation_type": "s_curve", "s_curve_contrast": 0.4}},
+                     {"type": "apply_lut", "lut_params": {"lut_generation_type": "log", "log_param": 5.0}}],
+    "bil7_g5": [{"type": "bilateral_filter", "bilateral_d": 7, "bilateral_sigma_color": 25.0, "bilateral_sigma_space": 3.0},
+                {"type": "gaussian_blur", "gaussian_ksize_x": 5, "gaussian_ksize_y": 5, "gaussian_sigma_x": 0.0}],
+    "none": [],
+}
+
+
+@pytest.mark.parametrize("chain", sorted(FUSED_CHAINS))
+@pytest.mark.parametrize("mode,F,metric", [("fixed_fade", 14.0, "chamfer5"), ("fixed_fade", 40.0, "chamfer5"),
+                                           ("weighted_stack", 14.0, "chamfer5"), ("fixed_fade", 0.0, "chamfer5"),
+                                           ("enhanced_edt", 20.0, "chamfer5"), ("fixed_fade", 11.0, "exact")])
+def test_fused_layer_kernel_vs_oracle(E, chain, mode, F, metric):
+    """ragged sizes (W % 16 != 0, partial tiles), raft cliff, image borders: fused path == oracle stack loop"""
+    from config import Config
+    W, H, L = 500, 301, 9
+    layers = small_stack(W=W, H=H, L=L, seed=13, raft=True, n_blobs=9)
+    gray_aa = [l.copy() for l in layers]
+    rng = np.random.default_rng(3)
+    for g in gray_aa:                                      # a few anti-aliased pixels: gray is not strictly binary
+        ys, xs = rng.integers(0, H, 200), rng.integers(0, W, 200)
+        g[ys, xs] = rng.integers(0, 256, 200)
+    base = {"blending_mode": mode, "receding_layers": 3, "use_fixed_fade_receding": True,
+            "fixed_fade_distance_receding": F, "manual_weights": [5, 3, 1], "fade_distances_receding": [14.0, 9.0, 5.0],
+            "xy_blend_pipeline": FUSED_CHAINS[chain]}
+    cfg = Config.from_dict(dict(base, distance_metric=metric))
+    want = O.run_stack(gray_aa, dict(base, metric=metric))
+    eng = engine_for_metric(E, cfg, W, H, metric)
+    got = [eng.process(g) for g in gray_aa]
+    eng.close()
+    for zi, (a, b) in enumerate(zip(got, want)):
+        d = np.abs(a.astype(int) - b.astype(int))
+        assert d.max() == 0, (chain, mode, zi, int((d > 0).sum()), int(d.max()), np.argwhere(d > 0)[:5].tolist())
+
+
+def engine_for_metric(E, cfg, W, H, metric):
+    import lut_manager, vsb_params as P
+    ops = P.xy_ops_from_pipeline(cfg.xy_blend_pipeline, lambda op: lut_manager.lut_from_params(op.lut_params))
+    return E.StackEngine(W, H, cfg, ops, metric=metric)
+
+
+def test_fused_equals_unfused_on_uniform_and_tiny(E, monkeypatch):
+    """quiet-tile shortcut: big uniform regions; and the fallback for images too small to fuse"""
+    from config import Config
+    W, H = 1100, 200
+    layers = []
+    for z in range(6):
+        g = np.zeros((H, W), np.uint8)
+        g[:, 600:] = 255                                    # large solid + large empty regions
+        g[60:140, 100 + 3 * z:300 - 2 * z] = 255            # one shrinking / moving box
+        layers.append(g)
+    base = {"blending_mode": "fixed_fade", "receding_layers": 3, "use_fixed_fade_receding": True,
+            "fixed_fade_distance_receding": 30.0, "xy_blend_pipeline": FUSED_CHAINS["lut_bil7_g3_lut"]}
+    want = O.run_stack(layers, base)
+    eng = engine_for_metric(E, Config.from_dict(base), W, H, "chamfer5")
+    for zi, g in enumerate(layers):
+        assert np.array_equal(eng.process(g), want[zi]), zi
+    eng.close()
+    tiny = [l[:7, :40].copy() for l in layers]
+    want = O.run_stack(tiny, base)
+    eng = engine_for_metric(E, Config.from_dict(base), 40, 7, "chamfer5")
+    for zi, g in enumerate(tiny):
+        assert np.array_equal(eng.process(g), want[zi]), zi
+    eng.close()

@@ -1,0 +1,501 @@
+// vsb_layer.cu -- the whole per-layer hot path in two launches:
+//
+//   k_pack_flags : threshold + bit-pack (K1) and, for every 128x32 tile, a uniformity flag (the tile's single
+//                  gray value, or MIXED).  Reads every input byte exactly once.
+//   k_layer      : one CTA per 128x32 output tile: receding mask, windowed distance search on rec pixels,
+//                  fade gradient, merge, leading LUT (stage 1), bilateral filter (stage 2), Gaussian blur,
+//                  trailing LUT, store.  Intermediate images never leave shared memory.
+//
+// Reference call sequence replaced (processing_pipeline.py:98-107): process_z_blending -> merge_to_output ->
+// process_xy_pipeline for chains of the shape [apply_lut*] [bilateral_filter] [gaussian_blur] [apply_lut*].
+//
+// The per-pixel filters are FP32/LDS-issue bound, not HBM bound, so the kernel never runs them where the
+// result is known: (a) tiles whose 3x3 tile neighbourhood is one uniform gray value and provably free of
+// receding pixels are written as a constant without even reading the input ("quiet" tiles, decided from the
+// flags of k_pack_flags); (b) inside other tiles, 4-pixel words whose whole filter window is one value copy
+// it (sum v*w / sum w == v exactly; Gaussian taps sum to 2^16), decided from three bit-planes per staged row
+// (word not uniform / differs from the word to the right / differs from the word below) OR-ed over the
+// window rows.  Only the remaining pixels run the real filters, from a compacted list.
+#include "vsb_tile.cuh"
+
+#define ZL_NONE 5               // stage-1 image is the input itself (XY-only use)
+#define LH_MAX 7                // max XY halo (bilateral radius + Gaussian radius)
+#define RG_W 160                // staged region: x0-16 .. x0+143
+#define RG_CH 10
+#define RG_ROWS_MAX (VSB_TH + 2 * LH_MAX)
+#define LBW 10                  // mask words per staged row: x0-96 .. x0+223
+#define LB_ROWS_MAX (RG_ROWS_MAX + 2 * VSB_FAST_REACH)
+#define FLAG_MIXED 0x100
+
+struct BilTapsL {
+    int8_t dy[96], dx[96];
+    float sw[96];
+    float cw[256];
+};
+
+struct LayerParams {
+    const uint8_t *in;
+    size_t ipitch;
+    uint8_t *out;
+    size_t opitch;
+    const uint32_t *cur;
+    const uint32_t *prior[VSB_MAX_PRIORS];
+    const uint16_t *cur_flags;
+    const uint16_t *prior_flags[VSB_MAX_PRIORS];
+    const float *T;
+    const uint8_t *lut1, *lut2;
+    int tiles_x, tiles_y;
+    int W, H, wpr, aligned;
+    int halo;            // hb + max(rx, ry)
+    int hb, ntaps;       // bilateral radius (0 = none) and tap count
+    int nkx, nky;        // Gaussian taps (0 = none)
+    int32_t kx[7], ky[7];
+    vsb_zparams z;
+};
+
+// ------------------------------------------------------------------------------------------------------
+template <bool ALIGNED>
+__global__ void __launch_bounds__(VSB_THREADS) k_pack_flags(const uint8_t *__restrict__ gray, size_t pitch, int W, int H,
+                                                            uint32_t thr4, uint32_t *__restrict__ bits, int wpr,
+                                                            uint16_t *__restrict__ flags, int tiles_x)
+{
+    const int t = threadIdx.x;
+    const int x0 = blockIdx.x * VSB_TW, y0 = blockIdx.y * VSB_TH;
+    const int r = t >> 3, c = t & 7;
+    const int y = y0 + r, x = x0 + c * 16;
+    const int nvalid = (y < H) ? max(0, min(16, W - x)) : 0;
+    uint4 gv = make_uint4(0, 0, 0, 0);
+    if (nvalid == 16 && ALIGNED) gv = vsb_ld16_stream(gray + (size_t)y * pitch + x);
+    else if (nvalid > 0) gv = vsb_ld_bytes(gray + (size_t)y * pitch + x, nvalid);
+    uint32_t b16 = vsb_gt_bits16(gv, thr4);
+    if (nvalid < 16) b16 &= (1u << nvalid) - 1u;
+    const uint32_t other = __shfl_xor_sync(0xffffffffu, b16, 1);
+    if ((c & 1) == 0) {
+        const int wx = (x0 >> 5) + (c >> 1);
+        if (y < H && wx < wpr) bits[(size_t)y * wpr + wx] = b16 | (other << 16);
+    }
+    const uint32_t first = gray[(size_t)y0 * pitch + x0];
+    const uint32_t bc = first * 0x01010101u;
+    bool ok = true;
+    if (nvalid == 16) ok = (gv.x == bc) & (gv.y == bc) & (gv.z == bc) & (gv.w == bc);
+    else if (nvalid > 0) {
+        const uint32_t w[4] = {gv.x, gv.y, gv.z, gv.w};
+        for (int i = 0; i < nvalid; ++i) ok = ok && (((w[i >> 2] >> ((i & 3) * 8)) & 255u) == first);
+    }
+    const int all = __syncthreads_and(ok);
+    if (t == 0) flags[blockIdx.y * tiles_x + blockIdx.x] = (uint16_t)(all ? first : FLAG_MIXED);
+}
+
+extern "C" int vsb_pack_flags(const uint8_t *gray, size_t pitch, int W, int H, int thresh, uint32_t *bits, int wpr,
+                              uint16_t *flags, vsb_stream_t stream)
+{
+    VSB_REQUIRE(gray && bits && flags, "vsb_pack_flags: null pointer");
+    VSB_REQUIRE(W > 0 && H > 0 && wpr >= ((W + 127) / 128) * 4 && pitch >= (size_t)W, "vsb_pack_flags: bad geometry");
+    VSB_REQUIRE(thresh >= 0 && thresh <= 255, "vsb_pack_flags: thresh out of range");
+    dim3 grid((W + VSB_TW - 1) / VSB_TW, (H + VSB_TH - 1) / VSB_TH);
+    const uint32_t thr4 = (uint32_t)thresh * 0x01010101u;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (vsb_aligned16(gray, pitch)) k_pack_flags<true><<<grid, VSB_THREADS, 0, s>>>(gray, pitch, W, H, thr4, bits, wpr, flags, grid.x);
+    else k_pack_flags<false><<<grid, VSB_THREADS, 0, s>>>(gray, pitch, W, H, thr4, bits, wpr, flags, grid.x);
+    return vsb_check_launch("k_pack_flags");
+}
+
+// ------------------------------------------------------------------------------------------------------
+template <int ZMODE, int METRIC>
+__global__ void __launch_bounds__(VSB_THREADS) k_layer(const __grid_constant__ LayerParams p,
+                                                       const __grid_constant__ BilTapsL taps)
+{
+    extern __shared__ float s_T[];
+    __shared__ __align__(16) uint8_t s1[RG_ROWS_MAX][RG_W];   // stage 1: LUT1[max(gray, g)]
+    __shared__ __align__(16) uint8_t s2buf[RG_ROWS_MAX][RG_W]; // stage 2: bilateral output
+    __shared__ uint32_t s_bits[LB_ROWS_MAX][LBW];
+    __shared__ uint32_t s_rowany[(LB_ROWS_MAX + 31) / 32];
+    __shared__ uint32_t s_recw[RG_ROWS_MAX][6];
+    __shared__ uint16_t s_list[RG_ROWS_MAX * RG_W];
+    __shared__ uint8_t s_nib[3][RG_ROWS_MAX][RG_CH];
+    __shared__ unsigned long long s_pl[6][RG_ROWS_MAX];
+    __shared__ float s_cw[256];
+    __shared__ __align__(4) uint8_t s_lut1[256];
+    __shared__ __align__(4) uint8_t s_lut2[256];
+    __shared__ int s_cnt, s_quiet;
+
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int tx = blockIdx.x, ty = blockIdx.y;
+    const int x0 = tx * VSB_TW, y0 = ty * VSB_TH;
+    const int W = p.W, H = p.H, wpr = p.wpr;
+    const int np = p.z.n_priors;
+    const int r = t >> 3, c = t & 7;
+    const int oy = y0 + r, ox = x0 + c * 16;
+    const int nvalid = (oy < H) ? max(0, min(16, W - ox)) : 0;
+
+    // ---- quiet tile: one uniform value over the 3x3 tile neighbourhood, provably no receding pixel -------
+    if (p.cur_flags != nullptr) {
+        if (warp == 0) {
+            const int dx = lane % 3 - 1, dy = (lane / 3) % 3 - 1;
+            const int nx = min(max(tx + dx, 0), p.tiles_x - 1), ny = min(max(ty + dy, 0), p.tiles_y - 1);
+            const int fi = ny * p.tiles_x + nx;
+            const uint32_t v = p.cur_flags[fi];
+            const uint32_t v0 = __shfl_sync(0xffffffffu, v, 4);
+            bool ok = (v < FLAG_MIXED) && (v == v0);
+            if (ZMODE != ZL_NONE && ok && v0 <= 127u) {
+                for (int i = 0; i < np; ++i) ok = ok && (p.prior_flags[i][fi] <= 127u);
+            }
+            const int all = __all_sync(0xffffffffu, ok);
+            if (lane == 0) s_quiet = all ? (int)v0 : -1;
+        }
+        __syncthreads();
+        const int q = s_quiet;
+        if (q >= 0) {
+            uint32_t cv = (uint32_t)q;
+            if (p.lut1) cv = p.lut1[cv];
+            if (p.lut2) cv = p.lut2[cv];
+            cv *= 0x01010101u;
+            if (nvalid > 0) {
+                uint8_t *dst = p.out + (size_t)oy * p.opitch + ox;
+                const uint4 o = make_uint4(cv, cv, cv, cv);
+                if (nvalid == 16 && p.aligned) vsb_st16_stream(dst, o);
+                else vsb_st_bytes(dst, o, nvalid);
+            }
+            return;
+        }
+    }
+
+    const int Hh = p.halo;
+    const int RH = VSB_TH + 2 * Hh;
+    const int R = p.z.reach;
+    VsbLut L1 = vsb_lut_stage(p.lut1, s_lut1);
+    VsbLut L2 = vsb_lut_stage(p.lut2, s_lut2);
+    if (p.hb > 0) s_cw[t] = taps.cw[t];
+    if (t == 0) s_cnt = 0;
+
+    // ---- P1: stage the input region, receding words ---------------------------------------------------
+    for (int i = t; i < RH * RG_CH; i += VSB_THREADS) {
+        const int rr = i / RG_CH, cc = i - rr * RG_CH;
+        const int y = y0 - Hh + rr, x = x0 - 16 + cc * 16;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (y >= 0 && y < H) {
+            if (x >= 0 && x + 16 <= W && p.aligned) v = vsb_ld16_stream(p.in + (size_t)y * p.ipitch + x);
+            else {
+                const int xa = max(x, 0), xb = min(x + 16, W);
+                if (xb > xa) {
+                    uint32_t w[4] = {0, 0, 0, 0};
+                    const uint8_t *src = p.in + (size_t)y * p.ipitch;
+                    for (int xx = xa; xx < xb; ++xx) { const int k = xx - x; w[k >> 2] |= (uint32_t)src[xx] << ((k & 3) * 8); }
+                    v = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+            }
+        }
+        *(uint4 *)&s1[rr][cc * 16] = v;
+    }
+    int myrec = 0;
+    if (ZMODE != ZL_NONE) {
+        for (int i = t; i < RH * 6; i += VSB_THREADS) {
+            const int rr = i / 6, k = i - rr * 6;
+            const int y = y0 - Hh + rr, wx = (x0 >> 5) - 1 + k;
+            uint32_t rw = 0;
+            if (y >= 0 && y < H && wx >= 0 && wx < wpr) {
+                const size_t o = (size_t)y * wpr + wx;
+                uint32_t acc = 0;
+                for (int j = 0; j < np; ++j) acc |= p.prior[j][o];
+                rw = acc & ~p.cur[o];
+                if (k == 0) rw &= Hh ? (0xFFFFFFFFu << (32 - Hh)) : 0u;
+                if (k == 5) rw &= (1u << Hh) - 1u;
+            }
+            s_recw[rr][k] = rw;
+            myrec |= (rw != 0);
+        }
+    }
+    const int any_rec = __syncthreads_or(myrec);
+
+    // ---- P2: distance search + gradient on the receding pixels of the region --------------------------------
+    if (ZMODE != ZL_NONE && any_rec) {
+        const int brows = RH + 2 * R;
+        if (ZMODE != VSB_Z_CONST) {
+            if (METRIC == VSB_METRIC_CHAMFER5) {
+                const int n1 = R + 1;
+                for (int i = t; i < n1 * n1; i += VSB_THREADS) s_T[i] = p.T[i];
+            }
+            stage_mask_rows<LBW>(s_bits, p.cur, wpr, H, (x0 >> 5) - 3, y0 - Hh - R, brows);
+        }
+        for (int i = t; i < RH * 6; i += VSB_THREADS) {
+            const int rr = i / 6, k = i - rr * 6;
+            uint32_t rw = s_recw[rr][k];
+            if (rw) {
+                int base = atomicAdd(&s_cnt, __popc(rw));
+                while (rw) {
+                    const int b = __ffs(rw) - 1;
+                    rw &= rw - 1;
+                    s_list[base++] = (uint16_t)((rr << 8) | (32 * k + b - 16));
+                }
+            }
+        }
+        __syncthreads();
+        if (ZMODE != VSB_Z_CONST) stage_rowany_rows<LBW>(s_rowany, s_bits, brows);
+        __syncthreads();
+        const int total = s_cnt;
+        const float Ff = p.z.fade;
+        for (int i = t; i < total; i += VSB_THREADS) {
+            const int code = s_list[i];
+            const int rr = code >> 8, rc = code & 255;
+            float best = 0.0f;
+            if (ZMODE != VSB_Z_CONST) best = tile_search<METRIC, LBW>(s_bits, s_rowany, s_T, R, rr + R, rc + 80);
+            int g;
+            if (ZMODE == VSB_Z_FIXED) {
+                const float n = __fdiv_rn(fminf(best, Ff), p.z.den);
+                g = (int)__fmul_rn(255.0f, __fsub_rn(1.0f, n));
+            } else if (ZMODE == VSB_Z_WEIGHTED) {
+                float acc = 0.0f;
+                const int x = x0 - 16 + rc, y = y0 - Hh + rr;
+                const size_t o = (size_t)y * wpr + (x >> 5);
+                const uint32_t ncur = ~p.cur[o];
+                for (int j = 0; j < np; ++j) {
+                    if (p.z.weights[j] > 0.0f && (((p.prior[j][o] & ncur) >> (x & 31)) & 1u)) {
+                        const float n = __fsub_rn(1.0f, __fdiv_rn(fminf(best, p.z.fades[j]), p.z.dens[j]));
+                        acc = __fadd_rn(acc, __fmul_rn(n, p.z.weights[j]));
+                    }
+                }
+                g = (int)__fmul_rn(255.0f, __fdiv_rn(acc, p.z.total_weight));
+            } else {
+                g = p.z.const_val;
+            }
+            s1[rr][rc] = (uint8_t)max((int)s1[rr][rc], g & 255);
+        }
+        __syncthreads();
+        if (t == 0) s_cnt = 0;
+    }
+
+    // ---- P3: leading LUT in place, REFLECT_101 fix-up of out-of-image halo positions ---------------------------
+    if (p.lut1 != nullptr) {
+        for (int i = t; i < RH * RG_CH; i += VSB_THREADS) {
+            uint4 *q = (uint4 *)&s1[0][0] + i;
+            *q = L1.map16(*q);
+        }
+    }
+    const bool border = (x0 - Hh < 0) || (x0 + VSB_TW + Hh > W) || (y0 - Hh < 0) || (y0 + VSB_TH + Hh > H);
+    __syncthreads();
+    if (border && Hh > 0) {
+        for (int i = t; i < RH * RG_W; i += VSB_THREADS) {
+            const int rr = i / RG_W, rc = i - rr * RG_W;
+            const int y = y0 - Hh + rr, x = x0 - 16 + rc;
+            if (x < -Hh || x >= W + Hh || y < -Hh || y >= H + Hh) continue;
+            if (y < 0 || y >= H || x < 0 || x >= W) {
+                const int ys = vsb_reflect101(y, H), xs = vsb_reflect101(x, W);
+                s1[rr][rc] = s1[ys - (y0 - Hh)][xs - (x0 - 16)];
+            }
+        }
+        __syncthreads();
+    }
+
+    const int hb = p.hb;
+    const int rx = p.nkx >> 1, ry = p.nky >> 1;
+    const int hg = max(rx, ry);
+    uint8_t (*S2)[RG_W] = hb > 0 ? s2buf : s1;
+
+    // ---- P4/P5: bilateral with the uniform-window bypass ------------------------------------------------------------
+    if (hb > 0) {
+        for (int i = t; i < RH * RG_CH; i += VSB_THREADS) {
+            const int rr = i / RG_CH, cc = i - rr * RG_CH;
+            const uint4 a = *(const uint4 *)&s1[rr][cc * 16];
+            const uint32_t wn = (cc < RG_CH - 1) ? *(const uint32_t *)&s1[rr][cc * 16 + 16] : a.w;
+            const uint4 b = (rr + 1 < RH) ? *(const uint4 *)&s1[rr + 1][cc * 16] : a;
+            const uint32_t nu = (uint32_t)(a.x != (a.x & 255u) * 0x01010101u) | ((uint32_t)(a.y != (a.y & 255u) * 0x01010101u) << 1) |
+                                ((uint32_t)(a.z != (a.z & 255u) * 0x01010101u) << 2) | ((uint32_t)(a.w != (a.w & 255u) * 0x01010101u) << 3);
+            const uint32_t dh = (uint32_t)(a.x != a.y) | ((uint32_t)(a.y != a.z) << 1) | ((uint32_t)(a.z != a.w) << 2) |
+                                ((uint32_t)(a.w != wn) << 3);
+            const uint32_t dv = (uint32_t)(a.x != b.x) | ((uint32_t)(a.y != b.y) << 1) | ((uint32_t)(a.z != b.z) << 2) |
+                                ((uint32_t)(a.w != b.w) << 3);
+            s_nib[0][rr][cc] = (uint8_t)nu; s_nib[1][rr][cc] = (uint8_t)dh; s_nib[2][rr][cc] = (uint8_t)dv;
+        }
+        __syncthreads();
+        if (t < RH) {
+            unsigned long long nu = 0, dh = 0, dv = 0;
+#pragma unroll
+            for (int cc = 0; cc < RG_CH; ++cc) {
+                nu |= (unsigned long long)s_nib[0][t][cc] << (4 * cc);
+                dh |= (unsigned long long)s_nib[1][t][cc] << (4 * cc);
+                dv |= (unsigned long long)s_nib[2][t][cc] << (4 * cc);
+            }
+            s_pl[0][t] = nu; s_pl[1][t] = dh; s_pl[2][t] = dv;
+        }
+        __syncthreads();
+        const int r_lo = Hh - hg, r_hi = Hh + VSB_TH + hg; // region rows on which stage 2 is needed
+        if (t >= r_lo && t < r_hi) {
+            unsigned long long A = 0, B = 0, C = 0;
+            for (int d = -hb; d <= hb; ++d) { A |= s_pl[0][t + d]; B |= s_pl[1][t + d]; }
+            for (int d = -hb; d < hb; ++d) C |= s_pl[2][t + d];
+            s_pl[3][t] = A; s_pl[4][t] = B; s_pl[5][t] = C;
+        }
+        __syncthreads();
+        const int w_lo = (16 - hg) >> 2, w_hi = (143 + hg) >> 2;
+        const int nw = w_hi - w_lo + 1, nr = r_hi - r_lo;
+        for (int i = t; i < nr * nw; i += VSB_THREADS) {
+            const int rr = r_lo + i / nw, w = w_lo + i % nw;
+            const int wl = (4 * w - hb) >> 2, wr = (4 * w + 3 + hb) >> 2;
+            const unsigned long long m_nu = ((2ULL << wr) - 1ULL) & ~((1ULL << wl) - 1ULL);
+            const unsigned long long m_dh = ((1ULL << wr) - 1ULL) & ~((1ULL << wl) - 1ULL);
+            const unsigned long long bad = ((s_pl[3][rr] | s_pl[5][rr]) & m_nu) | (s_pl[4][rr] & m_dh);
+            if (!bad) *(uint32_t *)&s2buf[rr][4 * w] = *(const uint32_t *)&s1[rr][4 * w];
+            else {
+                const int base = atomicAdd(&s_cnt, 4);
+                const int code = (rr << 8) | (4 * w);
+                s_list[base] = (uint16_t)code; s_list[base + 1] = (uint16_t)(code + 1);
+                s_list[base + 2] = (uint16_t)(code + 2); s_list[base + 3] = (uint16_t)(code + 3);
+            }
+        }
+        __syncthreads();
+        const int total = s_cnt;
+        const int ntaps = p.ntaps;
+        for (int i = t; i < total; i += VSB_THREADS) {
+            const int code = s_list[i];
+            const int rr = code >> 8, rc = code & 255;
+            const int y = y0 - Hh + rr, x = x0 - 16 + rc;
+            if (y < 0 || y >= H || x < 0 || x >= W) continue; // reflected below
+            const uint8_t *ctr = &s1[rr][rc];
+            const int v0 = *ctr;
+            float s = 0.0f, ws = 0.0f;
+            for (int k = 0; k < ntaps; ++k) {
+                const int v = ctr[taps.dy[k] * RG_W + taps.dx[k]];
+                const float w = __fmul_rn(taps.sw[k], s_cw[abs(v - v0)]);
+                s = __fmaf_rn((float)v, w, s);
+                ws = __fadd_rn(ws, w);
+            }
+            const int o = __float2int_rn(__fdiv_rn(s, ws));
+            s2buf[rr][rc] = (uint8_t)min(max(o, 0), 255);
+        }
+        __syncthreads();
+        if (border && hg > 0) {
+            for (int i = t; i < nr * RG_W; i += VSB_THREADS) {
+                const int rr = r_lo + i / RG_W, rc = i % RG_W;
+                const int y = y0 - Hh + rr, x = x0 - 16 + rc;
+                if (x < -hg || x >= W + hg || y < -hg || y >= H + hg) continue;
+                if (y < 0 || y >= H || x < 0 || x >= W) {
+                    const int ys = vsb_reflect101(y, H), xs = vsb_reflect101(x, W);
+                    s2buf[rr][rc] = s2buf[ys - (y0 - Hh)][xs - (x0 - 16)];
+                }
+            }
+            __syncthreads();
+        }
+    }
+
+    // ---- P6: Gaussian (Q8.8, uniform-chunk bypass), trailing LUT, store ---------------------------------------------
+    if (nvalid > 0) {
+        const int rr = r + Hh, rc0 = 16 + 16 * c;
+        uint4 o;
+        if (p.nkx > 0) {
+            const uint32_t bc = (uint32_t)S2[rr][rc0] * 0x01010101u;
+            bool uni = true;
+            for (int d = -ry; d <= ry; ++d) {
+                const uint8_t *row = &S2[rr + d][rc0];
+                const uint4 a = *(const uint4 *)row;
+                const uint32_t l = *(const uint32_t *)(row - 4), g = *(const uint32_t *)(row + 16);
+                uni = uni && (a.x == bc) && (a.y == bc) && (a.z == bc) && (a.w == bc) && (l == bc) && (g == bc);
+            }
+            if (uni) o = make_uint4(bc, bc, bc, bc);
+            else {
+                uint32_t w[4] = {0, 0, 0, 0};
+                for (int j = 0; j < 16; ++j) {
+                    uint32_t sum = 0;
+                    for (int dy = 0; dy < p.nky; ++dy) {
+                        const uint8_t *row = &S2[rr + dy - ry][rc0 + j - rx];
+                        uint32_t h = 0;
+                        for (int dx = 0; dx < p.nkx; ++dx) h += (uint32_t)p.kx[dx] * row[dx];
+                        sum += (uint32_t)p.ky[dy] * h;
+                    }
+                    const uint32_t v = min((sum + 32768u) >> 16, 255u);
+                    w[j >> 2] |= v << ((j & 3) * 8);
+                }
+                o = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+        } else {
+            o = *(const uint4 *)&S2[rr][rc0];
+        }
+        o = L2.map16(o);
+        uint8_t *dst = p.out + (size_t)oy * p.opitch + ox;
+        if (nvalid == 16 && p.aligned) vsb_st16_stream(dst, o);
+        else vsb_st_bytes(dst, o, nvalid);
+    }
+}
+
+template <int ZMODE, int METRIC>
+static int launch_layer(const LayerParams &p, const BilTapsL &taps, dim3 grid, size_t smem, cudaStream_t s)
+{
+    static bool attr_set = false;
+    if (!attr_set) {
+        VSB_CUDA(cudaFuncSetAttribute(k_layer<ZMODE, METRIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 17 * 1024));
+        attr_set = true;
+    }
+    k_layer<ZMODE, METRIC><<<grid, VSB_THREADS, smem, s>>>(p, taps);
+    return vsb_check_launch("k_layer");
+}
+
+extern "C" int vsb_layer_fused(const uint8_t *in, size_t in_pitch, int W, int H, const uint32_t *cur_bits,
+                               const uint32_t *const *prior_bits, const uint16_t *cur_flags,
+                               const uint16_t *const *prior_flags, int wpr, const vsb_zparams *zp, const float *T_dev,
+                               const uint8_t *lut1_dev, const vsb_xy_fused *xy, const uint8_t *lut2_dev, uint8_t *out,
+                               size_t out_pitch, vsb_stream_t stream)
+{
+    VSB_REQUIRE(in && out && zp && in != out, "vsb_layer_fused: null pointer / in-place");
+    VSB_REQUIRE(W >= 8 && H >= 8 && in_pitch >= (size_t)W && out_pitch >= (size_t)W,
+                "vsb_layer_fused: images smaller than 8x8 take the unfused kernels");
+    const int mode = zp->mode;
+    VSB_REQUIRE(mode == VSB_Z_FIXED || mode == VSB_Z_WEIGHTED || mode == VSB_Z_CONST || mode == VSB_Z_NONE,
+                "vsb_layer_fused: mode %d not fused", mode);
+    VSB_REQUIRE(zp->metric == VSB_METRIC_CHAMFER5 || zp->metric == VSB_METRIC_EXACT, "vsb_layer_fused: unknown metric");
+    if (mode != VSB_Z_NONE) {
+        VSB_REQUIRE(cur_bits && wpr >= ((W + 127) / 128) * 4, "vsb_layer_fused: mask missing or wpr not a multiple of 4 per 128 px");
+        VSB_REQUIRE(zp->n_priors >= 0 && zp->n_priors <= VSB_MAX_PRIORS && (zp->n_priors == 0 || prior_bits),
+                    "vsb_layer_fused: priors");
+        VSB_REQUIRE(zp->reach >= 0 && zp->reach <= VSB_FAST_REACH, "vsb_layer_fused: reach %d > %d", zp->reach, VSB_FAST_REACH);
+        VSB_REQUIRE(T_dev || mode == VSB_Z_CONST || zp->metric == VSB_METRIC_EXACT, "vsb_layer_fused: chamfer table missing");
+    }
+    LayerParams p;
+    memset(&p, 0, sizeof p);
+    BilTapsL taps;
+    memset(&taps, 0, sizeof taps);
+    p.in = in; p.ipitch = in_pitch; p.out = out; p.opitch = out_pitch;
+    p.cur = cur_bits; p.cur_flags = cur_flags;
+    p.z = *zp;
+    if (mode == VSB_Z_NONE) p.z.n_priors = 0;
+    if (mode == VSB_Z_CONST) p.z.reach = 0;
+    for (int i = 0; i < p.z.n_priors; ++i) {
+        p.prior[i] = prior_bits[i];
+        p.prior_flags[i] = prior_flags ? prior_flags[i] : nullptr;
+        if (cur_flags && !p.prior_flags[i]) p.cur_flags = nullptr; // no shortcut without all flags
+    }
+    p.T = T_dev; p.lut1 = lut1_dev; p.lut2 = lut2_dev;
+    p.tiles_x = (W + VSB_TW - 1) / VSB_TW; p.tiles_y = (H + VSB_TH - 1) / VSB_TH;
+    p.W = W; p.H = H; p.wpr = wpr;
+    p.aligned = (vsb_aligned16(in, in_pitch) && vsb_aligned16(out, out_pitch)) ? 1 : 0;
+    if (xy) {
+        if (xy->has_bilateral) {
+            VSB_REQUIRE(xy->radius >= 1 && xy->radius <= 4 && xy->ntaps >= 1 && xy->ntaps <= 96,
+                        "vsb_layer_fused: bilateral radius %d / %d taps not fused", xy->radius, xy->ntaps);
+            p.hb = xy->radius; p.ntaps = xy->ntaps;
+            for (int i = 0; i < xy->ntaps; ++i) { taps.dy[i] = xy->tap_dy[i]; taps.dx[i] = xy->tap_dx[i]; taps.sw[i] = xy->tap_sw[i]; }
+            for (int i = 0; i < 256; ++i) taps.cw[i] = xy->cw[i];
+        }
+        if (xy->nkx > 0 || xy->nky > 0) {
+            VSB_REQUIRE(xy->nkx >= 1 && xy->nkx <= 7 && (xy->nkx & 1) && xy->nky >= 1 && xy->nky <= 7 && (xy->nky & 1),
+                        "vsb_layer_fused: Gaussian %dx%d not fused", xy->nkx, xy->nky);
+            int sx = 0, sy = 0;
+            for (int i = 0; i < xy->nkx; ++i) { p.kx[i] = xy->kx[i]; sx += xy->kx[i]; }
+            for (int i = 0; i < xy->nky; ++i) { p.ky[i] = xy->ky[i]; sy += xy->ky[i]; }
+            VSB_REQUIRE(sx == 256 && sy == 256, "vsb_layer_fused: Q8.8 taps must sum to 256");
+            p.nkx = xy->nkx; p.nky = xy->nky;
+        }
+    }
+    p.halo = p.hb + max(p.nkx >> 1, p.nky >> 1);
+    VSB_REQUIRE(p.halo <= LH_MAX, "vsb_layer_fused: halo %d > %d", p.halo, LH_MAX);
+    dim3 grid(p.tiles_x, p.tiles_y);
+    const int n1 = p.z.reach + 1;
+    const size_t smem = (mode != VSB_Z_NONE && mode != VSB_Z_CONST && zp->metric == VSB_METRIC_CHAMFER5)
+                            ? (size_t)n1 * n1 * sizeof(float) : 16;
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool ex = zp->metric == VSB_METRIC_EXACT;
+    switch (mode) {
+    case VSB_Z_FIXED: return ex ? launch_layer<VSB_Z_FIXED, 1>(p, taps, grid, smem, s) : launch_layer<VSB_Z_FIXED, 0>(p, taps, grid, smem, s);
+    case VSB_Z_WEIGHTED: return ex ? launch_layer<VSB_Z_WEIGHTED, 1>(p, taps, grid, smem, s) : launch_layer<VSB_Z_WEIGHTED, 0>(p, taps, grid, smem, s);
+    case VSB_Z_CONST: return launch_layer<VSB_Z_CONST, 0>(p, taps, grid, smem, s);
+    default: return launch_layer<ZL_NONE, 0>(p, taps, grid, smem, s);
+    }
+}

@@ -7,6 +7,7 @@
 #include <vector>
 #include <new>
 #include <cstring>
+#include <cstdlib>
 #include "vsb_common.cuh"
 
 #define STACK_SLOTS 3
@@ -37,14 +38,20 @@ struct vsb_stack {
     float *dist;
     int32_t *labels;
     uint32_t *cmax;
+    // fused per-layer path (vsb_layer.cu): taken when the XY chain has the shape [bilateral][gaussian][lut]
+    bool fused;
+    vsb_xy_fused fx;
+    uint8_t *lut2_dev;
+    std::vector<uint16_t *> flag_ring;
     // optional per-stage CUDA-event profiling (bench.py roofline leg)
     bool prof_on;
     struct ProfRec { int stage; int launches; cudaEvent_t a, b; };
     std::vector<ProfRec> prof;
 };
 
-enum { ST_PACK = 0, ST_ZBLEND, ST_MASKDIFF, ST_ZDIST, ST_CCL, ST_EFADE, ST_OP0 };
-static const char *kStageNames[] = {"threshold_pack", "zblend_fused", "maskdiff", "zblend_dist", "ccl8_max", "enhanced_fade"};
+enum { ST_PACK = 0, ST_ZBLEND, ST_MASKDIFF, ST_ZDIST, ST_CCL, ST_EFADE, ST_PACKF, ST_LAYER, ST_OP0 };
+static const char *kStageNames[] = {"threshold_pack", "zblend_fused", "maskdiff", "zblend_dist", "ccl8_max", "enhanced_fade",
+                                    "pack_flags", "layer_fused"};
 static const char *kOpNames[] = {"none", "lut_apply", "gaussian_q88", "bilateral", "median"};
 
 struct ProfScope {
@@ -84,6 +91,8 @@ extern "C" int vsb_stack_destroy(vsb_stack *s)
     }
     for (int i = 0; i < 2; ++i) if (s->tmp[i]) cudaFree(s->tmp[i]);
     for (auto p : s->ring) if (p) cudaFree(p);
+    for (auto p : s->flag_ring) if (p) cudaFree(p);
+    if (s->lut2_dev) cudaFree(s->lut2_dev);
     for (auto &r : s->prof) { if (r.a) cudaEventDestroy(r.a); if (r.b) cudaEventDestroy(r.b); }
     if (s->rec_bits) cudaFree(s->rec_bits);
     if (s->dist) cudaFree(s->dist);
@@ -130,6 +139,8 @@ extern "C" int vsb_stack_create(int W, int H, int n_priors, const vsb_zparams *z
     s->head = 0; s->count = 0; s->submitted = 0;
     s->rec_bits = nullptr; s->dist = nullptr; s->labels = nullptr; s->cmax = nullptr;
     s->prof_on = false;
+    s->fused = false; s->lut2_dev = nullptr;
+    memset(&s->fx, 0, sizeof s->fx);
 
     // XY chain: compose runs of apply_lut; a leading run is folded into the Z-blend epilogue
     uint8_t lead[256];
@@ -152,6 +163,34 @@ extern "C" int vsb_stack_create(int W, int H, int n_priors, const vsb_zparams *z
         if (op.type == 4 && op.median_ksize <= 1) continue; // apply_median_blur no-op, xy_blend_processor.py:45
         if (op.type < 1 || op.type > 4) { vsb_set_error("vsb_stack_create: unknown op type %d", op.type); delete s; return VSB_ERR_ARG; }
         DevOp d; d.type = op.type; d.lut_dev = nullptr; d.op = op; s->ops.push_back(d);
+    }
+    {   // does the composed chain have the fusable shape [bilateral r<=4][gaussian k<=7][lut] ?
+        size_t i = 0;
+        const size_t n = s->ops.size();
+        bool ok = getenv("VSB_NO_FUSED") == nullptr && W >= 8 && H >= 8 &&
+                  (zp->mode == VSB_Z_FIXED || zp->mode == VSB_Z_WEIGHTED || zp->mode == VSB_Z_CONST || zp->mode == VSB_Z_ENHANCED);
+        const uint8_t *lut2 = nullptr;
+        if (ok && i < n && s->ops[i].type == 3) {
+            const vsb_xy_op &o = s->ops[i].op;
+            if (o.radius >= 1 && o.radius <= 4 && o.ntaps <= 96) {
+                s->fx.has_bilateral = 1; s->fx.radius = o.radius; s->fx.ntaps = o.ntaps;
+                memcpy(s->fx.tap_dy, o.tap_dy, o.ntaps); memcpy(s->fx.tap_dx, o.tap_dx, o.ntaps);
+                memcpy(s->fx.tap_sw, o.tap_sw, o.ntaps * sizeof(float)); memcpy(s->fx.cw, o.cw, sizeof s->fx.cw);
+                ++i;
+            }
+        }
+        if (ok && i < n && s->ops[i].type == 2 && s->ops[i].op.nkx <= 7 && s->ops[i].op.nky <= 7) {
+            const vsb_xy_op &o = s->ops[i].op;
+            s->fx.nkx = o.nkx; s->fx.nky = o.nky;
+            memcpy(s->fx.kx, o.kx, o.nkx * sizeof(int32_t)); memcpy(s->fx.ky, o.ky, o.nky * sizeof(int32_t));
+            ++i;
+        }
+        if (ok && i < n && s->ops[i].type == 1) { lut2 = s->ops[i].op.lut; ++i; }
+        s->fused = ok && i == n;
+        if (s->fused && lut2) {
+            STACK_CUDA(cudaMalloc((void **)&s->lut2_dev, 256));
+            STACK_CUDA(cudaMemcpy(s->lut2_dev, lut2, 256, cudaMemcpyHostToDevice));
+        }
     }
     STACK_CUDA(cudaStreamCreateWithFlags(&s->s_h2d, cudaStreamNonBlocking));
     STACK_CUDA(cudaStreamCreateWithFlags(&s->s_comp, cudaStreamNonBlocking));
@@ -185,6 +224,11 @@ extern "C" int vsb_stack_create(int W, int H, int n_priors, const vsb_zparams *z
     }
     s->ring.assign((size_t)n_priors + 1, nullptr);
     for (auto &p : s->ring) STACK_CUDA(cudaMalloc((void **)&p, (size_t)s->wpr * H * sizeof(uint32_t)));
+    if (s->fused) {
+        const size_t ntiles = (size_t)((W + VSB_TW - 1) / VSB_TW) * ((H + VSB_TH - 1) / VSB_TH);
+        s->flag_ring.assign((size_t)n_priors + 1, nullptr);
+        for (auto &p : s->flag_ring) STACK_CUDA(cudaMalloc((void **)&p, ntiles * sizeof(uint16_t)));
+    }
     *out_stack = s;
     return VSB_OK;
 }
@@ -217,7 +261,8 @@ static int run_layer(vsb_stack *s, const uint8_t *gray, size_t gpitch, uint8_t *
     const int nring = s->n_priors + 1;
     uint32_t *cur = s->ring[s->head];
     int rc;
-    { ProfScope ps(s, ST_PACK, 1); rc = vsb_threshold_pack(gray, gpitch, s->W, s->H, 127, cur, s->wpr, st); }
+    if (s->fused) { ProfScope ps(s, ST_PACKF, 1); rc = vsb_pack_flags(gray, gpitch, s->W, s->H, 127, cur, s->wpr, s->flag_ring[s->head], st); }
+    else { ProfScope ps(s, ST_PACK, 1); rc = vsb_threshold_pack(gray, gpitch, s->W, s->H, 127, cur, s->wpr, st); }
     if (rc) return rc;
     if (emit) {
         const uint32_t *pri[VSB_MAX_PRIORS];
@@ -235,6 +280,19 @@ static int run_layer(vsb_stack *s, const uint8_t *gray, size_t gpitch, uint8_t *
             zp.total_weight = tot;
         } else {
             zp.n_priors = np;
+        }
+        if (s->fused && zp.mode != VSB_Z_ENHANCED) {
+            const uint16_t *pfl[VSB_MAX_PRIORS];
+            for (int i = 0; i < np; ++i) pfl[i] = s->flag_ring[(s->head - 1 - i + 2 * nring) % nring];
+            {
+                ProfScope ps(s, ST_LAYER, 1);
+                rc = vsb_layer_fused(gray, gpitch, s->W, s->H, cur, pri, s->flag_ring[s->head], pfl, s->wpr, &zp, s->T_dev,
+                                     s->lead_lut_dev, &s->fx, s->lut2_dev, out, opitch, st);
+            }
+            if (rc) return rc;
+            s->head = (s->head + 1) % nring;
+            if (s->count < s->n_priors) ++s->count;
+            return VSB_OK;
         }
         const size_t nops = s->ops.size();
         uint8_t *zdst = nops ? s->tmp[0] : out;
@@ -263,6 +321,16 @@ static int run_layer(vsb_stack *s, const uint8_t *gray, size_t gpitch, uint8_t *
         }
         const uint8_t *src = zdst;
         size_t spitch = zpitch;
+        if (s->fused && nops) { // Enhanced EDT: its own stage 1, then the fused XY chain
+            vsb_zparams zn = zp; zn.mode = VSB_Z_NONE; zn.n_priors = 0;
+            ProfScope ps(s, ST_LAYER, 1);
+            rc = vsb_layer_fused(src, spitch, s->W, s->H, nullptr, nullptr, nullptr, nullptr, s->wpr, &zn, nullptr, nullptr,
+                                 &s->fx, s->lut2_dev, out, opitch, st);
+            if (rc) return rc;
+            s->head = (s->head + 1) % nring;
+            if (s->count < s->n_priors) ++s->count;
+            return VSB_OK;
+        }
         for (size_t i = 0; i < nops; ++i) {
             const bool last = (i + 1 == nops);
             uint8_t *dst = last ? out : s->tmp[(i + 1) & 1];

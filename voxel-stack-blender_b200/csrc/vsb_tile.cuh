@@ -35,6 +35,84 @@ __device__ __forceinline__ void stage_mask_tile(uint32_t (*s_cur)[ROW_WORDS], co
     }
 }
 
+// generic variant: `nrows` rows starting at image row ystart, RW words per row starting at word wbase
+template <int RW>
+__device__ __forceinline__ void stage_mask_rows(uint32_t (*s_cur)[RW], const uint32_t *__restrict__ bits, int wpr,
+                                                int H, int wbase, int ystart, int nrows)
+{
+    for (int i = threadIdx.x; i < nrows * RW; i += VSB_THREADS) {
+        const int hr = i / RW, hw = i - hr * RW;
+        const int yy = ystart + hr, wx = wbase + hw;
+        uint32_t v = 0;
+        if (yy >= 0 && yy < H && wx >= 0 && wx < wpr) v = bits[(size_t)yy * wpr + wx];
+        s_cur[hr][hw] = v;
+    }
+}
+
+template <int RW>
+__device__ __forceinline__ void stage_rowany_rows(uint32_t *s_rowany, const uint32_t (*s_cur)[RW], int nrows)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nmask = (nrows + 31) / 32;
+    if (warp < nmask) {
+        const int hr = warp * 32 + lane;
+        uint32_t v = 0;
+        if (hr < nrows) {
+#pragma unroll
+            for (int k = 0; k < RW; ++k) v |= s_cur[hr][k];
+        }
+        const uint32_t m = __ballot_sync(0xffffffffu, v != 0);
+        if (lane == 0) s_rowany[warp] = m;
+    }
+}
+
+// distance from staged-row position (hr0, px) to the nearest set bit of the staged mask, either metric;
+// returns a value >= 3e38 when nothing lies within reach R.  T monotone in |dx| per row => the nearest
+// set bit of each row is that row's minimum; rows are visited outwards while |dy| < best.
+template <int METRIC, int RW>
+__device__ __forceinline__ float tile_search(const uint32_t (*s_cur)[RW], const uint32_t *s_rowany, const float *s_T,
+                                             int R, int hr0, int px)
+{
+    const int n1 = R + 1;
+    if (METRIC == VSB_METRIC_CHAMFER5) {
+        float best = 3.0e38f;
+        {
+            const int dx = nearest_dx(s_cur[hr0], px);
+            if (dx <= R) best = s_T[dx * n1];
+        }
+        for (int k = 1; k <= R && (float)k < best; ++k) {
+            const int ha = hr0 - k, hb = hr0 + k;
+            if ((s_rowany[ha >> 5] >> (ha & 31)) & 1u) {
+                const int dx = nearest_dx(s_cur[ha], px);
+                if (dx <= R) best = fminf(best, s_T[max(k, dx) * n1 + min(k, dx)]);
+            }
+            if ((s_rowany[hb >> 5] >> (hb & 31)) & 1u) {
+                const int dx = nearest_dx(s_cur[hb], px);
+                if (dx <= R) best = fminf(best, s_T[max(k, dx) * n1 + min(k, dx)]);
+            }
+        }
+        return best;
+    } else {
+        int best2 = 0x7fffffff;
+        {
+            const int dx = nearest_dx(s_cur[hr0], px);
+            if (dx <= R) best2 = dx * dx;
+        }
+        for (int k = 1; k <= R && k * k < best2; ++k) {
+            const int ha = hr0 - k, hb = hr0 + k;
+            if ((s_rowany[ha >> 5] >> (ha & 31)) & 1u) {
+                const int dx = nearest_dx(s_cur[ha], px);
+                if (dx <= R) best2 = min(best2, k * k + dx * dx);
+            }
+            if ((s_rowany[hb >> 5] >> (hb & 31)) & 1u) {
+                const int dx = nearest_dx(s_cur[hb], px);
+                if (dx <= R) best2 = min(best2, k * k + dx * dx);
+            }
+        }
+        return best2 == 0x7fffffff ? 3.0e38f : __fsqrt_rn((float)best2);
+    }
+}
+
 // one bit per staged row: does the row hold any set bit (call after a __syncthreads())
 __device__ __forceinline__ void stage_rowany(uint32_t *s_rowany, const uint32_t (*s_cur)[ROW_WORDS], int nrows)
 {

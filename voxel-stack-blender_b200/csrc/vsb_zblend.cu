@@ -31,52 +31,6 @@ struct ZKParams {
     vsb_zparams z;
 };
 
-// distance from staged-row position (hr0, px) to the nearest set bit of the staged mask, either metric;
-// returns a value >= 3e38 when nothing lies within reach R.
-template <int METRIC>
-__device__ __forceinline__ float tile_search(const uint32_t (*s_cur)[ROW_WORDS], const uint32_t *s_rowany,
-                                             const float *s_T, int R, int hr0, int px)
-{
-    const int n1 = R + 1;
-    if (METRIC == VSB_METRIC_CHAMFER5) {
-        float best = 3.0e38f;
-        {
-            const int dx = nearest_dx(s_cur[hr0], px);
-            if (dx <= R) best = s_T[dx * n1];
-        }
-        for (int k = 1; k <= R && (float)k < best; ++k) {
-            const int ha = hr0 - k, hb = hr0 + k;
-            if ((s_rowany[ha >> 5] >> (ha & 31)) & 1u) {
-                const int dx = nearest_dx(s_cur[ha], px);
-                if (dx <= R) best = fminf(best, s_T[max(k, dx) * n1 + min(k, dx)]);
-            }
-            if ((s_rowany[hb >> 5] >> (hb & 31)) & 1u) {
-                const int dx = nearest_dx(s_cur[hb], px);
-                if (dx <= R) best = fminf(best, s_T[max(k, dx) * n1 + min(k, dx)]);
-            }
-        }
-        return best;
-    } else {
-        int best2 = 0x7fffffff;
-        {
-            const int dx = nearest_dx(s_cur[hr0], px);
-            if (dx <= R) best2 = dx * dx;
-        }
-        for (int k = 1; k <= R && k * k < best2; ++k) {
-            const int ha = hr0 - k, hb = hr0 + k;
-            if ((s_rowany[ha >> 5] >> (ha & 31)) & 1u) {
-                const int dx = nearest_dx(s_cur[ha], px);
-                if (dx <= R) best2 = min(best2, k * k + dx * dx);
-            }
-            if ((s_rowany[hb >> 5] >> (hb & 31)) & 1u) {
-                const int dx = nearest_dx(s_cur[hb], px);
-                if (dx <= R) best2 = min(best2, k * k + dx * dx);
-            }
-        }
-        return best2 == 0x7fffffff ? 3.0e38f : __fsqrt_rn((float)best2);
-    }
-}
-
 template <int MODE, int METRIC>
 __global__ void __launch_bounds__(VSB_THREADS) k_zblend(const __grid_constant__ ZKParams p)
 {
@@ -178,7 +132,7 @@ __global__ void __launch_bounds__(VSB_THREADS) k_zblend(const __grid_constant__ 
         const int pr = code >> 7, pc = code & 127;
         float best = 0.0f;
         if (MODE != VSB_Z_CONST)
-            best = tile_search<METRIC>(s_cur, s_rowany, s_T, R, pr + R, pc + 32 * HALO_WORDS);
+            best = tile_search<METRIC, ROW_WORDS>(s_cur, s_rowany, s_T, R, pr + R, pc + 32 * HALO_WORDS);
         if (MODE == VSB_Z_FIXED) {
             const float n = __fdiv_rn(fminf(best, Ff), p.z.den);
             const float v = __fmul_rn(255.0f, __fsub_rn(1.0f, n));

@@ -21,7 +21,7 @@ VSB_MAX_PRIORS = 16
 VSB_MAX_XY_OPS = 16
 VSB_FAST_REACH = 63
 
-Z_FIXED, Z_WEIGHTED, Z_CONST, Z_DIST, Z_ENHANCED = 0, 1, 2, 3, 4
+Z_FIXED, Z_WEIGHTED, Z_CONST, Z_DIST, Z_ENHANCED, Z_NONE = 0, 1, 2, 3, 4, 5
 METRIC_CHAMFER5, METRIC_EXACT = 0, 1
 OP_NONE, OP_LUT, OP_GAUSSIAN, OP_BILATERAL, OP_MEDIAN = 0, 1, 2, 3, 4
 
@@ -42,6 +42,12 @@ class XYOp(ctypes.Structure):
                 ("nkx", c_int), ("nky", c_int), ("radius", c_int), ("ntaps", c_int),
                 ("tap_dy", c_int8 * 1024), ("tap_dx", c_int8 * 1024), ("tap_sw", c_float * 1024),
                 ("cw", c_float * 256), ("median_ksize", c_int)]
+
+
+class XYFused(ctypes.Structure):
+    _fields_ = [("has_bilateral", c_int), ("radius", c_int), ("ntaps", c_int), ("tap_dy", c_int8 * 96),
+                ("tap_dx", c_int8 * 96), ("tap_sw", c_float * 96), ("cw", c_float * 256), ("nkx", c_int), ("nky", c_int),
+                ("kx", c_int32 * 7), ("ky", c_int32 * 7)]
 
 
 _SIGS = {
@@ -71,6 +77,9 @@ _SIGS = {
     "vsb_bilateral": (c_int, [c_void_p, c_size_t, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                               c_void_p, c_size_t, c_void_p]),
     "vsb_median": (c_int, [c_void_p, c_size_t, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    "vsb_pack_flags": (c_int, [c_void_p, c_size_t, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),
+    "vsb_layer_fused": (c_int, [c_void_p, c_size_t, c_int, c_int, c_void_p, POINTER(c_void_p), c_void_p, POINTER(c_void_p),
+                                c_int, POINTER(ZParams), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "vsb_stack_create": (c_int, [c_int, c_int, c_int, POINTER(ZParams), POINTER(XYOp), c_int, POINTER(c_void_p)]),
     "vsb_stack_destroy": (c_int, [c_void_p]),
     "vsb_stack_reset": (c_int, [c_void_p]),
