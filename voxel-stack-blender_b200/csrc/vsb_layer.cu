@@ -28,7 +28,7 @@
 #define FLAG_MIXED 0x100
 
 struct BilTapsL {
-    int8_t dy[96], dx[96];
+    int16_t off[96];   // dy * RG_W + dx
     float sw[96];
     float cw[256];
 };
@@ -101,23 +101,64 @@ extern "C" int vsb_pack_flags(const uint8_t *gray, size_t pitch, int W, int H, i
 }
 
 // ------------------------------------------------------------------------------------------------------
+// Gaussian of one 4-pixel word: rows rr-RY..rr+RY, columns 4w-RX..4w+3+RX of S (pitch RG_W), Q8.8 taps.
+template <int RX, int RY>
+__device__ __forceinline__ uint32_t gauss_word(const uint8_t (*S)[RG_W], int rr, int w, const int32_t *kx, const int32_t *ky)
+{
+    uint32_t acc[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int dy = 0; dy <= 2 * RY; ++dy) {
+        const uint32_t *row = (const uint32_t *)&S[rr + dy - RY][4 * w - 4];
+        const uint32_t wa = row[0], wb = row[1], wc = row[2];
+        uint32_t b[12];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            b[i] = (wa >> (8 * i)) & 255u; b[4 + i] = (wb >> (8 * i)) & 255u; b[8 + i] = (wc >> (8 * i)) & 255u;
+        }
+        const uint32_t kyv = (uint32_t)ky[dy];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            uint32_t h = 0;
+#pragma unroll
+            for (int dx = 0; dx <= 2 * RX; ++dx) h += (uint32_t)kx[dx] * b[4 + j + dx - RX];
+            acc[j] += kyv * h;
+        }
+    }
+    uint32_t o = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o |= min((acc[j] + 32768u) >> 16, 255u) << (8 * j);
+    return o;
+}
+
+template <int RX>
+__device__ __forceinline__ uint32_t gauss_word_ry(const uint8_t (*S)[RG_W], int rr, int w, const int32_t *kx,
+                                                  const int32_t *ky, int ry)
+{
+    switch (ry) {
+    case 0: return gauss_word<RX, 0>(S, rr, w, kx, ky);
+    case 1: return gauss_word<RX, 1>(S, rr, w, kx, ky);
+    case 2: return gauss_word<RX, 2>(S, rr, w, kx, ky);
+    default: return gauss_word<RX, 3>(S, rr, w, kx, ky);
+    }
+}
+
 template <int ZMODE, int METRIC>
 __global__ void __launch_bounds__(VSB_THREADS) k_layer(const __grid_constant__ LayerParams p,
                                                        const __grid_constant__ BilTapsL taps)
 {
     extern __shared__ float s_T[];
-    __shared__ __align__(16) uint8_t s1[RG_ROWS_MAX][RG_W];   // stage 1: LUT1[max(gray, g)]
+    __shared__ __align__(16) uint8_t s1[RG_ROWS_MAX][RG_W];    // stage 1: LUT1[max(gray, g)]; later the Gaussian output
     __shared__ __align__(16) uint8_t s2buf[RG_ROWS_MAX][RG_W]; // stage 2: bilateral output
     __shared__ uint32_t s_bits[LB_ROWS_MAX][LBW];
     __shared__ uint32_t s_rowany[(LB_ROWS_MAX + 31) / 32];
     __shared__ uint32_t s_recw[RG_ROWS_MAX][6];
     __shared__ uint16_t s_list[RG_ROWS_MAX * RG_W];
     __shared__ uint8_t s_nib[3][RG_ROWS_MAX][RG_CH];
-    __shared__ unsigned long long s_pl[6][RG_ROWS_MAX];
+    __shared__ unsigned long long s_pl[9][RG_ROWS_MAX];
     __shared__ float s_cw[256];
     __shared__ __align__(4) uint8_t s_lut1[256];
     __shared__ __align__(4) uint8_t s_lut2[256];
-    __shared__ int s_cnt, s_quiet;
+    __shared__ int s_cnt, s_gcnt, s_quiet;
 
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int tx = blockIdx.x, ty = blockIdx.y;
@@ -166,21 +207,31 @@ __global__ void __launch_bounds__(VSB_THREADS) k_layer(const __grid_constant__ L
     VsbLut L1 = vsb_lut_stage(p.lut1, s_lut1);
     VsbLut L2 = vsb_lut_stage(p.lut2, s_lut2);
     if (p.hb > 0) s_cw[t] = taps.cw[t];
-    if (t == 0) s_cnt = 0;
+    if (t == 0) { s_cnt = 0; s_gcnt = 0; }
+    __syncthreads();
 
-    // ---- P1: stage the input region, receding words ---------------------------------------------------
+    // ---- P1: stage LUT1[input] of the region, receding words, uniform-region test ---------------------------
+    const uint32_t ref = L1.map4((uint32_t)p.in[(size_t)y0 * p.ipitch + x0] * 0x01010101u);
+    bool uni = true;
     for (int i = t; i < RH * RG_CH; i += VSB_THREADS) {
         const int rr = i / RG_CH, cc = i - rr * RG_CH;
         const int y = y0 - Hh + rr, x = x0 - 16 + cc * 16;
         uint4 v = make_uint4(0, 0, 0, 0);
         if (y >= 0 && y < H) {
-            if (x >= 0 && x + 16 <= W && p.aligned) v = vsb_ld16_stream(p.in + (size_t)y * p.ipitch + x);
-            else {
+            if (x >= 0 && x + 16 <= W && p.aligned) {
+                v = L1.map16(vsb_ld16_stream(p.in + (size_t)y * p.ipitch + x));
+                uni = uni && (v.x == ref) && (v.y == ref) && (v.z == ref) && (v.w == ref);
+            } else {
                 const int xa = max(x, 0), xb = min(x + 16, W);
                 if (xb > xa) {
                     uint32_t w[4] = {0, 0, 0, 0};
                     const uint8_t *src = p.in + (size_t)y * p.ipitch;
-                    for (int xx = xa; xx < xb; ++xx) { const int k = xx - x; w[k >> 2] |= (uint32_t)src[xx] << ((k & 3) * 8); }
+                    for (int xx = xa; xx < xb; ++xx) {
+                        const int k = xx - x;
+                        const uint32_t b = L1.s ? L1.s[src[xx]] : src[xx];
+                        uni = uni && (b == (ref & 255u));
+                        w[k >> 2] |= b << ((k & 3) * 8);
+                    }
                     v = make_uint4(w[0], w[1], w[2], w[3]);
                 }
             }
@@ -206,6 +257,17 @@ __global__ void __launch_bounds__(VSB_THREADS) k_layer(const __grid_constant__ L
         }
     }
     const int any_rec = __syncthreads_or(myrec);
+    const int region_uniform = __syncthreads_and(uni);
+    if (region_uniform && !any_rec) { // every filter of a constant is that constant
+        if (nvalid > 0) {
+            const uint32_t cv = L2.map4(ref);
+            uint8_t *dst = p.out + (size_t)oy * p.opitch + ox;
+            const uint4 o = make_uint4(cv, cv, cv, cv);
+            if (nvalid == 16 && p.aligned) vsb_st16_stream(dst, o);
+            else vsb_st_bytes(dst, o, nvalid);
+        }
+        return;
+    }
 
     // ---- P2: distance search + gradient on the receding pixels of the region --------------------------------
     if (ZMODE != ZL_NONE && any_rec) {
@@ -237,6 +299,7 @@ __global__ void __launch_bounds__(VSB_THREADS) k_layer(const __grid_constant__ L
         for (int i = t; i < total; i += VSB_THREADS) {
             const int code = s_list[i];
             const int rr = code >> 8, rc = code & 255;
+            const int x = x0 - 16 + rc, y = y0 - Hh + rr;
             float best = 0.0f;
             if (ZMODE != VSB_Z_CONST) best = tile_search<METRIC, LBW>(s_bits, s_rowany, s_T, R, rr + R, rc + 80);
             int g;
@@ -245,7 +308,6 @@ __global__ void __launch_bounds__(VSB_THREADS) k_layer(const __grid_constant__ L
                 g = (int)__fmul_rn(255.0f, __fsub_rn(1.0f, n));
             } else if (ZMODE == VSB_Z_WEIGHTED) {
                 float acc = 0.0f;
-                const int x = x0 - 16 + rc, y = y0 - Hh + rr;
                 const size_t o = (size_t)y * wpr + (x >> 5);
                 const uint32_t ncur = ~p.cur[o];
                 for (int j = 0; j < np; ++j) {
@@ -258,21 +320,15 @@ __global__ void __launch_bounds__(VSB_THREADS) k_layer(const __grid_constant__ L
             } else {
                 g = p.z.const_val;
             }
-            s1[rr][rc] = (uint8_t)max((int)s1[rr][rc], g & 255);
+            const int m = max((int)p.in[(size_t)y * p.ipitch + x], g & 255); // merge with the raw gray value
+            s1[rr][rc] = L1.s ? L1.s[m] : (uint8_t)m;
         }
         __syncthreads();
         if (t == 0) s_cnt = 0;
     }
 
-    // ---- P3: leading LUT in place, REFLECT_101 fix-up of out-of-image halo positions ---------------------------
-    if (p.lut1 != nullptr) {
-        for (int i = t; i < RH * RG_CH; i += VSB_THREADS) {
-            uint4 *q = (uint4 *)&s1[0][0] + i;
-            *q = L1.map16(*q);
-        }
-    }
+    // ---- P3: REFLECT_101 fix-up of out-of-image halo positions (border tiles only) ---------------------------------
     const bool border = (x0 - Hh < 0) || (x0 + VSB_TW + Hh > W) || (y0 - Hh < 0) || (y0 + VSB_TH + Hh > H);
-    __syncthreads();
     if (border && Hh > 0) {
         for (int i = t; i < RH * RG_W; i += VSB_THREADS) {
             const int rr = i / RG_W, rc = i - rr * RG_W;
@@ -283,16 +339,18 @@ __global__ void __launch_bounds__(VSB_THREADS) k_layer(const __grid_constant__ L
                 s1[rr][rc] = s1[ys - (y0 - Hh)][xs - (x0 - 16)];
             }
         }
-        __syncthreads();
     }
+    __syncthreads();
 
     const int hb = p.hb;
     const int rx = p.nkx >> 1, ry = p.nky >> 1;
     const int hg = max(rx, ry);
-    uint8_t (*S2)[RG_W] = hb > 0 ? s2buf : s1;
+    const bool gauss = p.nkx > 0;
+    uint8_t (*S2)[RG_W] = hb > 0 ? s2buf : s1;        // Gaussian input
+    uint8_t (*OUT)[RG_W] = gauss ? (hb > 0 ? s1 : s2buf) : S2; // what the store phase reads
 
-    // ---- P4/P5: bilateral with the uniform-window bypass ------------------------------------------------------------
-    if (hb > 0) {
+    if (hb > 0 || gauss) {
+        // ---- P4: bit-planes of stage 1: word not uniform / differs from right neighbour / differs from the word below
         for (int i = t; i < RH * RG_CH; i += VSB_THREADS) {
             const int rr = i / RG_CH, cc = i - rr * RG_CH;
             const uint4 a = *(const uint4 *)&s1[rr][cc * 16];
@@ -318,97 +376,121 @@ __global__ void __launch_bounds__(VSB_THREADS) k_layer(const __grid_constant__ L
             s_pl[0][t] = nu; s_pl[1][t] = dh; s_pl[2][t] = dv;
         }
         __syncthreads();
+        // window-row ORs: planes 3..5 for the bilateral window (+-hb), 6..8 for bilateral followed by Gaussian (+-(hb+ry))
         const int r_lo = Hh - hg, r_hi = Hh + VSB_TH + hg; // region rows on which stage 2 is needed
         if (t >= r_lo && t < r_hi) {
             unsigned long long A = 0, B = 0, C = 0;
             for (int d = -hb; d <= hb; ++d) { A |= s_pl[0][t + d]; B |= s_pl[1][t + d]; }
             for (int d = -hb; d < hb; ++d) C |= s_pl[2][t + d];
-            s_pl[3][t] = A; s_pl[4][t] = B; s_pl[5][t] = C;
+            s_pl[3][t] = A | C; s_pl[4][t] = B;
+        }
+        if (t >= Hh && t < Hh + VSB_TH) {
+            const int e = hb + ry;
+            unsigned long long A = 0, B = 0, C = 0;
+            for (int d = -e; d <= e; ++d) { A |= s_pl[0][t + d]; B |= s_pl[1][t + d]; }
+            for (int d = -e; d < e; ++d) C |= s_pl[2][t + d];
+            s_pl[6][t] = A | C; s_pl[7][t] = B;
         }
         __syncthreads();
+
+        // ---- P5: per-word bypass tests (bilateral on the stage-2 rows, Gaussian on the tile rows) ----------------------
         const int w_lo = (16 - hg) >> 2, w_hi = (143 + hg) >> 2;
-        const int nw = w_hi - w_lo + 1, nr = r_hi - r_lo;
-        for (int i = t; i < nr * nw; i += VSB_THREADS) {
-            const int rr = r_lo + i / nw, w = w_lo + i % nw;
-            const int wl = (4 * w - hb) >> 2, wr = (4 * w + 3 + hb) >> 2;
-            const unsigned long long m_nu = ((2ULL << wr) - 1ULL) & ~((1ULL << wl) - 1ULL);
-            const unsigned long long m_dh = ((1ULL << wr) - 1ULL) & ~((1ULL << wl) - 1ULL);
-            const unsigned long long bad = ((s_pl[3][rr] | s_pl[5][rr]) & m_nu) | (s_pl[4][rr] & m_dh);
-            if (!bad) *(uint32_t *)&s2buf[rr][4 * w] = *(const uint32_t *)&s1[rr][4 * w];
-            else {
-                const int base = atomicAdd(&s_cnt, 4);
-                const int code = (rr << 8) | (4 * w);
-                s_list[base] = (uint16_t)code; s_list[base + 1] = (uint16_t)(code + 1);
-                s_list[base + 2] = (uint16_t)(code + 2); s_list[base + 3] = (uint16_t)(code + 3);
-            }
-        }
-        __syncthreads();
-        const int total = s_cnt;
-        const int ntaps = p.ntaps;
-        for (int i = t; i < total; i += VSB_THREADS) {
-            const int code = s_list[i];
-            const int rr = code >> 8, rc = code & 255;
-            const int y = y0 - Hh + rr, x = x0 - 16 + rc;
-            if (y < 0 || y >= H || x < 0 || x >= W) continue; // reflected below
-            const uint8_t *ctr = &s1[rr][rc];
-            const int v0 = *ctr;
-            float s = 0.0f, ws = 0.0f;
-            for (int k = 0; k < ntaps; ++k) {
-                const int v = ctr[taps.dy[k] * RG_W + taps.dx[k]];
-                const float w = __fmul_rn(taps.sw[k], s_cw[abs(v - v0)]);
-                s = __fmaf_rn((float)v, w, s);
-                ws = __fadd_rn(ws, w);
-            }
-            const int o = __float2int_rn(__fdiv_rn(s, ws));
-            s2buf[rr][rc] = (uint8_t)min(max(o, 0), 255);
-        }
-        __syncthreads();
-        if (border && hg > 0) {
-            for (int i = t; i < nr * RG_W; i += VSB_THREADS) {
-                const int rr = r_lo + i / RG_W, rc = i % RG_W;
-                const int y = y0 - Hh + rr, x = x0 - 16 + rc;
-                if (x < -hg || x >= W + hg || y < -hg || y >= H + hg) continue;
-                if (y < 0 || y >= H || x < 0 || x >= W) {
-                    const int ys = vsb_reflect101(y, H), xs = vsb_reflect101(x, W);
-                    s2buf[rr][rc] = s2buf[ys - (y0 - Hh)][xs - (x0 - 16)];
+        const int eb = hb, eg = hb + rx;
+        for (int rr = r_lo + warp; rr < r_hi; rr += 8) {
+            const unsigned long long AC = s_pl[3][rr], Bm = s_pl[4][rr];
+            const bool trow = rr >= Hh && rr < Hh + VSB_TH;
+            const unsigned long long AC2 = trow ? s_pl[6][rr] : 0ULL, B2 = trow ? s_pl[7][rr] : 0ULL;
+            for (int wbase = w_lo; wbase <= w_hi; wbase += 32) { // warp-uniform trip count
+                const int w = wbase + lane;
+                const bool valid = w <= w_hi;
+                if (hb > 0) {
+                    const int wl = (4 * w - eb) >> 2, wr = (4 * w + 3 + eb) >> 2, n = wr - wl;
+                    const bool bad = valid && ((((uint32_t)(AC >> wl) & ((2u << n) - 1u)) | ((uint32_t)(Bm >> wl) & ((1u << n) - 1u))) != 0);
+                    const uint32_t vote = __ballot_sync(0xffffffffu, bad);
+                    int base = 0;
+                    if (lane == 0 && vote) base = atomicAdd(&s_cnt, 4 * __popc(vote));
+                    base = __shfl_sync(0xffffffffu, base, 0) + 4 * __popc(vote & ((1u << lane) - 1u));
+                    if (bad) {
+                        const int code = (rr << 8) | (4 * w);
+                        s_list[base] = (uint16_t)code; s_list[base + 1] = (uint16_t)(code + 1);
+                        s_list[base + 2] = (uint16_t)(code + 2); s_list[base + 3] = (uint16_t)(code + 3);
+                    } else if (valid) {
+                        *(uint32_t *)&s2buf[rr][4 * w] = *(const uint32_t *)&s1[rr][4 * w];
+                    }
                 }
+                if (gauss && trow) {
+                    const bool gv = valid && w >= 4 && w < 36;
+                    const int wl = (4 * w - eg) >> 2, wr = (4 * w + 3 + eg) >> 2, n = wr - wl;
+                    const bool bad = gv && ((((uint32_t)(AC2 >> wl) & ((2u << n) - 1u)) | ((uint32_t)(B2 >> wl) & ((1u << n) - 1u))) != 0);
+                    const uint32_t vote = __ballot_sync(0xffffffffu, bad);
+                    int base = 0;
+                    if (lane == 0 && vote) base = atomicAdd(&s_gcnt, __popc(vote));
+                    base = __shfl_sync(0xffffffffu, base, 0) + __popc(vote & ((1u << lane) - 1u));
+                    if (bad) s_list[5000 + base] = (uint16_t)((rr << 8) | w);
+                    else if (gv && hb == 0) *(uint32_t *)&s2buf[rr][4 * w] = *(const uint32_t *)&s1[rr][4 * w];
+                }
+            }
+        }
+        __syncthreads();
+
+        if (hb > 0) {
+            const int total = s_cnt;
+            const int ntaps = p.ntaps;
+            for (int i = t; i < total; i += VSB_THREADS) {
+                const int code = s_list[i];
+                const int rr = code >> 8, rc = code & 255;
+                const int y = y0 - Hh + rr, x = x0 - 16 + rc;
+                if (y < 0 || y >= H || x < 0 || x >= W) continue; // reflected below
+                const uint8_t *ctr = &s1[rr][rc];
+                const int v0 = *ctr;
+                float s = 0.0f, ws = 0.0f;
+                for (int k = 0; k < ntaps; ++k) {
+                    const int v = ctr[taps.off[k]];
+                    const float w = __fmul_rn(taps.sw[k], s_cw[abs(v - v0)]);
+                    s = __fmaf_rn((float)v, w, s);
+                    ws = __fadd_rn(ws, w);
+                }
+                const int o = __float2int_rn(__fdiv_rn(s, ws));
+                s2buf[rr][rc] = (uint8_t)min(max(o, 0), 255);
+            }
+            __syncthreads();
+            if (border && hg > 0) {
+                const int nr = r_hi - r_lo;
+                for (int i = t; i < nr * RG_W; i += VSB_THREADS) {
+                    const int rr = r_lo + i / RG_W, rc = i % RG_W;
+                    const int y = y0 - Hh + rr, x = x0 - 16 + rc;
+                    if (x < -hg || x >= W + hg || y < -hg || y >= H + hg) continue;
+                    if (y < 0 || y >= H || x < 0 || x >= W) {
+                        const int ys = vsb_reflect101(y, H), xs = vsb_reflect101(x, W);
+                        s2buf[rr][rc] = s2buf[ys - (y0 - Hh)][xs - (x0 - 16)];
+                    }
+                }
+                __syncthreads();
+            }
+        }
+
+        // ---- P6: Gaussian on the words that are not provably constant --------------------------------------------------
+        if (gauss) {
+            const int gtotal = s_gcnt;
+            for (int i = t; i < gtotal; i += VSB_THREADS) {
+                const int code = s_list[5000 + i];
+                const int rr = code >> 8, w = code & 255;
+                uint32_t o;
+                switch (rx) {
+                case 0: o = gauss_word_ry<0>(S2, rr, w, p.kx, p.ky, ry); break;
+                case 1: o = gauss_word_ry<1>(S2, rr, w, p.kx, p.ky, ry); break;
+                case 2: o = gauss_word_ry<2>(S2, rr, w, p.kx, p.ky, ry); break;
+                default: o = gauss_word_ry<3>(S2, rr, w, p.kx, p.ky, ry); break;
+                }
+                *(uint32_t *)&OUT[rr][4 * w] = o;
             }
             __syncthreads();
         }
     }
 
-    // ---- P6: Gaussian (Q8.8, uniform-chunk bypass), trailing LUT, store ---------------------------------------------
+    // ---- P7: trailing LUT, store ----------------------------------------------------------------------------------
     if (nvalid > 0) {
-        const int rr = r + Hh, rc0 = 16 + 16 * c;
-        uint4 o;
-        if (p.nkx > 0) {
-            const uint32_t bc = (uint32_t)S2[rr][rc0] * 0x01010101u;
-            bool uni = true;
-            for (int d = -ry; d <= ry; ++d) {
-                const uint8_t *row = &S2[rr + d][rc0];
-                const uint4 a = *(const uint4 *)row;
-                const uint32_t l = *(const uint32_t *)(row - 4), g = *(const uint32_t *)(row + 16);
-                uni = uni && (a.x == bc) && (a.y == bc) && (a.z == bc) && (a.w == bc) && (l == bc) && (g == bc);
-            }
-            if (uni) o = make_uint4(bc, bc, bc, bc);
-            else {
-                uint32_t w[4] = {0, 0, 0, 0};
-                for (int j = 0; j < 16; ++j) {
-                    uint32_t sum = 0;
-                    for (int dy = 0; dy < p.nky; ++dy) {
-                        const uint8_t *row = &S2[rr + dy - ry][rc0 + j - rx];
-                        uint32_t h = 0;
-                        for (int dx = 0; dx < p.nkx; ++dx) h += (uint32_t)p.kx[dx] * row[dx];
-                        sum += (uint32_t)p.ky[dy] * h;
-                    }
-                    const uint32_t v = min((sum + 32768u) >> 16, 255u);
-                    w[j >> 2] |= v << ((j & 3) * 8);
-                }
-                o = make_uint4(w[0], w[1], w[2], w[3]);
-            }
-        } else {
-            o = *(const uint4 *)&S2[rr][rc0];
-        }
+        uint4 o = *(const uint4 *)&OUT[r + Hh][16 + 16 * c];
         o = L2.map16(o);
         uint8_t *dst = p.out + (size_t)oy * p.opitch + ox;
         if (nvalid == 16 && p.aligned) vsb_st16_stream(dst, o);
@@ -471,7 +553,7 @@ extern "C" int vsb_layer_fused(const uint8_t *in, size_t in_pitch, int W, int H,
             VSB_REQUIRE(xy->radius >= 1 && xy->radius <= 4 && xy->ntaps >= 1 && xy->ntaps <= 96,
                         "vsb_layer_fused: bilateral radius %d / %d taps not fused", xy->radius, xy->ntaps);
             p.hb = xy->radius; p.ntaps = xy->ntaps;
-            for (int i = 0; i < xy->ntaps; ++i) { taps.dy[i] = xy->tap_dy[i]; taps.dx[i] = xy->tap_dx[i]; taps.sw[i] = xy->tap_sw[i]; }
+            for (int i = 0; i < xy->ntaps; ++i) { taps.off[i] = (int16_t)(xy->tap_dy[i] * RG_W + xy->tap_dx[i]); taps.sw[i] = xy->tap_sw[i]; }
             for (int i = 0; i < 256; ++i) taps.cw[i] = xy->cw[i];
         }
         if (xy->nkx > 0 || xy->nky > 0) {
