@@ -215,6 +215,11 @@ typedef struct {
 int vsb_pack_flags(const uint8_t *gray, size_t pitch, int W, int H, int thresh, uint32_t *bits, int wpr,
                    uint16_t *flags, vsb_stream_t stream);
 
+/* work counters of vsb_layer_fused (debugging / DESIGN.md numbers): op 1 = enable + clear, 2 = read 8 counters
+ * (uniform tiles, worked tiles, tiles with receding pixels, receding pixels, bilateral pixels, Gaussian words,
+ * 0, 0) and clear, 0 = disable */
+int vsb_layer_stats(int op, unsigned long long *out8);
+
 int vsb_layer_fused(const uint8_t *in, size_t in_pitch, int W, int H, const uint32_t *cur_bits,
                     const uint32_t *const *prior_bits, const uint16_t *cur_flags,
                     const uint16_t *const *prior_flags, int wpr, const vsb_zparams *params, const float *T_dev,

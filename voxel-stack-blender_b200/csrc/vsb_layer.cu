@@ -28,7 +28,7 @@
 #define FLAG_MIXED 0x100
 
 struct BilTapsL {
-    int16_t off[96];   // dy * RG_W + dx
+    int32_t off[96];   // dy * RG_W + dx
     float sw[96];
     float cw[256];
 };
@@ -50,6 +50,7 @@ struct LayerParams {
     int hb, ntaps;       // bilateral radius (0 = none) and tap count
     int nkx, nky;        // Gaussian taps (0 = none)
     int32_t kx[7], ky[7];
+    unsigned long long *stats; // optional work counters (VSB_LAYER_STATS), 8 slots
     vsb_zparams z;
 };
 
@@ -142,6 +143,15 @@ __device__ __forceinline__ uint32_t gauss_word_ry(const uint8_t (*S)[RG_W], int 
     }
 }
 
+#define PHASE(slot)                                                                                     \
+    do {                                                                                                \
+        if (p.stats && t == 0) {                                                                        \
+            const long long now__ = clock64();                                                          \
+            atomicAdd(&p.stats[slot], (unsigned long long)(now__ - tprev));                             \
+            tprev = now__;                                                                              \
+        }                                                                                               \
+    } while (0)
+
 template <int ZMODE, int METRIC>
 __global__ void __launch_bounds__(VSB_THREADS) k_layer(const __grid_constant__ LayerParams p,
                                                        const __grid_constant__ BilTapsL taps)
@@ -156,6 +166,8 @@ __global__ void __launch_bounds__(VSB_THREADS) k_layer(const __grid_constant__ L
     __shared__ uint8_t s_nib[3][RG_ROWS_MAX][RG_CH];
     __shared__ unsigned long long s_pl[9][RG_ROWS_MAX];
     __shared__ float s_cw[256];
+    __shared__ int s_off[96];
+    __shared__ float s_sw[96];
     __shared__ __align__(4) uint8_t s_lut1[256];
     __shared__ __align__(4) uint8_t s_lut2[256];
     __shared__ int s_cnt, s_gcnt, s_quiet;
@@ -168,6 +180,7 @@ __global__ void __launch_bounds__(VSB_THREADS) k_layer(const __grid_constant__ L
     const int r = t >> 3, c = t & 7;
     const int oy = y0 + r, ox = x0 + c * 16;
     const int nvalid = (oy < H) ? max(0, min(16, W - ox)) : 0;
+    long long tprev = p.stats ? clock64() : 0;
 
     // ---- quiet tile: one uniform value over the 3x3 tile neighbourhood, provably no receding pixel -------
     if (p.cur_flags != nullptr) {
@@ -199,66 +212,108 @@ __global__ void __launch_bounds__(VSB_THREADS) k_layer(const __grid_constant__ L
             }
             return;
         }
+        __syncthreads(); // s_quiet is reused below
     }
 
     const int Hh = p.halo;
     const int RH = VSB_TH + 2 * Hh;
     const int R = p.z.reach;
-    VsbLut L1 = vsb_lut_stage(p.lut1, s_lut1);
-    VsbLut L2 = vsb_lut_stage(p.lut2, s_lut2);
-    if (p.hb > 0) s_cw[t] = taps.cw[t];
-    if (t == 0) { s_cnt = 0; s_gcnt = 0; }
-    __syncthreads();
 
-    // ---- P1: stage LUT1[input] of the region, receding words, uniform-region test ---------------------------
-    const uint32_t ref = L1.map4((uint32_t)p.in[(size_t)y0 * p.ipitch + x0] * 0x01010101u);
-    bool uni = true;
-    for (int i = t; i < RH * RG_CH; i += VSB_THREADS) {
-        const int rr = i / RG_CH, cc = i - rr * RG_CH;
-        const int y = y0 - Hh + rr, x = x0 - 16 + cc * 16;
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (y >= 0 && y < H) {
-            if (x >= 0 && x + 16 <= W && p.aligned) {
-                v = L1.map16(vsb_ld16_stream(p.in + (size_t)y * p.ipitch + x));
-                uni = uni && (v.x == ref) && (v.y == ref) && (v.z == ref) && (v.w == ref);
-            } else {
-                const int xa = max(x, 0), xb = min(x + 16, W);
-                if (xb > xa) {
-                    uint32_t w[4] = {0, 0, 0, 0};
-                    const uint8_t *src = p.in + (size_t)y * p.ipitch;
-                    for (int xx = xa; xx < xb; ++xx) {
-                        const int k = xx - x;
-                        const uint32_t b = L1.s ? L1.s[src[xx]] : src[xx];
-                        uni = uni && (b == (ref & 255u));
-                        w[k >> 2] |= b << ((k & 3) * 8);
-                    }
-                    v = make_uint4(w[0], w[1], w[2], w[3]);
+    // ---- P1: prologue.  All global loads of the tile are issued back to back (rec words, input chunks, LUTs,
+    //      tap tables) so their latencies overlap; two barriers later the tile knows whether it is trivial.
+    uint32_t rwv[2] = {0, 0};
+    if (ZMODE != ZL_NONE) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int i = t + u * VSB_THREADS;
+            if (i < RH * 6) {
+                const int rr = i / 6, k = i - rr * 6;
+                const int y = y0 - Hh + rr, wx = (x0 >> 5) - 1 + k;
+                if (y >= 0 && y < H && wx >= 0 && wx < wpr) {
+                    const size_t o = (size_t)y * wpr + wx;
+                    uint32_t acc = 0;
+                    for (int j = 0; j < np; ++j) acc |= p.prior[j][o];
+                    uint32_t rw = acc & ~p.cur[o];
+                    if (k == 0) rw &= Hh ? (0xFFFFFFFFu << (32 - Hh)) : 0u;
+                    if (k == 5) rw &= (1u << Hh) - 1u;
+                    rwv[u] = rw;
                 }
             }
         }
-        *(uint4 *)&s1[rr][cc * 16] = v;
     }
-    int myrec = 0;
-    if (ZMODE != ZL_NONE) {
-        for (int i = t; i < RH * 6; i += VSB_THREADS) {
-            const int rr = i / 6, k = i - rr * 6;
-            const int y = y0 - Hh + rr, wx = (x0 >> 5) - 1 + k;
-            uint32_t rw = 0;
-            if (y >= 0 && y < H && wx >= 0 && wx < wpr) {
-                const size_t o = (size_t)y * wpr + wx;
-                uint32_t acc = 0;
-                for (int j = 0; j < np; ++j) acc |= p.prior[j][o];
-                rw = acc & ~p.cur[o];
-                if (k == 0) rw &= Hh ? (0xFFFFFFFFu << (32 - Hh)) : 0u;
-                if (k == 5) rw &= (1u << Hh) - 1u;
+    uint4 gv[2];
+    int gstate[2]; // 0 = nothing in the image, 1 = full aligned chunk, 2 = partial (byte path)
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        const int i = t + u * VSB_THREADS;
+        gv[u] = make_uint4(0, 0, 0, 0);
+        gstate[u] = 0;
+        if (i < RH * RG_CH) {
+            const int rr = i / RG_CH, cc = i - rr * RG_CH;
+            const int y = y0 - Hh + rr, x = x0 - 16 + cc * 16;
+            if (y >= 0 && y < H) {
+                if (x >= 0 && x + 16 <= W && p.aligned) {
+                    gv[u] = vsb_ld16_stream(p.in + (size_t)y * p.ipitch + x);
+                    gstate[u] = 1;
+                } else if (min(x + 16, W) > max(x, 0)) gstate[u] = 2;
             }
-            s_recw[rr][k] = rw;
-            myrec |= (rw != 0);
         }
     }
-    const int any_rec = __syncthreads_or(myrec);
-    const int region_uniform = __syncthreads_and(uni);
-    if (region_uniform && !any_rec) { // every filter of a constant is that constant
+    const uint32_t ref_raw = p.in[(size_t)y0 * p.ipitch + x0];
+    VsbLut L1 = vsb_lut_stage(p.lut1, s_lut1);
+    VsbLut L2 = vsb_lut_stage(p.lut2, s_lut2);
+    if (p.hb > 0) {
+        s_cw[t] = taps.cw[t];
+        if (t < 96) { s_off[t] = taps.off[t]; s_sw[t] = taps.sw[t]; }
+    }
+    if (t == 0) { s_cnt = 0; s_gcnt = 0; s_quiet = 0; }
+    __syncthreads();
+
+    const uint32_t ref = L1.map4(ref_raw * 0x01010101u);
+    bool uni = true;
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        const int i = t + u * VSB_THREADS;
+        if (i < RH * RG_CH) {
+            const int rr = i / RG_CH, cc = i - rr * RG_CH;
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (gstate[u] == 1) {
+                v = L1.map16(gv[u]);
+                uni = uni && (v.x == ref) && (v.y == ref) && (v.z == ref) && (v.w == ref);
+            } else if (gstate[u] == 2) {
+                const int y = y0 - Hh + rr, x = x0 - 16 + cc * 16;
+                const int xa = max(x, 0), xb = min(x + 16, W);
+                uint32_t w[4] = {0, 0, 0, 0};
+                const uint8_t *src = p.in + (size_t)y * p.ipitch;
+                for (int xx = xa; xx < xb; ++xx) {
+                    const int k = xx - x;
+                    const uint32_t b = L1.s ? L1.s[src[xx]] : src[xx];
+                    uni = uni && (b == (ref & 255u));
+                    w[k >> 2] |= b << ((k & 3) * 8);
+                }
+                v = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+            *(uint4 *)&s1[rr][cc * 16] = v;
+        }
+    }
+    if (ZMODE != ZL_NONE) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int i = t + u * VSB_THREADS;
+            if (i < RH * 6) { const int rr = i / 6; s_recw[rr][i - rr * 6] = rwv[u]; }
+        }
+    }
+    {   // one barrier: bit 0 = some receding pixel, bit 1 = region not uniform
+        const uint32_t code = ((rwv[0] | rwv[1]) ? 1u : 0u) | (uni ? 0u : 2u);
+        const uint32_t wcode = __reduce_or_sync(0xffffffffu, code);
+        if (lane == 0 && wcode) atomicOr(&s_quiet, (int)wcode);
+    }
+    __syncthreads();
+    const int tile_state = s_quiet;
+    const int any_rec = tile_state & 1;
+    if (p.stats && t == 0) atomicAdd(&p.stats[tile_state == 0 ? 0 : 1], 1ULL);
+    PHASE(8);
+    if (tile_state == 0) { // uniform region, nothing recedes: every filter of a constant is that constant
         if (nvalid > 0) {
             const uint32_t cv = L2.map4(ref);
             uint8_t *dst = p.out + (size_t)oy * p.opitch + ox;
@@ -295,6 +350,8 @@ __global__ void __launch_bounds__(VSB_THREADS) k_layer(const __grid_constant__ L
         if (ZMODE != VSB_Z_CONST) stage_rowany_rows<LBW>(s_rowany, s_bits, brows);
         __syncthreads();
         const int total = s_cnt;
+        if (p.stats && t == 0) { atomicAdd(&p.stats[2], 1ULL); atomicAdd(&p.stats[3], (unsigned long long)total); }
+        PHASE(9);
         const float Ff = p.z.fade;
         for (int i = t; i < total; i += VSB_THREADS) {
             const int code = s_list[i];
@@ -325,6 +382,7 @@ __global__ void __launch_bounds__(VSB_THREADS) k_layer(const __grid_constant__ L
         }
         __syncthreads();
         if (t == 0) s_cnt = 0;
+        PHASE(10);
     }
 
     // ---- P3: REFLECT_101 fix-up of out-of-image halo positions (border tiles only) ---------------------------------
@@ -393,48 +451,83 @@ __global__ void __launch_bounds__(VSB_THREADS) k_layer(const __grid_constant__ L
         }
         __syncthreads();
 
-        // ---- P5: per-word bypass tests (bilateral on the stage-2 rows, Gaussian on the tile rows) ----------------------
-        const int w_lo = (16 - hg) >> 2, w_hi = (143 + hg) >> 2;
+        PHASE(11);
+        // ---- P5: bypass tests.  One item = one 16-byte chunk of one stage-2 row; a chunk whose 3-chunk x window-rows
+        //      neighbourhood carries no plane bit is copied whole, otherwise its four words are tested one by one.
         const int eb = hb, eg = hb + rx;
-        for (int rr = r_lo + warp; rr < r_hi; rr += 8) {
-            const unsigned long long AC = s_pl[3][rr], Bm = s_pl[4][rr];
+        const int nrow2 = r_hi - r_lo;
+        for (int it = t; it < ((nrow2 * RG_CH + 31) & ~31); it += VSB_THREADS) { // warp-uniform trip count
+            const bool live = it < nrow2 * RG_CH;
+            const int rq = it / RG_CH, cc = it - rq * RG_CH;
+            const int rr = r_lo + (live ? rq : 0);
             const bool trow = rr >= Hh && rr < Hh + VSB_TH;
+            const unsigned long long AC = s_pl[3][rr], Bm = s_pl[4][rr];
             const unsigned long long AC2 = trow ? s_pl[6][rr] : 0ULL, B2 = trow ? s_pl[7][rr] : 0ULL;
-            for (int wbase = w_lo; wbase <= w_hi; wbase += 32) { // warp-uniform trip count
-                const int w = wbase + lane;
-                const bool valid = w <= w_hi;
-                if (hb > 0) {
-                    const int wl = (4 * w - eb) >> 2, wr = (4 * w + 3 + eb) >> 2, n = wr - wl;
-                    const bool bad = valid && ((((uint32_t)(AC >> wl) & ((2u << n) - 1u)) | ((uint32_t)(Bm >> wl) & ((1u << n) - 1u))) != 0);
-                    const uint32_t vote = __ballot_sync(0xffffffffu, bad);
-                    int base = 0;
-                    if (lane == 0 && vote) base = atomicAdd(&s_cnt, 4 * __popc(vote));
-                    base = __shfl_sync(0xffffffffu, base, 0) + 4 * __popc(vote & ((1u << lane) - 1u));
-                    if (bad) {
-                        const int code = (rr << 8) | (4 * w);
-                        s_list[base] = (uint16_t)code; s_list[base + 1] = (uint16_t)(code + 1);
-                        s_list[base + 2] = (uint16_t)(code + 2); s_list[base + 3] = (uint16_t)(code + 3);
-                    } else if (valid) {
-                        *(uint32_t *)&s2buf[rr][4 * w] = *(const uint32_t *)&s1[rr][4 * w];
+            // plane bits of words 4cc-4 .. 4cc+7 (the chunk and one chunk either side), as 12-bit fields
+            const int sh = 4 * cc - 4;
+            const uint32_t fa = (uint32_t)(sh >= 0 ? (AC >> sh) : (AC << 4)) & 0xFFFu;
+            const uint32_t fb = (uint32_t)(sh >= 0 ? (Bm >> sh) : (Bm << 4)) & 0xFFFu;
+            const uint32_t ga = (uint32_t)(sh >= 0 ? (AC2 >> sh) : (AC2 << 4)) & 0xFFFu;
+            const uint32_t gb = (uint32_t)(sh >= 0 ? (B2 >> sh) : (B2 << 4)) & 0xFFFu;
+            uint32_t badb = 0, badg = 0; // per-word verdicts of this chunk (bit j = word 4cc+j)
+            if (live && cc >= 1 && cc <= 8 || (live && hg > 0)) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int w = 4 * cc + j;
+                    if (w < ((16 - hg) >> 2) || w > ((143 + hg) >> 2)) continue;
+                    if (hb > 0) {
+                        const int wl = (4 * w - eb) >> 2, wr = (4 * w + 3 + eb) >> 2, n = wr - wl, o = wl - (4 * cc - 4);
+                        if ((((fa >> o) & ((2u << n) - 1u)) | ((fb >> o) & ((1u << n) - 1u))) != 0) badb |= 1u << j;
+                    }
+                    if (gauss && trow && w >= 4 && w < 36) {
+                        const int wl = (4 * w - eg) >> 2, wr = (4 * w + 3 + eg) >> 2, n = wr - wl, o = wl - (4 * cc - 4);
+                        if ((((ga >> o) & ((2u << n) - 1u)) | ((gb >> o) & ((1u << n) - 1u))) != 0) badg |= 1u << j;
                     }
                 }
-                if (gauss && trow) {
-                    const bool gv = valid && w >= 4 && w < 36;
-                    const int wl = (4 * w - eg) >> 2, wr = (4 * w + 3 + eg) >> 2, n = wr - wl;
-                    const bool bad = gv && ((((uint32_t)(AC2 >> wl) & ((2u << n) - 1u)) | ((uint32_t)(B2 >> wl) & ((1u << n) - 1u))) != 0);
-                    const uint32_t vote = __ballot_sync(0xffffffffu, bad);
-                    int base = 0;
-                    if (lane == 0 && vote) base = atomicAdd(&s_gcnt, __popc(vote));
-                    base = __shfl_sync(0xffffffffu, base, 0) + __popc(vote & ((1u << lane) - 1u));
-                    if (bad) s_list[5000 + base] = (uint16_t)((rr << 8) | w);
-                    else if (gv && hb == 0) *(uint32_t *)&s2buf[rr][4 * w] = *(const uint32_t *)&s1[rr][4 * w];
+            }
+            // warp-aggregated list appends
+            const int nb = 4 * __popc(badb), ng = __popc(badg);
+            int pb = nb, pg = ng; // inclusive scans over the warp
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int vb = __shfl_up_sync(0xffffffffu, pb, o), vg = __shfl_up_sync(0xffffffffu, pg, o);
+                if (lane >= o) { pb += vb; pg += vg; }
+            }
+            int baseb = 0, baseg = 0;
+            if (lane == 31) { if (pb) baseb = atomicAdd(&s_cnt, pb); if (pg) baseg = atomicAdd(&s_gcnt, pg); }
+            baseb = __shfl_sync(0xffffffffu, baseb, 31) + pb - nb;
+            baseg = __shfl_sync(0xffffffffu, baseg, 31) + pg - ng;
+            if (!live) continue;
+            if (hb > 0) {
+                if (badb == 0) *(uint4 *)&s2buf[rr][16 * cc] = *(const uint4 *)&s1[rr][16 * cc];
+                else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int w = 4 * cc + j;
+                        if (badb & (1u << j)) {
+                            const int code = (rr << 8) | (4 * w);
+                            s_list[baseb] = (uint16_t)code; s_list[baseb + 1] = (uint16_t)(code + 1);
+                            s_list[baseb + 2] = (uint16_t)(code + 2); s_list[baseb + 3] = (uint16_t)(code + 3);
+                            baseb += 4;
+                        } else *(uint32_t *)&s2buf[rr][4 * w] = *(const uint32_t *)&s1[rr][4 * w];
+                    }
+                }
+            }
+            if (gauss && trow) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int w = 4 * cc + j;
+                    if (badg & (1u << j)) s_list[5000 + baseg++] = (uint16_t)((rr << 8) | w);
+                    else if (hb == 0 && w >= 4 && w < 36) *(uint32_t *)&s2buf[rr][4 * w] = *(const uint32_t *)&s1[rr][4 * w];
                 }
             }
         }
         __syncthreads();
 
+        PHASE(12);
         if (hb > 0) {
             const int total = s_cnt;
+            if (p.stats && t == 0) atomicAdd(&p.stats[4], (unsigned long long)total);
             const int ntaps = p.ntaps;
             for (int i = t; i < total; i += VSB_THREADS) {
                 const int code = s_list[i];
@@ -444,9 +537,10 @@ __global__ void __launch_bounds__(VSB_THREADS) k_layer(const __grid_constant__ L
                 const uint8_t *ctr = &s1[rr][rc];
                 const int v0 = *ctr;
                 float s = 0.0f, ws = 0.0f;
+#pragma unroll 4
                 for (int k = 0; k < ntaps; ++k) {
-                    const int v = ctr[taps.off[k]];
-                    const float w = __fmul_rn(taps.sw[k], s_cw[abs(v - v0)]);
+                    const int v = ctr[s_off[k]];
+                    const float w = __fmul_rn(s_sw[k], s_cw[abs(v - v0)]);
                     s = __fmaf_rn((float)v, w, s);
                     ws = __fadd_rn(ws, w);
                 }
@@ -469,9 +563,11 @@ __global__ void __launch_bounds__(VSB_THREADS) k_layer(const __grid_constant__ L
             }
         }
 
+        PHASE(13);
         // ---- P6: Gaussian on the words that are not provably constant --------------------------------------------------
         if (gauss) {
             const int gtotal = s_gcnt;
+            if (p.stats && t == 0) atomicAdd(&p.stats[5], (unsigned long long)gtotal);
             for (int i = t; i < gtotal; i += VSB_THREADS) {
                 const int code = s_list[5000 + i];
                 const int rr = code >> 8, w = code & 255;
@@ -488,6 +584,7 @@ __global__ void __launch_bounds__(VSB_THREADS) k_layer(const __grid_constant__ L
         }
     }
 
+    PHASE(14);
     // ---- P7: trailing LUT, store ----------------------------------------------------------------------------------
     if (nvalid > 0) {
         uint4 o = *(const uint4 *)&OUT[r + Hh][16 + 16 * c];
@@ -508,6 +605,22 @@ static int launch_layer(const LayerParams &p, const BilTapsL &taps, dim3 grid, s
     }
     k_layer<ZMODE, METRIC><<<grid, VSB_THREADS, smem, s>>>(p, taps);
     return vsb_check_launch("k_layer");
+}
+
+static unsigned long long *g_layer_stats = nullptr;
+// debugging aid: device counters [uniform tiles, worked tiles, tiles with receding pixels, receding pixels,
+// bilateral pixels, Gaussian words]; enabled by vsb_layer_stats(1), read-and-cleared by vsb_layer_stats(2)
+extern "C" int vsb_layer_stats(int op, unsigned long long *out8)
+{
+    if (op == 1) {
+        if (!g_layer_stats) { VSB_CUDA(cudaMalloc((void **)&g_layer_stats, 128)); }
+        VSB_CUDA(cudaMemset(g_layer_stats, 0, 128));
+    } else if (op == 2 && g_layer_stats && out8) {
+        VSB_CUDA(cudaDeviceSynchronize());
+        VSB_CUDA(cudaMemcpy(out8, g_layer_stats, 128, cudaMemcpyDeviceToHost));
+        VSB_CUDA(cudaMemset(g_layer_stats, 0, 128));
+    } else if (op == 0 && g_layer_stats) { cudaFree(g_layer_stats); g_layer_stats = nullptr; }
+    return VSB_OK;
 }
 
 extern "C" int vsb_layer_fused(const uint8_t *in, size_t in_pitch, int W, int H, const uint32_t *cur_bits,
@@ -553,7 +666,7 @@ extern "C" int vsb_layer_fused(const uint8_t *in, size_t in_pitch, int W, int H,
             VSB_REQUIRE(xy->radius >= 1 && xy->radius <= 4 && xy->ntaps >= 1 && xy->ntaps <= 96,
                         "vsb_layer_fused: bilateral radius %d / %d taps not fused", xy->radius, xy->ntaps);
             p.hb = xy->radius; p.ntaps = xy->ntaps;
-            for (int i = 0; i < xy->ntaps; ++i) { taps.off[i] = (int16_t)(xy->tap_dy[i] * RG_W + xy->tap_dx[i]); taps.sw[i] = xy->tap_sw[i]; }
+            for (int i = 0; i < xy->ntaps; ++i) { taps.off[i] = xy->tap_dy[i] * RG_W + xy->tap_dx[i]; taps.sw[i] = xy->tap_sw[i]; }
             for (int i = 0; i < 256; ++i) taps.cw[i] = xy->cw[i];
         }
         if (xy->nkx > 0 || xy->nky > 0) {
@@ -567,6 +680,7 @@ extern "C" int vsb_layer_fused(const uint8_t *in, size_t in_pitch, int W, int H,
         }
     }
     p.halo = p.hb + max(p.nkx >> 1, p.nky >> 1);
+    p.stats = g_layer_stats;
     VSB_REQUIRE(p.halo <= LH_MAX, "vsb_layer_fused: halo %d > %d", p.halo, LH_MAX);
     dim3 grid(p.tiles_x, p.tiles_y);
     const int n1 = p.z.reach + 1;

@@ -286,7 +286,9 @@ static int run_layer(vsb_stack *s, const uint8_t *gray, size_t gpitch, uint8_t *
             for (int i = 0; i < np; ++i) pfl[i] = s->flag_ring[(s->head - 1 - i + 2 * nring) % nring];
             {
                 ProfScope ps(s, ST_LAYER, 1);
-                rc = vsb_layer_fused(gray, gpitch, s->W, s->H, cur, pri, s->flag_ring[s->head], pfl, s->wpr, &zp, s->T_dev,
+                // the tile-flag shortcut saves the input read of quiet tiles; it only pays once the kernel is HBM bound
+                static const bool use_flags = getenv("VSB_TILE_FLAGS") != nullptr;
+                rc = vsb_layer_fused(gray, gpitch, s->W, s->H, cur, pri, use_flags ? s->flag_ring[s->head] : nullptr, pfl, s->wpr, &zp, s->T_dev,
                                      s->lead_lut_dev, &s->fx, s->lut2_dev, out, opitch, st);
             }
             if (rc) return rc;

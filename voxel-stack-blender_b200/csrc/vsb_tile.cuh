@@ -129,3 +129,4 @@ __device__ __forceinline__ void stage_rowany(uint32_t *s_rowany, const uint32_t 
         if (lane == 0) s_rowany[warp] = m;
     }
 }
+

@@ -312,7 +312,11 @@ class StackEngine:
             N.load().vsb_stack_destroy(self._h)
             self._h = None
 
-    __del__ = close
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def reset(self):
         N.check(N.load().vsb_stack_reset(self._h), "vsb_stack_reset")

@@ -78,6 +78,7 @@ _SIGS = {
                               c_void_p, c_size_t, c_void_p]),
     "vsb_median": (c_int, [c_void_p, c_size_t, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "vsb_pack_flags": (c_int, [c_void_p, c_size_t, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),
+    "vsb_layer_stats": (c_int, [c_int, c_void_p]),
     "vsb_layer_fused": (c_int, [c_void_p, c_size_t, c_int, c_int, c_void_p, POINTER(c_void_p), c_void_p, POINTER(c_void_p),
                                 c_int, POINTER(ZParams), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "vsb_stack_create": (c_int, [c_int, c_int, c_int, POINTER(ZParams), POINTER(XYOp), c_int, POINTER(c_void_p)]),
