@@ -169,6 +169,8 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--workload", default="preset", choices=["preset", "zlut"],
+                    help="preset = headline (Z-blend + Preset-Double-LUT chain); zlut = Z-blend + file LUT only")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -176,9 +178,10 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     W, H = args.width, args.height
     lut_path = write_lut_file()
-    cfg = workload_config(lut_path)
+    cfg = workload_config(lut_path) if args.workload == 'preset' else zlut_config(lut_path)
     cfg_dict = config_as_dict(cfg, lut_path)
-    base_config = {"workload": WORKLOAD if (W, H) == (W16, H16) else WORKLOAD.replace("15120x6230", f"{W}x{H}"),
+    wl = WORKLOAD if args.workload == "preset" else WORKLOAD.split(" + ")[0] + " + file LUT (no XY filter)"
+    base_config = {"workload": wl if (W, H) == (W16, H16) else wl.replace("15120x6230", f"{W}x{H}"),
                    "width": W, "height": H, "batch_layers_per_gpu": args.batch, "resident_layers_per_gpu": args.resident,
                    "z_shard": f"{world} contiguous slabs, 4-layer mask halo, no collective", "metric_variant": "chamfer5",
                    "l2": f"each step streams {args.batch} x {W * H / 1e6:.0f} MB of input per GPU (>> 126 MB L2)"}

@@ -473,14 +473,19 @@ FUSED_CHAINS = {
 }
 
 
+@pytest.mark.parametrize("size", [(500, 301), (512, 301), (1024, 77)])
 @pytest.mark.parametrize("chain", sorted(FUSED_CHAINS))
 @pytest.mark.parametrize("mode,F,metric", [("fixed_fade", 14.0, "chamfer5"), ("fixed_fade", 40.0, "chamfer5"),
                                            ("weighted_stack", 14.0, "chamfer5"), ("fixed_fade", 0.0, "chamfer5"),
                                            ("enhanced_edt", 20.0, "chamfer5"), ("fixed_fade", 11.0, "exact")])
-def test_fused_layer_kernel_vs_oracle(E, chain, mode, F, metric):
-    """ragged sizes (W % 16 != 0, partial tiles), raft cliff, image borders: fused path == oracle stack loop"""
+def test_fused_layer_kernel_vs_oracle(E, chain, mode, F, metric, size):
+    """ragged sizes (W % 16 != 0 -> one-tile-per-CTA variant; W % 16 == 0 -> persistent prefetching variant), partial
+    tiles, raft cliff, image borders: fused path == oracle stack loop"""
     from config import Config
-    W, H, L = 500, 301, 9
+    W, H = size
+    L = 9 if size == (500, 301) else 6
+    if size != (500, 301) and chain in ("bil9", "none") and mode != "fixed_fade":
+        pytest.skip("covered at the first size")
     layers = small_stack(W=W, H=H, L=L, seed=13, raft=True, n_blobs=9)
     gray_aa = [l.copy() for l in layers]
     rng = np.random.default_rng(3)

@@ -16,6 +16,7 @@
 // it (sum v*w / sum w == v exactly; Gaussian taps sum to 2^16), decided from three bit-planes per staged row
 // (word not uniform / differs from the word to the right / differs from the word below) OR-ed over the
 // window rows.  Only the remaining pixels run the real filters, from a compacted list.
+#include <cstdlib>
 #include "vsb_tile.cuh"
 
 #define ZL_NONE 5               // stage-1 image is the input itself (XY-only use)
@@ -50,41 +51,62 @@ struct LayerParams {
     int hb, ntaps;       // bilateral radius (0 = none) and tap count
     int nkx, nky;        // Gaussian taps (0 = none)
     int32_t kx[7], ky[7];
-    unsigned long long *stats; // optional work counters (VSB_LAYER_STATS), 8 slots
+    unsigned long long *stats; // optional work counters (vsb_layer_stats)
+    struct { int T, raw, src, s1, s2, bits, list, raw_stride, src_stride; } sm; // dynamic shared memory carve (bytes / words)
+    int ntiles;
     vsb_zparams z;
 };
+#define GL_OFF 1400 // Gaussian word list starts here in s_list (bilateral word list: at most 36*38 entries)
 
 // ------------------------------------------------------------------------------------------------------
+// One CTA packs PF_TILES vertically adjacent 128x32 tiles; all of its loads are issued before the first use so
+// that 4 x 16 bytes per thread are in flight (the kernel is a pure HBM read stream).
+#define PF_TILES 1
 template <bool ALIGNED>
 __global__ void __launch_bounds__(VSB_THREADS) k_pack_flags(const uint8_t *__restrict__ gray, size_t pitch, int W, int H,
                                                             uint32_t thr4, uint32_t *__restrict__ bits, int wpr,
-                                                            uint16_t *__restrict__ flags, int tiles_x)
+                                                            uint16_t *__restrict__ flags, int tiles_x, int tiles_y)
 {
     const int t = threadIdx.x;
-    const int x0 = blockIdx.x * VSB_TW, y0 = blockIdx.y * VSB_TH;
+    const int x0 = blockIdx.x * VSB_TW;
     const int r = t >> 3, c = t & 7;
-    const int y = y0 + r, x = x0 + c * 16;
-    const int nvalid = (y < H) ? max(0, min(16, W - x)) : 0;
-    uint4 gv = make_uint4(0, 0, 0, 0);
-    if (nvalid == 16 && ALIGNED) gv = vsb_ld16_stream(gray + (size_t)y * pitch + x);
-    else if (nvalid > 0) gv = vsb_ld_bytes(gray + (size_t)y * pitch + x, nvalid);
-    uint32_t b16 = vsb_gt_bits16(gv, thr4);
-    if (nvalid < 16) b16 &= (1u << nvalid) - 1u;
-    const uint32_t other = __shfl_xor_sync(0xffffffffu, b16, 1);
-    if ((c & 1) == 0) {
-        const int wx = (x0 >> 5) + (c >> 1);
-        if (y < H && wx < wpr) bits[(size_t)y * wpr + wx] = b16 | (other << 16);
+    const int x = x0 + c * 16;
+    uint4 gv[PF_TILES];
+    int nv[PF_TILES];
+    uint32_t first[PF_TILES];
+#pragma unroll
+    for (int q = 0; q < PF_TILES; ++q) {
+        const int ty = blockIdx.y * PF_TILES + q;
+        const int y = ty * VSB_TH + r;
+        nv[q] = (y < H) ? max(0, min(16, W - x)) : 0;
+        gv[q] = make_uint4(0, 0, 0, 0);
+        first[q] = 0;
+        if (nv[q] == 16 && ALIGNED) gv[q] = vsb_ld16_stream(gray + (size_t)y * pitch + x);
+        else if (nv[q] > 0) gv[q] = vsb_ld_bytes(gray + (size_t)y * pitch + x, nv[q]);
+        if (ty < tiles_y) first[q] = gray[(size_t)(ty * VSB_TH) * pitch + x0];
     }
-    const uint32_t first = gray[(size_t)y0 * pitch + x0];
-    const uint32_t bc = first * 0x01010101u;
-    bool ok = true;
-    if (nvalid == 16) ok = (gv.x == bc) & (gv.y == bc) & (gv.z == bc) & (gv.w == bc);
-    else if (nvalid > 0) {
-        const uint32_t w[4] = {gv.x, gv.y, gv.z, gv.w};
-        for (int i = 0; i < nvalid; ++i) ok = ok && (((w[i >> 2] >> ((i & 3) * 8)) & 255u) == first);
+#pragma unroll
+    for (int q = 0; q < PF_TILES; ++q) {
+        const int ty = blockIdx.y * PF_TILES + q;
+        if (ty >= tiles_y) break; // uniform across the CTA
+        const int y = ty * VSB_TH + r;
+        uint32_t b16 = vsb_gt_bits16(gv[q], thr4);
+        if (nv[q] < 16) b16 &= (1u << nv[q]) - 1u;
+        const uint32_t other = __shfl_xor_sync(0xffffffffu, b16, 1);
+        if ((c & 1) == 0) {
+            const int wx = (x0 >> 5) + (c >> 1);
+            if (y < H && wx < wpr) bits[(size_t)y * wpr + wx] = b16 | (other << 16);
+        }
+        const uint32_t bc = first[q] * 0x01010101u;
+        bool ok = true;
+        if (nv[q] == 16) ok = (gv[q].x == bc) & (gv[q].y == bc) & (gv[q].z == bc) & (gv[q].w == bc);
+        else if (nv[q] > 0) {
+            const uint32_t w[4] = {gv[q].x, gv[q].y, gv[q].z, gv[q].w};
+            for (int i = 0; i < nv[q]; ++i) ok = ok && (((w[i >> 2] >> ((i & 3) * 8)) & 255u) == first[q]);
+        }
+        const int all = __syncthreads_and(ok);
+        if (t == 0) flags[ty * tiles_x + blockIdx.x] = (uint16_t)(all ? first[q] : FLAG_MIXED);
     }
-    const int all = __syncthreads_and(ok);
-    if (t == 0) flags[blockIdx.y * tiles_x + blockIdx.x] = (uint16_t)(all ? first : FLAG_MIXED);
 }
 
 extern "C" int vsb_pack_flags(const uint8_t *gray, size_t pitch, int W, int H, int thresh, uint32_t *bits, int wpr,
@@ -93,11 +115,12 @@ extern "C" int vsb_pack_flags(const uint8_t *gray, size_t pitch, int W, int H, i
     VSB_REQUIRE(gray && bits && flags, "vsb_pack_flags: null pointer");
     VSB_REQUIRE(W > 0 && H > 0 && wpr >= ((W + 127) / 128) * 4 && pitch >= (size_t)W, "vsb_pack_flags: bad geometry");
     VSB_REQUIRE(thresh >= 0 && thresh <= 255, "vsb_pack_flags: thresh out of range");
-    dim3 grid((W + VSB_TW - 1) / VSB_TW, (H + VSB_TH - 1) / VSB_TH);
+    const int tiles_x = (W + VSB_TW - 1) / VSB_TW, tiles_y = (H + VSB_TH - 1) / VSB_TH;
+    dim3 grid(tiles_x, (tiles_y + PF_TILES - 1) / PF_TILES);
     const uint32_t thr4 = (uint32_t)thresh * 0x01010101u;
     cudaStream_t s = (cudaStream_t)stream;
-    if (vsb_aligned16(gray, pitch)) k_pack_flags<true><<<grid, VSB_THREADS, 0, s>>>(gray, pitch, W, H, thr4, bits, wpr, flags, grid.x);
-    else k_pack_flags<false><<<grid, VSB_THREADS, 0, s>>>(gray, pitch, W, H, thr4, bits, wpr, flags, grid.x);
+    if (vsb_aligned16(gray, pitch)) k_pack_flags<true><<<grid, VSB_THREADS, 0, s>>>(gray, pitch, W, H, thr4, bits, wpr, flags, tiles_x, tiles_y);
+    else k_pack_flags<false><<<grid, VSB_THREADS, 0, s>>>(gray, pitch, W, H, thr4, bits, wpr, flags, tiles_x, tiles_y);
     return vsb_check_launch("k_pack_flags");
 }
 
@@ -152,19 +175,38 @@ __device__ __forceinline__ uint32_t gauss_word_ry(const uint8_t (*S)[RG_W], int 
         }                                                                                               \
     } while (0)
 
-template <int ZMODE, int METRIC>
-__global__ void __launch_bounds__(VSB_THREADS) k_layer(const __grid_constant__ LayerParams p,
+__device__ __forceinline__ void cp_async16(void *smem, const void *g)
+{
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void *smem, const void *g)
+{
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// PERSIST: CTAs stride over the tiles; while tile i is processed the input region and the mask words of tile i+1
+// are already in flight (cp.async into the other half of a double buffer), so the DRAM/L2 latency of the
+// prologue is off the critical path and LUTs / tap tables / chamfer table are staged once per CTA.
+template <int ZMODE, int METRIC, bool PERSIST, bool XY>
+__global__ void __launch_bounds__(VSB_THREADS, XY ? 4 : 6) k_layer(const __grid_constant__ LayerParams p,
                                                        const __grid_constant__ BilTapsL taps)
 {
-    extern __shared__ float s_T[];
-    __shared__ __align__(16) uint8_t s1[RG_ROWS_MAX][RG_W];    // stage 1: LUT1[max(gray, g)]; later the Gaussian output
-    __shared__ __align__(16) uint8_t s2buf[RG_ROWS_MAX][RG_W]; // stage 2: bilateral output
-    __shared__ uint32_t s_bits[LB_ROWS_MAX][LBW];
+    extern __shared__ __align__(16) uint8_t dsm[];
+    float *s_T = (float *)(dsm + p.sm.T);
+    uint8_t *s_rawb = dsm + p.sm.raw;                             // PERSIST: [2][RH][RG_W] raw input region
+    uint32_t *s_srcw = (uint32_t *)(dsm + p.sm.src);              // PERSIST: [2][np+1][RH*6] mask words
+    uint8_t (*s1)[RG_W] = (uint8_t (*)[RG_W])(dsm + p.sm.s1);      // stage 1; later the Gaussian output
+    uint8_t (*s2buf)[RG_W] = (uint8_t (*)[RG_W])(dsm + p.sm.s2);   // stage 2 (bilateral output)
+    uint32_t (*s_bits)[LBW] = (uint32_t (*)[LBW])(dsm + p.sm.bits);
+    uint16_t *s_list = (uint16_t *)(dsm + p.sm.list);             // bilateral word list, Gaussian word list at +GL_OFF
+    uint16_t *s_rlist = (uint16_t *)(dsm + p.sm.s2);              // receding pixel list overlays [s2 | list]
     __shared__ uint32_t s_rowany[(LB_ROWS_MAX + 31) / 32];
-    __shared__ uint32_t s_recw[RG_ROWS_MAX][6];
-    __shared__ uint16_t s_list[RG_ROWS_MAX * RG_W];
     __shared__ uint8_t s_nib[3][RG_ROWS_MAX][RG_CH];
-    __shared__ unsigned long long s_pl[9][RG_ROWS_MAX];
+    __shared__ unsigned long long s_pl[8][RG_ROWS_MAX];
     __shared__ float s_cw[256];
     __shared__ int s_off[96];
     __shared__ float s_sw[96];
@@ -172,439 +214,529 @@ __global__ void __launch_bounds__(VSB_THREADS) k_layer(const __grid_constant__ L
     __shared__ __align__(4) uint8_t s_lut2[256];
     __shared__ int s_cnt, s_gcnt, s_quiet;
 
-    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    const int tx = blockIdx.x, ty = blockIdx.y;
-    const int x0 = tx * VSB_TW, y0 = ty * VSB_TH;
+    const int t = threadIdx.x, lane = t & 31;
     const int W = p.W, H = p.H, wpr = p.wpr;
     const int np = p.z.n_priors;
     const int r = t >> 3, c = t & 7;
-    const int oy = y0 + r, ox = x0 + c * 16;
-    const int nvalid = (oy < H) ? max(0, min(16, W - ox)) : 0;
-    long long tprev = p.stats ? clock64() : 0;
-
-    // ---- quiet tile: one uniform value over the 3x3 tile neighbourhood, provably no receding pixel -------
-    if (p.cur_flags != nullptr) {
-        if (warp == 0) {
-            const int dx = lane % 3 - 1, dy = (lane / 3) % 3 - 1;
-            const int nx = min(max(tx + dx, 0), p.tiles_x - 1), ny = min(max(ty + dy, 0), p.tiles_y - 1);
-            const int fi = ny * p.tiles_x + nx;
-            const uint32_t v = p.cur_flags[fi];
-            const uint32_t v0 = __shfl_sync(0xffffffffu, v, 4);
-            bool ok = (v < FLAG_MIXED) && (v == v0);
-            if (ZMODE != ZL_NONE && ok && v0 <= 127u) {
-                for (int i = 0; i < np; ++i) ok = ok && (p.prior_flags[i][fi] <= 127u);
-            }
-            const int all = __all_sync(0xffffffffu, ok);
-            if (lane == 0) s_quiet = all ? (int)v0 : -1;
-        }
-        __syncthreads();
-        const int q = s_quiet;
-        if (q >= 0) {
-            uint32_t cv = (uint32_t)q;
-            if (p.lut1) cv = p.lut1[cv];
-            if (p.lut2) cv = p.lut2[cv];
-            cv *= 0x01010101u;
-            if (nvalid > 0) {
-                uint8_t *dst = p.out + (size_t)oy * p.opitch + ox;
-                const uint4 o = make_uint4(cv, cv, cv, cv);
-                if (nvalid == 16 && p.aligned) vsb_st16_stream(dst, o);
-                else vsb_st_bytes(dst, o, nvalid);
-            }
-            return;
-        }
-        __syncthreads(); // s_quiet is reused below
-    }
-
-    const int Hh = p.halo;
+    const int Hh = XY ? p.halo : 0;
     const int RH = VSB_TH + 2 * Hh;
     const int R = p.z.reach;
+    const int nsrc = RH * 6;
+    long long tprev = p.stats ? clock64() : 0;
 
-    // ---- P1: prologue.  All global loads of the tile are issued back to back (rec words, input chunks, LUTs,
-    //      tap tables) so their latencies overlap; two barriers later the tile knows whether it is trivial.
-    uint32_t rwv[2] = {0, 0};
-    if (ZMODE != ZL_NONE) {
+    // ---- once per CTA: tables ------------------------------------------------------------------------------------
+    VsbLut L1, L2;
+    L1.s = p.lut1 ? s_lut1 : nullptr; L1.l0 = 0u; L1.l255 = 0xFFFFFFFFu; // broadcasts filled in after the first barrier
+    L2.s = p.lut2 ? s_lut2 : nullptr; L2.l0 = 0u; L2.l255 = 0xFFFFFFFFu;
+    if (t < 64) {
+        if (p.lut1) ((uint32_t *)s_lut1)[t] = ((const uint32_t *)p.lut1)[t];
+        if (p.lut2) ((uint32_t *)s_lut2)[t] = ((const uint32_t *)p.lut2)[t];
+    }
+    if (XY && p.hb > 0) {
+        s_cw[t] = taps.cw[t];
+        if (t < 96) { s_off[t] = taps.off[t]; s_sw[t] = taps.sw[t]; }
+    }
+    bool t_staged = false; // chamfer table (lower triangle, (M, m) -> M*(M+1)/2 + m): staged by the first tile that needs it
+
+    auto prefetch = [&](int tile, int b) {
+        const int px0 = (tile % p.tiles_x) * VSB_TW, py0 = (tile / p.tiles_x) * VSB_TH;
+        uint8_t *rawb = s_rawb + (size_t)b * p.sm.raw_stride;
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
             const int i = t + u * VSB_THREADS;
-            if (i < RH * 6) {
-                const int rr = i / 6, k = i - rr * 6;
-                const int y = y0 - Hh + rr, wx = (x0 >> 5) - 1 + k;
-                if (y >= 0 && y < H && wx >= 0 && wx < wpr) {
+            if (i < RH * RG_CH) {
+                const int rr = i / RG_CH, cc = i - rr * RG_CH;
+                const int y = py0 - Hh + rr, x = px0 - 16 + cc * 16;
+                uint8_t *dst = rawb + rr * RG_W + cc * 16;
+                if (y >= 0 && y < H && x >= 0 && x < W) cp_async16(dst, p.in + (size_t)y * p.ipitch + x);
+                else *(uint4 *)dst = make_uint4(0, 0, 0, 0);
+            }
+        }
+        if (ZMODE != ZL_NONE) {
+            uint32_t *srcb = s_srcw + (size_t)b * p.sm.src_stride;
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int i = t + u * VSB_THREADS;
+                if (i < nsrc) {
+                    const int rr = i / 6, k = i - rr * 6;
+                    const int y = py0 - Hh + rr, wx = (px0 >> 5) - 1 + k;
+                    const bool ok = y >= 0 && y < H && wx >= 0 && wx < wpr;
                     const size_t o = (size_t)y * wpr + wx;
+                    if (ok) cp_async4(srcb + i, p.cur + o); else srcb[i] = 0u;
+                    for (int j = 0; j < np; ++j) {
+                        if (ok) cp_async4(srcb + (j + 1) * nsrc + i, p.prior[j] + o); else srcb[(j + 1) * nsrc + i] = 0u;
+                    }
+                }
+            }
+        }
+        cp_async_commit();
+    };
+
+    int tile = PERSIST ? (int)blockIdx.x : (int)(blockIdx.y * gridDim.x + blockIdx.x);
+    int buf = 0;
+    if (PERSIST && tile < p.ntiles) prefetch(tile, 0);
+
+    for (; tile < p.ntiles; tile += PERSIST ? (int)gridDim.x : p.ntiles) {
+        const int tx = tile % p.tiles_x, ty = tile / p.tiles_x;
+        const int x0 = tx * VSB_TW, y0 = ty * VSB_TH;
+        const int oy = y0 + r, ox = x0 + c * 16;
+        const int nvalid = (oy < H) ? max(0, min(16, W - ox)) : 0;
+        const uint8_t *rawb = s_rawb + (size_t)buf * p.sm.raw_stride;
+        const uint32_t *srcb = s_srcw + (size_t)buf * p.sm.src_stride;
+
+        // ---- P1: prologue ---------------------------------------------------------------------------------------
+        uint32_t rwv[2] = {0, 0};
+        uint4 gv[2];
+        int gstate[2]; // 0 = outside the image, 1 = full chunk, 2 = partial (byte path, non-persistent only)
+        uint32_t ref_raw;
+        if (PERSIST) {
+            if (t == 0) { s_cnt = 0; s_gcnt = 0; s_quiet = 0; }
+            cp_async_wait_all();
+            __syncthreads(); // this tile's region has landed (it was requested one iteration ago)
+            const int nxt = tile + (int)gridDim.x;
+            if (nxt < p.ntiles) prefetch(nxt, buf ^ 1);
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int i = t + u * VSB_THREADS;
+                gv[u] = make_uint4(0, 0, 0, 0);
+                gstate[u] = 0;
+                if (i < RH * RG_CH) {
+                    const int rr = i / RG_CH, cc = i - rr * RG_CH;
+                    const int y = y0 - Hh + rr, x = x0 - 16 + cc * 16;
+                    if (y >= 0 && y < H && x >= 0 && x < W) { gv[u] = *(const uint4 *)(rawb + rr * RG_W + cc * 16); gstate[u] = 1; }
+                }
+                if (ZMODE != ZL_NONE && i < nsrc) {
+                    const int k = i % 6;
                     uint32_t acc = 0;
-                    for (int j = 0; j < np; ++j) acc |= p.prior[j][o];
-                    uint32_t rw = acc & ~p.cur[o];
+                    for (int j = 0; j < np; ++j) acc |= srcb[(j + 1) * nsrc + i];
+                    uint32_t rw = acc & ~srcb[i];
                     if (k == 0) rw &= Hh ? (0xFFFFFFFFu << (32 - Hh)) : 0u;
                     if (k == 5) rw &= (1u << Hh) - 1u;
                     rwv[u] = rw;
                 }
             }
-        }
-    }
-    uint4 gv[2];
-    int gstate[2]; // 0 = nothing in the image, 1 = full aligned chunk, 2 = partial (byte path)
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-        const int i = t + u * VSB_THREADS;
-        gv[u] = make_uint4(0, 0, 0, 0);
-        gstate[u] = 0;
-        if (i < RH * RG_CH) {
-            const int rr = i / RG_CH, cc = i - rr * RG_CH;
-            const int y = y0 - Hh + rr, x = x0 - 16 + cc * 16;
-            if (y >= 0 && y < H) {
-                if (x >= 0 && x + 16 <= W && p.aligned) {
-                    gv[u] = vsb_ld16_stream(p.in + (size_t)y * p.ipitch + x);
-                    gstate[u] = 1;
-                } else if (min(x + 16, W) > max(x, 0)) gstate[u] = 2;
-            }
-        }
-    }
-    const uint32_t ref_raw = p.in[(size_t)y0 * p.ipitch + x0];
-    VsbLut L1 = vsb_lut_stage(p.lut1, s_lut1);
-    VsbLut L2 = vsb_lut_stage(p.lut2, s_lut2);
-    if (p.hb > 0) {
-        s_cw[t] = taps.cw[t];
-        if (t < 96) { s_off[t] = taps.off[t]; s_sw[t] = taps.sw[t]; }
-    }
-    if (t == 0) { s_cnt = 0; s_gcnt = 0; s_quiet = 0; }
-    __syncthreads();
-
-    const uint32_t ref = L1.map4(ref_raw * 0x01010101u);
-    bool uni = true;
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-        const int i = t + u * VSB_THREADS;
-        if (i < RH * RG_CH) {
-            const int rr = i / RG_CH, cc = i - rr * RG_CH;
-            uint4 v = make_uint4(0, 0, 0, 0);
-            if (gstate[u] == 1) {
-                v = L1.map16(gv[u]);
-                uni = uni && (v.x == ref) && (v.y == ref) && (v.z == ref) && (v.w == ref);
-            } else if (gstate[u] == 2) {
-                const int y = y0 - Hh + rr, x = x0 - 16 + cc * 16;
-                const int xa = max(x, 0), xb = min(x + 16, W);
-                uint32_t w[4] = {0, 0, 0, 0};
-                const uint8_t *src = p.in + (size_t)y * p.ipitch;
-                for (int xx = xa; xx < xb; ++xx) {
-                    const int k = xx - x;
-                    const uint32_t b = L1.s ? L1.s[src[xx]] : src[xx];
-                    uni = uni && (b == (ref & 255u));
-                    w[k >> 2] |= b << ((k & 3) * 8);
+            ref_raw = rawb[Hh * RG_W + 16];
+        } else if (!XY) {
+            // no XY filter: the region is the tile itself -- thread t owns chunk (r, c), threads < 128 one mask word
+            gv[0] = gv[1] = make_uint4(0, 0, 0, 0);
+            gstate[0] = gstate[1] = 0;
+            if (ZMODE != ZL_NONE && t < 128) {
+                const int rr = t >> 2, k = t & 3;
+                const int y = y0 + rr, wx = (x0 >> 5) + k;
+                if (y < H && wx < wpr) {
+                    const size_t o = (size_t)y * wpr + wx;
+                    uint32_t acc = 0;
+                    for (int j = 0; j < np; ++j) acc |= p.prior[j][o];
+                    rwv[0] = acc & ~p.cur[o];
                 }
-                v = make_uint4(w[0], w[1], w[2], w[3]);
             }
-            *(uint4 *)&s1[rr][cc * 16] = v;
-        }
-    }
-    if (ZMODE != ZL_NONE) {
+            if (nvalid == 16 && p.aligned) { gv[0] = vsb_ld16_stream(p.in + (size_t)oy * p.ipitch + ox); gstate[0] = 1; }
+            else if (nvalid > 0) gstate[0] = 2;
+            ref_raw = p.in[(size_t)y0 * p.ipitch + x0];
+            if (t == 0) { s_cnt = 0; s_gcnt = 0; s_quiet = 0; }
+            __syncthreads();
+        } else {
+            if (ZMODE != ZL_NONE) {
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
+                for (int u = 0; u < 2; ++u) {
+                    const int i = t + u * VSB_THREADS;
+                    if (i < nsrc) {
+                        const int rr = i / 6, k = i - rr * 6;
+                        const int y = y0 - Hh + rr, wx = (x0 >> 5) - 1 + k;
+                        if (y >= 0 && y < H && wx >= 0 && wx < wpr) {
+                            const size_t o = (size_t)y * wpr + wx;
+                            uint32_t acc = 0;
+                            for (int j = 0; j < np; ++j) acc |= p.prior[j][o];
+                            uint32_t rw = acc & ~p.cur[o];
+                            if (k == 0) rw &= Hh ? (0xFFFFFFFFu << (32 - Hh)) : 0u;
+                            if (k == 5) rw &= (1u << Hh) - 1u;
+                            rwv[u] = rw;
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int i = t + u * VSB_THREADS;
+                gv[u] = make_uint4(0, 0, 0, 0);
+                gstate[u] = 0;
+                if (i < RH * RG_CH) {
+                    const int rr = i / RG_CH, cc = i - rr * RG_CH;
+                    const int y = y0 - Hh + rr, x = x0 - 16 + cc * 16;
+                    if (y >= 0 && y < H) {
+                        if (x >= 0 && x + 16 <= W && p.aligned) {
+                            gv[u] = vsb_ld16_stream(p.in + (size_t)y * p.ipitch + x);
+                            gstate[u] = 1;
+                        } else if (min(x + 16, W) > max(x, 0)) gstate[u] = 2;
+                    }
+                }
+            }
+            ref_raw = p.in[(size_t)y0 * p.ipitch + x0];
+            if (t == 0) { s_cnt = 0; s_gcnt = 0; s_quiet = 0; }
+            __syncthreads();
+        }
+
+        if (L1.s) { L1.l0 = (uint32_t)s_lut1[0] * 0x01010101u; L1.l255 = (uint32_t)s_lut1[255] * 0x01010101u; }
+        if (L2.s) { L2.l0 = (uint32_t)s_lut2[0] * 0x01010101u; L2.l255 = (uint32_t)s_lut2[255] * 0x01010101u; }
+        const uint32_t ref = L1.map4(ref_raw * 0x01010101u);
+        bool uni = true;
+#pragma unroll
+        for (int u = 0; u < (XY ? 2 : 1); ++u) {
             const int i = t + u * VSB_THREADS;
-            if (i < RH * 6) { const int rr = i / 6; s_recw[rr][i - rr * 6] = rwv[u]; }
-        }
-    }
-    {   // one barrier: bit 0 = some receding pixel, bit 1 = region not uniform
-        const uint32_t code = ((rwv[0] | rwv[1]) ? 1u : 0u) | (uni ? 0u : 2u);
-        const uint32_t wcode = __reduce_or_sync(0xffffffffu, code);
-        if (lane == 0 && wcode) atomicOr(&s_quiet, (int)wcode);
-    }
-    __syncthreads();
-    const int tile_state = s_quiet;
-    const int any_rec = tile_state & 1;
-    if (p.stats && t == 0) atomicAdd(&p.stats[tile_state == 0 ? 0 : 1], 1ULL);
-    PHASE(8);
-    if (tile_state == 0) { // uniform region, nothing recedes: every filter of a constant is that constant
-        if (nvalid > 0) {
-            const uint32_t cv = L2.map4(ref);
-            uint8_t *dst = p.out + (size_t)oy * p.opitch + ox;
-            const uint4 o = make_uint4(cv, cv, cv, cv);
-            if (nvalid == 16 && p.aligned) vsb_st16_stream(dst, o);
-            else vsb_st_bytes(dst, o, nvalid);
-        }
-        return;
-    }
-
-    // ---- P2: distance search + gradient on the receding pixels of the region --------------------------------
-    if (ZMODE != ZL_NONE && any_rec) {
-        const int brows = RH + 2 * R;
-        if (ZMODE != VSB_Z_CONST) {
-            if (METRIC == VSB_METRIC_CHAMFER5) {
-                const int n1 = R + 1;
-                for (int i = t; i < n1 * n1; i += VSB_THREADS) s_T[i] = p.T[i];
+            if (!XY || i < RH * RG_CH) {
+                const int rr = XY ? i / RG_CH : r, cc = XY ? i - rr * RG_CH : c + 1;
+                uint4 v = make_uint4(0, 0, 0, 0);
+                if (gstate[u] == 1) {
+                    v = L1.map16(gv[u]);
+                    uni = uni && (v.x == ref) && (v.y == ref) && (v.z == ref) && (v.w == ref);
+                } else if (gstate[u] == 2) {
+                    const int y = y0 - Hh + rr, x = x0 - 16 + cc * 16;
+                    const int xa = max(x, 0), xb = min(x + 16, W);
+                    uint32_t w[4] = {0, 0, 0, 0};
+                    const uint8_t *src = p.in + (size_t)y * p.ipitch;
+                    for (int xx = xa; xx < xb; ++xx) {
+                        const int k = xx - x;
+                        const uint32_t bb = L1.s ? L1.s[src[xx]] : src[xx];
+                        uni = uni && (bb == (ref & 255u));
+                        w[k >> 2] |= bb << ((k & 3) * 8);
+                    }
+                    v = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+                *(uint4 *)&s1[rr][cc * 16] = v;
             }
-            stage_mask_rows<LBW>(s_bits, p.cur, wpr, H, (x0 >> 5) - 3, y0 - Hh - R, brows);
         }
-        for (int i = t; i < RH * 6; i += VSB_THREADS) {
-            const int rr = i / 6, k = i - rr * 6;
-            uint32_t rw = s_recw[rr][k];
-            if (rw) {
-                int base = atomicAdd(&s_cnt, __popc(rw));
-                while (rw) {
-                    const int b = __ffs(rw) - 1;
-                    rw &= rw - 1;
-                    s_list[base++] = (uint16_t)((rr << 8) | (32 * k + b - 16));
+        {   // one barrier: bit 0 = some receding pixel, bit 1 = region not uniform
+            const uint32_t code = ((rwv[0] | rwv[1]) ? 1u : 0u) | (uni ? 0u : 2u);
+            const uint32_t wcode = __reduce_or_sync(0xffffffffu, code);
+            if (lane == 0 && wcode) atomicOr(&s_quiet, (int)wcode);
+        }
+        __syncthreads();
+        const int tile_state = s_quiet;
+        const int any_rec = tile_state & 1;
+        if (p.stats && t == 0) atomicAdd(&p.stats[tile_state == 0 ? 0 : 1], 1ULL);
+        PHASE(8);
+        do { // one pass; `break` = tile finished
+        if (tile_state == 0) { // uniform region, nothing recedes: every filter of a constant is that constant
+            if (nvalid > 0) {
+                const uint32_t cv = L2.map4(ref);
+                uint8_t *dst = p.out + (size_t)oy * p.opitch + ox;
+                const uint4 o = make_uint4(cv, cv, cv, cv);
+                if (nvalid == 16 && p.aligned) vsb_st16_stream(dst, o);
+                else vsb_st_bytes(dst, o, nvalid);
+            }
+            break;
+        }
+
+        // ---- P2: distance search + gradient on the receding pixels of the region ----------------------------
+        if (ZMODE != ZL_NONE && any_rec) {
+            const int brows = RH + 2 * R;
+            if (ZMODE != VSB_Z_CONST) {
+                if (METRIC == VSB_METRIC_CHAMFER5 && !t_staged) {
+                    const int n1 = R + 1;
+                    for (int M = (t >> 5); M <= R; M += VSB_THREADS / 32)
+                        for (int m = lane; m <= M; m += 32) s_T[((M * (M + 1)) >> 1) + m] = p.T[M * n1 + m];
+                    t_staged = true;
+                }
+                stage_mask_rows<LBW>(s_bits, p.cur, wpr, H, (x0 >> 5) - 3, y0 - Hh - R, brows);
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int i = t + u * VSB_THREADS;
+                uint32_t rw = rwv[u];
+                if (rw) {
+                    // XY: item i = (row i/6, word i%6 of the 6-word span starting one word left of the tile);
+                    // no XY: item t = (row t>>2, tile word t&3)
+                    const int rr = XY ? i / 6 : (t >> 2);
+                    const int k = XY ? i - rr * 6 : (t & 3) + 1;
+                    int base = atomicAdd(&s_cnt, __popc(rw));
+                    while (rw) {
+                        const int bq = __ffs(rw) - 1;
+                        rw &= rw - 1;
+                        s_rlist[base++] = (uint16_t)((rr << 8) | (32 * k + bq - 16));
+                    }
+                }
+            }
+            __syncthreads();
+            if (ZMODE != VSB_Z_CONST) stage_rowany_rows<LBW>(s_rowany, s_bits, brows);
+            __syncthreads();
+            const int total = s_cnt;
+            if (p.stats && t == 0) { atomicAdd(&p.stats[2], 1ULL); atomicAdd(&p.stats[3], (unsigned long long)total); }
+            PHASE(9);
+            const float Ff = p.z.fade;
+            for (int i = t; i < total; i += VSB_THREADS) {
+                const int code = s_rlist[i];
+                const int rr = code >> 8, rc = code & 255;
+                const int x = x0 - 16 + rc, y = y0 - Hh + rr;
+                float best = 0.0f;
+                if (ZMODE != VSB_Z_CONST) best = tile_search<METRIC, LBW, true>(s_bits, s_rowany, s_T, R, rr + R, rc + 80);
+                int g;
+                if (ZMODE == VSB_Z_FIXED) {
+                    const float n = __fdiv_rn(fminf(best, Ff), p.z.den);
+                    g = (int)__fmul_rn(255.0f, __fsub_rn(1.0f, n));
+                } else if (ZMODE == VSB_Z_WEIGHTED) {
+                    float acc = 0.0f;
+                    const size_t o = (size_t)y * wpr + (x >> 5);
+                    const uint32_t ncur = ~p.cur[o];
+                    for (int j = 0; j < np; ++j) {
+                        if (p.z.weights[j] > 0.0f && (((p.prior[j][o] & ncur) >> (x & 31)) & 1u)) {
+                            const float n = __fsub_rn(1.0f, __fdiv_rn(fminf(best, p.z.fades[j]), p.z.dens[j]));
+                            acc = __fadd_rn(acc, __fmul_rn(n, p.z.weights[j]));
+                        }
+                    }
+                    g = (int)__fmul_rn(255.0f, __fdiv_rn(acc, p.z.total_weight));
+                } else {
+                    g = p.z.const_val;
+                }
+                const int graw = PERSIST ? (int)rawb[rr * RG_W + rc] : (int)p.in[(size_t)y * p.ipitch + x];
+                const int m = max(graw, g & 255); // merge with the raw gray value
+                s1[rr][rc] = L1.s ? L1.s[m] : (uint8_t)m;
+            }
+            __syncthreads();
+            if (t == 0) s_cnt = 0;
+            PHASE(10);
+        }
+
+        // ---- P3: REFLECT_101 fix-up of out-of-image halo positions (border tiles only) -----------------------------
+        const bool border = (x0 - Hh < 0) || (x0 + VSB_TW + Hh > W) || (y0 - Hh < 0) || (y0 + VSB_TH + Hh > H);
+        if (XY && border && Hh > 0) {
+            for (int i = t; i < RH * RG_W; i += VSB_THREADS) {
+                const int rr = i / RG_W, rc = i - rr * RG_W;
+                const int y = y0 - Hh + rr, x = x0 - 16 + rc;
+                if (x < -Hh || x >= W + Hh || y < -Hh || y >= H + Hh) continue;
+                if (y < 0 || y >= H || x < 0 || x >= W) {
+                    const int ys = vsb_reflect101(y, H), xs = vsb_reflect101(x, W);
+                    s1[rr][rc] = s1[ys - (y0 - Hh)][xs - (x0 - 16)];
                 }
             }
         }
         __syncthreads();
-        if (ZMODE != VSB_Z_CONST) stage_rowany_rows<LBW>(s_rowany, s_bits, brows);
-        __syncthreads();
-        const int total = s_cnt;
-        if (p.stats && t == 0) { atomicAdd(&p.stats[2], 1ULL); atomicAdd(&p.stats[3], (unsigned long long)total); }
-        PHASE(9);
-        const float Ff = p.z.fade;
-        for (int i = t; i < total; i += VSB_THREADS) {
-            const int code = s_list[i];
-            const int rr = code >> 8, rc = code & 255;
-            const int x = x0 - 16 + rc, y = y0 - Hh + rr;
-            float best = 0.0f;
-            if (ZMODE != VSB_Z_CONST) best = tile_search<METRIC, LBW>(s_bits, s_rowany, s_T, R, rr + R, rc + 80);
-            int g;
-            if (ZMODE == VSB_Z_FIXED) {
-                const float n = __fdiv_rn(fminf(best, Ff), p.z.den);
-                g = (int)__fmul_rn(255.0f, __fsub_rn(1.0f, n));
-            } else if (ZMODE == VSB_Z_WEIGHTED) {
-                float acc = 0.0f;
-                const size_t o = (size_t)y * wpr + (x >> 5);
-                const uint32_t ncur = ~p.cur[o];
-                for (int j = 0; j < np; ++j) {
-                    if (p.z.weights[j] > 0.0f && (((p.prior[j][o] & ncur) >> (x & 31)) & 1u)) {
-                        const float n = __fsub_rn(1.0f, __fdiv_rn(fminf(best, p.z.fades[j]), p.z.dens[j]));
-                        acc = __fadd_rn(acc, __fmul_rn(n, p.z.weights[j]));
-                    }
+
+        const int hb = XY ? p.hb : 0;
+        const int rx = XY ? (p.nkx >> 1) : 0, ry = XY ? (p.nky >> 1) : 0;
+        const int hg = max(rx, ry);
+        const bool gauss = XY && p.nkx > 0;
+        uint8_t (*S2)[RG_W] = hb > 0 ? s2buf : s1;                  // Gaussian input
+        uint8_t (*OUT)[RG_W] = gauss ? (hb > 0 ? s1 : s2buf) : S2;  // what the store phase reads
+
+        if (XY && (hb > 0 || gauss)) {
+            // ---- P4: bit-planes of stage 1: word not uniform / differs from right neighbour / differs from the word below
+            for (int i = t; i < RH * RG_CH; i += VSB_THREADS) {
+                const int rr = i / RG_CH, cc = i - rr * RG_CH;
+                const uint4 a = *(const uint4 *)&s1[rr][cc * 16];
+                const uint32_t wn = (cc < RG_CH - 1) ? *(const uint32_t *)&s1[rr][cc * 16 + 16] : a.w;
+                const uint4 b = (rr + 1 < RH) ? *(const uint4 *)&s1[rr + 1][cc * 16] : a;
+                const uint32_t nu = (uint32_t)(a.x != (a.x & 255u) * 0x01010101u) | ((uint32_t)(a.y != (a.y & 255u) * 0x01010101u) << 1) |
+                                    ((uint32_t)(a.z != (a.z & 255u) * 0x01010101u) << 2) | ((uint32_t)(a.w != (a.w & 255u) * 0x01010101u) << 3);
+                const uint32_t dh = (uint32_t)(a.x != a.y) | ((uint32_t)(a.y != a.z) << 1) | ((uint32_t)(a.z != a.w) << 2) |
+                                    ((uint32_t)(a.w != wn) << 3);
+                const uint32_t dv = (uint32_t)(a.x != b.x) | ((uint32_t)(a.y != b.y) << 1) | ((uint32_t)(a.z != b.z) << 2) |
+                                    ((uint32_t)(a.w != b.w) << 3);
+                s_nib[0][rr][cc] = (uint8_t)nu; s_nib[1][rr][cc] = (uint8_t)dh; s_nib[2][rr][cc] = (uint8_t)dv;
+            }
+            __syncthreads();
+            if (t < RH) {
+                unsigned long long nu = 0, dh = 0, dv = 0;
+#pragma unroll
+                for (int cc = 0; cc < RG_CH; ++cc) {
+                    nu |= (unsigned long long)s_nib[0][t][cc] << (4 * cc);
+                    dh |= (unsigned long long)s_nib[1][t][cc] << (4 * cc);
+                    dv |= (unsigned long long)s_nib[2][t][cc] << (4 * cc);
                 }
-                g = (int)__fmul_rn(255.0f, __fdiv_rn(acc, p.z.total_weight));
-            } else {
-                g = p.z.const_val;
+                s_pl[0][t] = nu; s_pl[1][t] = dh; s_pl[2][t] = dv;
             }
-            const int m = max((int)p.in[(size_t)y * p.ipitch + x], g & 255); // merge with the raw gray value
-            s1[rr][rc] = L1.s ? L1.s[m] : (uint8_t)m;
-        }
-        __syncthreads();
-        if (t == 0) s_cnt = 0;
-        PHASE(10);
-    }
+            __syncthreads();
+            // window-row ORs: planes 3,4 for the bilateral window (+-hb), 6,7 for bilateral followed by Gaussian (+-(hb+ry))
+            const int r_lo = Hh - hg, r_hi = Hh + VSB_TH + hg; // region rows on which stage 2 is needed
+            if (t >= r_lo && t < r_hi) {
+                unsigned long long A = 0, B = 0, C = 0;
+                for (int d = -hb; d <= hb; ++d) { A |= s_pl[0][t + d]; B |= s_pl[1][t + d]; }
+                for (int d = -hb; d < hb; ++d) C |= s_pl[2][t + d];
+                s_pl[3][t] = A | C; s_pl[4][t] = B;
+            }
+            if (t >= Hh && t < Hh + VSB_TH) {
+                const int e = hb + ry;
+                unsigned long long A = 0, B = 0, C = 0;
+                for (int d = -e; d <= e; ++d) { A |= s_pl[0][t + d]; B |= s_pl[1][t + d]; }
+                for (int d = -e; d < e; ++d) C |= s_pl[2][t + d];
+                s_pl[6][t] = A | C; s_pl[7][t] = B;
+            }
+            __syncthreads();
+            PHASE(11);
 
-    // ---- P3: REFLECT_101 fix-up of out-of-image halo positions (border tiles only) ---------------------------------
-    const bool border = (x0 - Hh < 0) || (x0 + VSB_TW + Hh > W) || (y0 - Hh < 0) || (y0 + VSB_TH + Hh > H);
-    if (border && Hh > 0) {
-        for (int i = t; i < RH * RG_W; i += VSB_THREADS) {
-            const int rr = i / RG_W, rc = i - rr * RG_W;
-            const int y = y0 - Hh + rr, x = x0 - 16 + rc;
-            if (x < -Hh || x >= W + Hh || y < -Hh || y >= H + Hh) continue;
-            if (y < 0 || y >= H || x < 0 || x >= W) {
-                const int ys = vsb_reflect101(y, H), xs = vsb_reflect101(x, W);
-                s1[rr][rc] = s1[ys - (y0 - Hh)][xs - (x0 - 16)];
-            }
-        }
-    }
-    __syncthreads();
-
-    const int hb = p.hb;
-    const int rx = p.nkx >> 1, ry = p.nky >> 1;
-    const int hg = max(rx, ry);
-    const bool gauss = p.nkx > 0;
-    uint8_t (*S2)[RG_W] = hb > 0 ? s2buf : s1;        // Gaussian input
-    uint8_t (*OUT)[RG_W] = gauss ? (hb > 0 ? s1 : s2buf) : S2; // what the store phase reads
-
-    if (hb > 0 || gauss) {
-        // ---- P4: bit-planes of stage 1: word not uniform / differs from right neighbour / differs from the word below
-        for (int i = t; i < RH * RG_CH; i += VSB_THREADS) {
-            const int rr = i / RG_CH, cc = i - rr * RG_CH;
-            const uint4 a = *(const uint4 *)&s1[rr][cc * 16];
-            const uint32_t wn = (cc < RG_CH - 1) ? *(const uint32_t *)&s1[rr][cc * 16 + 16] : a.w;
-            const uint4 b = (rr + 1 < RH) ? *(const uint4 *)&s1[rr + 1][cc * 16] : a;
-            const uint32_t nu = (uint32_t)(a.x != (a.x & 255u) * 0x01010101u) | ((uint32_t)(a.y != (a.y & 255u) * 0x01010101u) << 1) |
-                                ((uint32_t)(a.z != (a.z & 255u) * 0x01010101u) << 2) | ((uint32_t)(a.w != (a.w & 255u) * 0x01010101u) << 3);
-            const uint32_t dh = (uint32_t)(a.x != a.y) | ((uint32_t)(a.y != a.z) << 1) | ((uint32_t)(a.z != a.w) << 2) |
-                                ((uint32_t)(a.w != wn) << 3);
-            const uint32_t dv = (uint32_t)(a.x != b.x) | ((uint32_t)(a.y != b.y) << 1) | ((uint32_t)(a.z != b.z) << 2) |
-                                ((uint32_t)(a.w != b.w) << 3);
-            s_nib[0][rr][cc] = (uint8_t)nu; s_nib[1][rr][cc] = (uint8_t)dh; s_nib[2][rr][cc] = (uint8_t)dv;
-        }
-        __syncthreads();
-        if (t < RH) {
-            unsigned long long nu = 0, dh = 0, dv = 0;
-#pragma unroll
-            for (int cc = 0; cc < RG_CH; ++cc) {
-                nu |= (unsigned long long)s_nib[0][t][cc] << (4 * cc);
-                dh |= (unsigned long long)s_nib[1][t][cc] << (4 * cc);
-                dv |= (unsigned long long)s_nib[2][t][cc] << (4 * cc);
-            }
-            s_pl[0][t] = nu; s_pl[1][t] = dh; s_pl[2][t] = dv;
-        }
-        __syncthreads();
-        // window-row ORs: planes 3..5 for the bilateral window (+-hb), 6..8 for bilateral followed by Gaussian (+-(hb+ry))
-        const int r_lo = Hh - hg, r_hi = Hh + VSB_TH + hg; // region rows on which stage 2 is needed
-        if (t >= r_lo && t < r_hi) {
-            unsigned long long A = 0, B = 0, C = 0;
-            for (int d = -hb; d <= hb; ++d) { A |= s_pl[0][t + d]; B |= s_pl[1][t + d]; }
-            for (int d = -hb; d < hb; ++d) C |= s_pl[2][t + d];
-            s_pl[3][t] = A | C; s_pl[4][t] = B;
-        }
-        if (t >= Hh && t < Hh + VSB_TH) {
-            const int e = hb + ry;
-            unsigned long long A = 0, B = 0, C = 0;
-            for (int d = -e; d <= e; ++d) { A |= s_pl[0][t + d]; B |= s_pl[1][t + d]; }
-            for (int d = -e; d < e; ++d) C |= s_pl[2][t + d];
-            s_pl[6][t] = A | C; s_pl[7][t] = B;
-        }
-        __syncthreads();
-
-        PHASE(11);
-        // ---- P5: bypass tests.  One item = one 16-byte chunk of one stage-2 row; a chunk whose 3-chunk x window-rows
-        //      neighbourhood carries no plane bit is copied whole, otherwise its four words are tested one by one.
-        const int eb = hb, eg = hb + rx;
-        const int nrow2 = r_hi - r_lo;
-        for (int it = t; it < ((nrow2 * RG_CH + 31) & ~31); it += VSB_THREADS) { // warp-uniform trip count
-            const bool live = it < nrow2 * RG_CH;
-            const int rq = it / RG_CH, cc = it - rq * RG_CH;
-            const int rr = r_lo + (live ? rq : 0);
-            const bool trow = rr >= Hh && rr < Hh + VSB_TH;
-            const unsigned long long AC = s_pl[3][rr], Bm = s_pl[4][rr];
-            const unsigned long long AC2 = trow ? s_pl[6][rr] : 0ULL, B2 = trow ? s_pl[7][rr] : 0ULL;
-            // plane bits of words 4cc-4 .. 4cc+7 (the chunk and one chunk either side), as 12-bit fields
-            const int sh = 4 * cc - 4;
-            const uint32_t fa = (uint32_t)(sh >= 0 ? (AC >> sh) : (AC << 4)) & 0xFFFu;
-            const uint32_t fb = (uint32_t)(sh >= 0 ? (Bm >> sh) : (Bm << 4)) & 0xFFFu;
-            const uint32_t ga = (uint32_t)(sh >= 0 ? (AC2 >> sh) : (AC2 << 4)) & 0xFFFu;
-            const uint32_t gb = (uint32_t)(sh >= 0 ? (B2 >> sh) : (B2 << 4)) & 0xFFFu;
-            uint32_t badb = 0, badg = 0; // per-word verdicts of this chunk (bit j = word 4cc+j)
-            if (live && cc >= 1 && cc <= 8 || (live && hg > 0)) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int w = 4 * cc + j;
-                    if (w < ((16 - hg) >> 2) || w > ((143 + hg) >> 2)) continue;
-                    if (hb > 0) {
-                        const int wl = (4 * w - eb) >> 2, wr = (4 * w + 3 + eb) >> 2, n = wr - wl, o = wl - (4 * cc - 4);
-                        if ((((fa >> o) & ((2u << n) - 1u)) | ((fb >> o) & ((1u << n) - 1u))) != 0) badb |= 1u << j;
-                    }
-                    if (gauss && trow && w >= 4 && w < 36) {
-                        const int wl = (4 * w - eg) >> 2, wr = (4 * w + 3 + eg) >> 2, n = wr - wl, o = wl - (4 * cc - 4);
-                        if ((((ga >> o) & ((2u << n) - 1u)) | ((gb >> o) & ((1u << n) - 1u))) != 0) badg |= 1u << j;
-                    }
-                }
-            }
-            // warp-aggregated list appends
-            const int nb = 4 * __popc(badb), ng = __popc(badg);
-            int pb = nb, pg = ng; // inclusive scans over the warp
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int vb = __shfl_up_sync(0xffffffffu, pb, o), vg = __shfl_up_sync(0xffffffffu, pg, o);
-                if (lane >= o) { pb += vb; pg += vg; }
-            }
-            int baseb = 0, baseg = 0;
-            if (lane == 31) { if (pb) baseb = atomicAdd(&s_cnt, pb); if (pg) baseg = atomicAdd(&s_gcnt, pg); }
-            baseb = __shfl_sync(0xffffffffu, baseb, 31) + pb - nb;
-            baseg = __shfl_sync(0xffffffffu, baseg, 31) + pg - ng;
-            if (!live) continue;
-            if (hb > 0) {
-                if (badb == 0) *(uint4 *)&s2buf[rr][16 * cc] = *(const uint4 *)&s1[rr][16 * cc];
-                else {
+            // ---- P5: bypass tests.  One item = one 16-byte chunk of one stage-2 row; a chunk whose neighbourhood carries
+            //      no plane bit is copied whole, otherwise its four words are tested one by one.
+            const int eb = hb, eg = hb + rx;
+            const int nrow2 = r_hi - r_lo;
+            for (int it = t; it < ((nrow2 * RG_CH + 31) & ~31); it += VSB_THREADS) { // warp-uniform trip count
+                const bool live = it < nrow2 * RG_CH;
+                const int rq = it / RG_CH, cc = it - rq * RG_CH;
+                const int rr = r_lo + (live ? rq : 0);
+                const bool trow = rr >= Hh && rr < Hh + VSB_TH;
+                const unsigned long long AC = s_pl[3][rr], Bm = s_pl[4][rr];
+                const unsigned long long AC2 = trow ? s_pl[6][rr] : 0ULL, B2 = trow ? s_pl[7][rr] : 0ULL;
+                const int sh = 4 * cc - 4; // plane bits of words 4cc-4 .. 4cc+7, as 12-bit fields
+                const uint32_t fa = (uint32_t)(sh >= 0 ? (AC >> sh) : (AC << 4)) & 0xFFFu;
+                const uint32_t fb = (uint32_t)(sh >= 0 ? (Bm >> sh) : (Bm << 4)) & 0xFFFu;
+                const uint32_t ga = (uint32_t)(sh >= 0 ? (AC2 >> sh) : (AC2 << 4)) & 0xFFFu;
+                const uint32_t gb = (uint32_t)(sh >= 0 ? (B2 >> sh) : (B2 << 4)) & 0xFFFu;
+                uint32_t badb = 0, badg = 0; // per-word verdicts of this chunk (bit j = word 4cc+j)
+                if (live && ((cc >= 1 && cc <= 8) || hg > 0) && (fa | fb | ga | gb)) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const int w = 4 * cc + j;
-                        if (badb & (1u << j)) {
-                            const int code = (rr << 8) | (4 * w);
-                            s_list[baseb] = (uint16_t)code; s_list[baseb + 1] = (uint16_t)(code + 1);
-                            s_list[baseb + 2] = (uint16_t)(code + 2); s_list[baseb + 3] = (uint16_t)(code + 3);
-                            baseb += 4;
-                        } else *(uint32_t *)&s2buf[rr][4 * w] = *(const uint32_t *)&s1[rr][4 * w];
+                        if (w < ((16 - hg) >> 2) || w > ((143 + hg) >> 2)) continue;
+                        if (hb > 0) {
+                            const int wl = (4 * w - eb) >> 2, wr = (4 * w + 3 + eb) >> 2, n = wr - wl, o = wl - (4 * cc - 4);
+                            if ((((fa >> o) & ((2u << n) - 1u)) | ((fb >> o) & ((1u << n) - 1u))) != 0) badb |= 1u << j;
+                        }
+                        if (gauss && trow && w >= 4 && w < 36) {
+                            const int wl = (4 * w - eg) >> 2, wr = (4 * w + 3 + eg) >> 2, n = wr - wl, o = wl - (4 * cc - 4);
+                            if ((((ga >> o) & ((2u << n) - 1u)) | ((gb >> o) & ((1u << n) - 1u))) != 0) badg |= 1u << j;
+                        }
                     }
                 }
-            }
-            if (gauss && trow) {
+                // warp-aggregated list appends (entries are words)
+                const uint32_t vb = __ballot_sync(0xffffffffu, badb != 0), vg = __ballot_sync(0xffffffffu, badg != 0);
+                if (vb | vg) {
+                    const int nb = __popc(badb), ng = __popc(badg);
+                    int pb = nb, pg = ng; // inclusive scans over the warp
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int w = 4 * cc + j;
-                    if (badg & (1u << j)) s_list[5000 + baseg++] = (uint16_t)((rr << 8) | w);
-                    else if (hb == 0 && w >= 4 && w < 36) *(uint32_t *)&s2buf[rr][4 * w] = *(const uint32_t *)&s1[rr][4 * w];
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int ub = __shfl_up_sync(0xffffffffu, pb, o), ug = __shfl_up_sync(0xffffffffu, pg, o);
+                        if (lane >= o) { pb += ub; pg += ug; }
+                    }
+                    int baseb = 0, baseg = 0;
+                    if (lane == 31) { if (pb) baseb = atomicAdd(&s_cnt, pb); if (pg) baseg = atomicAdd(&s_gcnt, pg); }
+                    baseb = __shfl_sync(0xffffffffu, baseb, 31) + pb - nb;
+                    baseg = __shfl_sync(0xffffffffu, baseg, 31) + pg - ng;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (badb & (1u << j)) s_list[baseb++] = (uint16_t)((rr << 8) | (4 * cc + j));
+                        if (badg & (1u << j)) s_list[GL_OFF + baseg++] = (uint16_t)((rr << 8) | (4 * cc + j));
+                    }
                 }
-            }
-        }
-        __syncthreads();
-
-        PHASE(12);
-        if (hb > 0) {
-            const int total = s_cnt;
-            if (p.stats && t == 0) atomicAdd(&p.stats[4], (unsigned long long)total);
-            const int ntaps = p.ntaps;
-            for (int i = t; i < total; i += VSB_THREADS) {
-                const int code = s_list[i];
-                const int rr = code >> 8, rc = code & 255;
-                const int y = y0 - Hh + rr, x = x0 - 16 + rc;
-                if (y < 0 || y >= H || x < 0 || x >= W) continue; // reflected below
-                const uint8_t *ctr = &s1[rr][rc];
-                const int v0 = *ctr;
-                float s = 0.0f, ws = 0.0f;
-#pragma unroll 4
-                for (int k = 0; k < ntaps; ++k) {
-                    const int v = ctr[s_off[k]];
-                    const float w = __fmul_rn(s_sw[k], s_cw[abs(v - v0)]);
-                    s = __fmaf_rn((float)v, w, s);
-                    ws = __fadd_rn(ws, w);
+                if (!live) continue;
+                if (hb > 0) {
+                    if (badb == 0) *(uint4 *)&s2buf[rr][16 * cc] = *(const uint4 *)&s1[rr][16 * cc];
+                    else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if (!(badb & (1u << j))) *(uint32_t *)&s2buf[rr][16 * cc + 4 * j] = *(const uint32_t *)&s1[rr][16 * cc + 4 * j];
+                    }
+                } else if (gauss && trow) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int w = 4 * cc + j;
+                        if (!(badg & (1u << j)) && w >= 4 && w < 36) *(uint32_t *)&s2buf[rr][4 * w] = *(const uint32_t *)&s1[rr][4 * w];
+                    }
                 }
-                const int o = __float2int_rn(__fdiv_rn(s, ws));
-                s2buf[rr][rc] = (uint8_t)min(max(o, 0), 255);
             }
             __syncthreads();
-            if (border && hg > 0) {
-                const int nr = r_hi - r_lo;
-                for (int i = t; i < nr * RG_W; i += VSB_THREADS) {
-                    const int rr = r_lo + i / RG_W, rc = i % RG_W;
+            PHASE(12);
+
+            if (hb > 0) {
+                const int total = s_cnt; // words; four lanes per word
+                if (p.stats && t == 0) atomicAdd(&p.stats[4], 4ULL * (unsigned long long)total);
+                const int ntaps = p.ntaps;
+                for (int i = t; i < 4 * total; i += VSB_THREADS) {
+                    const int code = s_list[i >> 2];
+                    const int rr = code >> 8, rc = 4 * (code & 255) + (i & 3);
                     const int y = y0 - Hh + rr, x = x0 - 16 + rc;
-                    if (x < -hg || x >= W + hg || y < -hg || y >= H + hg) continue;
-                    if (y < 0 || y >= H || x < 0 || x >= W) {
-                        const int ys = vsb_reflect101(y, H), xs = vsb_reflect101(x, W);
-                        s2buf[rr][rc] = s2buf[ys - (y0 - Hh)][xs - (x0 - 16)];
+                    if (y < 0 || y >= H || x < 0 || x >= W) continue; // reflected below
+                    const uint8_t *ctr = &s1[rr][rc];
+                    const int v0 = *ctr;
+                    float sacc = 0.0f, ws = 0.0f;
+#pragma unroll 4
+                    for (int k = 0; k < ntaps; ++k) {
+                        const int v = ctr[s_off[k]];
+                        const float w = __fmul_rn(s_sw[k], s_cw[abs(v - v0)]);
+                        sacc = __fmaf_rn((float)v, w, sacc);
+                        ws = __fadd_rn(ws, w);
                     }
+                    const int o = __float2int_rn(__fdiv_rn(sacc, ws));
+                    s2buf[rr][rc] = (uint8_t)min(max(o, 0), 255);
+                }
+                __syncthreads();
+                if (border && hg > 0) {
+                    const int nr = r_hi - r_lo;
+                    for (int i = t; i < nr * RG_W; i += VSB_THREADS) {
+                        const int rr = r_lo + i / RG_W, rc = i % RG_W;
+                        const int y = y0 - Hh + rr, x = x0 - 16 + rc;
+                        if (x < -hg || x >= W + hg || y < -hg || y >= H + hg) continue;
+                        if (y < 0 || y >= H || x < 0 || x >= W) {
+                            const int ys = vsb_reflect101(y, H), xs = vsb_reflect101(x, W);
+                            s2buf[rr][rc] = s2buf[ys - (y0 - Hh)][xs - (x0 - 16)];
+                        }
+                    }
+                    __syncthreads();
+                }
+            }
+            PHASE(13);
+
+            // ---- P6: Gaussian on the words that are not provably constant ----------------------------------------------
+            if (gauss) {
+                const int gtotal = s_gcnt;
+                if (p.stats && t == 0) atomicAdd(&p.stats[5], (unsigned long long)gtotal);
+                for (int i = t; i < gtotal; i += VSB_THREADS) {
+                    const int code = s_list[GL_OFF + i];
+                    const int rr = code >> 8, w = code & 255;
+                    uint32_t o;
+                    switch (rx) {
+                    case 0: o = gauss_word_ry<0>(S2, rr, w, p.kx, p.ky, ry); break;
+                    case 1: o = gauss_word_ry<1>(S2, rr, w, p.kx, p.ky, ry); break;
+                    case 2: o = gauss_word_ry<2>(S2, rr, w, p.kx, p.ky, ry); break;
+                    default: o = gauss_word_ry<3>(S2, rr, w, p.kx, p.ky, ry); break;
+                    }
+                    *(uint32_t *)&OUT[rr][4 * w] = o;
                 }
                 __syncthreads();
             }
         }
+        PHASE(14);
 
-        PHASE(13);
-        // ---- P6: Gaussian on the words that are not provably constant --------------------------------------------------
-        if (gauss) {
-            const int gtotal = s_gcnt;
-            if (p.stats && t == 0) atomicAdd(&p.stats[5], (unsigned long long)gtotal);
-            for (int i = t; i < gtotal; i += VSB_THREADS) {
-                const int code = s_list[5000 + i];
-                const int rr = code >> 8, w = code & 255;
-                uint32_t o;
-                switch (rx) {
-                case 0: o = gauss_word_ry<0>(S2, rr, w, p.kx, p.ky, ry); break;
-                case 1: o = gauss_word_ry<1>(S2, rr, w, p.kx, p.ky, ry); break;
-                case 2: o = gauss_word_ry<2>(S2, rr, w, p.kx, p.ky, ry); break;
-                default: o = gauss_word_ry<3>(S2, rr, w, p.kx, p.ky, ry); break;
-                }
-                *(uint32_t *)&OUT[rr][4 * w] = o;
-            }
-            __syncthreads();
+        // ---- P7: trailing LUT, store ----------------------------------------------------------------------------------
+        if (nvalid > 0) {
+            uint4 o = *(const uint4 *)&OUT[r + Hh][16 + 16 * c];
+            o = L2.map16(o);
+            uint8_t *dst = p.out + (size_t)oy * p.opitch + ox;
+            if (nvalid == 16 && p.aligned) vsb_st16_stream(dst, o);
+            else vsb_st_bytes(dst, o, nvalid);
         }
-    }
-
-    PHASE(14);
-    // ---- P7: trailing LUT, store ----------------------------------------------------------------------------------
-    if (nvalid > 0) {
-        uint4 o = *(const uint4 *)&OUT[r + Hh][16 + 16 * c];
-        o = L2.map16(o);
-        uint8_t *dst = p.out + (size_t)oy * p.opitch + ox;
-        if (nvalid == 16 && p.aligned) vsb_st16_stream(dst, o);
-        else vsb_st_bytes(dst, o, nvalid);
+        } while (0);
+        if (PERSIST) { __syncthreads(); buf ^= 1; } // shared buffers are reused by the next tile
     }
 }
 
-template <int ZMODE, int METRIC>
-static int launch_layer(const LayerParams &p, const BilTapsL &taps, dim3 grid, size_t smem, cudaStream_t s)
+template <int ZMODE, int METRIC, bool PERSIST, bool XY>
+static int launch_layer_v(LayerParams &p, const BilTapsL &taps, size_t smem, cudaStream_t s)
 {
-    static bool attr_set = false;
-    if (!attr_set) {
-        VSB_CUDA(cudaFuncSetAttribute(k_layer<ZMODE, METRIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 17 * 1024));
-        attr_set = true;
+    static int n_sms = 0; // per instantiation
+    if (n_sms == 0) {
+        VSB_CUDA(cudaFuncSetAttribute(k_layer<ZMODE, METRIC, PERSIST, XY>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        int dev = 0, sms = 0;
+        VSB_CUDA(cudaGetDevice(&dev));
+        VSB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        n_sms = sms > 0 ? sms : 148;
     }
-    k_layer<ZMODE, METRIC><<<grid, VSB_THREADS, smem, s>>>(p, taps);
+    if (PERSIST) {
+        int per_sm = 0;
+        VSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_layer<ZMODE, METRIC, PERSIST, XY>, VSB_THREADS, smem));
+        if (per_sm < 1) per_sm = 1;
+        const int grid = p.ntiles < n_sms * per_sm ? p.ntiles : n_sms * per_sm;
+        k_layer<ZMODE, METRIC, PERSIST, XY><<<grid, VSB_THREADS, smem, s>>>(p, taps);
+    } else {
+        dim3 grid(p.tiles_x, p.tiles_y);
+        k_layer<ZMODE, METRIC, PERSIST, XY><<<grid, VSB_THREADS, smem, s>>>(p, taps);
+    }
     return vsb_check_launch("k_layer");
+}
+
+template <int ZMODE, int METRIC>
+static int launch_layer(LayerParams &p, const BilTapsL &taps, bool persist, size_t smem, cudaStream_t s)
+{
+    const bool xy = p.hb > 0 || p.nkx > 0;
+    if (persist) return launch_layer_v<ZMODE, METRIC, true, true>(p, taps, smem, s); // the prefetching variant keeps the general body
+    return xy ? launch_layer_v<ZMODE, METRIC, false, true>(p, taps, smem, s) : launch_layer_v<ZMODE, METRIC, false, false>(p, taps, smem, s);
 }
 
 static unsigned long long *g_layer_stats = nullptr;
@@ -682,16 +814,33 @@ extern "C" int vsb_layer_fused(const uint8_t *in, size_t in_pitch, int W, int H,
     p.halo = p.hb + max(p.nkx >> 1, p.nky >> 1);
     p.stats = g_layer_stats;
     VSB_REQUIRE(p.halo <= LH_MAX, "vsb_layer_fused: halo %d > %d", p.halo, LH_MAX);
-    dim3 grid(p.tiles_x, p.tiles_y);
+    p.ntiles = p.tiles_x * p.tiles_y;
+    // persistent + prefetch variant: whole 16-byte chunks only, at most 7 masks staged per tile
+    const bool persist = getenv("VSB_PERSIST") != nullptr && p.aligned && (W % 16) == 0 && p.z.n_priors <= 7;
+    const int RH = VSB_TH + 2 * p.halo;
     const int n1 = p.z.reach + 1;
-    const size_t smem = (mode != VSB_Z_NONE && mode != VSB_Z_CONST && zp->metric == VSB_METRIC_CHAMFER5)
-                            ? (size_t)n1 * n1 * sizeof(float) : 16;
+    auto up16 = [](size_t v) { return (v + 15) & ~(size_t)15; };
+    const bool searching = mode != VSB_Z_NONE && mode != VSB_Z_CONST;
+    size_t off = 0;
+    p.sm.T = (int)off; off += up16((searching && zp->metric == VSB_METRIC_CHAMFER5) ? (size_t)n1 * (n1 + 1) * 2 : 16);
+    p.sm.raw_stride = (int)up16((size_t)RH * RG_W);
+    p.sm.raw = (int)off; off += persist ? 2 * (size_t)p.sm.raw_stride : 0;
+    p.sm.src_stride = (p.z.n_priors + 1) * RH * 6;
+    p.sm.src = (int)off; off += (persist && mode != VSB_Z_NONE) ? up16(2 * (size_t)p.sm.src_stride * 4) : 0;
+    p.sm.s1 = (int)off; off += up16((size_t)RH * RG_W);
+    p.sm.bits = (int)off; off += searching ? up16((size_t)(RH + 2 * p.z.reach) * LBW * 4) : 16;
+    const size_t s2bytes = up16((size_t)RH * RG_W);
+    p.sm.s2 = (int)off; off += s2bytes;
+    const size_t rlist = (mode != VSB_Z_NONE) ? (size_t)RH * (VSB_TW + 2 * p.halo) * 2 : 0; // overlays [s2 | list]
+    const size_t lmin = (size_t)(GL_OFF + 1100) * 2;
+    p.sm.list = (int)off; off += up16(rlist > s2bytes + lmin ? rlist - s2bytes : lmin);
+    const size_t smem = off;
     cudaStream_t s = (cudaStream_t)stream;
     const bool ex = zp->metric == VSB_METRIC_EXACT;
     switch (mode) {
-    case VSB_Z_FIXED: return ex ? launch_layer<VSB_Z_FIXED, 1>(p, taps, grid, smem, s) : launch_layer<VSB_Z_FIXED, 0>(p, taps, grid, smem, s);
-    case VSB_Z_WEIGHTED: return ex ? launch_layer<VSB_Z_WEIGHTED, 1>(p, taps, grid, smem, s) : launch_layer<VSB_Z_WEIGHTED, 0>(p, taps, grid, smem, s);
-    case VSB_Z_CONST: return launch_layer<VSB_Z_CONST, 0>(p, taps, grid, smem, s);
-    default: return launch_layer<ZL_NONE, 0>(p, taps, grid, smem, s);
+    case VSB_Z_FIXED: return ex ? launch_layer<VSB_Z_FIXED, 1>(p, taps, persist, smem, s) : launch_layer<VSB_Z_FIXED, 0>(p, taps, persist, smem, s);
+    case VSB_Z_WEIGHTED: return ex ? launch_layer<VSB_Z_WEIGHTED, 1>(p, taps, persist, smem, s) : launch_layer<VSB_Z_WEIGHTED, 0>(p, taps, persist, smem, s);
+    case VSB_Z_CONST: return launch_layer<VSB_Z_CONST, 0>(p, taps, persist, smem, s);
+    default: return launch_layer<ZL_NONE, 0>(p, taps, persist, smem, s);
     }
 }

@@ -69,7 +69,8 @@ __device__ __forceinline__ void stage_rowany_rows(uint32_t *s_rowany, const uint
 // distance from staged-row position (hr0, px) to the nearest set bit of the staged mask, either metric;
 // returns a value >= 3e38 when nothing lies within reach R.  T monotone in |dx| per row => the nearest
 // set bit of each row is that row's minimum; rows are visited outwards while |dy| < best.
-template <int METRIC, int RW>
+// TRI: the table is stored as its lower triangle, entry (M, m) at M*(M+1)/2 + m
+template <int METRIC, int RW, bool TRI = false>
 __device__ __forceinline__ float tile_search(const uint32_t (*s_cur)[RW], const uint32_t *s_rowany, const float *s_T,
                                              int R, int hr0, int px)
 {
@@ -78,17 +79,17 @@ __device__ __forceinline__ float tile_search(const uint32_t (*s_cur)[RW], const 
         float best = 3.0e38f;
         {
             const int dx = nearest_dx(s_cur[hr0], px);
-            if (dx <= R) best = s_T[dx * n1];
+            if (dx <= R) best = TRI ? s_T[(dx * (dx + 1)) >> 1] : s_T[dx * n1];
         }
         for (int k = 1; k <= R && (float)k < best; ++k) {
             const int ha = hr0 - k, hb = hr0 + k;
             if ((s_rowany[ha >> 5] >> (ha & 31)) & 1u) {
                 const int dx = nearest_dx(s_cur[ha], px);
-                if (dx <= R) best = fminf(best, s_T[max(k, dx) * n1 + min(k, dx)]);
+                if (dx <= R) { const int M = max(k, dx), m = min(k, dx); best = fminf(best, TRI ? s_T[((M * (M + 1)) >> 1) + m] : s_T[M * n1 + m]); }
             }
             if ((s_rowany[hb >> 5] >> (hb & 31)) & 1u) {
                 const int dx = nearest_dx(s_cur[hb], px);
-                if (dx <= R) best = fminf(best, s_T[max(k, dx) * n1 + min(k, dx)]);
+                if (dx <= R) { const int M = max(k, dx), m = min(k, dx); best = fminf(best, TRI ? s_T[((M * (M + 1)) >> 1) + m] : s_T[M * n1 + m]); }
             }
         }
         return best;
