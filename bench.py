@@ -222,7 +222,7 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     L, B, K, Wm = args.resident, args.batch, args.steps, max(3, args.warmup)
     # this rank's slab of an (world * 1000)-layer stack; the first layers of the slab double as the halo
     z0 = 20 + rank * 1000
