@@ -221,6 +221,7 @@ def main():
 
     torch.cuda.set_device(local_rank)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line (a VERSION banner would precede it)
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     L, B, K, Wm = args.resident, args.batch, args.steps, max(3, args.warmup)
