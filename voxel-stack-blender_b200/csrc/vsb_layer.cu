@@ -59,54 +59,49 @@ struct LayerParams {
 #define GL_OFF 1400 // Gaussian word list starts here in s_list (bilateral word list: at most 36*38 entries)
 
 // ------------------------------------------------------------------------------------------------------
-// One CTA packs PF_TILES vertically adjacent 128x32 tiles; all of its loads are issued before the first use so
-// that 4 x 16 bytes per thread are in flight (the kernel is a pure HBM read stream).
-#define PF_TILES 1
+// One CTA = two vertically adjacent 128x32 tiles; a thread owns one mask word (32 pixels, two 128-bit loads, both
+// issued before first use), so there is no cross-lane combine; the uniformity flag of each tile is a warp vote per
+// 8 rows plus one shared-memory AND.
 template <bool ALIGNED>
 __global__ void __launch_bounds__(VSB_THREADS) k_pack_flags(const uint8_t *__restrict__ gray, size_t pitch, int W, int H,
                                                             uint32_t thr4, uint32_t *__restrict__ bits, int wpr,
                                                             uint16_t *__restrict__ flags, int tiles_x, int tiles_y)
 {
-    const int t = threadIdx.x;
-    const int x0 = blockIdx.x * VSB_TW;
-    const int r = t >> 3, c = t & 7;
-    const int x = x0 + c * 16;
-    uint4 gv[PF_TILES];
-    int nv[PF_TILES];
-    uint32_t first[PF_TILES];
-#pragma unroll
-    for (int q = 0; q < PF_TILES; ++q) {
-        const int ty = blockIdx.y * PF_TILES + q;
-        const int y = ty * VSB_TH + r;
-        nv[q] = (y < H) ? max(0, min(16, W - x)) : 0;
-        gv[q] = make_uint4(0, 0, 0, 0);
-        first[q] = 0;
-        if (nv[q] == 16 && ALIGNED) gv[q] = vsb_ld16_stream(gray + (size_t)y * pitch + x);
-        else if (nv[q] > 0) gv[q] = vsb_ld_bytes(gray + (size_t)y * pitch + x, nv[q]);
-        if (ty < tiles_y) first[q] = gray[(size_t)(ty * VSB_TH) * pitch + x0];
+    __shared__ int s_ok[2];
+    const int t = threadIdx.x, half = t >> 7, u = t & 127;
+    const int ty = blockIdx.y * 2 + half;
+    const int x0 = blockIdx.x * VSB_TW, y0 = ty * VSB_TH;
+    const int r = u >> 2, wq = u & 3;
+    const int y = y0 + r, x = x0 + wq * 32;
+    if (t < 2) s_ok[t] = 1;
+    const int n = (y < H) ? max(0, min(32, W - x)) : 0;
+    uint4 a = make_uint4(0, 0, 0, 0), b = make_uint4(0, 0, 0, 0);
+    uint32_t first = 0;
+    if (ty < tiles_y) first = gray[(size_t)y0 * pitch + x0];
+    if (n == 32 && ALIGNED) {
+        const uint8_t *src = gray + (size_t)y * pitch + x;
+        a = vsb_ld16_stream(src);
+        b = vsb_ld16_stream(src + 16);
+    } else if (n > 0) {
+        const uint8_t *src = gray + (size_t)y * pitch + x;
+        a = vsb_ld_bytes(src, n);
+        if (n > 16) b = vsb_ld_bytes(src + 16, n - 16);
     }
-#pragma unroll
-    for (int q = 0; q < PF_TILES; ++q) {
-        const int ty = blockIdx.y * PF_TILES + q;
-        if (ty >= tiles_y) break; // uniform across the CTA
-        const int y = ty * VSB_TH + r;
-        uint32_t b16 = vsb_gt_bits16(gv[q], thr4);
-        if (nv[q] < 16) b16 &= (1u << nv[q]) - 1u;
-        const uint32_t other = __shfl_xor_sync(0xffffffffu, b16, 1);
-        if ((c & 1) == 0) {
-            const int wx = (x0 >> 5) + (c >> 1);
-            if (y < H && wx < wpr) bits[(size_t)y * wpr + wx] = b16 | (other << 16);
-        }
-        const uint32_t bc = first[q] * 0x01010101u;
-        bool ok = true;
-        if (nv[q] == 16) ok = (gv[q].x == bc) & (gv[q].y == bc) & (gv[q].z == bc) & (gv[q].w == bc);
-        else if (nv[q] > 0) {
-            const uint32_t w[4] = {gv[q].x, gv[q].y, gv[q].z, gv[q].w};
-            for (int i = 0; i < nv[q]; ++i) ok = ok && (((w[i >> 2] >> ((i & 3) * 8)) & 255u) == first[q]);
-        }
-        const int all = __syncthreads_and(ok);
-        if (t == 0) flags[ty * tiles_x + blockIdx.x] = (uint16_t)(all ? first[q] : FLAG_MIXED);
+    __syncthreads();
+    uint32_t word = vsb_gt_bits16(a, thr4) | (vsb_gt_bits16(b, thr4) << 16);
+    if (n < 32) word &= n > 0 ? ((1u << n) - 1u) : 0u;
+    const int wx = (x0 >> 5) + wq;
+    if (y < H && wx < wpr) bits[(size_t)y * wpr + wx] = word;
+    const uint32_t bc = first * 0x01010101u;
+    bool ok = true;
+    if (n == 32) ok = (a.x == bc) & (a.y == bc) & (a.z == bc) & (a.w == bc) & (b.x == bc) & (b.y == bc) & (b.z == bc) & (b.w == bc);
+    else if (n > 0) {
+        const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        for (int i = 0; i < n; ++i) ok = ok && (((w[i >> 2] >> ((i & 3) * 8)) & 255u) == first);
     }
+    if (!__all_sync(0xffffffffu, ok) && (t & 31) == 0) s_ok[half] = 0;
+    __syncthreads();
+    if (u == 0 && ty < tiles_y) flags[ty * tiles_x + blockIdx.x] = (uint16_t)(s_ok[half] ? first : FLAG_MIXED);
 }
 
 extern "C" int vsb_pack_flags(const uint8_t *gray, size_t pitch, int W, int H, int thresh, uint32_t *bits, int wpr,
@@ -116,7 +111,7 @@ extern "C" int vsb_pack_flags(const uint8_t *gray, size_t pitch, int W, int H, i
     VSB_REQUIRE(W > 0 && H > 0 && wpr >= ((W + 127) / 128) * 4 && pitch >= (size_t)W, "vsb_pack_flags: bad geometry");
     VSB_REQUIRE(thresh >= 0 && thresh <= 255, "vsb_pack_flags: thresh out of range");
     const int tiles_x = (W + VSB_TW - 1) / VSB_TW, tiles_y = (H + VSB_TH - 1) / VSB_TH;
-    dim3 grid(tiles_x, (tiles_y + PF_TILES - 1) / PF_TILES);
+    dim3 grid(tiles_x, (tiles_y + 1) / 2);
     const uint32_t thr4 = (uint32_t)thresh * 0x01010101u;
     cudaStream_t s = (cudaStream_t)stream;
     if (vsb_aligned16(gray, pitch)) k_pack_flags<true><<<grid, VSB_THREADS, 0, s>>>(gray, pitch, W, H, thr4, bits, wpr, flags, tiles_x, tiles_y);
