@@ -96,6 +96,29 @@ int vsb_dt_exact(const uint32_t *seed_bits, int wpr, int W, int H, uint16_t *col
                  int32_t *d2_out, float *dist_out, size_t pitch_elems, vsb_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Unbounded reach (csrc/vsb_unbounded.cu): column distances + pruned row search.
+ *   vsb_coldist      : g[y][x] = vertical distance to the nearest set bit of column x (uint16, 0xFFFF = none) and
+ *                      gmin64[y][b] = min of g over columns 64b..64b+63 (uint16 [H][ceil(W/64)]).
+ *   vsb_dt_unbounded : dense distance map, metric chamfer5 (exact integer chamfer cost in 2^-23 units, correctly
+ *                      rounded to float32) or exact (d2 = integer squared distance, dist = sqrtf); 3e38 / INT32_MAX
+ *                      where the image has no set bit.     replaces cv2.distanceTransform(src, DIST_L2, 5 | PRECISE)
+ *   vsb_zblend_unbounded : fixed fade with any F (norm 0) or the global min-max normalisation (norm 1,
+ *                      processing_core.py:141-145: minMaxLoc over the receding pixels, (d-min)/(max-min), zeros if
+ *                      max <= min), merged with gray, leading LUT.  Scratch: g, gmin64, dist float [H][pitch],
+ *                      minmax2 = 2 x uint32.
+ * ------------------------------------------------------------------------------------------- */
+int vsb_coldist(const uint32_t *seed_bits, int wpr, int W, int H, uint16_t *g, size_t g_pitch_elems,
+                uint16_t *gmin64, vsb_stream_t stream);
+int vsb_dt_unbounded(const uint32_t *seed_bits, int wpr, int W, int H, int metric, uint16_t *g,
+                     size_t g_pitch_elems, uint16_t *gmin64, float *dist_out, int32_t *d2_out,
+                     size_t pitch_elems, vsb_stream_t stream);
+int vsb_zblend_unbounded(const uint8_t *gray, size_t gray_pitch, int W, int H, const uint32_t *cur_bits,
+                         const uint32_t *const *prior_bits, int n_priors, int wpr, int metric, int norm,
+                         float fade, float den, uint16_t *g, size_t g_pitch_elems, uint16_t *gmin64,
+                         float *dist, size_t dist_pitch_elems, uint32_t *minmax2, const uint8_t *lut256_dev,
+                         uint8_t *out, size_t out_pitch, vsb_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * K3  fused Z-blend: rec mask, windowed chamfer distance, fade gradient, merge with the gray
  *     layer, composed LUT gather.  One launch per layer.
  *     replaces processing_core.py:107-153 (fixed fade), :222-284 (weighted stack), :442-460
@@ -108,7 +131,9 @@ typedef enum {
     VSB_Z_DIST = 3,     /* no image output: write min(d,F) at rec pixels into dist_out (Enhanced EDT
                            stage 1, :379-381) */
     VSB_Z_ENHANCED = 4, /* stack level only: VSB_Z_DIST + vsb_ccl8_max + vsb_enhanced_fade  :338-404 */
-    VSB_Z_NONE = 5      /* vsb_layer_fused only: no Z-blend, the input already is the stage-1 image */
+    VSB_Z_NONE = 5,     /* vsb_layer_fused only: no Z-blend, the input already is the stage-1 image */
+    VSB_Z_MINMAX = 6,   /* stack level only: vsb_zblend_unbounded norm 1 (global min-max, :141-145) */
+    VSB_Z_FIXED_FAR = 7 /* stack level only: vsb_zblend_unbounded norm 0 (fixed fade, reach > VSB_FAST_REACH) */
 } vsb_zmode;
 
 typedef enum {

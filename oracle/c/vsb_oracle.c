@@ -400,3 +400,48 @@ ORC_API void orc_median(const uint8_t *src, int W, int H, int k, uint8_t *dst)
         }
     }
 }
+
+/* Chamfer 5x5 with unbounded reach, exact integer arithmetic: costs in units of 2^-23 (a = 2^23, b = 1.4f and
+ * c = 2.1969f as exact binary fractions), result = the correctly rounded float32 of the exact minimum.  This is the
+ * definition the unbounded device path (csrc/vsb_unbounded.cu) matches bit for bit; it differs from the tabulated
+ * sequential-sum definition above by at most a few float32 ulps.  +inf where the image has no seed.
+ * Used for the global min-max normalisation (processing_core.py:141-145) and fade distances > 64 px.          */
+ORC_API int orc_chamfer5_unbounded(const uint8_t *seed, int W, int H, float *dist)
+{
+    const int64_t A = 8388608, B = 11744051, C = 18428932;
+    const int32_t NONE = 0x7fffffff;
+    int32_t *g = (int32_t *)malloc((size_t)W * H * sizeof(int32_t));
+    if (!g) return -1;
+    for (int x = 0; x < W; ++x) {
+        int32_t run = NONE;
+        for (int y = 0; y < H; ++y) {
+            run = seed[(size_t)y * W + x] ? 0 : (run == NONE ? NONE : run + 1);
+            g[(size_t)y * W + x] = run;
+        }
+        run = NONE;
+        for (int y = H - 1; y >= 0; --y) {
+            run = seed[(size_t)y * W + x] ? 0 : (run == NONE ? NONE : run + 1);
+            if (run < g[(size_t)y * W + x]) g[(size_t)y * W + x] = run;
+        }
+    }
+#pragma omp parallel for schedule(dynamic, 16)
+    for (int y = 0; y < H; ++y) {
+        const int32_t *gr = g + (size_t)y * W;
+        for (int x = 0; x < W; ++x) {
+            int64_t best = INT64_MAX;
+            for (int side = -1; side <= 1; side += 2)
+                for (int k = (side < 0 ? 0 : 1);; ++k) {
+                    int xx = x + side * k;
+                    if (xx < 0 || xx >= W || (int64_t)k * A >= best) break;
+                    if (gr[xx] == NONE) continue;
+                    int M = k > gr[xx] ? k : gr[xx], m = k > gr[xx] ? gr[xx] : k;
+                    int64_t c = (2 * m <= M) ? (int64_t)(M - 2 * m) * A + (int64_t)m * C
+                                             : (int64_t)(2 * m - M) * B + (int64_t)(M - m) * C;
+                    if (c < best) best = c;
+                }
+            dist[(size_t)y * W + x] = best == INT64_MAX ? INFINITY : (float)((double)best / 8388608.0);
+        }
+    }
+    free(g);
+    return 0;
+}

@@ -54,6 +54,8 @@ def lib():
         L.orc_chamfer5.argtypes = [vp, i, i, i, vp, vp]
         L.orc_chamfer5.restype = i
         L.orc_chamfer5_twopass.argtypes = [vp, i, i, vp]
+        L.orc_chamfer5_unbounded.argtypes = [vp, i, i, vp]
+        L.orc_chamfer5_unbounded.restype = i
         L.orc_edt_exact_sq.argtypes = [vp, i, i, vp]
         L.orc_edt_exact_sq.restype = i
         L.orc_ccl8.argtypes = [vp, i, i, vp]
@@ -132,6 +134,19 @@ def chamfer5_twopass(cur_white: np.ndarray) -> np.ndarray:
     return out
 
 
+def chamfer5_unbounded(cur_white: np.ndarray) -> np.ndarray:
+    """Unbounded-reach chamfer distance, exact integer costs rounded once to float32 (inf if no seed).  The
+    definition of the unbounded device path; within a few ulps of the tabulated `chamfer5`."""
+    cur_white = _u8(cur_white)
+    H, W = cur_white.shape
+    out = np.empty((H, W), np.float32)
+    assert lib().orc_chamfer5_unbounded(_p(cur_white), W, H, _p(out)) == 0
+    return out
+
+
+FAST_REACH = 63   # the tabulated (sequential-sum) definition covers reach <= 63; beyond it the exact-integer one applies
+
+
 def edt_exact_sq(cur_white: np.ndarray) -> np.ndarray:
     """Exact squared Euclidean distance (int32) to the nearest cur_white!=0 pixel; -1 if none."""
     cur_white = _u8(cur_white)
@@ -151,6 +166,8 @@ def edt_exact(cur_white: np.ndarray) -> np.ndarray:
 
 def distance(cur_white: np.ndarray, F: float, metric: str = "chamfer5") -> np.ndarray:
     if metric == "chamfer5":
+        if chamfer_reach(F) > FAST_REACH:
+            return chamfer5_unbounded(cur_white)
         return chamfer5(cur_white, chamfer_reach(F))
     if metric == "exact":
         return edt_exact(cur_white)
@@ -186,8 +203,7 @@ def fixed_fade(cur: np.ndarray, prior_combined: Optional[np.ndarray], F: float,
         clipped = np.minimum(np.maximum(rd, f32(0)), Ff)               # np.clip(rd, 0, F)
         g = _fade_u8(clipped, den)
     else:                                                              # :141-145 global min-max
-        H, W = cur.shape
-        d = chamfer5(cur, max(H, W)) if metric == "chamfer5" else edt_exact(cur)
+        d = chamfer5_unbounded(cur) if metric == "chamfer5" else edt_exact(cur)
         big = f32(np.finfo(np.float32).max)
         d = np.where(np.isinf(d), big, d)
         rd = np.where(rec > 0, d, f32(0)).astype(np.float32)

@@ -160,7 +160,15 @@ def test_modes_vs_reference_goldens(E, slices, ref_modes):
         parts = key.split("_")
         kind = parts[0]
         if kind == "minmax":
-            continue                                    # SURVEY 8f rank 1, raises UnsupportedOnDevice (below)
+            wn, lz = parts[1], parts[2]
+            cur, pri = crop(slices, int(lz), 4, wins[wn])
+            from config import Config
+            got = core.process_z_blending(cur, core.find_prior_combined_white_mask(pri), Config(), [])
+            assert np.array_equal(got, O.fixed_fade(cur, O.combine_priors(pri), 10.0, False)), key   # bit-exact vs oracle
+            d = np.abs(got.astype(int) - z[key].astype(int))
+            assert d.max() <= 1 and (d > 0).sum() <= 5, key                                          # +-1 LSB vs reference
+            n += 1
+            continue
         if kind == "enh":
             flavour, wn, lz, Fs = parts[1], parts[2], parts[3], parts[4]
             cur, pri = crop(slices, int(lz), 4, wins[wn])
@@ -186,10 +194,7 @@ def test_modes_vs_reference_goldens(E, slices, ref_modes):
             got = core.process_z_blending(cur, pri, cfg, [])
         assert np.array_equal(got, z[key]), key
         n += 1
-    assert n > 140
-    with pytest.raises(P.UnsupportedOnDevice):
-        from config import Config
-        core.process_z_blending(cur, pri[0], Config(), [])
+    assert n > 150
 
 
 def test_reference_unit_tests_on_device(E, ref_scenes):
@@ -533,4 +538,41 @@ def test_fused_equals_unfused_on_uniform_and_tiny(E, monkeypatch):
     eng = engine_for_metric(E, Config.from_dict(base), 40, 7, "chamfer5")
     for zi, g in enumerate(tiny):
         assert np.array_equal(eng.process(g), want[zi]), zi
+    eng.close()
+
+
+def test_unbounded_distance_and_far_fade(E):
+    """column distances + pruned row search: dense maps vs the oracle (both metrics), fixed fade with F > 64"""
+    import processing_core as core
+    rng = np.random.default_rng(8)
+    for shape, p in (((150, 700), 0.0008), ((333, 257), 0.02), ((64, 1000), 0.0)):
+        seed = (rng.random(shape) < p).astype(np.uint8) * 255
+        if p == 0.0:
+            seed[40, 3] = 255                                  # one pixel: distances up to ~1000
+        d, _ = E.dt_unbounded_np(seed, "chamfer5")
+        assert np.array_equal(d, O.chamfer5_unbounded(seed))
+        de, d2 = E.dt_unbounded_np(seed, "exact")
+        assert np.array_equal(d2, O.edt_exact_sq(seed)) and np.array_equal(de, np.sqrt(O.edt_exact_sq(seed).astype(np.float32)))
+    d, _ = E.dt_unbounded_np(np.zeros((50, 130), np.uint8), "chamfer5")
+    assert (d > 1e38).all()
+    layers = small_stack(W=640, H=400, L=6, seed=31, raft=True, n_blobs=6, r_range=(60.0, 150.0), r_turn=200.0)
+    for F in (100.0, 257.5):
+        cfg = make_cfg(fixed_fade_distance_receding=F)
+        cur = O.threshold(layers[5]); pri = [O.threshold(l) for l in reversed(layers[1:5])]
+        comb = O.combine_priors(pri)
+        assert np.array_equal(core.process_z_blending(cur, comb, cfg, []), O.fixed_fade(cur, comb, F, True)), F
+
+
+@pytest.mark.parametrize("mode", ["minmax", "far"])
+def test_stack_engine_unbounded_modes(E, mode):
+    """the dataclass-default min-max normalisation and F > 64 through the stack engine, with a fusable XY chain"""
+    from config import Config
+    W, H = 512, 300
+    layers = small_stack(W=W, H=H, L=7, seed=17, raft=True, n_blobs=8)
+    base = {"blending_mode": "fixed_fade", "receding_layers": 3, "use_fixed_fade_receding": mode == "far",
+            "fixed_fade_distance_receding": 90.0, "xy_blend_pipeline": FUSED_CHAINS["lut_bil7_g3_lut"]}
+    want = O.run_stack(layers, base)
+    eng = engine_for_metric(E, Config.from_dict(base), W, H, "chamfer5")
+    for zi, g in enumerate(layers):
+        assert np.array_equal(eng.process(g), want[zi]), (mode, zi)
     eng.close()

@@ -157,11 +157,9 @@ def test_zparams_from_config():
     z = P.zparams_from_config(c)
     assert (z.mode, z.const_val) == (N.Z_CONST, 255)
     c.fixed_fade_distance_receding = 200.0
-    with pytest.raises(P.UnsupportedOnDevice):
-        P.zparams_from_config(c)
+    assert P.zparams_from_config(c).mode == N.Z_FIXED_FAR        # beyond the tile reach: unbounded path
     c = Config()
-    with pytest.raises(P.UnsupportedOnDevice):      # dataclass default = global min-max
-        P.zparams_from_config(c)
+    assert P.zparams_from_config(c).mode == N.Z_MINMAX           # dataclass default = global min-max
     c.blending_mode = ProcessingMode.WEIGHTED_STACK
     c.manual_weights = [100, 0, 50]; c.fade_distances_receding = [20.0, 90.0]; c.fixed_fade_distance_receding = 12.0
     z = P.zparams_from_config(c)

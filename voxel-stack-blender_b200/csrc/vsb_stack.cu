@@ -38,6 +38,10 @@ struct vsb_stack {
     float *dist;
     int32_t *labels;
     uint32_t *cmax;
+    // unbounded-reach scratch (min-max normalisation, fade distances beyond the tile reach; allocated on first use)
+    uint16_t *ub_g, *ub_gmin;
+    float *ub_dist;
+    uint32_t *ub_mm;
     // fused per-layer path (vsb_layer.cu): taken when the XY chain has the shape [bilateral][gaussian][lut]
     bool fused;
     vsb_xy_fused fx;
@@ -98,6 +102,10 @@ extern "C" int vsb_stack_destroy(vsb_stack *s)
     if (s->dist) cudaFree(s->dist);
     if (s->labels) cudaFree(s->labels);
     if (s->cmax) cudaFree(s->cmax);
+    if (s->ub_g) cudaFree(s->ub_g);
+    if (s->ub_gmin) cudaFree(s->ub_gmin);
+    if (s->ub_dist) cudaFree(s->ub_dist);
+    if (s->ub_mm) cudaFree(s->ub_mm);
     if (s->s_h2d) cudaStreamDestroy(s->s_h2d);
     if (s->s_comp) cudaStreamDestroy(s->s_comp);
     if (s->s_d2h) cudaStreamDestroy(s->s_d2h);
@@ -122,7 +130,8 @@ extern "C" int vsb_stack_create(int W, int H, int n_priors, const vsb_zparams *z
     VSB_REQUIRE(W > 0 && H > 0 && n_priors >= 0 && n_priors <= VSB_MAX_PRIORS,
                 "vsb_stack_create: bad geometry or more than %d receding layers", VSB_MAX_PRIORS);
     VSB_REQUIRE(n_ops >= 0 && n_ops <= VSB_MAX_XY_OPS && (n_ops == 0 || ops), "vsb_stack_create: bad op list");
-    VSB_REQUIRE(zp->reach >= 0 && zp->reach <= VSB_FAST_REACH, "vsb_stack_create: reach %d > %d", zp->reach,
+    const bool far_mode = zp->mode == VSB_Z_MINMAX || zp->mode == VSB_Z_FIXED_FAR;
+    VSB_REQUIRE(far_mode || (zp->reach >= 0 && zp->reach <= VSB_FAST_REACH), "vsb_stack_create: reach %d > %d", zp->reach,
                 VSB_FAST_REACH);
     vsb_stack *s = new (std::nothrow) vsb_stack();
     VSB_REQUIRE(s, "vsb_stack_create: out of memory");
@@ -138,6 +147,7 @@ extern "C" int vsb_stack_create(int W, int H, int n_priors, const vsb_zparams *z
     s->tmp[0] = s->tmp[1] = nullptr;
     s->head = 0; s->count = 0; s->submitted = 0;
     s->rec_bits = nullptr; s->dist = nullptr; s->labels = nullptr; s->cmax = nullptr;
+    s->ub_g = s->ub_gmin = nullptr; s->ub_dist = nullptr; s->ub_mm = nullptr;
     s->prof_on = false;
     s->fused = false; s->lut2_dev = nullptr;
     memset(&s->fx, 0, sizeof s->fx);
@@ -168,7 +178,7 @@ extern "C" int vsb_stack_create(int W, int H, int n_priors, const vsb_zparams *z
         size_t i = 0;
         const size_t n = s->ops.size();
         bool ok = getenv("VSB_NO_FUSED") == nullptr && W >= 8 && H >= 8 &&
-                  (zp->mode == VSB_Z_FIXED || zp->mode == VSB_Z_WEIGHTED || zp->mode == VSB_Z_CONST || zp->mode == VSB_Z_ENHANCED);
+                  (zp->mode == VSB_Z_FIXED || zp->mode == VSB_Z_WEIGHTED || zp->mode == VSB_Z_CONST || zp->mode == VSB_Z_ENHANCED || far_mode);
         const uint8_t *lut2 = nullptr;
         if (ok && i < n && s->ops[i].type == 3) {
             const vsb_xy_op &o = s->ops[i].op;
@@ -216,9 +226,10 @@ extern "C" int vsb_stack_create(int W, int H, int n_priors, const vsb_zparams *z
             STACK_CUDA(cudaMemcpy(o.lut_dev, o.op.lut, 256, cudaMemcpyHostToDevice));
         }
     {
-        const int n1 = zp->reach + 1;
+        const int treach = far_mode ? 0 : zp->reach;
+        const int n1 = treach + 1;
         std::vector<float> T((size_t)n1 * n1);
-        vsb_chamfer_table(T.data(), zp->reach);
+        vsb_chamfer_table(T.data(), treach);
         STACK_CUDA(cudaMalloc((void **)&s->T_dev, T.size() * sizeof(float)));
         STACK_CUDA(cudaMemcpy(s->T_dev, T.data(), T.size() * sizeof(float), cudaMemcpyHostToDevice));
     }
@@ -242,6 +253,17 @@ extern "C" int vsb_stack_reset(vsb_stack *s)
 
 extern "C" int vsb_stack_slots(vsb_stack *s) { return s ? STACK_SLOTS : 0; }
 extern "C" vsb_stream_t vsb_stack_stream(vsb_stack *s) { return s ? (vsb_stream_t)s->s_comp : nullptr; }
+
+static int ensure_unbounded_scratch(vsb_stack *s)
+{
+    if (s->ub_g) return VSB_OK;
+    const size_t n = (size_t)s->W * s->H;
+    VSB_CUDA(cudaMalloc((void **)&s->ub_g, n * sizeof(uint16_t)));
+    VSB_CUDA(cudaMalloc((void **)&s->ub_gmin, (size_t)((s->W + 63) / 64) * s->H * sizeof(uint16_t)));
+    VSB_CUDA(cudaMalloc((void **)&s->ub_dist, n * sizeof(float)));
+    VSB_CUDA(cudaMalloc((void **)&s->ub_mm, 2 * sizeof(uint32_t)));
+    return VSB_OK;
+}
 
 static int ensure_enhanced_scratch(vsb_stack *s)
 {
@@ -281,7 +303,8 @@ static int run_layer(vsb_stack *s, const uint8_t *gray, size_t gpitch, uint8_t *
         } else {
             zp.n_priors = np;
         }
-        if (s->fused && zp.mode != VSB_Z_ENHANCED) {
+        const bool far_mode = zp.mode == VSB_Z_MINMAX || zp.mode == VSB_Z_FIXED_FAR;
+        if (s->fused && zp.mode != VSB_Z_ENHANCED && !far_mode) {
             const uint16_t *pfl[VSB_MAX_PRIORS];
             for (int i = 0; i < np; ++i) pfl[i] = s->flag_ring[(s->head - 1 - i + 2 * nring) % nring];
             {
@@ -299,7 +322,15 @@ static int run_layer(vsb_stack *s, const uint8_t *gray, size_t gpitch, uint8_t *
         const size_t nops = s->ops.size();
         uint8_t *zdst = nops ? s->tmp[0] : out;
         const size_t zpitch = nops ? s->pitch : opitch;
-        if (zp.mode == VSB_Z_ENHANCED) {
+        if (far_mode) {
+            rc = ensure_unbounded_scratch(s);
+            if (rc) return rc;
+            ProfScope ps(s, ST_ZBLEND, 5);
+            rc = vsb_zblend_unbounded(gray, gpitch, s->W, s->H, cur, pri, np, s->wpr, zp.metric, zp.mode == VSB_Z_MINMAX ? 1 : 0,
+                                      zp.fade, zp.den, s->ub_g, (size_t)s->W, s->ub_gmin, s->ub_dist, (size_t)s->W, s->ub_mm,
+                                      s->lead_lut_dev, zdst, zpitch, st);
+            if (rc) return rc;
+        } else if (zp.mode == VSB_Z_ENHANCED) {
             rc = ensure_enhanced_scratch(s);
             if (rc) return rc;
             { ProfScope ps(s, ST_MASKDIFF, 1); rc = vsb_maskdiff(cur, pri, np, s->wpr, s->H, s->rec_bits, nullptr, st); }

@@ -55,7 +55,8 @@ def _debug_dump(debug_info, suffix, image):
 
 
 def _calculate_receding_gradient_field_fixed_fade(current_white_mask, prior_white_combined_mask, config, debug_info=None):
-    """reference :107-153 (fixed normalisation).  The global min-max variant (:141-145) is SURVEY 8f rank 1."""
+    """reference :107-153: fixed normalisation, or the global min-max variant (:141-145) when
+    config.use_fixed_fade_receding is False (the dataclass default)."""
     if prior_white_combined_mask is None:
         return _zeros_like(current_white_mask)
     cur, prior = _bits(current_white_mask), _bits(prior_white_combined_mask)
@@ -66,6 +67,8 @@ def _calculate_receding_gradient_field_fixed_fade(current_white_mask, prior_whit
     if E.count_receding(cur, [prior]) == 0:
         return _zeros_like(current_white_mask)
     z = P.zparams_from_config(_as_mode(config, ProcessingMode.FIXED_FADE), getattr(config, "distance_metric", "chamfer5"))
+    if z.mode in (N.Z_MINMAX, N.Z_FIXED_FAR):
+        return E.zblend_unbounded(None, cur, [prior], z).numpy()
     return E.zblend(None, cur, [prior], z).numpy()
 
 

@@ -159,6 +159,43 @@ def zblend(gray: Optional[DevImage], cur: DevBits, priors: Sequence[DevBits], z:
     return out
 
 
+def zblend_unbounded(gray: Optional[DevImage], cur: DevBits, priors: Sequence[DevBits], z: N.ZParams,
+                     lut: Optional[np.ndarray] = None) -> DevImage:
+    """Fixed fade with any F, or the global min-max normalisation, through the unbounded distance path."""
+    t = torch()
+    H, W = cur.H, cur.W
+    if gray is None:
+        gray = DevImage(H, W, zero=True)
+    out = DevImage(H, W)
+    g = t.empty((H, W), dtype=t.int16, device="cuda")
+    gmin = t.empty((H, (W + 63) // 64), dtype=t.int16, device="cuda")
+    dist = t.empty((H, W), dtype=t.float32, device="cuda")
+    mm = t.empty(2, dtype=t.int32, device="cuda")
+    ld = lut_dev(lut) if lut is not None else None
+    N.check(N.load().vsb_zblend_unbounded(gray.ptr, gray.pitch, W, H, cur.ptr, N.ptr_array([p.ptr for p in priors]),
+                                          len(priors), cur.wpr, int(z.metric), 1 if z.mode == N.Z_MINMAX else 0,
+                                          float(z.fade), float(z.den), g.data_ptr(), W, gmin.data_ptr(), dist.data_ptr(), W,
+                                          mm.data_ptr(), ld.data_ptr() if ld is not None else None, out.ptr, out.pitch,
+                                          _stream()), "vsb_zblend_unbounded")
+    return out
+
+
+def dt_unbounded_np(cur_white: np.ndarray, metric: str = "chamfer5"):
+    """Dense unbounded distance map (float32) and, for the exact metric, the integer squared distances."""
+    t = torch()
+    img = DevImage.from_numpy(cur_white)
+    b = pack(img)
+    H, W = img.H, img.W
+    g = t.empty((H, W), dtype=t.int16, device="cuda")
+    gmin = t.empty((H, (W + 63) // 64), dtype=t.int16, device="cuda")
+    dist = t.empty((H, W), dtype=t.float32, device="cuda")
+    d2 = t.empty((H, W), dtype=t.int32, device="cuda") if metric == "exact" else None
+    N.check(N.load().vsb_dt_unbounded(b.ptr, b.wpr, W, H, N.METRIC_EXACT if metric == "exact" else N.METRIC_CHAMFER5,
+                                      g.data_ptr(), W, gmin.data_ptr(), dist.data_ptr(),
+                                      d2.data_ptr() if d2 is not None else None, W, _stream()), "vsb_dt_unbounded")
+    return dist.cpu().numpy(), (d2.cpu().numpy() if d2 is not None else None)
+
+
 def enhanced(gray: Optional[DevImage], cur: DevBits, priors: Sequence[DevBits], z: N.ZParams,
              lut: Optional[np.ndarray] = None) -> DevImage:
     """Enhanced EDT: rec mask -> clipped distance at rec pixels -> CCL + per-component max -> fade."""

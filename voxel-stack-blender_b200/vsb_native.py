@@ -21,7 +21,7 @@ VSB_MAX_PRIORS = 16
 VSB_MAX_XY_OPS = 16
 VSB_FAST_REACH = 63
 
-Z_FIXED, Z_WEIGHTED, Z_CONST, Z_DIST, Z_ENHANCED, Z_NONE = 0, 1, 2, 3, 4, 5
+Z_FIXED, Z_WEIGHTED, Z_CONST, Z_DIST, Z_ENHANCED, Z_NONE, Z_MINMAX, Z_FIXED_FAR = 0, 1, 2, 3, 4, 5, 6, 7
 METRIC_CHAMFER5, METRIC_EXACT = 0, 1
 OP_NONE, OP_LUT, OP_GAUSSIAN, OP_BILATERAL, OP_MEDIAN = 0, 1, 2, 3, 4
 
@@ -77,6 +77,12 @@ _SIGS = {
     "vsb_bilateral": (c_int, [c_void_p, c_size_t, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                               c_void_p, c_size_t, c_void_p]),
     "vsb_median": (c_int, [c_void_p, c_size_t, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    "vsb_coldist": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "vsb_dt_unbounded": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p,
+                                 c_size_t, c_void_p]),
+    "vsb_zblend_unbounded": (c_int, [c_void_p, c_size_t, c_int, c_int, c_void_p, POINTER(c_void_p), c_int, c_int, c_int,
+                                     c_int, c_float, c_float, c_void_p, c_size_t, c_void_p, c_void_p, c_size_t, c_void_p,
+                                     c_void_p, c_void_p, c_size_t, c_void_p]),
     "vsb_pack_flags": (c_int, [c_void_p, c_size_t, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     "vsb_layer_stats": (c_int, [c_int, c_void_p]),
     "vsb_layer_fused": (c_int, [c_void_p, c_size_t, c_int, c_int, c_void_p, POINTER(c_void_p), c_void_p, POINTER(c_void_p),

@@ -74,11 +74,19 @@ def zparams_from_config(cfg, metric: str = "chamfer5") -> N.ZParams:
         z.den = f32(F) if F > 0 else f32(1.0)
         z.reach = chamfer_reach(F)
     else:  # fixed_fade (the dispatcher's default branch, processing_core.py:434-440)
-        if not cfg.use_fixed_fade_receding:
-            raise UnsupportedOnDevice("global min-max normalisation (use_fixed_fade_receding=False) needs an "
-                                      "unbounded distance transform: SURVEY.md 8f rank 1")
         z.n_priors = N.VSB_MAX_PRIORS
-        if F > 0:
+        if not cfg.use_fixed_fade_receding:
+            # global min-max normalisation over the receding pixels (:141-145): unbounded distances
+            z.mode = N.Z_MINMAX
+            z.fade = f32(F)
+            z.den = f32(1.0)
+            z.reach = 0
+        elif F > 0 and chamfer_reach(F) > N.VSB_FAST_REACH:
+            z.mode = N.Z_FIXED_FAR          # beyond the tile kernels' reach: column distances + row search
+            z.fade = f32(F)
+            z.den = f32(F)
+            z.reach = 0
+        elif F > 0:
             z.mode = N.Z_FIXED
             z.fade = f32(F)
             z.den = f32(F)
@@ -93,8 +101,8 @@ def zparams_from_config(cfg, metric: str = "chamfer5") -> N.ZParams:
             z.fade = f32(F)
             z.den = f32(1.0)
     if z.reach > N.VSB_FAST_REACH:
-        raise UnsupportedOnDevice(f"fade distance {F} needs reach {z.reach} > {N.VSB_FAST_REACH}: the large-F "
-                                  "global-scan transform is SURVEY.md 8f rank 1")
+        raise UnsupportedOnDevice(f"{mode}: fade distance needs reach {z.reach} > {N.VSB_FAST_REACH} (only the fixed fade "
+                                  "has the unbounded path so far)")
     return z
 
 
