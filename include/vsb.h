@@ -107,6 +107,9 @@ int vsb_dt_exact(const uint32_t *seed_bits, int wpr, int W, int H, uint16_t *col
  *                      max <= min), merged with gray, leading LUT.  Scratch: g, gmin64, dist float [H][pitch],
  *                      minmax2 = 2 x uint32.
  * ------------------------------------------------------------------------------------------- */
+/* number of uint16 elements the `gmin64` scratch of the three entry points below must hold (block minima plus the
+ * per-band first/last-white-row records of the column pass) */
+size_t vsb_coldist_scratch_elems(int W, int H, int wpr);
 int vsb_coldist(const uint32_t *seed_bits, int wpr, int W, int H, uint16_t *g, size_t g_pitch_elems,
                 uint16_t *gmin64, vsb_stream_t stream);
 int vsb_dt_unbounded(const uint32_t *seed_bits, int wpr, int W, int H, int metric, uint16_t *g,

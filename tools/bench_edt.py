@@ -44,7 +44,15 @@ res["chamfer5_R63"] = ms
 ms = timed(lambda i=0: N.check(lib.vsb_dt_exact_windowed(bits[i % 4].ptr, bits[0].wpr, W, H, 63, 64.0, dist.data_ptr(), W, 0)))
 res["exact_R63"] = ms
 ms = timed(lambda i=0: N.check(lib.vsb_dt_exact(bits[i % 4].ptr, bits[0].wpr, W, H, col.data_ptr(), d2.data_ptr(), dist.data_ptr(), W, 0)), n=3)
+res["exact_unbounded_v1_bruteforce_rows"] = ms
+g16 = t.empty((H, W), dtype=t.int16, device="cuda")
+gmin = t.empty(int(lib.vsb_coldist_scratch_elems(W, H, bits[0].wpr)), dtype=t.int16, device="cuda")
+ms = timed(lambda i=0: N.check(lib.vsb_dt_unbounded(bits[i % 4].ptr, bits[0].wpr, W, H, 1, g16.data_ptr(), W, gmin.data_ptr(), dist.data_ptr(), d2.data_ptr(), W, 0)), n=4)
 res["exact_unbounded"] = ms
+ms = timed(lambda i=0: N.check(lib.vsb_dt_unbounded(bits[i % 4].ptr, bits[0].wpr, W, H, 0, g16.data_ptr(), W, gmin.data_ptr(), dist.data_ptr(), None, W, 0)), n=4)
+res["chamfer5_unbounded"] = ms
+ms = timed(lambda i=0: N.check(lib.vsb_coldist(bits[i % 4].ptr, bits[0].wpr, W, H, g16.data_ptr(), W, gmin.data_ptr(), 0)), n=4)
+res["column_pass_only"] = ms
 out = {k: {"ms_per_image": round(v, 3), "images_per_s": round(1000 / v, 1), "gbs_algorithmic": round(alg / (v * 1e-3) / 1e9, 1),
            "frac_of_measured_peak": round(alg / (v * 1e-3) / 1e9 / peak, 4)} for k, v in res.items()}
 try:

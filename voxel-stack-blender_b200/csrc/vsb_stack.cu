@@ -259,7 +259,7 @@ static int ensure_unbounded_scratch(vsb_stack *s)
     if (s->ub_g) return VSB_OK;
     const size_t n = (size_t)s->W * s->H;
     VSB_CUDA(cudaMalloc((void **)&s->ub_g, n * sizeof(uint16_t)));
-    VSB_CUDA(cudaMalloc((void **)&s->ub_gmin, (size_t)((s->W + 63) / 64) * s->H * sizeof(uint16_t)));
+    VSB_CUDA(cudaMalloc((void **)&s->ub_gmin, vsb_coldist_scratch_elems(s->W, s->H, s->wpr) * sizeof(uint16_t)));
     VSB_CUDA(cudaMalloc((void **)&s->ub_dist, n * sizeof(float)));
     VSB_CUDA(cudaMalloc((void **)&s->ub_mm, 2 * sizeof(uint32_t)));
     return VSB_OK;

@@ -28,43 +28,71 @@ __device__ __forceinline__ long long chamfer_cost(int k, int g)
 }
 
 // ---- (1) column pass ------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_coldist(const uint32_t *__restrict__ bits, int wpr, int W, int H,
-                                                 uint16_t *__restrict__ g, size_t gpitch)
+// first: per 128-row band and column, the offset of the first and of the last white row of the band (0xFFFF = none),
+// so the carry across bands is a walk over at most H/128 band records instead of over rows
+__global__ void __launch_bounds__(128) k_bandseeds(const uint32_t *__restrict__ bits, int wpr, int H,
+                                                   uint16_t *__restrict__ btop, uint16_t *__restrict__ bbot)
 {
-    __shared__ uint16_t s_down[4][UB_BAND][32];
     const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
     const int wx = blockIdx.x * 4 + wq;
     const int y0 = blockIdx.y * UB_BAND;
     if (wx >= wpr) return;
-    const int x = wx * 32 + lane;
-    const int y1 = min(H, y0 + UB_BAND);
-    // carry from above: distance from row y0-1 to the nearest white pixel at or above it (walk the packed mask upwards
-    // until every lane has met one)
-    uint32_t run = G_NONE;
-    {
-        uint32_t found = 0;
-        for (int yy = y0 - 1; yy >= 0 && found != 0xffffffffu; --yy) {
-            const uint32_t w = bits[(size_t)yy * wpr + wx];
-            if (((w >> lane) & 1u) && !((found >> lane) & 1u)) run = (uint32_t)min(y0 - 1 - yy, 0xFFFD);
-            found |= w;
+    uint32_t top = G_NONE, bot = G_NONE;
+#pragma unroll
+    for (int q = 0; q < UB_BAND / 32; ++q) {
+        const int yy = y0 + 32 * q + lane;
+        const uint32_t mine = yy < H ? bits[(size_t)yy * wpr + wx] : 0u;
+        for (int j = 0; j < 32; ++j) {
+            const uint32_t w = __shfl_sync(0xffffffffu, mine, j);
+            if ((w >> lane) & 1u) { if (top == G_NONE) top = 32 * q + j; bot = 32 * q + j; }
         }
     }
+    const size_t o = (size_t)blockIdx.y * wpr * 32 + (size_t)wx * 32 + lane;
+    btop[o] = (uint16_t)top;
+    bbot[o] = (uint16_t)bot;
+}
+
+__global__ void __launch_bounds__(128) k_coldist(const uint32_t *__restrict__ bits, int wpr, int W, int H,
+                                                 const uint16_t *__restrict__ btop, const uint16_t *__restrict__ bbot,
+                                                 int nbands, uint16_t *__restrict__ g, size_t gpitch)
+{
+    __shared__ uint16_t s_down[4][UB_BAND][32];
+    const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
+    const int wx = blockIdx.x * 4 + wq;
+    const int band = blockIdx.y;
+    const int y0 = band * UB_BAND;
+    if (wx >= wpr) return;
+    const int x = wx * 32 + lane;
+    const int y1 = min(H, y0 + UB_BAND);
+    const size_t bstride = (size_t)wpr * 32;
+    // carry from above: distance from row y0-1 to the nearest white pixel at or above it
+    uint32_t run = G_NONE;
+    for (int bb = band - 1; bb >= 0; --bb) {
+        const uint32_t v = bbot[(size_t)bb * bstride + x];
+        if (v != G_NONE) { run = (uint32_t)min(y0 - 1 - (bb * UB_BAND + (int)v), 0xFFFD); break; }
+    }
+    uint32_t wv[UB_BAND / 32];
+#pragma unroll
+    for (int q = 0; q < UB_BAND / 32; ++q) {
+        const int yy = y0 + 32 * q + lane;
+        wv[q] = yy < H ? bits[(size_t)yy * wpr + wx] : 0u;
+    }
     for (int yy = y0; yy < y1; ++yy) { // downward: distance to the nearest white pixel at or above row yy
-        const uint32_t w = bits[(size_t)yy * wpr + wx];
+        const int q = (yy - y0) >> 5;
+        const uint32_t src = q == 0 ? wv[0] : (q == 1 ? wv[1] : (q == 2 ? wv[2] : wv[3]));
+        const uint32_t w = __shfl_sync(0xffffffffu, src, (yy - y0) & 31);
         run = ((w >> lane) & 1u) ? 0u : (run == G_NONE ? G_NONE : min(run + 1u, 0xFFFEu));
         s_down[wq][yy - y0][lane] = (uint16_t)run;
     }
     run = G_NONE; // carry from below: distance from row y1 to the nearest white pixel at or below it
-    {
-        uint32_t found = 0;
-        for (int yy = y1; yy < H && found != 0xffffffffu; ++yy) {
-            const uint32_t w = bits[(size_t)yy * wpr + wx];
-            if (((w >> lane) & 1u) && !((found >> lane) & 1u)) run = (uint32_t)min(yy - y1, 0xFFFD);
-            found |= w;
-        }
+    for (int bb = band + 1; bb < nbands; ++bb) {
+        const uint32_t v = btop[(size_t)bb * bstride + x];
+        if (v != G_NONE) { run = (uint32_t)min(bb * UB_BAND + (int)v - y1, 0xFFFD); break; }
     }
     for (int yy = y1 - 1; yy >= y0; --yy) { // upward, combined with the downward result
-        const uint32_t w = bits[(size_t)yy * wpr + wx];
+        const int q = (yy - y0) >> 5;
+        const uint32_t src = q == 0 ? wv[0] : (q == 1 ? wv[1] : (q == 2 ? wv[2] : wv[3]));
+        const uint32_t w = __shfl_sync(0xffffffffu, src, (yy - y0) & 31);
         run = ((w >> lane) & 1u) ? 0u : (run == G_NONE ? G_NONE : min(run + 1u, 0xFFFEu));
         const uint32_t v = min(run, (uint32_t)s_down[wq][yy - y0][lane]);
         if (x < W) g[(size_t)yy * gpitch + x] = (uint16_t)v;
@@ -89,10 +117,44 @@ __global__ void __launch_bounds__(256) k_blockmin(const uint16_t *__restrict__ g
 
 // ---- (3) row search ---------------------------------------------------------------------------------------------
 // METRIC 0: chamfer cost in 2^-23 units; METRIC 1: squared Euclidean distance.  Returns COST_INF if no white pixel.
+// exact metric in 32-bit arithmetic (d^2 < 2^31 for any image the uint16 column distances allow up to 46340 px)
+__device__ __forceinline__ long long row_search_exact32(const uint16_t *__restrict__ grow, const uint16_t *__restrict__ gmrow,
+                                                        int W, int x)
+{
+    const uint32_t INF32 = 0x7fffffffu;
+    uint32_t best = INF32;
+    {
+        const uint32_t g0 = grow[x];
+        if (g0 != G_NONE) best = min(g0, 46340u) * min(g0, 46340u);
+    }
+    for (int k = 1; x - k >= 0 && (uint32_t)k * (uint32_t)k < best && k < 46340;) {
+        const int xx = x - k;
+        if ((xx & 63) == 63) {
+            const uint32_t gm = gmrow[xx >> 6];
+            if (gm == G_NONE || gm >= 46340u || (uint32_t)k * k + gm * gm >= best) { k += 64; continue; }
+        }
+        const uint32_t gg = grow[xx];
+        if (gg < 46340u) best = min(best, (uint32_t)k * k + gg * gg);
+        ++k;
+    }
+    for (int k = 1; x + k < W && (uint32_t)k * (uint32_t)k < best && k < 46340;) {
+        const int xx = x + k;
+        if ((xx & 63) == 0) {
+            const uint32_t gm = gmrow[xx >> 6];
+            if (gm == G_NONE || gm >= 46340u || (uint32_t)k * k + gm * gm >= best) { k += 64; continue; }
+        }
+        const uint32_t gg = grow[xx];
+        if (gg < 46340u) best = min(best, (uint32_t)k * k + gg * gg);
+        ++k;
+    }
+    return best >= INF32 ? COST_INF : (long long)best;
+}
+
 template <int METRIC>
 __device__ __forceinline__ long long row_search(const uint16_t *__restrict__ grow, const uint16_t *__restrict__ gmrow,
                                                 int W, int x, long long cap)
 {
+    if (METRIC == 1 && W < 32768) return row_search_exact32(grow, gmrow, W, x);
     auto cost = [](int k, int gg) -> long long {
         return METRIC == 0 ? chamfer_cost(k, gg) : (long long)k * k + (long long)gg * gg;
     };
@@ -261,17 +323,30 @@ __global__ void __launch_bounds__(256) k_fade_unbounded(const __grid_constant__ 
 }
 
 // ---- C-ABI --------------------------------------------------------------------------------------------------------
+extern "C" size_t vsb_coldist_scratch_elems(int W, int H, int wpr)
+{
+    const size_t nbands = (size_t)(H + UB_BAND - 1) / UB_BAND;
+    return (size_t)H * ((W + 63) / 64) + 2 * nbands * (size_t)wpr * 32;
+}
+
 extern "C" int vsb_coldist(const uint32_t *seed_bits, int wpr, int W, int H, uint16_t *g, size_t g_pitch_elems,
                            uint16_t *gmin64, vsb_stream_t stream)
 {
     VSB_REQUIRE(seed_bits && g && gmin64, "vsb_coldist: null pointer");
     VSB_REQUIRE(W > 0 && H > 0 && H < 65534 && wpr >= (W + 31) / 32 && g_pitch_elems >= (size_t)W, "vsb_coldist: bad geometry");
     cudaStream_t s = (cudaStream_t)stream;
-    dim3 grid((wpr + 3) / 4, (H + UB_BAND - 1) / UB_BAND);
-    k_coldist<<<grid, 128, 0, s>>>(seed_bits, wpr, W, H, g, g_pitch_elems);
-    int rc = vsb_check_launch("k_coldist");
-    if (rc) return rc;
+    const int nbands = (H + UB_BAND - 1) / UB_BAND;
     const int nblk = (W + 63) / 64;
+    // band records live behind the block minima in the same scratch buffer (see vsb_coldist_scratch_elems)
+    uint16_t *btop = gmin64 + (size_t)H * nblk;
+    uint16_t *bbot = btop + (size_t)nbands * wpr * 32;
+    dim3 grid((wpr + 3) / 4, nbands);
+    k_bandseeds<<<grid, 128, 0, s>>>(seed_bits, wpr, H, btop, bbot);
+    int rc = vsb_check_launch("k_bandseeds");
+    if (rc) return rc;
+    k_coldist<<<grid, 128, 0, s>>>(seed_bits, wpr, W, H, btop, bbot, nbands, g, g_pitch_elems);
+    rc = vsb_check_launch("k_coldist");
+    if (rc) return rc;
     dim3 grid2((nblk + 7) / 8, H);
     k_blockmin<<<grid2, 256, 0, s>>>(g, g_pitch_elems, W, H, gmin64, nblk);
     return vsb_check_launch("k_blockmin");

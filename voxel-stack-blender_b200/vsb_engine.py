@@ -168,7 +168,7 @@ def zblend_unbounded(gray: Optional[DevImage], cur: DevBits, priors: Sequence[De
         gray = DevImage(H, W, zero=True)
     out = DevImage(H, W)
     g = t.empty((H, W), dtype=t.int16, device="cuda")
-    gmin = t.empty((H, (W + 63) // 64), dtype=t.int16, device="cuda")
+    gmin = t.empty(int(N.load().vsb_coldist_scratch_elems(W, H, cur.wpr)), dtype=t.int16, device="cuda")
     dist = t.empty((H, W), dtype=t.float32, device="cuda")
     mm = t.empty(2, dtype=t.int32, device="cuda")
     ld = lut_dev(lut) if lut is not None else None
@@ -187,7 +187,7 @@ def dt_unbounded_np(cur_white: np.ndarray, metric: str = "chamfer5"):
     b = pack(img)
     H, W = img.H, img.W
     g = t.empty((H, W), dtype=t.int16, device="cuda")
-    gmin = t.empty((H, (W + 63) // 64), dtype=t.int16, device="cuda")
+    gmin = t.empty(int(N.load().vsb_coldist_scratch_elems(W, H, b.wpr)), dtype=t.int16, device="cuda")
     dist = t.empty((H, W), dtype=t.float32, device="cuda")
     d2 = t.empty((H, W), dtype=t.int32, device="cuda") if metric == "exact" else None
     N.check(N.load().vsb_dt_unbounded(b.ptr, b.wpr, W, H, N.METRIC_EXACT if metric == "exact" else N.METRIC_CHAMFER5,

@@ -77,6 +77,7 @@ _SIGS = {
     "vsb_bilateral": (c_int, [c_void_p, c_size_t, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                               c_void_p, c_size_t, c_void_p]),
     "vsb_median": (c_int, [c_void_p, c_size_t, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    "vsb_coldist_scratch_elems": (c_size_t, [c_int, c_int, c_int]),
     "vsb_coldist": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p, c_void_p]),
     "vsb_dt_unbounded": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p,
                                  c_size_t, c_void_p]),
