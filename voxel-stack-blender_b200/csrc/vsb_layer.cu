@@ -188,7 +188,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // prologue is off the critical path and LUTs / tap tables / chamfer table are staged once per CTA.
 template <int ZMODE, int METRIC, bool PERSIST, bool XY>
 __global__ void __launch_bounds__(VSB_THREADS, XY ? 4 : 6) k_layer(const __grid_constant__ LayerParams p,
-                                                       const __grid_constant__ BilTapsL taps)
+                                                       const BilTapsL *__restrict__ taps)
 {
     extern __shared__ __align__(16) uint8_t dsm[];
     float *s_T = (float *)(dsm + p.sm.T);
@@ -223,14 +223,8 @@ __global__ void __launch_bounds__(VSB_THREADS, XY ? 4 : 6) k_layer(const __grid_
     VsbLut L1, L2;
     L1.s = p.lut1 ? s_lut1 : nullptr; L1.l0 = 0u; L1.l255 = 0xFFFFFFFFu; // broadcasts filled in after the first barrier
     L2.s = p.lut2 ? s_lut2 : nullptr; L2.l0 = 0u; L2.l255 = 0xFFFFFFFFu;
-    if (t < 64) {
-        if (p.lut1) ((uint32_t *)s_lut1)[t] = ((const uint32_t *)p.lut1)[t];
-        if (p.lut2) ((uint32_t *)s_lut2)[t] = ((const uint32_t *)p.lut2)[t];
-    }
-    if (XY && p.hb > 0) {
-        s_cw[t] = taps.cw[t];
-        if (t < 96) { s_off[t] = taps.off[t]; s_sw[t] = taps.sw[t]; }
-    }
+    if (t < 64 && p.lut1) ((uint32_t *)s_lut1)[t] = ((const uint32_t *)p.lut1)[t];
+    bool late_staged = false; // trailing LUT and bilateral tables: staged by the first tile that is not trivially uniform
     bool t_staged = false; // chamfer table (lower triangle, (M, m) -> M*(M+1)/2 + m): staged by the first tile that needs it
 
     auto prefetch = [&](int tile, int b) {
@@ -372,7 +366,6 @@ __global__ void __launch_bounds__(VSB_THREADS, XY ? 4 : 6) k_layer(const __grid_
         }
 
         if (L1.s) { L1.l0 = (uint32_t)s_lut1[0] * 0x01010101u; L1.l255 = (uint32_t)s_lut1[255] * 0x01010101u; }
-        if (L2.s) { L2.l0 = (uint32_t)s_lut2[0] * 0x01010101u; L2.l255 = (uint32_t)s_lut2[255] * 0x01010101u; }
         const uint32_t ref = L1.map4(ref_raw * 0x01010101u);
         bool uni = true;
 #pragma unroll
@@ -413,13 +406,22 @@ __global__ void __launch_bounds__(VSB_THREADS, XY ? 4 : 6) k_layer(const __grid_
         do { // one pass; `break` = tile finished
         if (tile_state == 0) { // uniform region, nothing recedes: every filter of a constant is that constant
             if (nvalid > 0) {
-                const uint32_t cv = L2.map4(ref);
+                const uint32_t cv = p.lut2 ? (uint32_t)p.lut2[ref & 255u] * 0x01010101u : ref;
                 uint8_t *dst = p.out + (size_t)oy * p.opitch + ox;
                 const uint4 o = make_uint4(cv, cv, cv, cv);
                 if (nvalid == 16 && p.aligned) vsb_st16_stream(dst, o);
                 else vsb_st_bytes(dst, o, nvalid);
             }
             break;
+        }
+
+        if (!late_staged) { // visible to all threads after the next barrier (every path below has one before first use)
+            if (t < 64 && p.lut2) ((uint32_t *)s_lut2)[t] = ((const uint32_t *)p.lut2)[t];
+            if (XY && p.hb > 0) {
+                s_cw[t] = taps->cw[t];
+                if (t < 96) { s_off[t] = taps->off[t]; s_sw[t] = taps->sw[t]; }
+            }
+            late_staged = true;
         }
 
         // ---- P2: distance search + gradient on the receding pixels of the region ----------------------------
@@ -690,6 +692,7 @@ __global__ void __launch_bounds__(VSB_THREADS, XY ? 4 : 6) k_layer(const __grid_
         PHASE(14);
 
         // ---- P7: trailing LUT, store ----------------------------------------------------------------------------------
+        if (L2.s) { L2.l0 = (uint32_t)s_lut2[0] * 0x01010101u; L2.l255 = (uint32_t)s_lut2[255] * 0x01010101u; }
         if (nvalid > 0) {
             uint4 o = *(const uint4 *)&OUT[r + Hh][16 + 16 * c];
             o = L2.map16(o);
@@ -703,7 +706,7 @@ __global__ void __launch_bounds__(VSB_THREADS, XY ? 4 : 6) k_layer(const __grid_
 }
 
 template <int ZMODE, int METRIC, bool PERSIST, bool XY>
-static int launch_layer_v(LayerParams &p, const BilTapsL &taps, size_t smem, cudaStream_t s)
+static int launch_layer_v(LayerParams &p, const BilTapsL *taps, size_t smem, cudaStream_t s)
 {
     static int n_sms = 0; // per instantiation
     if (n_sms == 0) {
@@ -727,11 +730,34 @@ static int launch_layer_v(LayerParams &p, const BilTapsL &taps, size_t smem, cud
 }
 
 template <int ZMODE, int METRIC>
-static int launch_layer(LayerParams &p, const BilTapsL &taps, bool persist, size_t smem, cudaStream_t s)
+static int launch_layer(LayerParams &p, const BilTapsL *taps, bool persist, size_t smem, cudaStream_t s)
 {
     const bool xy = p.hb > 0 || p.nkx > 0;
     if (persist) return launch_layer_v<ZMODE, METRIC, true, true>(p, taps, smem, s); // the prefetching variant keeps the general body
     return xy ? launch_layer_v<ZMODE, METRIC, false, true>(p, taps, smem, s) : launch_layer_v<ZMODE, METRIC, false, false>(p, taps, smem, s);
+}
+
+// Device copies of bilateral tap tables, keyed by content (a handful of distinct filters per process).
+#include <mutex>
+#include <vector>
+struct TapCacheEntry { unsigned long long hash; int dev; BilTapsL *d; };
+static std::vector<TapCacheEntry> g_tap_cache;
+static std::mutex g_tap_mutex;
+static int taps_on_device(const BilTapsL &h, const BilTapsL **out)
+{
+    unsigned long long hash = 1469598103934665603ULL;
+    const unsigned char *b = (const unsigned char *)&h;
+    for (size_t i = 0; i < sizeof h; ++i) { hash ^= b[i]; hash *= 1099511628211ULL; }
+    int dev = 0;
+    VSB_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(g_tap_mutex);
+    for (auto &e : g_tap_cache) if (e.hash == hash && e.dev == dev) { *out = e.d; return VSB_OK; }
+    BilTapsL *d = nullptr;
+    VSB_CUDA(cudaMalloc((void **)&d, sizeof h));
+    VSB_CUDA(cudaMemcpy(d, &h, sizeof h, cudaMemcpyHostToDevice));
+    g_tap_cache.push_back({hash, dev, d});
+    *out = d;
+    return VSB_OK;
 }
 
 static unsigned long long *g_layer_stats = nullptr;
@@ -810,6 +836,8 @@ extern "C" int vsb_layer_fused(const uint8_t *in, size_t in_pitch, int W, int H,
     p.stats = g_layer_stats;
     VSB_REQUIRE(p.halo <= LH_MAX, "vsb_layer_fused: halo %d > %d", p.halo, LH_MAX);
     p.ntiles = p.tiles_x * p.tiles_y;
+    const BilTapsL *taps_dev = nullptr;
+    if (p.hb > 0) { const int rc = taps_on_device(taps, &taps_dev); if (rc) return rc; }
     // persistent + prefetch variant: whole 16-byte chunks only, at most 7 masks staged per tile
     const bool persist = getenv("VSB_PERSIST") != nullptr && p.aligned && (W % 16) == 0 && p.z.n_priors <= 7;
     const int RH = VSB_TH + 2 * p.halo;
@@ -833,9 +861,9 @@ extern "C" int vsb_layer_fused(const uint8_t *in, size_t in_pitch, int W, int H,
     cudaStream_t s = (cudaStream_t)stream;
     const bool ex = zp->metric == VSB_METRIC_EXACT;
     switch (mode) {
-    case VSB_Z_FIXED: return ex ? launch_layer<VSB_Z_FIXED, 1>(p, taps, persist, smem, s) : launch_layer<VSB_Z_FIXED, 0>(p, taps, persist, smem, s);
-    case VSB_Z_WEIGHTED: return ex ? launch_layer<VSB_Z_WEIGHTED, 1>(p, taps, persist, smem, s) : launch_layer<VSB_Z_WEIGHTED, 0>(p, taps, persist, smem, s);
-    case VSB_Z_CONST: return launch_layer<VSB_Z_CONST, 0>(p, taps, persist, smem, s);
-    default: return launch_layer<ZL_NONE, 0>(p, taps, persist, smem, s);
+    case VSB_Z_FIXED: return ex ? launch_layer<VSB_Z_FIXED, 1>(p, taps_dev, persist, smem, s) : launch_layer<VSB_Z_FIXED, 0>(p, taps_dev, persist, smem, s);
+    case VSB_Z_WEIGHTED: return ex ? launch_layer<VSB_Z_WEIGHTED, 1>(p, taps_dev, persist, smem, s) : launch_layer<VSB_Z_WEIGHTED, 0>(p, taps_dev, persist, smem, s);
+    case VSB_Z_CONST: return launch_layer<VSB_Z_CONST, 0>(p, taps_dev, persist, smem, s);
+    default: return launch_layer<ZL_NONE, 0>(p, taps_dev, persist, smem, s);
     }
 }
