@@ -200,8 +200,9 @@ __global__ void __launch_bounds__(VSB_THREADS, XY ? 4 : 6) k_layer(const __grid_
     uint16_t *s_list = (uint16_t *)(dsm + p.sm.list);             // bilateral word list, Gaussian word list at +GL_OFF
     uint16_t *s_rlist = (uint16_t *)(dsm + p.sm.s2);              // receding pixel list overlays [s2 | list]
     __shared__ uint32_t s_rowany[(LB_ROWS_MAX + 31) / 32];
-    __shared__ uint8_t s_nib[3][RG_ROWS_MAX][RG_CH];
-    __shared__ unsigned long long s_pl[8][RG_ROWS_MAX];
+    __shared__ __align__(8) uint32_t s_zpl32[RG_ROWS_MAX][2], s_wpl32[RG_ROWS_MAX][2]; // per row: words equal to LUT1[0]x4 / LUT1[255]x4
+    unsigned long long *s_zpl = (unsigned long long *)s_zpl32, *s_wpl = (unsigned long long *)s_wpl32; // (32-bit halves: native shared atomics)
+    __shared__ unsigned long long s_pl[4][RG_ROWS_MAX];                   // the same AND-ed over the window rows
     __shared__ float s_cw[256];
     __shared__ int s_off[96];
     __shared__ float s_sw[96];
@@ -280,6 +281,7 @@ __global__ void __launch_bounds__(VSB_THREADS, XY ? 4 : 6) k_layer(const __grid_
         uint32_t ref_raw;
         if (PERSIST) {
             if (t == 0) { s_cnt = 0; s_gcnt = 0; s_quiet = 0; }
+            if (XY && t < RH) { s_zpl[t] = 0ULL; s_wpl[t] = 0ULL; }
             cp_async_wait_all();
             __syncthreads(); // this tile's region has landed (it was requested one iteration ago)
             const int nxt = tile + (int)gridDim.x;
@@ -323,6 +325,7 @@ __global__ void __launch_bounds__(VSB_THREADS, XY ? 4 : 6) k_layer(const __grid_
             else if (nvalid > 0) gstate[0] = 2;
             ref_raw = p.in[(size_t)y0 * p.ipitch + x0];
             if (t == 0) { s_cnt = 0; s_gcnt = 0; s_quiet = 0; }
+            if (XY && t < RH) { s_zpl[t] = 0ULL; s_wpl[t] = 0ULL; }
             __syncthreads();
         } else {
             if (ZMODE != ZL_NONE) {
@@ -362,6 +365,7 @@ __global__ void __launch_bounds__(VSB_THREADS, XY ? 4 : 6) k_layer(const __grid_
             }
             ref_raw = p.in[(size_t)y0 * p.ipitch + x0];
             if (t == 0) { s_cnt = 0; s_gcnt = 0; s_quiet = 0; }
+            if (XY && t < RH) { s_zpl[t] = 0ULL; s_wpl[t] = 0ULL; }
             __syncthreads();
         }
 
@@ -377,6 +381,13 @@ __global__ void __launch_bounds__(VSB_THREADS, XY ? 4 : 6) k_layer(const __grid_
                 if (gstate[u] == 1) {
                     v = L1.map16(gv[u]);
                     uni = uni && (v.x == ref) && (v.y == ref) && (v.z == ref) && (v.w == ref);
+                    if (XY) { // value planes for the filter bypass (out-of-image and ragged chunks stay "unknown")
+                        const uint32_t Z4 = L1.l0, W4 = L1.l255;
+                        const uint32_t zb = (uint32_t)(v.x == Z4) | ((uint32_t)(v.y == Z4) << 1) | ((uint32_t)(v.z == Z4) << 2) | ((uint32_t)(v.w == Z4) << 3);
+                        const uint32_t wb = (uint32_t)(v.x == W4) | ((uint32_t)(v.y == W4) << 1) | ((uint32_t)(v.z == W4) << 2) | ((uint32_t)(v.w == W4) << 3);
+                        if (zb) atomicOr(&s_zpl32[rr][cc >> 3], zb << ((4 * cc) & 31));
+                        if (wb) atomicOr(&s_wpl32[rr][cc >> 3], wb << ((4 * cc) & 31));
+                    }
                 } else if (gstate[u] == 2) {
                     const int y = y0 - Hh + rr, x = x0 - 16 + cc * 16;
                     const int xa = max(x, 0), xb = min(x + 16, W);
@@ -487,6 +498,10 @@ __global__ void __launch_bounds__(VSB_THREADS, XY ? 4 : 6) k_layer(const __grid_
                 const int graw = PERSIST ? (int)rawb[rr * RG_W + rc] : (int)p.in[(size_t)y * p.ipitch + x];
                 const int m = max(graw, g & 255); // merge with the raw gray value
                 s1[rr][rc] = L1.s ? L1.s[m] : (uint8_t)m;
+                if (XY) { // the word no longer holds a known constant
+                    atomicAnd(&s_zpl32[rr][rc >> 7], ~(1u << ((rc >> 2) & 31)));
+                    atomicAnd(&s_wpl32[rr][rc >> 7], ~(1u << ((rc >> 2) & 31)));
+                }
             }
             __syncthreads();
             if (t == 0) s_cnt = 0;
@@ -516,46 +531,20 @@ __global__ void __launch_bounds__(VSB_THREADS, XY ? 4 : 6) k_layer(const __grid_
         uint8_t (*OUT)[RG_W] = gauss ? (hb > 0 ? s1 : s2buf) : S2;  // what the store phase reads
 
         if (XY && (hb > 0 || gauss)) {
-            // ---- P4: bit-planes of stage 1: word not uniform / differs from right neighbour / differs from the word below
-            for (int i = t; i < RH * RG_CH; i += VSB_THREADS) {
-                const int rr = i / RG_CH, cc = i - rr * RG_CH;
-                const uint4 a = *(const uint4 *)&s1[rr][cc * 16];
-                const uint32_t wn = (cc < RG_CH - 1) ? *(const uint32_t *)&s1[rr][cc * 16 + 16] : a.w;
-                const uint4 b = (rr + 1 < RH) ? *(const uint4 *)&s1[rr + 1][cc * 16] : a;
-                const uint32_t nu = (uint32_t)(a.x != (a.x & 255u) * 0x01010101u) | ((uint32_t)(a.y != (a.y & 255u) * 0x01010101u) << 1) |
-                                    ((uint32_t)(a.z != (a.z & 255u) * 0x01010101u) << 2) | ((uint32_t)(a.w != (a.w & 255u) * 0x01010101u) << 3);
-                const uint32_t dh = (uint32_t)(a.x != a.y) | ((uint32_t)(a.y != a.z) << 1) | ((uint32_t)(a.z != a.w) << 2) |
-                                    ((uint32_t)(a.w != wn) << 3);
-                const uint32_t dv = (uint32_t)(a.x != b.x) | ((uint32_t)(a.y != b.y) << 1) | ((uint32_t)(a.z != b.z) << 2) |
-                                    ((uint32_t)(a.w != b.w) << 3);
-                s_nib[0][rr][cc] = (uint8_t)nu; s_nib[1][rr][cc] = (uint8_t)dh; s_nib[2][rr][cc] = (uint8_t)dv;
-            }
-            __syncthreads();
-            if (t < RH) {
-                unsigned long long nu = 0, dh = 0, dv = 0;
-#pragma unroll
-                for (int cc = 0; cc < RG_CH; ++cc) {
-                    nu |= (unsigned long long)s_nib[0][t][cc] << (4 * cc);
-                    dh |= (unsigned long long)s_nib[1][t][cc] << (4 * cc);
-                    dv |= (unsigned long long)s_nib[2][t][cc] << (4 * cc);
-                }
-                s_pl[0][t] = nu; s_pl[1][t] = dh; s_pl[2][t] = dv;
-            }
-            __syncthreads();
-            // window-row ORs: planes 3,4 for the bilateral window (+-hb), 6,7 for bilateral followed by Gaussian (+-(hb+ry))
+            // ---- P4: value planes AND-ed over the window rows: planes 0,1 for the bilateral window (+-hb), 2,3 for
+            //      bilateral followed by Gaussian (+-(hb+ry)).  A set bit = "this word is LUT1[0] (resp. LUT1[255]) in
+            //      every row of the window"; rows with out-of-image or receding words simply have no bit.
             const int r_lo = Hh - hg, r_hi = Hh + VSB_TH + hg; // region rows on which stage 2 is needed
             if (t >= r_lo && t < r_hi) {
-                unsigned long long A = 0, B = 0, C = 0;
-                for (int d = -hb; d <= hb; ++d) { A |= s_pl[0][t + d]; B |= s_pl[1][t + d]; }
-                for (int d = -hb; d < hb; ++d) C |= s_pl[2][t + d];
-                s_pl[3][t] = A | C; s_pl[4][t] = B;
+                unsigned long long Z = ~0ULL, Wp = ~0ULL;
+                for (int d = -hb; d <= hb; ++d) { Z &= s_zpl[t + d]; Wp &= s_wpl[t + d]; }
+                s_pl[0][t] = Z; s_pl[1][t] = Wp;
             }
             if (t >= Hh && t < Hh + VSB_TH) {
                 const int e = hb + ry;
-                unsigned long long A = 0, B = 0, C = 0;
-                for (int d = -e; d <= e; ++d) { A |= s_pl[0][t + d]; B |= s_pl[1][t + d]; }
-                for (int d = -e; d < e; ++d) C |= s_pl[2][t + d];
-                s_pl[6][t] = A | C; s_pl[7][t] = B;
+                unsigned long long Z = ~0ULL, Wp = ~0ULL;
+                for (int d = -e; d <= e; ++d) { Z &= s_zpl[t + d]; Wp &= s_wpl[t + d]; }
+                s_pl[2][t] = Z; s_pl[3][t] = Wp;
             }
             __syncthreads();
             PHASE(11);
@@ -569,26 +558,30 @@ __global__ void __launch_bounds__(VSB_THREADS, XY ? 4 : 6) k_layer(const __grid_
                 const int rq = it / RG_CH, cc = it - rq * RG_CH;
                 const int rr = r_lo + (live ? rq : 0);
                 const bool trow = rr >= Hh && rr < Hh + VSB_TH;
-                const unsigned long long AC = s_pl[3][rr], Bm = s_pl[4][rr];
-                const unsigned long long AC2 = trow ? s_pl[6][rr] : 0ULL, B2 = trow ? s_pl[7][rr] : 0ULL;
+                const unsigned long long Zb = s_pl[0][rr], Wb = s_pl[1][rr];
+                const unsigned long long Zg = trow ? s_pl[2][rr] : ~0ULL, Wg = trow ? s_pl[3][rr] : ~0ULL;
                 const int sh = 4 * cc - 4; // plane bits of words 4cc-4 .. 4cc+7, as 12-bit fields
-                const uint32_t fa = (uint32_t)(sh >= 0 ? (AC >> sh) : (AC << 4)) & 0xFFFu;
-                const uint32_t fb = (uint32_t)(sh >= 0 ? (Bm >> sh) : (Bm << 4)) & 0xFFFu;
-                const uint32_t ga = (uint32_t)(sh >= 0 ? (AC2 >> sh) : (AC2 << 4)) & 0xFFFu;
-                const uint32_t gb = (uint32_t)(sh >= 0 ? (B2 >> sh) : (B2 << 4)) & 0xFFFu;
+                const uint32_t fa = (uint32_t)(sh >= 0 ? (Zb >> sh) : (Zb << 4)) & 0xFFFu;
+                const uint32_t fb = (uint32_t)(sh >= 0 ? (Wb >> sh) : (Wb << 4)) & 0xFFFu;
+                const uint32_t ga = (uint32_t)(sh >= 0 ? (Zg >> sh) : (Zg << 4)) & 0xFFFu;
+                const uint32_t gb = (uint32_t)(sh >= 0 ? (Wg >> sh) : (Wg << 4)) & 0xFFFu;
                 uint32_t badb = 0, badg = 0; // per-word verdicts of this chunk (bit j = word 4cc+j)
-                if (live && ((cc >= 1 && cc <= 8) || hg > 0) && (fa | fb | ga | gb)) {
+                const bool quick = ((fa & 0x3FCu) == 0x3FCu || (fb & 0x3FCu) == 0x3FCu) &&
+                                   ((ga & 0x3FCu) == 0x3FCu || (gb & 0x3FCu) == 0x3FCu); // words 4cc-2 .. 4cc+5 all one constant
+                if (live && ((cc >= 1 && cc <= 8) || hg > 0) && !quick) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const int w = 4 * cc + j;
                         if (w < ((16 - hg) >> 2) || w > ((143 + hg) >> 2)) continue;
                         if (hb > 0) {
                             const int wl = (4 * w - eb) >> 2, wr = (4 * w + 3 + eb) >> 2, n = wr - wl, o = wl - (4 * cc - 4);
-                            if ((((fa >> o) & ((2u << n) - 1u)) | ((fb >> o) & ((1u << n) - 1u))) != 0) badb |= 1u << j;
+                            const uint32_t mk = (2u << n) - 1u;
+                            if (((fa >> o) & mk) != mk && ((fb >> o) & mk) != mk) badb |= 1u << j;
                         }
                         if (gauss && trow && w >= 4 && w < 36) {
                             const int wl = (4 * w - eg) >> 2, wr = (4 * w + 3 + eg) >> 2, n = wr - wl, o = wl - (4 * cc - 4);
-                            if ((((ga >> o) & ((2u << n) - 1u)) | ((gb >> o) & ((1u << n) - 1u))) != 0) badg |= 1u << j;
+                            const uint32_t mk = (2u << n) - 1u;
+                            if (((ga >> o) & mk) != mk && ((gb >> o) & mk) != mk) badg |= 1u << j;
                         }
                     }
                 }
