@@ -202,7 +202,6 @@ __global__ void __launch_bounds__(VSB_THREADS, XY ? 4 : 6) k_layer(const __grid_
     __shared__ uint32_t s_rowany[(LB_ROWS_MAX + 31) / 32];
     __shared__ __align__(8) uint32_t s_zpl32[RG_ROWS_MAX][2], s_wpl32[RG_ROWS_MAX][2]; // per row: words equal to LUT1[0]x4 / LUT1[255]x4
     unsigned long long *s_zpl = (unsigned long long *)s_zpl32, *s_wpl = (unsigned long long *)s_wpl32; // (32-bit halves: native shared atomics)
-    __shared__ unsigned long long s_pl[4][RG_ROWS_MAX];                   // the same AND-ed over the window rows
     __shared__ float s_cw[256];
     __shared__ int s_off[96];
     __shared__ float s_sw[96];
@@ -226,7 +225,7 @@ __global__ void __launch_bounds__(VSB_THREADS, XY ? 4 : 6) k_layer(const __grid_
     L2.s = p.lut2 ? s_lut2 : nullptr; L2.l0 = 0u; L2.l255 = 0xFFFFFFFFu;
     if (t < 64 && p.lut1) ((uint32_t *)s_lut1)[t] = ((const uint32_t *)p.lut1)[t];
     bool late_staged = false; // trailing LUT and bilateral tables: staged by the first tile that is not trivially uniform
-    bool t_staged = false; // chamfer table (lower triangle, (M, m) -> M*(M+1)/2 + m): staged by the first tile that needs it
+    bool t_staged = false; // chamfer table [(R+1) x (R+1)]: staged by the first tile that needs it
 
     auto prefetch = [&](int tile, int b) {
         const int px0 = (tile % p.tiles_x) * VSB_TW, py0 = (tile / p.tiles_x) * VSB_TH;
@@ -440,9 +439,10 @@ __global__ void __launch_bounds__(VSB_THREADS, XY ? 4 : 6) k_layer(const __grid_
             const int brows = RH + 2 * R;
             if (ZMODE != VSB_Z_CONST) {
                 if (METRIC == VSB_METRIC_CHAMFER5 && !t_staged) {
-                    const int n1 = R + 1;
-                    for (int M = (t >> 5); M <= R; M += VSB_THREADS / 32)
-                        for (int m = lane; m <= M; m += 32) s_T[((M * (M + 1)) >> 1) + m] = p.T[M * n1 + m];
+                    const int nT = (R + 1) * (R + 1);
+                    const int nfull = ((((size_t)p.T) & 15) == 0) ? (nT >> 2) : 0; // 16-byte groups when the table is aligned
+                    for (int i = t; i < nfull; i += VSB_THREADS) ((float4 *)s_T)[i] = ((const float4 *)p.T)[i];
+                    for (int i = 4 * nfull + t; i < nT; i += VSB_THREADS) s_T[i] = p.T[i];
                     t_staged = true;
                 }
                 stage_mask_rows<LBW>(s_bits, p.cur, wpr, H, (x0 >> 5) - 3, y0 - Hh - R, brows);
@@ -476,7 +476,7 @@ __global__ void __launch_bounds__(VSB_THREADS, XY ? 4 : 6) k_layer(const __grid_
                 const int rr = code >> 8, rc = code & 255;
                 const int x = x0 - 16 + rc, y = y0 - Hh + rr;
                 float best = 0.0f;
-                if (ZMODE != VSB_Z_CONST) best = tile_search<METRIC, LBW, true>(s_bits, s_rowany, s_T, R, rr + R, rc + 80);
+                if (ZMODE != VSB_Z_CONST) best = tile_search<METRIC, LBW, false>(s_bits, s_rowany, s_T, R, rr + R, rc + 80);
                 int g;
                 if (ZMODE == VSB_Z_FIXED) {
                     const float n = __fdiv_rn(fminf(best, Ff), p.z.den);
@@ -531,97 +531,50 @@ __global__ void __launch_bounds__(VSB_THREADS, XY ? 4 : 6) k_layer(const __grid_
         uint8_t (*OUT)[RG_W] = gauss ? (hb > 0 ? s1 : s2buf) : S2;  // what the store phase reads
 
         if (XY && (hb > 0 || gauss)) {
-            // ---- P4: value planes AND-ed over the window rows: planes 0,1 for the bilateral window (+-hb), 2,3 for
-            //      bilateral followed by Gaussian (+-(hb+ry)).  A set bit = "this word is LUT1[0] (resp. LUT1[255]) in
-            //      every row of the window"; rows with out-of-image or receding words simply have no bit.
+            // ---- P4/P5: bypass lists from the value planes.  A row's plane has one bit per 4-byte word: "the word is
+            //      LUT1[0]x4" (Z) or "LUT1[255]x4" (W); rows hold no bit for out-of-image or receding words.  One thread
+            //      per stage-2 row ANDs the planes over the window rows and, with shifts, over the window words: a word
+            //      whose whole window is one constant keeps its value through the bilateral (and the Gaussian); all
+            //      other words are appended to the bilateral / Gaussian word lists.  Meanwhile every thread copies
+            //      stage 1 to the buffer the listed words are overwritten in.
             const int r_lo = Hh - hg, r_hi = Hh + VSB_TH + hg; // region rows on which stage 2 is needed
+            const int eb = hb, eg = hb + rx;
             if (t >= r_lo && t < r_hi) {
+                const bool trow = t >= Hh && t < Hh + VSB_TH;
                 unsigned long long Z = ~0ULL, Wp = ~0ULL;
                 for (int d = -hb; d <= hb; ++d) { Z &= s_zpl[t + d]; Wp &= s_wpl[t + d]; }
-                s_pl[0][t] = Z; s_pl[1][t] = Wp;
+                unsigned long long badb = 0ULL, badg = 0ULL;
+                if (hb > 0) {
+                    unsigned long long cz = Z, cw = Wp;
+                    for (int sft = 1; sft <= ((eb + 3) >> 2); ++sft) { cz &= (Z >> sft) & (Z << sft); cw &= (Wp >> sft) & (Wp << sft); }
+                    const int wlo = (16 - hg) >> 2, whi = (143 + hg) >> 2; // words stage 2 is needed on
+                    badb = ~(cz | cw) & ((~0ULL << wlo) & ((2ULL << whi) - 1ULL));
+                }
+                if (gauss && trow) {
+                    for (int d = hb + 1; d <= hb + ry; ++d) { Z &= s_zpl[t + d] & s_zpl[t - d]; Wp &= s_wpl[t + d] & s_wpl[t - d]; }
+                    unsigned long long cz = Z, cw = Wp;
+                    for (int sft = 1; sft <= ((eg + 3) >> 2); ++sft) { cz &= (Z >> sft) & (Z << sft); cw &= (Wp >> sft) & (Wp << sft); }
+                    badg = ~(cz | cw) & 0xFFFFFFFF0ULL; // tile words 4 .. 35
+                }
+                if (badb) {
+                    int base = atomicAdd(&s_cnt, __popcll(badb));
+                    while (badb) { const int w = __ffsll((long long)badb) - 1; badb &= badb - 1ULL; s_list[base++] = (uint16_t)((t << 8) | w); }
+                }
+                if (badg) {
+                    int base = GL_OFF + atomicAdd(&s_gcnt, __popcll(badg));
+                    while (badg) { const int w = __ffsll((long long)badg) - 1; badg &= badg - 1ULL; s_list[base++] = (uint16_t)((t << 8) | w); }
+                }
             }
-            if (t >= Hh && t < Hh + VSB_TH) {
-                const int e = hb + ry;
-                unsigned long long Z = ~0ULL, Wp = ~0ULL;
-                for (int d = -e; d <= e; ++d) { Z &= s_zpl[t + d]; Wp &= s_wpl[t + d]; }
-                s_pl[2][t] = Z; s_pl[3][t] = Wp;
+            if (hb > 0) {
+                for (int i = t; i < (r_hi - r_lo) * RG_CH; i += VSB_THREADS) {
+                    const int rq = i / RG_CH, cc = i - rq * RG_CH;
+                    *(uint4 *)&s2buf[r_lo + rq][16 * cc] = *(const uint4 *)&s1[r_lo + rq][16 * cc];
+                }
+            } else {
+                *(uint4 *)&s2buf[r + Hh][16 + 16 * c] = *(const uint4 *)&s1[r + Hh][16 + 16 * c];
             }
             __syncthreads();
             PHASE(11);
-
-            // ---- P5: bypass tests.  One item = one 16-byte chunk of one stage-2 row; a chunk whose neighbourhood carries
-            //      no plane bit is copied whole, otherwise its four words are tested one by one.
-            const int eb = hb, eg = hb + rx;
-            const int nrow2 = r_hi - r_lo;
-            for (int it = t; it < ((nrow2 * RG_CH + 31) & ~31); it += VSB_THREADS) { // warp-uniform trip count
-                const bool live = it < nrow2 * RG_CH;
-                const int rq = it / RG_CH, cc = it - rq * RG_CH;
-                const int rr = r_lo + (live ? rq : 0);
-                const bool trow = rr >= Hh && rr < Hh + VSB_TH;
-                const unsigned long long Zb = s_pl[0][rr], Wb = s_pl[1][rr];
-                const unsigned long long Zg = trow ? s_pl[2][rr] : ~0ULL, Wg = trow ? s_pl[3][rr] : ~0ULL;
-                const int sh = 4 * cc - 4; // plane bits of words 4cc-4 .. 4cc+7, as 12-bit fields
-                const uint32_t fa = (uint32_t)(sh >= 0 ? (Zb >> sh) : (Zb << 4)) & 0xFFFu;
-                const uint32_t fb = (uint32_t)(sh >= 0 ? (Wb >> sh) : (Wb << 4)) & 0xFFFu;
-                const uint32_t ga = (uint32_t)(sh >= 0 ? (Zg >> sh) : (Zg << 4)) & 0xFFFu;
-                const uint32_t gb = (uint32_t)(sh >= 0 ? (Wg >> sh) : (Wg << 4)) & 0xFFFu;
-                uint32_t badb = 0, badg = 0; // per-word verdicts of this chunk (bit j = word 4cc+j)
-                const bool quick = ((fa & 0x3FCu) == 0x3FCu || (fb & 0x3FCu) == 0x3FCu) &&
-                                   ((ga & 0x3FCu) == 0x3FCu || (gb & 0x3FCu) == 0x3FCu); // words 4cc-2 .. 4cc+5 all one constant
-                if (live && ((cc >= 1 && cc <= 8) || hg > 0) && !quick) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int w = 4 * cc + j;
-                        if (w < ((16 - hg) >> 2) || w > ((143 + hg) >> 2)) continue;
-                        if (hb > 0) {
-                            const int wl = (4 * w - eb) >> 2, wr = (4 * w + 3 + eb) >> 2, n = wr - wl, o = wl - (4 * cc - 4);
-                            const uint32_t mk = (2u << n) - 1u;
-                            if (((fa >> o) & mk) != mk && ((fb >> o) & mk) != mk) badb |= 1u << j;
-                        }
-                        if (gauss && trow && w >= 4 && w < 36) {
-                            const int wl = (4 * w - eg) >> 2, wr = (4 * w + 3 + eg) >> 2, n = wr - wl, o = wl - (4 * cc - 4);
-                            const uint32_t mk = (2u << n) - 1u;
-                            if (((ga >> o) & mk) != mk && ((gb >> o) & mk) != mk) badg |= 1u << j;
-                        }
-                    }
-                }
-                // warp-aggregated list appends (entries are words)
-                const uint32_t vb = __ballot_sync(0xffffffffu, badb != 0), vg = __ballot_sync(0xffffffffu, badg != 0);
-                if (vb | vg) {
-                    const int nb = __popc(badb), ng = __popc(badg);
-                    int pb = nb, pg = ng; // inclusive scans over the warp
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const int ub = __shfl_up_sync(0xffffffffu, pb, o), ug = __shfl_up_sync(0xffffffffu, pg, o);
-                        if (lane >= o) { pb += ub; pg += ug; }
-                    }
-                    int baseb = 0, baseg = 0;
-                    if (lane == 31) { if (pb) baseb = atomicAdd(&s_cnt, pb); if (pg) baseg = atomicAdd(&s_gcnt, pg); }
-                    baseb = __shfl_sync(0xffffffffu, baseb, 31) + pb - nb;
-                    baseg = __shfl_sync(0xffffffffu, baseg, 31) + pg - ng;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        if (badb & (1u << j)) s_list[baseb++] = (uint16_t)((rr << 8) | (4 * cc + j));
-                        if (badg & (1u << j)) s_list[GL_OFF + baseg++] = (uint16_t)((rr << 8) | (4 * cc + j));
-                    }
-                }
-                if (!live) continue;
-                if (hb > 0) {
-                    if (badb == 0) *(uint4 *)&s2buf[rr][16 * cc] = *(const uint4 *)&s1[rr][16 * cc];
-                    else {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            if (!(badb & (1u << j))) *(uint32_t *)&s2buf[rr][16 * cc + 4 * j] = *(const uint32_t *)&s1[rr][16 * cc + 4 * j];
-                    }
-                } else if (gauss && trow) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int w = 4 * cc + j;
-                        if (!(badg & (1u << j)) && w >= 4 && w < 36) *(uint32_t *)&s2buf[rr][4 * w] = *(const uint32_t *)&s1[rr][4 * w];
-                    }
-                }
-            }
-            __syncthreads();
             PHASE(12);
 
             if (hb > 0) {
@@ -838,7 +791,7 @@ extern "C" int vsb_layer_fused(const uint8_t *in, size_t in_pitch, int W, int H,
     auto up16 = [](size_t v) { return (v + 15) & ~(size_t)15; };
     const bool searching = mode != VSB_Z_NONE && mode != VSB_Z_CONST;
     size_t off = 0;
-    p.sm.T = (int)off; off += up16((searching && zp->metric == VSB_METRIC_CHAMFER5) ? (size_t)n1 * (n1 + 1) * 2 : 16);
+    p.sm.T = (int)off; off += up16((searching && zp->metric == VSB_METRIC_CHAMFER5) ? (size_t)n1 * n1 * 4 : 16);
     p.sm.raw_stride = (int)up16((size_t)RH * RG_W);
     p.sm.raw = (int)off; off += persist ? 2 * (size_t)p.sm.raw_stride : 0;
     p.sm.src_stride = (p.z.n_priors + 1) * RH * 6;
