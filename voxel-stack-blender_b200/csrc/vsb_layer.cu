@@ -28,6 +28,13 @@
 #define LB_ROWS_MAX (RG_ROWS_MAX + 2 * VSB_FAST_REACH)
 #define FLAG_MIXED 0x100
 
+static __device__ __forceinline__ float lds_f32(uint32_t a)
+{
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+    return v;
+}
+
 struct BilTapsL {
     int32_t off[96];   // dy * RG_W + dx
     float sw[96];
@@ -51,6 +58,8 @@ struct LayerParams {
     int hb, ntaps;       // bilateral radius (0 = none) and tap count
     int nkx, nky;        // Gaussian taps (0 = none)
     int32_t kx[7], ky[7];
+    alignas(16) int tap_off[96];     // bilateral taps as byte offsets in the staged region, and their space weights: read through
+    alignas(16) float tap_sw[96];    // the constant bank with a warp-uniform index, so they cost no vector instruction
     unsigned long long *stats; // optional work counters (vsb_layer_stats)
     struct { int T, raw, src, s1, s2, bits, list, raw_stride, src_stride; } sm; // dynamic shared memory carve (bytes / words)
     int ntiles;
@@ -202,9 +211,7 @@ __global__ void __launch_bounds__(VSB_THREADS, XY ? 4 : 6) k_layer(const __grid_
     __shared__ uint32_t s_rowany[(LB_ROWS_MAX + 31) / 32];
     __shared__ __align__(8) uint32_t s_zpl32[RG_ROWS_MAX][2], s_wpl32[RG_ROWS_MAX][2]; // per row: words equal to LUT1[0]x4 / LUT1[255]x4
     unsigned long long *s_zpl = (unsigned long long *)s_zpl32, *s_wpl = (unsigned long long *)s_wpl32; // (32-bit halves: native shared atomics)
-    __shared__ float s_cw[256];
-    __shared__ int s_off[96];
-    __shared__ float s_sw[96];
+    __shared__ float s_cw2[512]; // colour weight by signed difference: s_cw2[255 + d] = cw[|d|]
     __shared__ __align__(4) uint8_t s_lut1[256];
     __shared__ __align__(4) uint8_t s_lut2[256];
     __shared__ int s_cnt, s_gcnt, s_quiet;
@@ -428,8 +435,8 @@ __global__ void __launch_bounds__(VSB_THREADS, XY ? 4 : 6) k_layer(const __grid_
         if (!late_staged) { // visible to all threads after the next barrier (every path below has one before first use)
             if (t < 64 && p.lut2) ((uint32_t *)s_lut2)[t] = ((const uint32_t *)p.lut2)[t];
             if (XY && p.hb > 0) {
-                s_cw[t] = taps->cw[t];
-                if (t < 96) { s_off[t] = taps->off[t]; s_sw[t] = taps->sw[t]; }
+                const float cwt = taps->cw[t];
+                s_cw2[255 + t] = cwt; s_cw2[255 - t] = cwt;
             }
             late_staged = true;
         }
@@ -588,11 +595,13 @@ __global__ void __launch_bounds__(VSB_THREADS, XY ? 4 : 6) k_layer(const __grid_
                     if (y < 0 || y >= H || x < 0 || x >= W) continue; // reflected below
                     const uint8_t *ctr = &s1[rr][rc];
                     const int v0 = *ctr;
+                    uint32_t cwa = (uint32_t)__cvta_generic_to_shared(s_cw2) + 4u * (uint32_t)(255 - v0);
+                    asm volatile("" : "+r"(cwa)); // opaque: keeps the per-tap address at one IMAD
                     float sacc = 0.0f, ws = 0.0f;
 #pragma unroll 4
                     for (int k = 0; k < ntaps; ++k) {
-                        const int v = ctr[s_off[k]];
-                        const float w = __fmul_rn(s_sw[k], s_cw[abs(v - v0)]);
+                        const int v = ctr[p.tap_off[k]];
+                        const float w = __fmul_rn(p.tap_sw[k], lds_f32(cwa + 4u * (uint32_t)v));
                         sacc = __fmaf_rn((float)v, w, sacc);
                         ws = __fadd_rn(ws, w);
                     }
@@ -765,7 +774,7 @@ extern "C" int vsb_layer_fused(const uint8_t *in, size_t in_pitch, int W, int H,
             VSB_REQUIRE(xy->radius >= 1 && xy->radius <= 4 && xy->ntaps >= 1 && xy->ntaps <= 96,
                         "vsb_layer_fused: bilateral radius %d / %d taps not fused", xy->radius, xy->ntaps);
             p.hb = xy->radius; p.ntaps = xy->ntaps;
-            for (int i = 0; i < xy->ntaps; ++i) { taps.off[i] = xy->tap_dy[i] * RG_W + xy->tap_dx[i]; taps.sw[i] = xy->tap_sw[i]; }
+            for (int i = 0; i < xy->ntaps; ++i) { taps.off[i] = p.tap_off[i] = xy->tap_dy[i] * RG_W + xy->tap_dx[i]; taps.sw[i] = p.tap_sw[i] = xy->tap_sw[i]; }
             for (int i = 0; i < 256; ++i) taps.cw[i] = xy->cw[i];
         }
         if (xy->nkx > 0 || xy->nky > 0) {
