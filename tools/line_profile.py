@@ -50,6 +50,7 @@ for k, c in smp.most_common():
 print("--- top lines by samples")
 srcs = {"layer": layer, "tile": open(f"{ROOT}/voxel-stack-blender_b200/csrc/vsb_tile.cuh").read().split("\n"),
         "common": open(f"{ROOT}/voxel-stack-blender_b200/csrc/vsb_common.cuh").read().split("\n")}
-for (f, l), c in lsmp.most_common(28):
+for (f, l), c in (sorted(lagg.items(), key=lambda kv: -kv[1])[:int(os.environ.get("TOPN","28"))] if os.environ.get("BYINSTR") else lsmp.most_common(int(os.environ.get("TOPN","28")))):
+    c = lsmp[(f, l)]
     t = srcs.get(f, [""])[l - 1].strip()[:88] if f in srcs and 0 < l <= len(srcs[f]) else ""
     print(f"{100*c/tots:5.1f}% smp {100*lagg[(f,l)]/tot:5.1f}% instr  {f}:{l:4}  {t}")

@@ -41,6 +41,10 @@ struct BilTapsL {
     float cw[256];
 };
 
+#ifndef VSB_LAYER_CTAS_XY
+#define VSB_LAYER_CTAS_XY 4 // resident CTAs per SM the XY instantiations are register-budgeted for
+#endif
+
 struct LayerParams {
     const uint8_t *in;
     size_t ipitch;
@@ -196,7 +200,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // are already in flight (cp.async into the other half of a double buffer), so the DRAM/L2 latency of the
 // prologue is off the critical path and LUTs / tap tables / chamfer table are staged once per CTA.
 template <int ZMODE, int METRIC, bool PERSIST, bool XY>
-__global__ void __launch_bounds__(VSB_THREADS, XY ? 4 : 6) k_layer(const __grid_constant__ LayerParams p,
+__global__ void __launch_bounds__(VSB_THREADS, XY ? VSB_LAYER_CTAS_XY : 6) k_layer(const __grid_constant__ LayerParams p,
                                                        const BilTapsL *__restrict__ taps)
 {
     extern __shared__ __align__(16) uint8_t dsm[];
@@ -273,7 +277,7 @@ __global__ void __launch_bounds__(VSB_THREADS, XY ? 4 : 6) k_layer(const __grid_
     if (PERSIST && tile < p.ntiles) prefetch(tile, 0);
 
     for (; tile < p.ntiles; tile += PERSIST ? (int)gridDim.x : p.ntiles) {
-        const int tx = tile % p.tiles_x, ty = tile / p.tiles_x;
+        const int tx = PERSIST ? tile % p.tiles_x : (int)blockIdx.x, ty = PERSIST ? tile / p.tiles_x : (int)blockIdx.y; // 2-D grid: no division
         const int x0 = tx * VSB_TW, y0 = ty * VSB_TH;
         const int oy = y0 + r, ox = x0 + c * 16;
         const int nvalid = (oy < H) ? max(0, min(16, W - ox)) : 0;

@@ -15,7 +15,7 @@ from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int8, c_int32,
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvsb_b200.so")
+LIB_PATH = os.environ.get("VSB_B200_LIB") or os.path.join(_HERE, "libvsb_b200.so")  # override: A/B builds of the same ABI
 
 VSB_MAX_PRIORS = 16
 VSB_MAX_XY_OPS = 16
