@@ -28,6 +28,8 @@ from typing import Iterable, List, Optional, Sequence
 
 import numpy as np
 
+import vsb_oracle_geom as geom
+
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "_build", "libvsb_oracle.so")
 _lib = None
@@ -296,8 +298,10 @@ def enhanced_from_distance(rd: np.ndarray, labels: np.ndarray, num_labels: int, 
 
 
 def enhanced_fade(cur: np.ndarray, priors: Sequence[np.ndarray], F: float, flavour: str = "scipy",
-                  metric: str = "chamfer5") -> np.ndarray:
-    """_calculate_receding_gradient_field_enhanced_edt (processing_core.py:338-404), isotropic."""
+                  metric: str = "chamfer5", anisotropic: Optional[Sequence[float]] = None) -> np.ndarray:
+    """_calculate_receding_gradient_field_enhanced_edt (processing_core.py:338-404).  `anisotropic` = (x_factor,
+    y_factor) of an enabled AnisotropicParams: the distance map is then taken on the nearest-resized mask and
+    resized back bilinearly (:357-377); distances stay in resized-pixel units, exactly like the reference."""
     if not priors:
         return np.zeros_like(cur)
     comb = combine_priors(priors)
@@ -305,7 +309,17 @@ def enhanced_fade(cur: np.ndarray, priors: Sequence[np.ndarray], F: float, flavo
     if not rec.any():
         return np.zeros_like(cur)
     # per-label denominators are min(max_label(d), F) == max_label(min(d, F)): clipped distances suffice
-    d = distance(cur, F, metric)
+    d = None
+    if anisotropic is not None:
+        # reach F + 3: bilinear taps are adjacent pixels, so a tap beyond the reach only occurs where every tap is >= F
+        far = f32(max(F, 0.0) + 4.0)   # stands in for "no seed within reach"; any value >= F fades to 0 all the same
+
+        def clipped(m):
+            dm = distance(m, max(F, 0.0) + 3.0, metric)
+            return np.where(np.isfinite(dm), dm, far).astype(np.float32)
+        d = geom.anisotropic_distance(cur, anisotropic[0], anisotropic[1], clipped)
+    if d is None:
+        d = distance(cur, F, metric)
     d = np.minimum(d, f32(max(F, 0.0)) if F > 0 else f32(np.finfo(np.float32).max))
     rd = np.where(rec > 0, d, f32(0)).astype(np.float32)
     n, labels = ccl8(rec)
@@ -330,8 +344,10 @@ def z_blend(cur: np.ndarray, priors_newest_first: Sequence[np.ndarray], cfg: dic
         return weighted_fade(cur, list(priors_newest_first), cfg.get("manual_weights", [100, 75, 50, 25]),
                              cfg.get("fade_distances_receding", [10.0] * 4), F, metric)
     if mode == "enhanced_edt":
+        ap = cfg.get("anisotropic_params") or {}
         return enhanced_fade(cur, list(priors_newest_first), F,
-                             "numba" if cfg.get("use_numba_jit", False) else "scipy", metric)
+                             "numba" if cfg.get("use_numba_jit", False) else "scipy", metric,
+                             (ap.get("x_factor", 1.0), ap.get("y_factor", 1.0)) if ap.get("enabled") else None)
     if mode == "fixed_fade":
         return fixed_fade(cur, combine_priors(list(priors_newest_first)), F,
                           cfg.get("use_fixed_fade_receding", False), metric)
@@ -538,6 +554,11 @@ def xy_pipeline(img: np.ndarray, ops: Iterable[dict]) -> np.ndarray:
             out = median_blur(out, _odd(op.get("median_ksize", 5)))
         elif t == "apply_lut":
             out = apply_lut(out, lut_from_params(op.get("lut_params", {})))
+        elif t == "unsharp_mask":
+            out = geom.unsharp_mask(out, op.get("unsharp_amount", 1.0), int(op.get("unsharp_threshold", 0)),
+                                    _odd(op.get("unsharp_blur_ksize", 5)), op.get("unsharp_blur_sigma", 0.0), gaussian_blur)
+        elif t == "resize":
+            out = geom.apply_resize(out, op.get("resize_width"), op.get("resize_height"), op.get("resample_mode", "LANCZOS4"))
     return out
 
 
