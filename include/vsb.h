@@ -157,7 +157,10 @@ typedef struct {
     float fades[VSB_MAX_PRIORS];
     float dens[VSB_MAX_PRIORS];
     int enhanced_arith;  /* VSB_Z_ENHANCED: 0 = float32 (SciPy flavour), 1 = float64 (Numba flavour) */
-    double fade_limit;   /* VSB_Z_ENHANCED: F as the Python float the reference passes on */
+    double fade_limit;
+    /* Enhanced EDT, anisotropic correction (processing_core.py:357-377): size of the nearest-resized mask the
+     * distance transform runs on (0 = disabled) and the search reach there (covers fade_limit + 3) */
+    int aniso_w, aniso_h, aniso_reach;   /* VSB_Z_ENHANCED: F as the Python float the reference passes on */
 } vsb_zparams;
 
 int vsb_zblend_fused(const uint8_t *gray, size_t gray_pitch, int W, int H, const uint32_t *cur_bits,
@@ -255,6 +258,40 @@ int vsb_layer_fused(const uint8_t *in, size_t in_pitch, int W, int H, const uint
                     const uint8_t *lut2_dev, uint8_t *out, size_t out_pitch, vsb_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * unsharp mask, resize, and the two resizes of the anisotropic
+ * Enhanced-EDT branch.
+ * ------------------------------------------------------------------------------------------- */
+/* cv2.addWeighted(img, 1+amount, blurred, -amount, 0) followed by the absdiff / THRESH_BINARY_INV select of
+ * apply_unsharp_mask (xy_blend_processor.py:58-67); `blurred` = vsb_gaussian_q88 of img with a k x k kernel.
+ * float32: saturate(rint(fma(img, alpha, blurred * beta))); threshold <= 0 keeps the sharpened value everywhere. */
+int vsb_unsharp_combine(const uint8_t *img, size_t pitch, const uint8_t *blurred, size_t bpitch, int W, int H,
+                        float amount, int threshold, uint8_t *out, size_t opitch, vsb_stream_t stream);
+
+/* cv2.resize(image, (width, height), interpolation=...) of apply_resize (xy_blend_processor.py:84-90).  A plan holds
+ * the coordinate / coefficient tables of one (source size, target size, interpolation) triple on the current
+ * device; it is immutable and may be shared by streams. */
+enum vsb_interp {
+    VSB_INTER_NEAREST = 0,   /* "NEAREST"  */
+    VSB_INTER_LINEAR = 1,    /* "BILINEAR": Q11 fixed point */
+    VSB_INTER_CUBIC = 2,     /* "BICUBIC":  OpenCV's own kernel (cv2 built with IPP differs by +-1 LSB) */
+    VSB_INTER_LANCZOS4 = 3,  /* "LANCZOS4" and the reference's fallback for unknown names */
+    VSB_INTER_AREA = 4,      /* "AREA": box sums / float area weights / 2-tap when enlarging */
+    VSB_INTER_LINEAR_F32 = 5 /* float32 INTER_LINEAR (distance map of processing_core.py:373) */
+};
+typedef struct vsb_resize_plan vsb_resize_plan;
+int vsb_resize_plan_create(int src_W, int src_H, int dst_W, int dst_H, int interp, vsb_resize_plan **out_plan);
+int vsb_resize_plan_destroy(vsb_resize_plan *plan);
+int vsb_resize_plan_dims(const vsb_resize_plan *plan, int *src_W, int *src_H, int *dst_W, int *dst_H);
+int vsb_resize_u8(const vsb_resize_plan *plan, const uint8_t *in, size_t in_pitch, uint8_t *out, size_t out_pitch,
+                  vsb_stream_t stream);
+/* cv2.resize(resized_dist_map, (W, H), INTER_LINEAR) on float32 (processing_core.py:373); pitches in elements */
+int vsb_resize_f32_linear(const vsb_resize_plan *plan, const float *in, size_t in_pitch_elems, float *out,
+                          size_t out_pitch_elems, vsb_stream_t stream);
+/* cv2.resize(distance_transform_src, (new_w, new_h), INTER_NEAREST) (processing_core.py:369) on the bit-packed mask */
+int vsb_resize_bits_nearest(const vsb_resize_plan *plan, const uint32_t *bits, int wpr, uint32_t *out_bits, int out_wpr,
+                            vsb_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Host-buffer entry points (the plugin path measured as `e2e`): pinned or pageable HOST arrays
  * in, HOST array out; device staging buffers are owned by an opaque stack context.
  *     replaces ProcessingPipelineThread._process_single_image_task + the producer loop
@@ -263,7 +300,7 @@ int vsb_layer_fused(const uint8_t *in, size_t in_pitch, int W, int H, const uint
 typedef struct vsb_stack vsb_stack;
 
 typedef struct {
-    int type;   /* 0 none, 1 lut, 2 gaussian, 3 bilateral, 4 median */
+    int type;   /* 0 none, 1 lut, 2 gaussian, 3 bilateral, 4 median, 5 unsharp mask (Gaussian taps in kx/ky), 6 resize */
     uint8_t lut[256];
     int32_t kx[63], ky[63];
     int nkx, nky;
@@ -272,11 +309,16 @@ typedef struct {
     float tap_sw[1024];
     float cw[256];
     int median_ksize;
+    float unsharp_amount;             /* type 5: apply_unsharp_mask, xy_blend_processor.py:48-67 */
+    int unsharp_threshold;
+    int resize_w, resize_h, interp;   /* type 6: resolved target size (apply_resize's rule, :71-82) and vsb_interp */
 } vsb_xy_op;
 
 int vsb_stack_create(int W, int H, int n_priors, const vsb_zparams *zp, const vsb_xy_op *ops,
                      int n_ops, vsb_stack **out_stack);
 int vsb_stack_destroy(vsb_stack *s);
+/* size of the layers the stack emits (differs from W x H when the XY chain holds a resize) */
+int vsb_stack_out_size(vsb_stack *s, int *out_W, int *out_H);
 /* forget the sliding window of prior masks (start of a new stack / Z-shard) */
 int vsb_stack_reset(vsb_stack *s);
 /* feed a halo layer: thresholded and pushed into the window, no output */

@@ -76,15 +76,11 @@ def test_anisotropic_enhanced(geom, slices):
                         if key not in geom.files:
                             continue
                         got = O.enhanced_fade(cur, pri, F, fl, "chamfer5", (xf, yf))
-                        ref = geom[key + "_noipp"]
-                        diff = np.abs(got.astype(int) - ref.astype(int))
-                        # float32 distances of the two-pass library transform differ from the closed-form chamfer
-                        # by a few 1e-5; after the bilinear resize that flips an occasional
-                        # truncation: one grey level on a tiny fraction of the pixels
-                        assert diff.max() <= 1, (key, int(diff.max()))
-                        assert (diff > 0).mean() < 2e-3, (key, float((diff > 0).mean()))
-                        d2 = np.abs(got.astype(int) - geom[key].astype(int))
-                        assert d2.max() <= 1, key
+                        # bit-exact against the reference as it runs by default (cv2 with IPP); the IPP-less
+                        # code path of cv2 differs from that by one grey level on ~1e-4 of the pixels
+                        assert np.array_equal(got, geom[key]), key
+                        d2 = np.abs(got.astype(int) - geom[key + "_noipp"].astype(int))
+                        assert d2.max() <= 1 and (d2 > 0).mean() < 2e-3, key
                         worst = max(worst, float((d2 > 0).mean()))
                         n += 1
     assert n >= 30

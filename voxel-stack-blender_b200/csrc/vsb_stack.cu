@@ -13,14 +13,23 @@
 #define STACK_SLOTS 3
 
 struct DevOp {
-    int type; // 1 lut, 2 gaussian, 3 bilateral, 4 median
+    int type; // 1 lut, 2 gaussian, 3 bilateral, 4 median, 5 unsharp mask, 6 resize
     uint8_t *lut_dev;
     vsb_xy_op op; // host copy of the parameters
+    int iw, ih, ow, oh;      // geometry before / after the op (only a resize changes it)
+    vsb_resize_plan *plan;   // type 6
 };
 
 struct vsb_stack {
     int W, H, wpr, n_priors;
-    size_t pitch; // device pitch of staging / temporaries (multiple of 128)
+    size_t pitch; // device pitch of the input staging slots (multiple of 128)
+    int oW, oH;   // size of the emitted layers (a resize in the XY chain changes it)
+    size_t opitch, tpitch; // pitch of the output slots / of the chain temporaries (widest intermediate)
+    size_t tsize;          // bytes of one chain temporary
+    uint8_t *tmp_blur;     // unsharp mask: the blurred image
+    // anisotropic Enhanced EDT (allocated on first use)
+    vsb_resize_plan *an_near, *an_lin;
+    uint32_t *an_bits; float *an_dist, *an_T; int an_wpr;
     vsb_zparams zp;
     std::vector<DevOp> ops;      // XY chain after LUT composition
     uint8_t *lead_lut_dev;       // leading apply_lut ops composed, or nullptr
@@ -56,7 +65,7 @@ struct vsb_stack {
 enum { ST_PACK = 0, ST_ZBLEND, ST_MASKDIFF, ST_ZDIST, ST_CCL, ST_EFADE, ST_PACKF, ST_LAYER, ST_OP0 };
 static const char *kStageNames[] = {"threshold_pack", "zblend_fused", "maskdiff", "zblend_dist", "ccl8_max", "enhanced_fade",
                                     "pack_flags", "layer_fused"};
-static const char *kOpNames[] = {"none", "lut_apply", "gaussian_q88", "bilateral", "median"};
+static const char *kOpNames[] = {"none", "lut_apply", "gaussian_q88", "bilateral", "median", "unsharp_mask", "resize"};
 
 struct ProfScope {
     vsb_stack *s; size_t idx; bool on;
@@ -83,7 +92,13 @@ extern "C" int vsb_stack_destroy(vsb_stack *s)
 {
     if (!s) return VSB_OK;
     cudaStreamSynchronize(s->s_h2d); cudaStreamSynchronize(s->s_comp); cudaStreamSynchronize(s->s_d2h);
-    for (auto &o : s->ops) if (o.lut_dev) cudaFree(o.lut_dev);
+    for (auto &o : s->ops) { if (o.lut_dev) cudaFree(o.lut_dev); if (o.plan) vsb_resize_plan_destroy(o.plan); }
+    if (s->tmp_blur) cudaFree(s->tmp_blur);
+    if (s->an_near) vsb_resize_plan_destroy(s->an_near);
+    if (s->an_lin) vsb_resize_plan_destroy(s->an_lin);
+    if (s->an_bits) cudaFree(s->an_bits);
+    if (s->an_dist) cudaFree(s->an_dist);
+    if (s->an_T) cudaFree(s->an_T);
     if (s->lead_lut_dev) cudaFree(s->lead_lut_dev);
     if (s->T_dev) cudaFree(s->T_dev);
     for (int i = 0; i < STACK_SLOTS; ++i) {
@@ -144,7 +159,9 @@ extern "C" int vsb_stack_create(int W, int H, int n_priors, const vsb_zparams *z
         s->ev_h2d[i] = s->ev_comp[i] = s->ev_d2h[i] = nullptr;
         s->slot_used[i] = false; s->gray_dev[i] = s->out_dev[i] = nullptr;
     }
-    s->tmp[0] = s->tmp[1] = nullptr;
+    s->tmp[0] = s->tmp[1] = nullptr; s->tmp_blur = nullptr;
+    s->an_near = s->an_lin = nullptr; s->an_bits = nullptr; s->an_dist = s->an_T = nullptr; s->an_wpr = 0;
+    s->oW = W; s->oH = H; s->opitch = s->tpitch = s->pitch; s->tsize = 0;
     s->head = 0; s->count = 0; s->submitted = 0;
     s->rec_bits = nullptr; s->dist = nullptr; s->labels = nullptr; s->cmax = nullptr;
     s->ub_g = s->ub_gmin = nullptr; s->ub_dist = nullptr; s->ub_mm = nullptr;
@@ -165,14 +182,34 @@ extern "C" int vsb_stack_create(int W, int H, int n_priors, const vsb_zparams *z
             } else if (!s->ops.empty() && s->ops.back().type == 1) {
                 compose(s->ops.back().op.lut, op.lut);
             } else {
-                DevOp d; d.type = 1; d.lut_dev = nullptr; d.op = op; s->ops.push_back(d);
+                DevOp d; d.type = 1; d.lut_dev = nullptr; d.plan = nullptr; d.op = op; s->ops.push_back(d);
             }
             continue;
         }
         leading = false;
         if (op.type == 4 && op.median_ksize <= 1) continue; // apply_median_blur no-op, xy_blend_processor.py:45
-        if (op.type < 1 || op.type > 4) { vsb_set_error("vsb_stack_create: unknown op type %d", op.type); delete s; return VSB_ERR_ARG; }
-        DevOp d; d.type = op.type; d.lut_dev = nullptr; d.op = op; s->ops.push_back(d);
+        if (op.type < 1 || op.type > 6) { vsb_set_error("vsb_stack_create: unknown op type %d", op.type); delete s; return VSB_ERR_ARG; }
+        DevOp d; d.type = op.type; d.lut_dev = nullptr; d.plan = nullptr; d.op = op; s->ops.push_back(d);
+    }
+    {   // geometry along the chain
+        int cw = W, ch = H;
+        size_t maxw = (size_t)W, maxh = (size_t)H;
+        bool bad = false;
+        for (auto &o : s->ops) {
+            o.iw = cw; o.ih = ch;
+            if (o.type == 6) {
+                if (o.op.resize_w <= 0 || o.op.resize_h <= 0 || o.op.interp < VSB_INTER_NEAREST || o.op.interp > VSB_INTER_AREA) { bad = true; break; }
+                cw = o.op.resize_w; ch = o.op.resize_h;
+            }
+            o.ow = cw; o.oh = ch;
+            if ((size_t)cw > maxw) maxw = (size_t)cw;
+            if ((size_t)ch > maxh) maxh = (size_t)ch;
+        }
+        if (bad) { vsb_set_error("vsb_stack_create: resize op needs a positive target size and a vsb_interp mode"); delete s; return VSB_ERR_ARG; }
+        s->oW = cw; s->oH = ch;
+        s->opitch = ((size_t)cw + 127) & ~(size_t)127;
+        s->tpitch = (maxw + 127) & ~(size_t)127;
+        s->tsize = s->tpitch * maxh;
     }
     {   // does the composed chain have the fusable shape [bilateral r<=4][gaussian k<=7][lut] ?
         size_t i = 0;
@@ -210,11 +247,15 @@ extern "C" int vsb_stack_create(int W, int H, int n_priors, const vsb_zparams *z
         STACK_CUDA(cudaEventCreateWithFlags(&s->ev_comp[i], cudaEventDisableTiming));
         STACK_CUDA(cudaEventCreateWithFlags(&s->ev_d2h[i], cudaEventDisableTiming));
         STACK_CUDA(cudaMalloc((void **)&s->gray_dev[i], s->pitch * H));
-        STACK_CUDA(cudaMalloc((void **)&s->out_dev[i], s->pitch * H));
+        STACK_CUDA(cudaMalloc((void **)&s->out_dev[i], s->opitch * s->oH));
     }
     if (!s->ops.empty()) {
-        STACK_CUDA(cudaMalloc((void **)&s->tmp[0], s->pitch * H));
-        if (s->ops.size() > 1) STACK_CUDA(cudaMalloc((void **)&s->tmp[1], s->pitch * H));
+        STACK_CUDA(cudaMalloc((void **)&s->tmp[0], s->tsize));
+        if (s->ops.size() > 1) STACK_CUDA(cudaMalloc((void **)&s->tmp[1], s->tsize));
+    }
+    for (auto &o : s->ops) {
+        if (o.type == 5 && !s->tmp_blur) STACK_CUDA(cudaMalloc((void **)&s->tmp_blur, s->tsize));
+        if (o.type == 6 && vsb_resize_plan_create(o.iw, o.ih, o.ow, o.oh, o.op.interp, &o.plan) != VSB_OK) { vsb_stack_destroy(s); return VSB_ERR_CUDA; }
     }
     if (have_lead) {
         STACK_CUDA(cudaMalloc((void **)&s->lead_lut_dev, 256));
@@ -252,6 +293,14 @@ extern "C" int vsb_stack_reset(vsb_stack *s)
 }
 
 extern "C" int vsb_stack_slots(vsb_stack *s) { return s ? STACK_SLOTS : 0; }
+
+extern "C" int vsb_stack_out_size(vsb_stack *s, int *out_W, int *out_H)
+{
+    VSB_REQUIRE(s, "vsb_stack_out_size: null stack");
+    if (out_W) *out_W = s->oW;
+    if (out_H) *out_H = s->oH;
+    return VSB_OK;
+}
 extern "C" vsb_stream_t vsb_stack_stream(vsb_stack *s) { return s ? (vsb_stream_t)s->s_comp : nullptr; }
 
 static int ensure_unbounded_scratch(vsb_stack *s)
@@ -273,6 +322,27 @@ static int ensure_enhanced_scratch(vsb_stack *s)
     VSB_CUDA(cudaMalloc((void **)&s->dist, n * sizeof(float)));
     VSB_CUDA(cudaMalloc((void **)&s->labels, n * sizeof(int32_t)));
     VSB_CUDA(cudaMalloc((void **)&s->cmax, n * sizeof(uint32_t)));
+    return VSB_OK;
+}
+
+static int ensure_aniso_scratch(vsb_stack *s, const vsb_zparams &zp)
+{
+    if (s->an_near) return VSB_OK;
+    const int aw = zp.aniso_w, ah = zp.aniso_h;
+    VSB_REQUIRE(aw > 0 && ah > 0 && zp.aniso_reach >= 0 && zp.aniso_reach <= VSB_FAST_REACH,
+                "anisotropic Enhanced EDT: resized mask %dx%d / reach %d not supported", aw, ah, zp.aniso_reach);
+    int rc = vsb_resize_plan_create(s->W, s->H, aw, ah, VSB_INTER_NEAREST, &s->an_near);
+    if (rc) return rc;
+    rc = vsb_resize_plan_create(aw, ah, s->W, s->H, VSB_INTER_LINEAR_F32, &s->an_lin);
+    if (rc) return rc;
+    s->an_wpr = ((aw + 127) / 128) * 4;
+    VSB_CUDA(cudaMalloc((void **)&s->an_bits, (size_t)s->an_wpr * ah * sizeof(uint32_t)));
+    VSB_CUDA(cudaMalloc((void **)&s->an_dist, (size_t)aw * ah * sizeof(float)));
+    const int n1 = zp.aniso_reach + 1;
+    std::vector<float> T((size_t)n1 * n1);
+    vsb_chamfer_table(T.data(), zp.aniso_reach);
+    VSB_CUDA(cudaMalloc((void **)&s->an_T, T.size() * sizeof(float)));
+    VSB_CUDA(cudaMemcpy(s->an_T, T.data(), T.size() * sizeof(float), cudaMemcpyHostToDevice));
     return VSB_OK;
 }
 
@@ -321,7 +391,7 @@ static int run_layer(vsb_stack *s, const uint8_t *gray, size_t gpitch, uint8_t *
         }
         const size_t nops = s->ops.size();
         uint8_t *zdst = nops ? s->tmp[0] : out;
-        const size_t zpitch = nops ? s->pitch : opitch;
+        const size_t zpitch = nops ? s->tpitch : opitch;
         if (far_mode) {
             rc = ensure_unbounded_scratch(s);
             if (rc) return rc;
@@ -335,10 +405,24 @@ static int run_layer(vsb_stack *s, const uint8_t *gray, size_t gpitch, uint8_t *
             if (rc) return rc;
             { ProfScope ps(s, ST_MASKDIFF, 1); rc = vsb_maskdiff(cur, pri, np, s->wpr, s->H, s->rec_bits, nullptr, st); }
             if (rc) return rc;
-            vsb_zparams zd = zp; zd.mode = VSB_Z_DIST;
-            { ProfScope ps(s, ST_ZDIST, 1);
-              rc = vsb_zblend_fused(nullptr, 0, s->W, s->H, cur, pri, s->wpr, &zd, s->T_dev, nullptr, nullptr, 0, s->dist,
-                                    (size_t)s->W, st); }
+            if (zp.aniso_w > 0) {
+                // processing_core.py:357-377: nearest-resize the mask, transform there, bilinear-resize the map back.
+                // Distances stay in resized-pixel units; pixels farther than the reach get a stand-in >= fade_limit,
+                // which fades to 0 exactly like the true distance (bilinear taps are adjacent pixels, reach covers +3)
+                rc = ensure_aniso_scratch(s, zp);
+                if (rc) return rc;
+                ProfScope ps(s, ST_ZDIST, 3);
+                const float far = (float)((zp.fade_limit > 0.0 ? zp.fade_limit : 0.0) + 4.0);
+                rc = vsb_resize_bits_nearest(s->an_near, cur, s->wpr, s->an_bits, s->an_wpr, st);
+                if (!rc) rc = vsb_dt_chamfer5(s->an_bits, s->an_wpr, zp.aniso_w, zp.aniso_h, zp.aniso_reach, s->an_T, far, s->an_dist,
+                                              (size_t)zp.aniso_w, st);
+                if (!rc) rc = vsb_resize_f32_linear(s->an_lin, s->an_dist, (size_t)zp.aniso_w, s->dist, (size_t)s->W, st);
+            } else {
+                vsb_zparams zd = zp; zd.mode = VSB_Z_DIST;
+                ProfScope ps(s, ST_ZDIST, 1);
+                rc = vsb_zblend_fused(nullptr, 0, s->W, s->H, cur, pri, s->wpr, &zd, s->T_dev, nullptr, nullptr, 0, s->dist,
+                                      (size_t)s->W, st);
+            }
             if (rc) return rc;
             { ProfScope ps(s, ST_CCL, 3); rc = vsb_ccl8_max(s->rec_bits, s->wpr, s->W, s->H, s->dist, (size_t)s->W, s->labels, s->cmax, st); }
             if (rc) return rc;
@@ -367,15 +451,21 @@ static int run_layer(vsb_stack *s, const uint8_t *gray, size_t gpitch, uint8_t *
         for (size_t i = 0; i < nops; ++i) {
             const bool last = (i + 1 == nops);
             uint8_t *dst = last ? out : s->tmp[(i + 1) & 1];
-            const size_t dpitch = last ? opitch : s->pitch;
+            const size_t dpitch = last ? opitch : s->tpitch;
             const DevOp &o = s->ops[i];
-            ProfScope ps(s, ST_OP0 + (int)i, 1);
+            ProfScope ps(s, ST_OP0 + (int)i, o.type == 5 ? 3 : 1);
             switch (o.type) {
-            case 1: rc = vsb_lut_apply(src, spitch, s->W, s->H, o.lut_dev, dst, dpitch, st); break;
-            case 2: rc = vsb_gaussian_q88(src, spitch, s->W, s->H, o.op.kx, o.op.nkx, o.op.ky, o.op.nky, dst, dpitch, st); break;
-            case 3: rc = vsb_bilateral(src, spitch, s->W, s->H, o.op.radius, o.op.ntaps, o.op.tap_dy, o.op.tap_dx,
+            case 1: rc = vsb_lut_apply(src, spitch, o.iw, o.ih, o.lut_dev, dst, dpitch, st); break;
+            case 2: rc = vsb_gaussian_q88(src, spitch, o.iw, o.ih, o.op.kx, o.op.nkx, o.op.ky, o.op.nky, dst, dpitch, st); break;
+            case 3: rc = vsb_bilateral(src, spitch, o.iw, o.ih, o.op.radius, o.op.ntaps, o.op.tap_dy, o.op.tap_dx,
                                        o.op.tap_sw, o.op.cw, dst, dpitch, st); break;
-            case 4: rc = vsb_median(src, spitch, s->W, s->H, o.op.median_ksize, dst, dpitch, st); break;
+            case 4: rc = vsb_median(src, spitch, o.iw, o.ih, o.op.median_ksize, dst, dpitch, st); break;
+            case 5:
+                rc = vsb_gaussian_q88(src, spitch, o.iw, o.ih, o.op.kx, o.op.nkx, o.op.ky, o.op.nky, s->tmp_blur, s->tpitch, st);
+                if (!rc) rc = vsb_unsharp_combine(src, spitch, s->tmp_blur, s->tpitch, o.iw, o.ih, o.op.unsharp_amount,
+                                                  o.op.unsharp_threshold, dst, dpitch, st);
+                break;
+            case 6: rc = vsb_resize_u8(o.plan, src, spitch, dst, dpitch, st); break;
             default: rc = VSB_ERR_ARG;
             }
             if (rc) return rc;
@@ -424,12 +514,12 @@ static int submit(vsb_stack *s, const uint8_t *gray_host, size_t in_pitch, uint8
                                cudaMemcpyHostToDevice, s->s_h2d));
     VSB_CUDA(cudaEventRecord(s->ev_h2d[slot], s->s_h2d));
     VSB_CUDA(cudaStreamWaitEvent(s->s_comp, s->ev_h2d[slot], 0));
-    int rc = run_layer(s, s->gray_dev[slot], s->pitch, s->out_dev[slot], s->pitch, emit);
+    int rc = run_layer(s, s->gray_dev[slot], s->pitch, s->out_dev[slot], s->opitch, emit);
     if (rc) return rc;
     VSB_CUDA(cudaEventRecord(s->ev_comp[slot], s->s_comp));
     VSB_CUDA(cudaStreamWaitEvent(s->s_d2h, s->ev_comp[slot], 0));
     if (emit)
-        VSB_CUDA(cudaMemcpy2DAsync(out_host, out_pitch, s->out_dev[slot], s->pitch, (size_t)s->W, (size_t)s->H,
+        VSB_CUDA(cudaMemcpy2DAsync(out_host, out_pitch, s->out_dev[slot], s->opitch, (size_t)s->oW, (size_t)s->oH,
                                    cudaMemcpyDeviceToHost, s->s_d2h));
     VSB_CUDA(cudaEventRecord(s->ev_d2h[slot], s->s_d2h));
     s->slot_used[slot] = true;
@@ -441,7 +531,7 @@ extern "C" int vsb_stack_submit_host(vsb_stack *s, const uint8_t *gray_host, siz
                                      size_t out_pitch)
 {
     VSB_REQUIRE(s && gray_host && out_host, "vsb_stack_submit_host: null pointer");
-    VSB_REQUIRE(in_pitch >= (size_t)s->W && out_pitch >= (size_t)s->W, "vsb_stack_submit_host: pitch < width");
+    VSB_REQUIRE(in_pitch >= (size_t)s->W && out_pitch >= (size_t)s->oW, "vsb_stack_submit_host: pitch < width");
     return submit(s, gray_host, in_pitch, out_host, out_pitch, true);
 }
 

@@ -105,10 +105,11 @@ def _calculate_receding_gradient_field_enhanced_edt_numba(receding_distance_map,
 
 
 def _calculate_receding_gradient_field_enhanced_edt(current_white_mask, prior_binary_masks, config, debug_info=None):
-    """reference :338-404 (isotropic; the anisotropic resize round trip :357-377 is SURVEY 8f rank 2)."""
+    """reference :338-404, including the anisotropic resize round trip of the distance map (:357-377)."""
     if not prior_binary_masks:
         return _zeros_like(current_white_mask)
-    z = P.zparams_from_config(_as_mode(config, ProcessingMode.ENHANCED_EDT), getattr(config, "distance_metric", "chamfer5"))
+    z = P.zparams_from_config(_as_mode(config, ProcessingMode.ENHANCED_EDT), getattr(config, "distance_metric", "chamfer5"),
+                              current_white_mask.shape[1], current_white_mask.shape[0])
     cur = _bits(current_white_mask)
     priors = [_bits(m) for m in prior_binary_masks]
     if len(priors) > N.VSB_MAX_PRIORS:

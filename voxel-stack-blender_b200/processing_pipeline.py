@@ -133,7 +133,7 @@ class ProcessingPipelineThread(QThread):
     # ---- the device-backed stack loop -------------------------------------------------------------------------
     def _make_engine(self, H, W):
         cfg = self.app_config
-        ops = P.xy_ops_from_pipeline(cfg.xy_blend_pipeline, lambda op: lut_manager.lut_from_params(op.lut_params))
+        ops = P.xy_ops_from_pipeline(cfg.xy_blend_pipeline, lambda op: lut_manager.lut_from_params(op.lut_params), W, H)
         return E.StackEngine(W, H, cfg, ops, metric=getattr(cfg, "distance_metric", "chamfer5"))
 
     def _blend_stack(self, input_path, filenames, output_path):
@@ -172,7 +172,7 @@ class ProcessingPipelineThread(QThread):
         def retire(encoder):
             ticket, buf, path = inflight.popleft()
             engine.wait(ticket)
-            encode_jobs.add(encoder.submit(encode, buf, path, engine.W))
+            encode_jobs.add(encoder.submit(encode, buf, path, engine.out_W))
 
         with concurrent.futures.ThreadPoolExecutor(workers) as decoder, \
                 concurrent.futures.ThreadPoolExecutor(workers) as encoder:
@@ -210,7 +210,7 @@ class ProcessingPipelineThread(QThread):
                     engine = self._make_engine(H, W)
                     for _ in range(engine.slots + workers):
                         pin_in = torch.empty((H, engine.pitch), dtype=torch.uint8, pin_memory=True)
-                        pin_out = torch.empty((H, engine.pitch), dtype=torch.uint8, pin_memory=True)
+                        pin_out = torch.empty((engine.out_H, E.pitch_for(engine.out_W)), dtype=torch.uint8, pin_memory=True)
                         free_bufs.put((pin_in.numpy(), pin_out.numpy(), pin_in, pin_out))
                 if gray.shape != (engine.H, engine.W):
                     raise ValueError(f"{name}: layer size {gray.shape[::-1]} differs from the stack's "
@@ -218,7 +218,7 @@ class ProcessingPipelineThread(QThread):
                 finish_encodes()
                 buf = free_bufs.get()
                 np.copyto(buf[0][:, : engine.W], gray)
-                ticket = engine.submit(buf[2].data_ptr(), engine.pitch, buf[3].data_ptr(), engine.pitch)
+                ticket = engine.submit(buf[2].data_ptr(), engine.pitch, buf[3].data_ptr(), E.pitch_for(engine.out_W))
                 inflight.append((ticket, buf, os.path.join(output_path, name)))
                 while len(inflight) >= engine.slots:
                     retire(encoder)

@@ -211,11 +211,26 @@ def enhanced(gray: Optional[DevImage], cur: DevBits, priors: Sequence[DevBits], 
     dist = t.empty((H, W), dtype=t.float32, device="cuda")
     labels = t.empty((H, W), dtype=t.int32, device="cuda")
     cmax = t.empty((H, W), dtype=t.int32, device="cuda")
-    zd = N.ZParams.from_buffer_copy(z)
-    zd.mode, zd.n_priors = N.Z_DIST, len(priors)
-    T = table_dev(zd.reach)
-    N.check(lib.vsb_zblend_fused(None, 0, W, H, cur.ptr, pri, cur.wpr, ctypes.byref(zd), T.data_ptr(), None, None, 0,
-                                 dist.data_ptr(), W, _stream()), "vsb_zblend_fused(dist)")
+    if z.aniso_w > 0:
+        # anisotropic branch (processing_core.py:357-377): nearest-resize the mask, transform there, resize back
+        aw, ah = int(z.aniso_w), int(z.aniso_h)
+        near = ResizePlan(W, H, aw, ah, N.INTER_NEAREST)
+        lin = ResizePlan(aw, ah, W, H, N.INTER_LINEAR_F32)
+        small = DevBits(ah, aw)
+        N.check(lib.vsb_resize_bits_nearest(near.h, cur.ptr, cur.wpr, small.ptr, small.wpr, _stream()), "vsb_resize_bits_nearest")
+        sd = t.empty((ah, aw), dtype=t.float32, device="cuda")
+        far = float(max(float(z.fade_limit), 0.0) + 4.0)
+        N.check(lib.vsb_dt_chamfer5(small.ptr, small.wpr, aw, ah, int(z.aniso_reach), table_dev(int(z.aniso_reach)).data_ptr(),
+                                    far, sd.data_ptr(), aw, _stream()), "vsb_dt_chamfer5")
+        N.check(lib.vsb_resize_f32_linear(lin.h, sd.data_ptr(), aw, dist.data_ptr(), W, _stream()), "vsb_resize_f32_linear")
+        t.cuda.current_stream().synchronize()
+        near.close(); lin.close()
+    else:
+        zd = N.ZParams.from_buffer_copy(z)
+        zd.mode, zd.n_priors = N.Z_DIST, len(priors)
+        T = table_dev(zd.reach)
+        N.check(lib.vsb_zblend_fused(None, 0, W, H, cur.ptr, pri, cur.wpr, ctypes.byref(zd), T.data_ptr(), None, None, 0,
+                                     dist.data_ptr(), W, _stream()), "vsb_zblend_fused(dist)")
     N.check(lib.vsb_ccl8_max(rec.ptr, rec.wpr, W, H, dist.data_ptr(), W, labels.data_ptr(), cmax.data_ptr(), _stream()),
             "vsb_ccl8_max")
     ld = lut_dev(lut) if lut is not None else None
@@ -309,6 +324,60 @@ def median(img: DevImage, ksize: int) -> DevImage:
     return o
 
 
+class ResizePlan:
+    """Device tables of one cv2.resize geometry (csrc/vsb_geom.cu)."""
+
+    def __init__(self, sw: int, sh: int, dw: int, dh: int, interp: int):
+        h = c_void_p()
+        N.check(N.load().vsb_resize_plan_create(int(sw), int(sh), int(dw), int(dh), int(interp), ctypes.byref(h)),
+                "vsb_resize_plan_create")
+        self.h, self.dw, self.dh = h, int(dw), int(dh)
+
+    def close(self):
+        if getattr(self, "h", None):
+            N.load().vsb_resize_plan_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def unsharp(img: DevImage, amount: float, threshold: int, ksize: int, sigma: float) -> DevImage:
+    """apply_unsharp_mask (xy_blend_processor.py:48-67): Gaussian, addWeighted, optional threshold select."""
+    q = P.gaussian_taps_q88(P.odd_ksize(int(ksize)), float(sigma))
+    blurred = gaussian(img, q, q)
+    o = DevImage(img.H, img.W)
+    N.check(N.load().vsb_unsharp_combine(img.ptr, img.pitch, blurred.ptr, blurred.pitch, img.W, img.H, float(amount),
+                                         int(threshold), o.ptr, o.pitch, _stream()), "vsb_unsharp_combine")
+    return o
+
+
+def resize(img: DevImage, dw: int, dh: int, interp: int) -> DevImage:
+    """cv2.resize(image, (dw, dh), interpolation) on uint8 (xy_blend_processor.py:90)."""
+    plan = ResizePlan(img.W, img.H, dw, dh, interp)
+    o = DevImage(int(dh), int(dw))
+    N.check(N.load().vsb_resize_u8(plan.h, img.ptr, img.pitch, o.ptr, o.pitch, _stream()), "vsb_resize_u8")
+    torch().cuda.current_stream().synchronize()
+    plan.close()
+    return o
+
+
+def resize_f32_linear_np(a: np.ndarray, dw: int, dh: int) -> np.ndarray:
+    t = torch()
+    a = np.ascontiguousarray(a, np.float32)
+    sh, sw = a.shape
+    plan = ResizePlan(sw, sh, dw, dh, N.INTER_LINEAR_F32)
+    d = t.from_numpy(a).cuda()
+    o = t.empty((dh, dw), dtype=t.float32, device="cuda")
+    N.check(N.load().vsb_resize_f32_linear(plan.h, d.data_ptr(), sw, o.data_ptr(), dw, _stream()), "vsb_resize_f32_linear")
+    r = o.cpu().numpy()
+    plan.close()
+    return r
+
+
 # ---- synthetic stacks (measurement utility) -----------------------------------------------------------------
 def synth_layer(prims_dev, n_prims: int, raft: Optional[np.ndarray], z: int, W: int, H: int, out_ptr: int, pitch: int):
     r = np.ascontiguousarray(raft, np.float32) if raft is not None else None
@@ -330,7 +399,7 @@ class StackEngine:
         self.device = t.cuda.current_device()
         self.W, self.H = int(W), int(H)
         self.pitch = pitch_for(W)
-        z = P.zparams_from_config(cfg, metric)
+        z = P.zparams_from_config(cfg, metric, self.W, self.H)
         n_priors = max(0, int(cfg.receding_layers))
         if n_priors > N.VSB_MAX_PRIORS:
             raise P.UnsupportedOnDevice(f"more than {N.VSB_MAX_PRIORS} receding layers")
@@ -343,6 +412,9 @@ class StackEngine:
                 "vsb_stack_create")
         self._h = h
         self.slots = N.load().vsb_stack_slots(h)
+        ow, oh = ctypes.c_int(), ctypes.c_int()
+        N.check(N.load().vsb_stack_out_size(h, ctypes.byref(ow), ctypes.byref(oh)), "vsb_stack_out_size")
+        self.out_W, self.out_H = ow.value, oh.value   # differs from (W, H) when the XY chain holds a resize
 
     def close(self):
         if getattr(self, "_h", None):
@@ -366,7 +438,7 @@ class StackEngine:
         gray = np.ascontiguousarray(gray, np.uint8)
         if gray.shape != (self.H, self.W):
             raise ValueError(f"layer shape {gray.shape} != engine shape {(self.H, self.W)}")
-        out = np.empty_like(gray)
+        out = np.empty((self.out_H, self.out_W), np.uint8)
         N.check(N.load().vsb_stack_process_host(self._h, gray.ctypes.data_as(c_void_p), gray.strides[0],
                                                 out.ctypes.data_as(c_void_p), out.strides[0]), "vsb_stack_process_host")
         return out

@@ -23,7 +23,10 @@ VSB_FAST_REACH = 63
 
 Z_FIXED, Z_WEIGHTED, Z_CONST, Z_DIST, Z_ENHANCED, Z_NONE, Z_MINMAX, Z_FIXED_FAR = 0, 1, 2, 3, 4, 5, 6, 7
 METRIC_CHAMFER5, METRIC_EXACT = 0, 1
-OP_NONE, OP_LUT, OP_GAUSSIAN, OP_BILATERAL, OP_MEDIAN = 0, 1, 2, 3, 4
+OP_NONE, OP_LUT, OP_GAUSSIAN, OP_BILATERAL, OP_MEDIAN, OP_UNSHARP, OP_RESIZE = 0, 1, 2, 3, 4, 5, 6
+INTER_NEAREST, INTER_LINEAR, INTER_CUBIC, INTER_LANCZOS4, INTER_AREA, INTER_LINEAR_F32 = 0, 1, 2, 3, 4, 5
+INTERP_BY_NAME = {"NEAREST": INTER_NEAREST, "BILINEAR": INTER_LINEAR, "BICUBIC": INTER_CUBIC, "LANCZOS4": INTER_LANCZOS4,
+                  "AREA": INTER_AREA}   # xy_blend_processor.py:84-88; unknown names fall back to LANCZOS4 (:89)
 
 
 class VsbError(RuntimeError):
@@ -34,14 +37,16 @@ class ZParams(ctypes.Structure):
     _fields_ = [("mode", c_int), ("metric", c_int), ("n_priors", c_int), ("reach", c_int), ("const_val", c_int),
                 ("fade", c_float), ("den", c_float), ("total_weight", c_float),
                 ("weights", c_float * VSB_MAX_PRIORS), ("fades", c_float * VSB_MAX_PRIORS),
-                ("dens", c_float * VSB_MAX_PRIORS), ("enhanced_arith", c_int), ("fade_limit", c_double)]
+                ("dens", c_float * VSB_MAX_PRIORS), ("enhanced_arith", c_int), ("fade_limit", c_double),
+                ("aniso_w", c_int), ("aniso_h", c_int), ("aniso_reach", c_int)]
 
 
 class XYOp(ctypes.Structure):
     _fields_ = [("type", c_int), ("lut", c_uint8 * 256), ("kx", c_int32 * 63), ("ky", c_int32 * 63),
                 ("nkx", c_int), ("nky", c_int), ("radius", c_int), ("ntaps", c_int),
                 ("tap_dy", c_int8 * 1024), ("tap_dx", c_int8 * 1024), ("tap_sw", c_float * 1024),
-                ("cw", c_float * 256), ("median_ksize", c_int)]
+                ("cw", c_float * 256), ("median_ksize", c_int), ("unsharp_amount", c_float), ("unsharp_threshold", c_int),
+                ("resize_w", c_int), ("resize_h", c_int), ("interp", c_int)]
 
 
 class XYFused(ctypes.Structure):
@@ -90,6 +95,15 @@ _SIGS = {
                                 c_int, POINTER(ZParams), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "vsb_stack_create": (c_int, [c_int, c_int, c_int, POINTER(ZParams), POINTER(XYOp), c_int, POINTER(c_void_p)]),
     "vsb_stack_destroy": (c_int, [c_void_p]),
+    "vsb_stack_out_size": (c_int, [c_void_p, POINTER(c_int), POINTER(c_int)]),
+    "vsb_unsharp_combine": (c_int, [c_void_p, c_size_t, c_void_p, c_size_t, c_int, c_int, c_float, c_int, c_void_p, c_size_t,
+                                    c_void_p]),
+    "vsb_resize_plan_create": (c_int, [c_int, c_int, c_int, c_int, c_int, POINTER(c_void_p)]),
+    "vsb_resize_plan_destroy": (c_int, [c_void_p]),
+    "vsb_resize_plan_dims": (c_int, [c_void_p, POINTER(c_int), POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
+    "vsb_resize_u8": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_void_p]),
+    "vsb_resize_f32_linear": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_void_p]),
+    "vsb_resize_bits_nearest": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p]),
     "vsb_stack_reset": (c_int, [c_void_p]),
     "vsb_stack_push_halo": (c_int, [c_void_p, c_void_p, c_size_t]),
     "vsb_stack_process_host": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_size_t]),

@@ -9,7 +9,7 @@ Numerics that must match third-party code bit for bit use the same C library rou
 from __future__ import annotations
 
 import math
-from typing import List, Sequence
+from typing import Optional, List, Sequence
 
 import numpy as np
 
@@ -32,9 +32,19 @@ def chamfer_reach(F: float) -> int:
     return max(0, int(math.ceil(F)) - 1)
 
 
-def zparams_from_config(cfg, metric: str = "chamfer5") -> N.ZParams:
+def anisotropic_dims(width: int, height: int, x_factor: float, y_factor: float):
+    """Size of the resized mask of the anisotropic branch (processing_core.py:360-367); None = factors clamp to 1."""
+    xf = max(0.1, min(10.0, x_factor))
+    yf = max(0.1, min(10.0, y_factor))
+    if xf == 1.0 and yf == 1.0:
+        return None
+    return int(width * xf), int(height * yf)
+
+
+def zparams_from_config(cfg, metric: str = "chamfer5", width: Optional[int] = None, height: Optional[int] = None) -> N.ZParams:
     """Fade parameters as the reference derives them from Config (processing_core.py:112-113,
-    :138-140, :227-257, :387).  Raises UnsupportedOnDevice for the section-8(f) configurations."""
+    :138-140, :227-257, :387).  `width`/`height` (the layer size) are needed by the anisotropic Enhanced EDT only.
+    Raises UnsupportedOnDevice for the section-8(f) configurations that are not on the device yet."""
     z = N.ZParams()
     z.metric = N.METRIC_EXACT if metric == "exact" else N.METRIC_CHAMFER5
     mode = _mode_name(cfg)
@@ -66,8 +76,18 @@ def zparams_from_config(cfg, metric: str = "chamfer5") -> N.ZParams:
     elif mode == "enhanced_edt":
         if getattr(getattr(cfg, "anisotropic_params", None), "enabled", False):
             ap = cfg.anisotropic_params
-            if max(0.1, min(10.0, ap.x_factor)) != 1.0 or max(0.1, min(10.0, ap.y_factor)) != 1.0:
-                raise UnsupportedOnDevice("anisotropic correction (resize round trip) is SURVEY.md 8f rank 2")
+            if anisotropic_dims(1000, 1000, ap.x_factor, ap.y_factor) is not None:
+                if width is None or height is None:
+                    raise ValueError("anisotropic Enhanced EDT: zparams_from_config needs the layer width and height")
+                if metric != "chamfer5":
+                    raise UnsupportedOnDevice("anisotropic correction with the exact metric")
+                z.aniso_w, z.aniso_h = anisotropic_dims(width, height, ap.x_factor, ap.y_factor)
+                if z.aniso_w < 1 or z.aniso_h < 1:
+                    raise ValueError("anisotropic Enhanced EDT: the resized mask would be empty")   # cv2.resize raises too
+                z.aniso_reach = chamfer_reach(max(F, 0.0) + 3.0)   # bilinear taps of a pixel with d < F lie within +3
+                if z.aniso_reach > N.VSB_FAST_REACH:
+                    raise UnsupportedOnDevice(f"anisotropic Enhanced EDT with fade distance {F} (reach {z.aniso_reach} > "
+                                              f"{N.VSB_FAST_REACH})")
         z.mode = N.Z_ENHANCED
         z.n_priors = N.VSB_MAX_PRIORS
         z.fade = f32(F)
@@ -167,10 +187,26 @@ def odd_ksize(k: int) -> int:
     return k if k % 2 else k + 1
 
 
-def xy_ops_from_pipeline(pipeline_ops: Sequence, lut_for_op) -> List[N.XYOp]:
+def resize_dims(cur_w: int, cur_h: int, width, height):
+    """Target size rule of apply_resize (xy_blend_processor.py:71-82); None = the op returns its input."""
+    if width is None and height is None:
+        return None
+    if width is None:
+        width = int(cur_w * (height / cur_h))
+    elif height is None:
+        height = int(cur_h * (width / cur_w))
+    if width == cur_w and height == cur_h:
+        return None
+    return int(width), int(height)
+
+
+def xy_ops_from_pipeline(pipeline_ops: Sequence, lut_for_op, width: Optional[int] = None,
+                         height: Optional[int] = None) -> List[N.XYOp]:
     """XYBlendOperation list -> device op descriptors.  `lut_for_op(op)` returns the uint8[256] table of an
-    apply_lut op (identity on any failure, xy_blend_processor.py:125-130)."""
+    apply_lut op (identity on any failure, xy_blend_processor.py:125-130).  `width`/`height` = size of the layers
+    entering the chain; only a resize op needs them (its target size may depend on the current size)."""
     out: List[N.XYOp] = []
+    cur_w, cur_h = width, height
     for op in pipeline_ops or []:
         t = str(getattr(op, "type", "none")).lower()
         x = N.XYOp()
@@ -204,8 +240,31 @@ def xy_ops_from_pipeline(pipeline_ops: Sequence, lut_for_op) -> List[N.XYOp]:
         elif t == "median_blur":
             x.type = N.OP_MEDIAN
             x.median_ksize = odd_ksize(int(op.median_ksize))
-        elif t in ("unsharp_mask", "resize"):
-            raise UnsupportedOnDevice(f"XY op '{t}' is SURVEY.md 8f rank 2, not on the B200 path yet")
+        elif t == "unsharp_mask":
+            x.type = N.OP_UNSHARP
+            k = odd_ksize(int(op.unsharp_blur_ksize))
+            if k > 63:
+                raise UnsupportedOnDevice("Gaussian kernels wider than 63 taps")
+            q = gaussian_taps_q88(k, float(op.unsharp_blur_sigma))
+            x.nkx = x.nky = k
+            ctypes_copy(x.kx, q)
+            ctypes_copy(x.ky, q)
+            x.unsharp_amount = float(op.unsharp_amount)
+            x.unsharp_threshold = int(op.unsharp_threshold)
+        elif t == "resize":
+            if op.resize_width is None and op.resize_height is None:
+                continue
+            if cur_w is None or cur_h is None:
+                raise ValueError("a resize op needs the layer size: pass width= and height= to xy_ops_from_pipeline")
+            dims = resize_dims(cur_w, cur_h, op.resize_width, op.resize_height)
+            if dims is None:
+                continue
+            if dims[0] < 1 or dims[1] < 1:
+                raise ValueError(f"resize to {dims[0]}x{dims[1]}")   # cv2.resize raises on an empty target as well
+            x.type = N.OP_RESIZE
+            x.resize_w, x.resize_h = dims
+            x.interp = N.INTERP_BY_NAME.get(str(op.resample_mode).upper(), N.INTER_LANCZOS4)
+            cur_w, cur_h = dims
         elif t == "none":
             continue
         else:

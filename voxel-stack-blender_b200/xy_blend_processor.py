@@ -3,7 +3,6 @@ xy_blend_processor -- the reference's per-layer 2-D operation chain (xy_blend_pr
 device: same function names, `XYBlendOperation` semantics and printed warnings.  Each apply_* takes and
 returns numpy uint8 [H, W]; process_xy_pipeline keeps the intermediate images on the device and composes
 consecutive apply_lut operations into one table (final = cur[final], pyside_xy_blend_tab.py:314-321).
-unsharp_mask / resize are SURVEY.md 8f rank 2 and raise UnsupportedOnDevice.
 """
 from __future__ import annotations
 
@@ -43,14 +42,32 @@ def apply_median_blur(image: np.ndarray, op: XYBlendOperation) -> np.ndarray:
     return E.median(E.DevImage.from_numpy(image), P.odd_ksize(int(op.median_ksize))).numpy()
 
 
+def _unsharp_dev(img: E.DevImage, op) -> E.DevImage:
+    return E.unsharp(img, float(op.unsharp_amount), int(op.unsharp_threshold), int(op.unsharp_blur_ksize),
+                     float(op.unsharp_blur_sigma))
+
+
 def apply_unsharp_mask(image: np.ndarray, op: XYBlendOperation) -> np.ndarray:
-    raise P.UnsupportedOnDevice("unsharp_mask is SURVEY.md 8f rank 2, not on the B200 path yet")
+    """GaussianBlur + addWeighted + absdiff/threshold select, reference :48-67"""
+    return _unsharp_dev(E.DevImage.from_numpy(image), op).numpy()
+
+
+def _resize_dev(img: E.DevImage, op):
+    """None when the op leaves the image alone (reference :73, :82)."""
+    dims = P.resize_dims(img.W, img.H, op.resize_width, op.resize_height)
+    if dims is None:
+        return None
+    if dims[0] < 1 or dims[1] < 1:
+        raise ValueError(f"resize to {dims[0]}x{dims[1]}")
+    return E.resize(img, dims[0], dims[1], E.N.INTERP_BY_NAME.get(str(op.resample_mode).upper(), E.N.INTER_LANCZOS4))
 
 
 def apply_resize(image: np.ndarray, op: XYBlendOperation) -> np.ndarray:
-    if op.resize_width is None and op.resize_height is None:
+    """cv2.resize with the reference's size rule and mode table; returns the input object itself when there is
+    nothing to do, reference :69-90"""
+    if P.resize_dims(image.shape[1], image.shape[0], op.resize_width, op.resize_height) is None:
         return image
-    raise P.UnsupportedOnDevice("resize is SURVEY.md 8f rank 2, not on the B200 path yet")
+    return _resize_dev(E.DevImage.from_numpy(image), op).numpy()
 
 
 def _lut_for(op) -> np.ndarray:
@@ -91,10 +108,11 @@ def process_xy_pipeline(image: np.ndarray, pipeline_ops: List[XYBlendOperation])
         elif t == "median_blur":
             if op.median_ksize > 1:
                 dev = E.median(flush(dev), P.odd_ksize(int(op.median_ksize))); touched = True
-        elif t in ("unsharp_mask", "resize"):
-            if t == "resize" and op.resize_width is None and op.resize_height is None:
-                continue
-            raise P.UnsupportedOnDevice(f"XY op '{t}' is SURVEY.md 8f rank 2, not on the B200 path yet")
+        elif t == "unsharp_mask":
+            dev = _unsharp_dev(flush(dev), op); touched = True
+        elif t == "resize":
+            if P.resize_dims(dev.W, dev.H, op.resize_width, op.resize_height) is not None:
+                dev = _resize_dev(flush(dev), op); touched = True
         elif t != "none":
             print(f"Warning: Unknown XY blend operation type '{t}'. Skipping.")
     if not touched:
