@@ -292,6 +292,36 @@ int vsb_resize_bits_nearest(const vsb_resize_plan *plan, const uint32_t *bits, i
                             vsb_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * ROI_FADE.
+ * ------------------------------------------------------------------------------------------- */
+/* cv2.connectedComponentsWithStats(binary_image, 8, CV_32S) of identify_rois (processing_core.py:69-105) on the
+ * bit-packed mask.  labels: int32 [H*W] scratch (root pixel index at foreground pixels); cid: int32 [H*W], on return
+ * component id + 1 at foreground pixels and 0 elsewhere (ids are compact, in no particular order); stats_dev[id] /
+ * *count_dev: per-component statistics and the number of components (may exceed max_components: rerun with a larger
+ * table).  first_block = smallest (y/2)*ceil(W/2) + x/2 over the component: sorting by it reproduces the library's
+ * label order, which the tracker's tie-breaking depends on. */
+typedef struct {
+    int root;                 /* linear index of the first pixel (raster order) */
+    int area;
+    int x0, y0, x1, y1;       /* inclusive bounding box */
+    int first_block;
+    int pad;
+    unsigned long long sum_x, sum_y; /* centroid = sum / area */
+} vsb_roi_stat;
+int vsb_roi_components(const uint32_t *bits, int wpr, int W, int H, int32_t *labels, int32_t *cid,
+                       vsb_roi_stat *stats_dev, int *count_dev, int max_components, vsb_stream_t stream);
+
+/* _calculate_receding_gradient_field_roi_fade (processing_core.py:155-220) + merge_to_output + leading apply_lut.
+ * eligible_dev[id] != 0: component id is an ROI (area >= min_size) that is not skipped as raft / support.
+ * dilate_radius = min(51, 2*int(F)+1) / 2; reach: search reach in pixels (table T_dev = vsb_chamfer_table(reach));
+ * use_fixed = config.use_fixed_fade_receding (0: per-ROI min-max normalisation, needs minmax_scratch uint32[2*n]). */
+int vsb_roi_fade(const uint8_t *gray, size_t gray_pitch, int W, int H, const uint32_t *cur_bits,
+                 const uint32_t *const *prior_bits, int n_priors, int wpr, const int32_t *cid,
+                 const uint8_t *eligible_dev, int n_components, int dilate_radius, int reach, const float *T_dev,
+                 int use_fixed, float fade, float den, uint32_t *minmax_scratch, const uint8_t *lut256_dev,
+                 uint8_t *out, size_t out_pitch, vsb_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Host-buffer entry points (the plugin path measured as `e2e`): pinned or pageable HOST arrays
  * in, HOST array out; device staging buffers are owned by an opaque stack context.
  *     replaces ProcessingPipelineThread._process_single_image_task + the producer loop

@@ -274,3 +274,95 @@ extern "C" int vsb_enhanced_from_labels(const float *dist, const int32_t *labels
     else k_fade_from_labels<1><<<grid, 256, 0, s>>>(dist, labels, n, num_labels, fade_limit, cmax, out);
     return vsb_check_launch("k_fade_from_labels");
 }
+
+// ---- components with statistics (ROI_FADE: identify_rois, processing_core.py:69-105) -----------------------------
+// cv2.connectedComponentsWithStats(binary, 8): area, bounding box, centroid sums per component, plus the index of
+// the first 2x2 block (block raster order) touching the component -- the library numbers its labels in that order.
+// Components get compact ids in arrival order; `cid` holds id + 1 at every foreground pixel, 0 elsewhere.
+__global__ void __launch_bounds__(256) k_roi_roots(const uint32_t *__restrict__ bits, int wpr, int W, int H,
+                                                   int32_t *__restrict__ L, int32_t *__restrict__ cid,
+                                                   vsb_roi_stat *__restrict__ stats, int *__restrict__ count, int max_comp)
+{
+    const int wx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (wx >= wpr) return;
+    uint32_t m = bits[(size_t)y * wpr + wx];
+    const int base = y * W + (wx << 5);
+    for (int b = 0; b < 32 && (wx << 5) + b < W; ++b) {
+        const int p = base + b;
+        if (!((m >> b) & 1u)) { cid[p] = 0; continue; }
+        const int root = uf_find(L, p);
+        L[p] = root;
+        if (root == p) {
+            const int id = atomicAdd(count, 1);
+            if (id < max_comp) {
+                vsb_roi_stat s;
+                s.root = p; s.area = 0; s.x0 = W; s.y0 = H; s.x1 = -1; s.y1 = -1; s.first_block = 0x7fffffff; s.pad = 0;
+                s.sum_x = 0ULL; s.sum_y = 0ULL;
+                stats[id] = s;
+            }
+            cid[p] = id + 1;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_roi_stats(const uint32_t *__restrict__ bits, int wpr, int W, int H,
+                                                   const int32_t *__restrict__ L, int32_t *__restrict__ cid,
+                                                   vsb_roi_stat *__restrict__ stats, int max_comp)
+{
+    const int wx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (wx >= wpr) return;
+    uint32_t m = bits[(size_t)y * wpr + wx];
+    if (!m) return;
+    const int base = y * W + (wx << 5);
+    const int bw = (W + 1) >> 1;
+    // runs of pixels with the same root are accumulated locally, one set of atomics per run
+    int run_id = -1, area = 0, xmin = 0, xmax = 0, fb = 0;
+    unsigned long long sx = 0;
+    auto flush = [&]() {
+        if (run_id < 0 || run_id >= max_comp) return;
+        vsb_roi_stat *s = &stats[run_id];
+        atomicAdd(&s->area, area);
+        atomicMin(&s->x0, xmin); atomicMax(&s->x1, xmax);
+        atomicMin(&s->y0, y); atomicMax(&s->y1, y);
+        atomicMin(&s->first_block, fb);
+        atomicAdd(&s->sum_x, sx);
+        atomicAdd(&s->sum_y, (unsigned long long)y * (unsigned long long)area);
+    };
+    while (m) {
+        const int b = __ffs(m) - 1;
+        m &= m - 1;
+        const int p = base + b, x = (wx << 5) + b;
+        const int id = cid[L[p]] - 1; // the root's own entry was written by k_roi_roots
+        cid[p] = id + 1;
+        if (id != run_id) {
+            flush();
+            run_id = id; area = 0; xmin = x; sx = 0; fb = (y >> 1) * bw + (x >> 1);
+        }
+        ++area; xmax = x; sx += (unsigned long long)x;
+    }
+    flush();
+}
+
+extern "C" int vsb_roi_components(const uint32_t *bits, int wpr, int W, int H, int32_t *labels, int32_t *cid,
+                                  vsb_roi_stat *stats_dev, int *count_dev, int max_components, vsb_stream_t stream)
+{
+    VSB_REQUIRE(bits && labels && cid && stats_dev && count_dev, "vsb_roi_components: null pointer");
+    VSB_REQUIRE(W > 0 && H > 0 && wpr >= (W + 31) / 32 && max_components > 0, "vsb_roi_components: bad geometry");
+    VSB_REQUIRE((long long)W * H < 0x7fffffffLL, "vsb_roi_components: image too large for int32 labels");
+    cudaStream_t s = (cudaStream_t)stream;
+    dim3 grid((wpr + 255) / 256, H);
+    VSB_CUDA(cudaMemsetAsync(count_dev, 0, sizeof(int), s));
+    k_ccl_init<<<grid, 256, 0, s>>>(bits, wpr, W, H, labels, (uint32_t *)cid);
+    int rc = vsb_check_launch("k_ccl_init");
+    if (rc) return rc;
+    k_ccl_merge<<<grid, 256, 0, s>>>(bits, wpr, W, H, labels);
+    rc = vsb_check_launch("k_ccl_merge");
+    if (rc) return rc;
+    k_roi_roots<<<grid, 256, 0, s>>>(bits, wpr, W, H, labels, cid, stats_dev, count_dev, max_components);
+    rc = vsb_check_launch("k_roi_roots");
+    if (rc) return rc;
+    k_roi_stats<<<grid, 256, 0, s>>>(bits, wpr, W, H, labels, cid, stats_dev, max_components);
+    return vsb_check_launch("k_roi_stats");
+}

@@ -42,7 +42,9 @@ def find_prior_combined_white_mask(prior_images_list):
 
 
 def identify_rois(binary_image, min_size=100):
-    raise P.UnsupportedOnDevice("identify_rois / ROI_FADE are not on the B200 path (SURVEY.md 8f rank 3)")
+    """8-connected components of at least min_size pixels, in the library's label order, each with label / area /
+    bbox / centroid / mask.  reference :69-105 (components + statistics on the device, masks cut on the host)."""
+    return E.Components(_bits(binary_image)).rois(int(min_size), with_masks=True)
 
 
 def _zeros_like(mask):
@@ -74,7 +76,27 @@ def _calculate_receding_gradient_field_fixed_fade(current_white_mask, prior_whit
 
 def _calculate_receding_gradient_field_roi_fade(current_white_mask, prior_white_combined_mask, config, classified_rois,
                                                 debug_info=None):
-    raise P.UnsupportedOnDevice("ROI_FADE is not on the B200 path (SURVEY.md 8f rank 3)")
+    """reference :155-220.  The ROI masks are taken as given (a label map is assembled from them on the host, later
+    masks winning where masks overlap); like in the reference's pipeline they are subsets of the current mask."""
+    if prior_white_combined_mask is None or not classified_rois:
+        return _zeros_like(current_white_mask)
+    cur, prior = _bits(current_white_mask), _bits(prior_white_combined_mask)
+    if debug_info:
+        _debug_dump(debug_info, "debug_03a_global_receding_areas",
+                    np.bitwise_and(prior_white_combined_mask, np.bitwise_not(current_white_mask)))
+    if E.count_receding(cur, [prior]) == 0:
+        return _zeros_like(current_white_mask)
+    skip = bool(config.roi_params.enable_raft_support_handling)
+    cid = np.zeros(current_white_mask.shape, np.int32)
+    eligible = np.zeros(len(classified_rois), np.uint8)
+    for i, roi in enumerate(classified_rois):
+        if skip and roi["classification"] in ("raft", "support"):
+            continue
+        eligible[i] = 1
+        cid[roi["mask"] > 0] = i + 1
+    t = E.torch()
+    return E.roi_fade(None, cur, [prior], t.from_numpy(cid).cuda(), len(classified_rois), eligible,
+                      float(config.fixed_fade_distance_receding), bool(config.use_fixed_fade_receding)).numpy()
 
 
 def _calculate_weighted_receding_gradient_field(current_white_mask, prior_binary_masks, config, debug_info=None):

@@ -1,0 +1,86 @@
+"""
+roi_tracker -- frame-to-frame identity and raft / support / model classification of the ROIs of consecutive
+layers (reference roi_tracker.py:3-109, same public names).  Pure host logic on bounding boxes and areas: the
+per-layer component statistics come from the device (vsb_roi_components), the decision which ROIs take part in
+the fade goes back as a one-byte-per-component table (vsb_roi_fade).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def calculate_iou(boxA, boxB):
+    """Overlap of two (x, y, w, h) boxes as intersection over the SMALLER box area (so containment scores 1),
+    0.0 when either box is empty.  reference :3-23"""
+    left, top = max(boxA[0], boxB[0]), max(boxA[1], boxB[1])
+    right, bottom = min(boxA[0] + boxA[2], boxB[0] + boxB[2]), min(boxA[1] + boxA[3], boxB[1] + boxB[3])
+    inter = max(0, right - left) * max(0, bottom - top)
+    smaller = min(boxA[2] * boxA[3], boxB[2] * boxB[3])
+    return inter / float(smaller) if smaller != 0 else 0.0
+
+
+class ROITracker:
+    """reference :25-109.  State: next_roi_id and previous_rois {id: roi dict}."""
+
+    MATCH_THRESHOLD = 0.5
+
+    def __init__(self):
+        self.next_roi_id = 0
+        self.previous_rois = {}
+
+    def _classify_new_roi(self, roi, layer_index, config):
+        rp = config.roi_params
+        if not rp.enable_raft_support_handling:
+            return "model"
+        if layer_index < rp.raft_layer_count and roi["area"] >= rp.raft_min_size:
+            return "raft"
+        if roi["area"] <= rp.support_max_size and layer_index < rp.support_max_layer:
+            return "support"
+        return "model"
+
+    def _admit(self, roi, layer_index, config, into):
+        roi["id"] = self.next_roi_id
+        self.next_roi_id += 1
+        roi["classification"] = self._classify_new_roi(roi, layer_index, config)
+        into[roi["id"]] = roi
+
+    def update_and_classify(self, current_rois_raw, layer_index, config):
+        tracked = {}
+        if not self.previous_rois:                       # nothing to match against: everything is new
+            for roi in current_rois_raw:
+                self._admit(roi, layer_index, config, tracked)
+            self.previous_rois = tracked
+            return list(tracked.values())
+
+        prev_ids = list(self.previous_rois)
+        scores = np.zeros((len(current_rois_raw), len(prev_ids)))
+        for ci, roi in enumerate(current_rois_raw):
+            for pj, pid in enumerate(prev_ids):
+                scores[ci, pj] = calculate_iou(roi["bbox"], self.previous_rois[pid]["bbox"])
+
+        # greedy one-to-one assignment, best score first; equal scores keep their flattened (row-major) order
+        assigned, taken = {}, set()
+        for flat in np.argsort(-scores, axis=None):
+            ci, pj = divmod(int(flat), scores.shape[1]) if scores.shape[1] else (0, 0)
+            if scores.size == 0 or scores[ci, pj] < self.MATCH_THRESHOLD:
+                break
+            pid = prev_ids[pj]
+            if ci in assigned or pid in taken:
+                continue
+            assigned[ci] = pid
+            taken.add(pid)
+
+        for ci, pid in assigned.items():
+            roi, before = current_rois_raw[ci], self.previous_rois[pid]
+            roi["id"] = pid
+            if before["classification"] == "support":
+                growth = roi["area"] / before["area"] if before["area"] > 0 else float("inf")
+                roi["classification"] = "model" if growth > config.roi_params.support_max_growth else "support"
+            else:
+                roi["classification"] = before["classification"]
+            tracked[pid] = roi
+        for ci, roi in enumerate(current_rois_raw):
+            if ci not in assigned:
+                self._admit(roi, layer_index, config, tracked)
+        self.previous_rois = tracked
+        return list(tracked.values())

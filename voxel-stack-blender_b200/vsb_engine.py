@@ -13,6 +13,7 @@ No CPU fallback: without a CUDA device every entry point raises.
 from __future__ import annotations
 
 import ctypes
+import math
 import threading
 from ctypes import c_void_p
 from typing import List, Optional, Sequence
@@ -322,6 +323,75 @@ def median(img: DevImage, ksize: int) -> DevImage:
     o = DevImage(img.H, img.W)
     N.check(N.load().vsb_median(img.ptr, img.pitch, img.W, img.H, int(ksize), o.ptr, o.pitch, _stream()), "vsb_median")
     return o
+
+
+# ---- ROI_FADE -----------------------------------------------------------------------------
+class Components:
+    """8-connected components of a packed mask with cv2.connectedComponentsWithStats' statistics and label order.
+    `cid` (device int32 [H, W]) holds compact component id + 1; `order[i]` = compact id of the library's label i+1."""
+
+    def __init__(self, bits: DevBits):
+        t = torch()
+        H, W = bits.H, bits.W
+        self.H, self.W = H, W
+        labels = t.empty((H, W), dtype=t.int32, device="cuda")
+        self.cid = t.empty((H, W), dtype=t.int32, device="cuda")
+        count = t.zeros(1, dtype=t.int32, device="cuda")
+        cap = 1 << 14
+        while True:
+            stats = t.empty(cap * ctypes.sizeof(N.RoiStat), dtype=t.uint8, device="cuda")
+            N.check(N.load().vsb_roi_components(bits.ptr, bits.wpr, W, H, labels.data_ptr(), self.cid.data_ptr(),
+                                                stats.data_ptr(), count.data_ptr(), cap, _stream()), "vsb_roi_components")
+            n = int(count.item())
+            if n <= cap:
+                break
+            cap = 1 << int(n - 1).bit_length()
+        raw = stats[: n * ctypes.sizeof(N.RoiStat)].cpu().numpy()
+        dt = np.dtype([("root", "<i4"), ("area", "<i4"), ("x0", "<i4"), ("y0", "<i4"), ("x1", "<i4"), ("y1", "<i4"),
+                       ("first_block", "<i4"), ("pad", "<i4"), ("sum_x", "<u8"), ("sum_y", "<u8")])
+        self.stats = raw.view(dt) if n else np.zeros(0, dt)
+        self.n = n
+        self.order = np.argsort(self.stats["first_block"], kind="stable") if n else np.zeros(0, np.int64)
+
+    def rois(self, min_size: int, with_masks: bool = False) -> List[dict]:
+        """identify_rois' list (processing_core.py:82-103): label, area, bbox, centroid (+ mask on request)."""
+        out = []
+        cid_host = self.cid.cpu().numpy() if with_masks else None
+        for rank, c in enumerate(self.order):
+            st = self.stats[c]
+            if st["area"] >= min_size:
+                r = {"label": rank + 1, "area": int(st["area"]),
+                     "bbox": (int(st["x0"]), int(st["y0"]), int(st["x1"] - st["x0"] + 1), int(st["y1"] - st["y0"] + 1)),
+                     "centroid": np.array([st["sum_x"] / st["area"], st["sum_y"] / st["area"]]), "component": int(c)}
+                if with_masks:
+                    r["mask"] = (cid_host == c + 1).astype(np.uint8) * 255
+                out.append(r)
+        return out
+
+
+def roi_fade(gray: Optional[DevImage], cur: DevBits, priors: Sequence[DevBits], cid, n_components: int,
+             eligible: np.ndarray, F: float, use_fixed: bool, lut: Optional[np.ndarray] = None) -> DevImage:
+    """_calculate_receding_gradient_field_roi_fade + merge (+ leading LUT) on the device.  `cid`: device int32 map of
+    component id + 1, `eligible`: uint8 per component."""
+    t = torch()
+    H, W = cur.H, cur.W
+    out = DevImage(H, W)
+    K = min(51, int(F) * 2 + 1) // 2 if int(F) >= 0 else 0
+    K = max(K, 0)
+    near_reach = int(math.floor(1.4 * K)) + 1
+    R = min(P.chamfer_reach(F), near_reach) if use_fixed else near_reach
+    R = max(0, min(R, N.VSB_FAST_REACH))
+    el = t.from_numpy(np.ascontiguousarray(eligible, np.uint8)).cuda() if n_components else None
+    mm = t.empty(max(1, 2 * n_components), dtype=t.int32, device="cuda")
+    pri = N.ptr_array([p.ptr for p in priors])
+    ld = lut_dev(lut) if lut is not None else None
+    den = float(F) if F > 0 else 1.0
+    N.check(N.load().vsb_roi_fade(gray.ptr if gray is not None else None, gray.pitch if gray is not None else 0, W, H,
+                                  cur.ptr, pri, len(priors), cur.wpr, cid.data_ptr(),
+                                  el.data_ptr() if el is not None else None, int(n_components), K, R,
+                                  table_dev(R).data_ptr(), 1 if use_fixed else 0, float(F), den, mm.data_ptr(),
+                                  ld.data_ptr() if ld is not None else None, out.ptr, out.pitch, _stream()), "vsb_roi_fade")
+    return out
 
 
 class ResizePlan:

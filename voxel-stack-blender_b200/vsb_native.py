@@ -49,6 +49,11 @@ class XYOp(ctypes.Structure):
                 ("resize_w", c_int), ("resize_h", c_int), ("interp", c_int)]
 
 
+class RoiStat(ctypes.Structure):
+    _fields_ = [("root", c_int), ("area", c_int), ("x0", c_int), ("y0", c_int), ("x1", c_int), ("y1", c_int),
+                ("first_block", c_int), ("pad", c_int), ("sum_x", c_ulonglong), ("sum_y", c_ulonglong)]
+
+
 class XYFused(ctypes.Structure):
     _fields_ = [("has_bilateral", c_int), ("radius", c_int), ("ntaps", c_int), ("tap_dy", c_int8 * 96),
                 ("tap_dx", c_int8 * 96), ("tap_sw", c_float * 96), ("cw", c_float * 256), ("nkx", c_int), ("nky", c_int),
@@ -94,6 +99,10 @@ _SIGS = {
     "vsb_layer_fused": (c_int, [c_void_p, c_size_t, c_int, c_int, c_void_p, POINTER(c_void_p), c_void_p, POINTER(c_void_p),
                                 c_int, POINTER(ZParams), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "vsb_stack_create": (c_int, [c_int, c_int, c_int, POINTER(ZParams), POINTER(XYOp), c_int, POINTER(c_void_p)]),
+    "vsb_roi_components": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "vsb_roi_fade": (c_int, [c_void_p, c_size_t, c_int, c_int, c_void_p, POINTER(c_void_p), c_int, c_int, c_void_p, c_void_p,
+                             c_int, c_int, c_int, c_void_p, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p, c_size_t,
+                             c_void_p]),
     "vsb_stack_destroy": (c_int, [c_void_p]),
     "vsb_stack_out_size": (c_int, [c_void_p, POINTER(c_int), POINTER(c_int)]),
     "vsb_unsharp_combine": (c_int, [c_void_p, c_size_t, c_void_p, c_size_t, c_int, c_int, c_float, c_int, c_void_p, c_size_t,
