@@ -117,3 +117,29 @@ def test_roi_fade_many_components_per_window(E):
             r["classification"] = "model"
         want = R.roi_fade(cur, prev, F, fixed, orois, False)
         assert np.array_equal(got, want), (fixed, F, int((got != want).sum()))
+
+
+def test_pipeline_thread_roi_mode(E, roi, slices, tmp_path):
+    """ProcessingPipelineThread.run() in ROI_FADE mode on PNG files (the device stack loop with the host tracker in
+    the middle): same pixels as the reference's producer loop; layer_index comes from the file name."""
+    import cv2
+    import processing_pipeline as pp
+    name = "fix40"
+    wn, fixed, F, N, rp = json.loads(str(roi["configs"]))[name]
+    y0, y1, x0, x1 = json.loads(str(roi["wins"]))[wn]
+    src, dst = tmp_path / "in", tmp_path / "out"
+    src.mkdir(); dst.mkdir()
+    os.chdir(tmp_path)
+    for z in range(20):
+        cv2.imwrite(str(src / f"layer{z:03d}.png"), np.ascontiguousarray(slices[z][y0:y1, x0:x1]))
+    cfg = _cfg(fixed, F, N, rp)
+    cfg.input_mode = "folder"; cfg.input_folder = str(src); cfg.output_folder = str(dst)
+    cfg.xy_blend_pipeline = []
+    th = pp.ProcessingPipelineThread(cfg, max_workers=3)
+    errors = []
+    th.error_signal.connect(errors.append)
+    th.run()
+    assert not errors and not th.error_occurred, errors
+    for z in range(20):
+        got = cv2.imread(str(dst / f"layer{z:03d}.png"), cv2.IMREAD_GRAYSCALE)
+        assert hashlib.sha1(np.ascontiguousarray(got).tobytes()).hexdigest() == str(roi[f"{name}_sha1"][z]), z

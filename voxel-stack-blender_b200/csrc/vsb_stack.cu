@@ -510,17 +510,22 @@ static int submit(vsb_stack *s, const uint8_t *gray_host, size_t in_pitch, uint8
 {
     const int slot = (int)(s->submitted % STACK_SLOTS);
     if (s->slot_used[slot]) VSB_CUDA(cudaEventSynchronize(s->ev_d2h[slot])); // slot's previous layer fully drained
-    VSB_CUDA(cudaMemcpy2DAsync(s->gray_dev[slot], s->pitch, gray_host, in_pitch, (size_t)s->W, (size_t)s->H,
-                               cudaMemcpyHostToDevice, s->s_h2d));
+    // equal pitches: one linear copy up to the last valid byte (the padding columns travel along, the DMA engine
+    // runs at full rate)
+    if (in_pitch == s->pitch) VSB_CUDA(cudaMemcpyAsync(s->gray_dev[slot], gray_host, s->pitch * (size_t)(s->H - 1) + (size_t)s->W, cudaMemcpyHostToDevice, s->s_h2d));
+    else VSB_CUDA(cudaMemcpy2DAsync(s->gray_dev[slot], s->pitch, gray_host, in_pitch, (size_t)s->W, (size_t)s->H,
+                                    cudaMemcpyHostToDevice, s->s_h2d));
     VSB_CUDA(cudaEventRecord(s->ev_h2d[slot], s->s_h2d));
     VSB_CUDA(cudaStreamWaitEvent(s->s_comp, s->ev_h2d[slot], 0));
     int rc = run_layer(s, s->gray_dev[slot], s->pitch, s->out_dev[slot], s->opitch, emit);
     if (rc) return rc;
     VSB_CUDA(cudaEventRecord(s->ev_comp[slot], s->s_comp));
     VSB_CUDA(cudaStreamWaitEvent(s->s_d2h, s->ev_comp[slot], 0));
-    if (emit)
-        VSB_CUDA(cudaMemcpy2DAsync(out_host, out_pitch, s->out_dev[slot], s->opitch, (size_t)s->oW, (size_t)s->oH,
-                                   cudaMemcpyDeviceToHost, s->s_d2h));
+    if (emit) {
+        if (out_pitch == s->opitch) VSB_CUDA(cudaMemcpyAsync(out_host, s->out_dev[slot], s->opitch * (size_t)(s->oH - 1) + (size_t)s->oW, cudaMemcpyDeviceToHost, s->s_d2h));
+        else VSB_CUDA(cudaMemcpy2DAsync(out_host, out_pitch, s->out_dev[slot], s->opitch, (size_t)s->oW, (size_t)s->oH,
+                                        cudaMemcpyDeviceToHost, s->s_d2h));
+    }
     VSB_CUDA(cudaEventRecord(s->ev_d2h[slot], s->s_d2h));
     s->slot_used[slot] = true;
     const long long ticket = s->submitted++;

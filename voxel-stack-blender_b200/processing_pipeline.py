@@ -136,7 +136,72 @@ class ProcessingPipelineThread(QThread):
         ops = P.xy_ops_from_pipeline(cfg.xy_blend_pipeline, lambda op: lut_manager.lut_from_params(op.lut_params), W, H)
         return E.StackEngine(W, H, cfg, ops, metric=getattr(cfg, "distance_metric", "chamfer5"))
 
+    def _blend_stack_roi(self, input_path, filenames, output_path):
+        """ROI_FADE: the tracker is sequential host state, so layers go through one at a time (decode and encode
+        still run on the worker pools around it).  processing_pipeline.py:205-223"""
+        import xy_blend_processor
+        cfg = self.app_config
+        total = len(filenames)
+        done = 0
+        workers = self.max_workers
+        engine = None
+        with concurrent.futures.ThreadPoolExecutor(workers) as decoder, \
+                concurrent.futures.ThreadPoolExecutor(workers) as encoder:
+            pending = collections.deque()
+            it = iter(filenames)
+
+            def top_up():
+                while len(pending) < 2 * workers:
+                    name = next(it, None)
+                    if name is None:
+                        return
+                    pending.append((name, decoder.submit(cv2.imread, os.path.join(input_path, name), cv2.IMREAD_GRAYSCALE)))
+
+            def write(path, image):
+                cv2.imwrite(path, image)
+                print(f"Successfully wrote output file: {path}")
+
+            top_up()
+            jobs = []
+            index = 0
+            while pending:
+                if not self._is_running:
+                    self.logger.log("Processing stopped by user.")
+                    self.status_update.emit("Processing stopped by user.")
+                    break
+                name, fut = pending.popleft()
+                top_up()
+                index += 1
+                self.status_update.emit(f"Analyzing {name} ({index}/{total})")
+                gray = fut.result()
+                if gray is None:
+                    print(f"Warning: Could not load image at {os.path.join(input_path, name)}")
+                    self.status_update.emit(f"Skipping unloadable image: {name}")
+                    total = max(1, total - 1)
+                    continue
+                if engine is None:
+                    H, W = gray.shape
+                    ops = list(cfg.xy_blend_pipeline or [])
+                    chain = (lambda d: xy_blend_processor.process_xy_pipeline_dev(d, ops)[0]) if ops else None
+                    engine = E.RoiStackEngine(W, H, cfg, chain)
+                out = engine.process(gray, _layer_number(name))
+                jobs.append(encoder.submit(write, os.path.join(output_path, name), out))
+                while jobs and (jobs[0].done() or len(jobs) > 2 * workers):
+                    jobs.pop(0).result()
+                    done += 1
+                    self.status_update.emit(f"Completed processing images ({done}/{total})")
+                    self.progress_update.emit(int((done / total) * 100))
+            for j in jobs:
+                j.result()
+                done += 1
+                self.status_update.emit(f"Completed processing images ({done}/{total})")
+                self.progress_update.emit(int((done / total) * 100))
+        if engine is not None:
+            engine.close()
+
     def _blend_stack(self, input_path, filenames, output_path):
+        if self.app_config.blending_mode == ProcessingMode.ROI_FADE:
+            return self._blend_stack_roi(input_path, filenames, output_path)
         total = len(filenames)
         done = 0
         torch = E.torch()

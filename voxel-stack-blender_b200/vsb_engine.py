@@ -394,6 +394,61 @@ def roi_fade(gray: Optional[DevImage], cur: DevBits, priors: Sequence[DevBits], 
     return out
 
 
+class RoiStackEngine:
+    """ROI_FADE stack loop (processing_pipeline.py:163-164, :205-223): per layer the device labels the current mask
+    and returns the component statistics, the host tracker classifies them, the device fades per ROI, merges and
+    runs the XY chain.  One host round trip per layer (a few KB of statistics down, one byte per component up)."""
+
+    def __init__(self, W: int, H: int, cfg, xy_chain=None, device: Optional[int] = None):
+        import roi_tracker
+        t = torch()
+        if device is not None:
+            t.cuda.set_device(device)
+        self.W, self.H, self.cfg = int(W), int(H), cfg
+        self.tracker = roi_tracker.ROITracker()
+        self.window: List[DevBits] = []
+        self.n_priors = max(0, int(cfg.receding_layers))
+        if self.n_priors > N.VSB_MAX_PRIORS:
+            raise P.UnsupportedOnDevice(f"more than {N.VSB_MAX_PRIORS} receding layers")
+        self.xy_chain = xy_chain          # callable DevImage -> DevImage, or None
+        self.last_rois: List[dict] = []
+
+    def reset(self):
+        import roi_tracker
+        self.tracker = roi_tracker.ROITracker()
+        self.window = []
+
+    def process(self, gray: np.ndarray, layer_index: int) -> np.ndarray:
+        gray = np.ascontiguousarray(gray, np.uint8)
+        if gray.shape != (self.H, self.W):
+            raise ValueError(f"layer shape {gray.shape} != engine shape {(self.H, self.W)}")
+        cfg = self.cfg
+        img = DevImage.from_numpy(gray)
+        cur = pack(img)
+        comp = Components(cur)
+        rois = comp.rois(int(cfg.roi_params.min_size))
+        classified = self.tracker.update_and_classify(rois, layer_index, cfg)
+        self.last_rois = classified
+        eligible = np.zeros(max(1, comp.n), np.uint8)
+        skip = bool(cfg.roi_params.enable_raft_support_handling)
+        for r in classified:
+            if not (skip and r["classification"] in ("raft", "support")):
+                eligible[r["component"]] = 1
+        priors = list(reversed(self.window))     # newest first (only their OR matters here)
+        out = roi_fade(img, cur, priors, comp.cid, comp.n if (classified and priors) else 0, eligible,
+                       float(cfg.fixed_fade_distance_receding), bool(cfg.use_fixed_fade_receding))
+        if self.xy_chain is not None:
+            out = self.xy_chain(out)
+        if self.n_priors > 0:
+            self.window.append(cur)
+            if len(self.window) > self.n_priors:
+                self.window.pop(0)
+        return out.numpy()
+
+    def close(self):
+        self.window = []
+
+
 class ResizePlan:
     """Device tables of one cv2.resize geometry (csrc/vsb_geom.cu)."""
 

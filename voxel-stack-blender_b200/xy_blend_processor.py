@@ -79,11 +79,8 @@ def apply_lut_operation(image: np.ndarray, op: XYBlendOperation) -> np.ndarray:
     return lut_manager.apply_z_lut(image, _lut_for(op))
 
 
-def process_xy_pipeline(image: np.ndarray, pipeline_ops: List[XYBlendOperation]) -> np.ndarray:
-    """reference :135-164: copy, dispatch by op.type, unknown types warn and are skipped."""
-    if not pipeline_ops:
-        return image.copy()
-    dev = E.DevImage.from_numpy(image)
+def process_xy_pipeline_dev(dev: E.DevImage, pipeline_ops: List[XYBlendOperation]):
+    """The chain on a device image: (result, touched).  Consecutive apply_lut ops are composed into one table."""
     pending_lut = None
 
     def flush(d):
@@ -94,7 +91,7 @@ def process_xy_pipeline(image: np.ndarray, pipeline_ops: List[XYBlendOperation])
         return d
 
     touched = False
-    for op in pipeline_ops:
+    for op in pipeline_ops or []:
         t = op.type
         if t == "apply_lut":
             table = _lut_for(op)
@@ -115,6 +112,14 @@ def process_xy_pipeline(image: np.ndarray, pipeline_ops: List[XYBlendOperation])
                 dev = _resize_dev(flush(dev), op); touched = True
         elif t != "none":
             print(f"Warning: Unknown XY blend operation type '{t}'. Skipping.")
+    return flush(dev), touched
+
+
+def process_xy_pipeline(image: np.ndarray, pipeline_ops: List[XYBlendOperation]) -> np.ndarray:
+    """reference :135-164: copy, dispatch by op.type, unknown types warn and are skipped."""
+    if not pipeline_ops:
+        return image.copy()
+    dev, touched = process_xy_pipeline_dev(E.DevImage.from_numpy(image), pipeline_ops)
     if not touched:
         return image.copy()
-    return flush(dev).numpy()
+    return dev.numpy()
