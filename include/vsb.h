@@ -136,7 +136,9 @@ typedef enum {
     VSB_Z_ENHANCED = 4, /* stack level only: VSB_Z_DIST + vsb_ccl8_max + vsb_enhanced_fade  :338-404 */
     VSB_Z_NONE = 5,     /* vsb_layer_fused only: no Z-blend, the input already is the stage-1 image */
     VSB_Z_MINMAX = 6,   /* stack level only: vsb_zblend_unbounded norm 1 (global min-max, :141-145) */
-    VSB_Z_FIXED_FAR = 7 /* stack level only: vsb_zblend_unbounded norm 0 (fixed fade, reach > VSB_FAST_REACH) */
+    VSB_Z_FIXED_FAR = 7, /* stack level only: vsb_zblend_unbounded norm 0 (fixed fade, reach > VSB_FAST_REACH) */
+    VSB_Z_WEIGHTED_FAR = 8, /* stack level only: vsb_weighted_unbounded (a fade distance beyond VSB_FAST_REACH) */
+    VSB_Z_ENHANCED_FAR = 9  /* stack level only: vsb_rec_dist_unbounded + vsb_ccl8_max + vsb_enhanced_fade */
 } vsb_zmode;
 
 typedef enum {
@@ -256,6 +258,18 @@ int vsb_layer_fused(const uint8_t *in, size_t in_pitch, int W, int H, const uint
                     const uint16_t *const *prior_flags, int wpr, const vsb_zparams *params, const float *T_dev,
                     const uint8_t *lut1_dev, const vsb_xy_fused *xy /* host, may be NULL */,
                     const uint8_t *lut2_dev, uint8_t *out, size_t out_pitch, vsb_stream_t stream);
+
+/* vsb_zblend_unbounded's two halves, for the other modes with fade distances beyond VSB_FAST_REACH:
+ * distances at the receding pixels only (dist is untouched elsewhere; minmax2 receives their min / max float bits) */
+int vsb_rec_dist_unbounded(const uint32_t *cur_bits, const uint32_t *const *prior_bits, int n_priors, int wpr, int W, int H,
+                           int metric, uint16_t *g, size_t g_pitch_elems, uint16_t *gmin64, float *dist,
+                           size_t dist_pitch_elems, uint32_t *minmax2, vsb_stream_t stream);
+/* weighted stack (processing_core.py:222-284) with unbounded distances; params->weights / fades / dens /
+ * total_weight / n_priors / metric as for VSB_Z_WEIGHTED */
+int vsb_weighted_unbounded(const uint8_t *gray, size_t gray_pitch, int W, int H, const uint32_t *cur_bits,
+                           const uint32_t *const *prior_bits, int wpr, const vsb_zparams *params, uint16_t *g,
+                           size_t g_pitch_elems, uint16_t *gmin64, float *dist, size_t dist_pitch_elems, uint32_t *minmax2,
+                           const uint8_t *lut256_dev, uint8_t *out, size_t out_pitch, vsb_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * unsharp mask, resize, and the two resizes of the anisotropic

@@ -576,3 +576,42 @@ def test_stack_engine_unbounded_modes(E, mode):
     for zi, g in enumerate(layers):
         assert np.array_equal(eng.process(g), want[zi]), (mode, zi)
     eng.close()
+
+
+# ---- fade distances beyond the tile kernels' reach for the weighted and Enhanced modes ------------------------------
+def test_weighted_and_enhanced_far_vs_oracle(E):
+    import processing_core as core
+    from config import Config, ProcessingMode
+    layers = small_stack(W=700, H=420, L=6, seed=4, r_range=(30.0, 160.0), r_turn=200.0)
+    cur = O.threshold(layers[5])
+    pri = [O.threshold(layers[k]) for k in (4, 3, 2, 1)]
+    c = Config(); c.blending_mode = ProcessingMode.WEIGHTED_STACK
+    c.manual_weights = [100, 60, 0, 25]; c.fade_distances_receding = [150.0, 20.0, 33.0]; c.fixed_fade_distance_receding = 90.0
+    got = core.process_z_blending(cur, pri, c, [])
+    want = O.weighted_fade(cur, pri, c.manual_weights, c.fade_distances_receding, 90.0)
+    assert got.any() and np.array_equal(got, want), int((got != want).sum())
+    for nb in (False, True):
+        c = Config(); c.blending_mode = ProcessingMode.ENHANCED_EDT; c.fixed_fade_distance_receding = 120.0; c.use_numba_jit = nb
+        got = core.process_z_blending(cur, pri, c, [])
+        want = O.enhanced_fade(cur, pri, 120.0, "numba" if nb else "scipy")
+        assert got.any() and np.array_equal(got, want), (nb, int((got != want).sum()))
+
+
+@pytest.mark.parametrize("mode", ["weighted_stack", "enhanced_edt"])
+def test_stack_engine_far_modes(E, mode):
+    import lut_manager, vsb_params as P
+    from config import Config
+    layers = small_stack(W=520, H=300, L=7, seed=9, r_range=(25.0, 120.0), r_turn=150.0)
+    d = {"blending_mode": mode, "receding_layers": 3, "fixed_fade_distance_receding": 100.0, "use_numba_jit": True,
+         "manual_weights": [50, 30, 20], "fade_distances_receding": [100.0, 70.0, 10.0],
+         "xy_blend_pipeline": [{"type": "gaussian_blur", "gaussian_ksize_x": 3, "gaussian_ksize_y": 3, "gaussian_sigma_x": 0.0,
+                                "gaussian_sigma_y": 0.0}]}
+    cfg = Config.from_dict(d)
+    H, W = layers[0].shape
+    ops = P.xy_ops_from_pipeline(cfg.xy_blend_pipeline, lambda o: lut_manager.lut_from_params(o.lut_params), W, H)
+    eng = E.StackEngine(W, H, cfg, ops)
+    outs = [eng.process(g) for g in layers]
+    eng.close()
+    want = O.run_stack(layers, d)
+    for i, (a, b) in enumerate(zip(outs, want)):
+        assert np.array_equal(a, b), (mode, i, int((a != b).sum()))

@@ -165,9 +165,38 @@ def test_zparams_from_config():
     z = P.zparams_from_config(c)
     assert z.mode == N.Z_WEIGHTED and z.n_priors == 3 and z.reach == 19
     assert list(z.fades)[:3] == [20.0, 90.0, 12.0] and z.total_weight == 150.0
+    c.fade_distances_receding = [20.0, 90.0, 300.0]
+    z = P.zparams_from_config(c)
+    assert z.mode == N.Z_WEIGHTED_FAR and z.reach == 0 and z.fade == 300.0   # a fade beyond the tile reach
+    c.blending_mode = ProcessingMode.ENHANCED_EDT; c.fixed_fade_distance_receding = 100.0
+    assert P.zparams_from_config(c).mode == N.Z_ENHANCED_FAR
+    c.fixed_fade_distance_receding = 40.0
+    c.anisotropic_params.enabled = True; c.anisotropic_params.x_factor = 2.0; c.anisotropic_params.y_factor = 0.05
+    z = P.zparams_from_config(c, "chamfer5", 400, 200)
+    assert (z.mode, z.aniso_w, z.aniso_h, z.aniso_reach) == (N.Z_ENHANCED, 800, 20, 42)   # y factor clamps to 0.1
+    with pytest.raises(ValueError):
+        P.zparams_from_config(c)                                   # the resized-mask size needs the layer size
     c.blending_mode = ProcessingMode.ROI_FADE
     with pytest.raises(P.UnsupportedOnDevice):
-        P.zparams_from_config(c)
+        P.zparams_from_config(c)                                   # ROI_FADE runs through RoiStackEngine instead
+
+
+def test_xy_ops_geometry_descriptors():
+    import vsb_native as N
+    import vsb_params as P
+    from config import XYBlendOperation
+    ops = [XYBlendOperation(type="unsharp_mask", unsharp_amount=0.5, unsharp_threshold=3, unsharp_blur_ksize=4),
+           XYBlendOperation(type="resize", resize_width=100, resample_mode="area"),
+           XYBlendOperation(type="resize"),                                     # no target: dropped
+           XYBlendOperation(type="resize", resize_width=100, resize_height=50),  # already that size: dropped
+           XYBlendOperation(type="resize", resize_height=25, resample_mode="nonsense")]
+    x = P.xy_ops_from_pipeline(ops, None, 400, 200)
+    assert [o.type for o in x] == [N.OP_UNSHARP, N.OP_RESIZE, N.OP_RESIZE]
+    assert (x[0].nkx, x[0].nky, x[0].unsharp_threshold) == (5, 5, 3) and abs(x[0].unsharp_amount - 0.5) < 1e-7
+    assert (x[1].resize_w, x[1].resize_h, x[1].interp) == (100, 50, N.INTER_AREA)
+    assert (x[2].resize_w, x[2].resize_h, x[2].interp) == (50, 25, N.INTER_LANCZOS4)
+    with pytest.raises(ValueError):
+        P.xy_ops_from_pipeline(ops, None)                                       # a resize needs the layer size
 
 
 def test_file_ordering_rules(tmp_path):

@@ -145,7 +145,8 @@ extern "C" int vsb_stack_create(int W, int H, int n_priors, const vsb_zparams *z
     VSB_REQUIRE(W > 0 && H > 0 && n_priors >= 0 && n_priors <= VSB_MAX_PRIORS,
                 "vsb_stack_create: bad geometry or more than %d receding layers", VSB_MAX_PRIORS);
     VSB_REQUIRE(n_ops >= 0 && n_ops <= VSB_MAX_XY_OPS && (n_ops == 0 || ops), "vsb_stack_create: bad op list");
-    const bool far_mode = zp->mode == VSB_Z_MINMAX || zp->mode == VSB_Z_FIXED_FAR;
+    const bool far_mode = zp->mode == VSB_Z_MINMAX || zp->mode == VSB_Z_FIXED_FAR || zp->mode == VSB_Z_WEIGHTED_FAR ||
+                          zp->mode == VSB_Z_ENHANCED_FAR;
     VSB_REQUIRE(far_mode || (zp->reach >= 0 && zp->reach <= VSB_FAST_REACH), "vsb_stack_create: reach %d > %d", zp->reach,
                 VSB_FAST_REACH);
     vsb_stack *s = new (std::nothrow) vsb_stack();
@@ -361,7 +362,7 @@ static int run_layer(vsb_stack *s, const uint8_t *gray, size_t gpitch, uint8_t *
         const int np = s->count < s->n_priors ? s->count : s->n_priors;
         for (int i = 0; i < np; ++i) pri[i] = s->ring[(s->head - 1 - i + 2 * nring) % nring]; // newest first
         vsb_zparams zp = s->zp;
-        if (zp.mode == VSB_Z_WEIGHTED) {
+        if (zp.mode == VSB_Z_WEIGHTED || zp.mode == VSB_Z_WEIGHTED_FAR) {
             // k = min(len(priors), len(weights)); total weight is over the k used weights (processing_core.py:231-238)
             const int k = np < zp.n_priors ? np : zp.n_priors;
             float tot = 0.0f;
@@ -373,8 +374,9 @@ static int run_layer(vsb_stack *s, const uint8_t *gray, size_t gpitch, uint8_t *
         } else {
             zp.n_priors = np;
         }
-        const bool far_mode = zp.mode == VSB_Z_MINMAX || zp.mode == VSB_Z_FIXED_FAR;
-        if (s->fused && zp.mode != VSB_Z_ENHANCED && !far_mode) {
+        const bool far_mode = zp.mode == VSB_Z_MINMAX || zp.mode == VSB_Z_FIXED_FAR || zp.mode == VSB_Z_WEIGHTED_FAR;
+        const bool enhanced = zp.mode == VSB_Z_ENHANCED || zp.mode == VSB_Z_ENHANCED_FAR;
+        if (s->fused && !enhanced && !far_mode) {
             const uint16_t *pfl[VSB_MAX_PRIORS];
             for (int i = 0; i < np; ++i) pfl[i] = s->flag_ring[(s->head - 1 - i + 2 * nring) % nring];
             {
@@ -396,16 +398,26 @@ static int run_layer(vsb_stack *s, const uint8_t *gray, size_t gpitch, uint8_t *
             rc = ensure_unbounded_scratch(s);
             if (rc) return rc;
             ProfScope ps(s, ST_ZBLEND, 5);
-            rc = vsb_zblend_unbounded(gray, gpitch, s->W, s->H, cur, pri, np, s->wpr, zp.metric, zp.mode == VSB_Z_MINMAX ? 1 : 0,
-                                      zp.fade, zp.den, s->ub_g, (size_t)s->W, s->ub_gmin, s->ub_dist, (size_t)s->W, s->ub_mm,
-                                      s->lead_lut_dev, zdst, zpitch, st);
+            if (zp.mode == VSB_Z_WEIGHTED_FAR)
+                rc = vsb_weighted_unbounded(gray, gpitch, s->W, s->H, cur, pri, s->wpr, &zp, s->ub_g, (size_t)s->W, s->ub_gmin,
+                                            s->ub_dist, (size_t)s->W, s->ub_mm, s->lead_lut_dev, zdst, zpitch, st);
+            else
+                rc = vsb_zblend_unbounded(gray, gpitch, s->W, s->H, cur, pri, np, s->wpr, zp.metric, zp.mode == VSB_Z_MINMAX ? 1 : 0,
+                                          zp.fade, zp.den, s->ub_g, (size_t)s->W, s->ub_gmin, s->ub_dist, (size_t)s->W, s->ub_mm,
+                                          s->lead_lut_dev, zdst, zpitch, st);
             if (rc) return rc;
-        } else if (zp.mode == VSB_Z_ENHANCED) {
+        } else if (enhanced) {
             rc = ensure_enhanced_scratch(s);
             if (rc) return rc;
             { ProfScope ps(s, ST_MASKDIFF, 1); rc = vsb_maskdiff(cur, pri, np, s->wpr, s->H, s->rec_bits, nullptr, st); }
             if (rc) return rc;
-            if (zp.aniso_w > 0) {
+            if (zp.mode == VSB_Z_ENHANCED_FAR) {
+                rc = ensure_unbounded_scratch(s);
+                if (rc) return rc;
+                ProfScope ps(s, ST_ZDIST, 4);
+                rc = vsb_rec_dist_unbounded(cur, pri, np, s->wpr, s->W, s->H, zp.metric, s->ub_g, (size_t)s->W, s->ub_gmin, s->dist,
+                                            (size_t)s->W, s->ub_mm, st);
+            } else if (zp.aniso_w > 0) {
                 // processing_core.py:357-377: nearest-resize the mask, transform there, bilinear-resize the map back.
                 // Distances stay in resized-pixel units; pixels farther than the reach get a stand-in >= fade_limit,
                 // which fades to 0 exactly like the true distance (bilinear taps are adjacent pixels, reach covers +3)

@@ -266,7 +266,8 @@ __global__ void __launch_bounds__(256) k_rec_dist(const uint32_t *__restrict__ c
 }
 
 // gradient from the distances at the receding pixels, merge with gray, LUT.  norm 0: fixed fade
-// g = trunc(255*(1 - min(d,F)/den)); norm 1: global min-max g = trunc(255*(1 - (d-min)/(max-min))), 0 if max<=min.
+// g = trunc(255*(1 - min(d,F)/den)); norm 1: global min-max g = trunc(255*(1 - (d-min)/(max-min))), 0 if max<=min;
+// norm 2: weighted stack, acc += (1 - min(d,F_j)/den_j)*w_j over the priors the pixel recedes from, g = trunc(255*acc/W).
 struct UFParams {
     const uint8_t *gray; size_t gpitch;
     uint8_t *out; size_t opitch;
@@ -276,6 +277,7 @@ struct UFParams {
     const uint8_t *lut;
     float F, den;
     int norm, W, H, aligned;
+    float w[VSB_MAX_PRIORS], wf[VSB_MAX_PRIORS], wden[VSB_MAX_PRIORS], wtotal; // norm 2: weighted stack
 };
 
 __global__ void __launch_bounds__(256) k_fade_unbounded(const __grid_constant__ UFParams p)
@@ -308,10 +310,21 @@ __global__ void __launch_bounds__(256) k_fade_unbounded(const __grid_constant__ 
             const int b = __ffs(m) - 1;
             m &= m - 1;
             const float d = p.dist[(size_t)y * p.dpitch + x + b];
-            float nrm;
-            if (p.norm == 1) nrm = __fdiv_rn(__fsub_rn(d, mn), den);
-            else nrm = __fdiv_rn(fminf(d, p.F), den);
-            const uint32_t g = dead ? 0u : (uint32_t)(int)__fmul_rn(255.0f, __fsub_rn(1.0f, nrm));
+            uint32_t g;
+            if (p.norm == 2) {
+                float a = 0.0f;
+                const uint32_t ncur = ~p.cur[o];
+                const int bit = (x & 16) + b;
+                for (int j = 0; j < p.np; ++j)
+                    if (p.w[j] > 0.0f && (((p.pri.p[j][o] & ncur) >> bit) & 1u))
+                        a = __fadd_rn(a, __fmul_rn(__fsub_rn(1.0f, __fdiv_rn(fminf(d, p.wf[j]), p.wden[j])), p.w[j]));
+                g = (uint32_t)(int)__fmul_rn(255.0f, __fdiv_rn(a, p.wtotal));
+            } else {
+                float nrm;
+                if (p.norm == 1) nrm = __fdiv_rn(__fsub_rn(d, mn), den);
+                else nrm = __fdiv_rn(fminf(d, p.F), den);
+                g = dead ? 0u : (uint32_t)(int)__fmul_rn(255.0f, __fsub_rn(1.0f, nrm));
+            }
             gw[b >> 2] |= (g & 255u) << ((b & 3) * 8);
         }
         gv = make_uint4(__vmaxu4(gv.x, gw[0]), __vmaxu4(gv.y, gw[1]), __vmaxu4(gv.z, gw[2]), __vmaxu4(gv.w, gw[3]));
@@ -370,17 +383,13 @@ extern "C" int vsb_dt_unbounded(const uint32_t *seed_bits, int wpr, int W, int H
     return vsb_check_launch("k_dense_dist");
 }
 
-extern "C" int vsb_zblend_unbounded(const uint8_t *gray, size_t gray_pitch, int W, int H, const uint32_t *cur_bits,
-                                    const uint32_t *const *prior_bits, int n_priors, int wpr, int metric, int norm,
-                                    float fade, float den, uint16_t *g, size_t g_pitch_elems, uint16_t *gmin64,
-                                    float *dist, size_t dist_pitch_elems, uint32_t *minmax2, const uint8_t *lut256_dev,
-                                    uint8_t *out, size_t out_pitch, vsb_stream_t stream)
+extern "C" int vsb_rec_dist_unbounded(const uint32_t *cur_bits, const uint32_t *const *prior_bits, int n_priors, int wpr,
+                                      int W, int H, int metric, uint16_t *g, size_t g_pitch_elems, uint16_t *gmin64,
+                                      float *dist, size_t dist_pitch_elems, uint32_t *minmax2, vsb_stream_t stream)
 {
-    VSB_REQUIRE(gray && cur_bits && g && gmin64 && dist && minmax2 && out, "vsb_zblend_unbounded: null pointer");
-    VSB_REQUIRE(n_priors >= 0 && n_priors <= VSB_MAX_PRIORS && (n_priors == 0 || prior_bits), "vsb_zblend_unbounded: priors");
-    VSB_REQUIRE(norm == 0 || norm == 1, "vsb_zblend_unbounded: norm must be 0 (fixed) or 1 (min-max)");
-    VSB_REQUIRE(W > 0 && H > 0 && gray_pitch >= (size_t)W && out_pitch >= (size_t)W && dist_pitch_elems >= (size_t)W,
-                "vsb_zblend_unbounded: bad geometry");
+    VSB_REQUIRE(cur_bits && g && gmin64 && dist && minmax2, "vsb_rec_dist_unbounded: null pointer");
+    VSB_REQUIRE(n_priors >= 0 && n_priors <= VSB_MAX_PRIORS && (n_priors == 0 || prior_bits), "vsb_rec_dist_unbounded: priors");
+    VSB_REQUIRE(W > 0 && H > 0 && dist_pitch_elems >= (size_t)W, "vsb_rec_dist_unbounded: bad geometry");
     cudaStream_t s = (cudaStream_t)stream;
     int rc = vsb_coldist(cur_bits, wpr, W, H, g, g_pitch_elems, gmin64, stream);
     if (rc) return rc;
@@ -394,14 +403,58 @@ extern "C" int vsb_zblend_unbounded(const uint8_t *gray, size_t gray_pitch, int 
         k_rec_dist<1><<<tgrid, 256, 0, s>>>(cur_bits, pp, n_priors, wpr, g, g_pitch_elems, gmin64, nblk, W, H, dist, dist_pitch_elems, minmax2);
     else
         k_rec_dist<0><<<tgrid, 256, 0, s>>>(cur_bits, pp, n_priors, wpr, g, g_pitch_elems, gmin64, nblk, W, H, dist, dist_pitch_elems, minmax2);
-    rc = vsb_check_launch("k_rec_dist");
-    if (rc) return rc;
+    return vsb_check_launch("k_rec_dist");
+}
+
+static int fade_from_dist(const uint8_t *gray, size_t gray_pitch, int W, int H, const uint32_t *cur_bits,
+                          const uint32_t *const *prior_bits, int n_priors, int wpr, int norm, float fade, float den,
+                          const vsb_zparams *zp, const float *dist, size_t dist_pitch_elems, const uint32_t *minmax2,
+                          const uint8_t *lut256_dev, uint8_t *out, size_t out_pitch, vsb_stream_t stream)
+{
     UFParams p;
-    p.gray = gray; p.gpitch = gray_pitch; p.out = out; p.opitch = out_pitch; p.cur = cur_bits; p.pri = pp; p.np = n_priors;
+    memset(&p, 0, sizeof p);
+    for (int i = 0; i < VSB_MAX_PRIORS; ++i) p.pri.p[i] = i < n_priors ? prior_bits[i] : nullptr;
+    p.gray = gray; p.gpitch = gray_pitch; p.out = out; p.opitch = out_pitch; p.cur = cur_bits; p.np = n_priors;
     p.wpr = wpr; p.dist = dist; p.dpitch = dist_pitch_elems; p.mm = minmax2; p.lut = lut256_dev; p.F = fade; p.den = den;
     p.norm = norm; p.W = W; p.H = H;
+    if (norm == 2) {
+        for (int i = 0; i < n_priors; ++i) { p.w[i] = zp->weights[i]; p.wf[i] = zp->fades[i]; p.wden[i] = zp->dens[i]; }
+        p.wtotal = zp->total_weight;
+    }
     p.aligned = (vsb_aligned16(gray, gray_pitch) && vsb_aligned16(out, out_pitch)) ? 1 : 0;
     dim3 grid(((W + 15) / 16 + 63) / 64, (H + 3) / 4);
-    k_fade_unbounded<<<grid, 256, 0, s>>>(p);
+    k_fade_unbounded<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
     return vsb_check_launch("k_fade_unbounded");
+}
+
+extern "C" int vsb_zblend_unbounded(const uint8_t *gray, size_t gray_pitch, int W, int H, const uint32_t *cur_bits,
+                                    const uint32_t *const *prior_bits, int n_priors, int wpr, int metric, int norm,
+                                    float fade, float den, uint16_t *g, size_t g_pitch_elems, uint16_t *gmin64,
+                                    float *dist, size_t dist_pitch_elems, uint32_t *minmax2, const uint8_t *lut256_dev,
+                                    uint8_t *out, size_t out_pitch, vsb_stream_t stream)
+{
+    VSB_REQUIRE(gray && out, "vsb_zblend_unbounded: null pointer");
+    VSB_REQUIRE(norm == 0 || norm == 1, "vsb_zblend_unbounded: norm must be 0 (fixed) or 1 (min-max)");
+    VSB_REQUIRE(gray_pitch >= (size_t)W && out_pitch >= (size_t)W, "vsb_zblend_unbounded: bad geometry");
+    int rc = vsb_rec_dist_unbounded(cur_bits, prior_bits, n_priors, wpr, W, H, metric, g, g_pitch_elems, gmin64, dist,
+                                    dist_pitch_elems, minmax2, stream);
+    if (rc) return rc;
+    return fade_from_dist(gray, gray_pitch, W, H, cur_bits, prior_bits, n_priors, wpr, norm, fade, den, nullptr, dist,
+                          dist_pitch_elems, minmax2, lut256_dev, out, out_pitch, stream);
+}
+
+extern "C" int vsb_weighted_unbounded(const uint8_t *gray, size_t gray_pitch, int W, int H, const uint32_t *cur_bits,
+                                      const uint32_t *const *prior_bits, int wpr, const vsb_zparams *zp, uint16_t *g,
+                                      size_t g_pitch_elems, uint16_t *gmin64, float *dist, size_t dist_pitch_elems,
+                                      uint32_t *minmax2, const uint8_t *lut256_dev, uint8_t *out, size_t out_pitch,
+                                      vsb_stream_t stream)
+{
+    VSB_REQUIRE(gray && out && zp, "vsb_weighted_unbounded: null pointer");
+    VSB_REQUIRE(gray_pitch >= (size_t)W && out_pitch >= (size_t)W, "vsb_weighted_unbounded: bad geometry");
+    VSB_REQUIRE(zp->n_priors >= 0 && zp->n_priors <= VSB_MAX_PRIORS, "vsb_weighted_unbounded: priors");
+    int rc = vsb_rec_dist_unbounded(cur_bits, prior_bits, zp->n_priors, wpr, W, H, zp->metric, g, g_pitch_elems, gmin64, dist,
+                                    dist_pitch_elems, minmax2, stream);
+    if (rc) return rc;
+    return fade_from_dist(gray, gray_pitch, W, H, cur_bits, prior_bits, zp->n_priors, wpr, 2, 0.0f, 1.0f, zp, dist,
+                          dist_pitch_elems, minmax2, lut256_dev, out, out_pitch, stream);
 }

@@ -113,6 +113,8 @@ def _calculate_weighted_receding_gradient_field(current_white_mask, prior_binary
     z.n_priors = k
     z.total_weight = np.float32(float(sum(weights[:k])))
     cur = _bits(current_white_mask)
+    if z.mode == N.Z_WEIGHTED_FAR:
+        return E.weighted_unbounded(None, cur, [_bits(m) for m in prior_binary_masks[:k]], z).numpy()
     return E.zblend(None, cur, [_bits(m) for m in prior_binary_masks[:k]], z).numpy()
 
 

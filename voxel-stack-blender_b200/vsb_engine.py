@@ -181,6 +181,33 @@ def zblend_unbounded(gray: Optional[DevImage], cur: DevBits, priors: Sequence[De
     return out
 
 
+def _unbounded_scratch(H: int, W: int, wpr: int):
+    t = torch()
+    g = t.empty((H, W), dtype=t.int16, device="cuda")
+    gmin = t.empty(int(N.load().vsb_coldist_scratch_elems(W, H, wpr)), dtype=t.int16, device="cuda")
+    mm = t.empty(2, dtype=t.int32, device="cuda")
+    return g, gmin, mm
+
+
+def weighted_unbounded(gray: Optional[DevImage], cur: DevBits, priors: Sequence[DevBits], z: N.ZParams,
+                       lut: Optional[np.ndarray] = None) -> DevImage:
+    """Weighted stack with a fade distance beyond the tile kernels' reach (unbounded distances)."""
+    t = torch()
+    H, W = cur.H, cur.W
+    if gray is None:
+        gray = DevImage(H, W, zero=True)
+    out = DevImage(H, W)
+    g, gmin, mm = _unbounded_scratch(H, W, cur.wpr)
+    dist = t.empty((H, W), dtype=t.float32, device="cuda")
+    ld = lut_dev(lut) if lut is not None else None
+    zz = N.ZParams.from_buffer_copy(z)
+    N.check(N.load().vsb_weighted_unbounded(gray.ptr, gray.pitch, W, H, cur.ptr, N.ptr_array([p.ptr for p in priors]), cur.wpr,
+                                            ctypes.byref(zz), g.data_ptr(), W, gmin.data_ptr(), dist.data_ptr(), W,
+                                            mm.data_ptr(), ld.data_ptr() if ld is not None else None, out.ptr, out.pitch,
+                                            _stream()), "vsb_weighted_unbounded")
+    return out
+
+
 def dt_unbounded_np(cur_white: np.ndarray, metric: str = "chamfer5"):
     """Dense unbounded distance map (float32) and, for the exact metric, the integer squared distances."""
     t = torch()
@@ -212,7 +239,11 @@ def enhanced(gray: Optional[DevImage], cur: DevBits, priors: Sequence[DevBits], 
     dist = t.empty((H, W), dtype=t.float32, device="cuda")
     labels = t.empty((H, W), dtype=t.int32, device="cuda")
     cmax = t.empty((H, W), dtype=t.int32, device="cuda")
-    if z.aniso_w > 0:
+    if z.mode == N.Z_ENHANCED_FAR:
+        g, gmin, mm = _unbounded_scratch(H, W, cur.wpr)
+        N.check(lib.vsb_rec_dist_unbounded(cur.ptr, pri, len(priors), cur.wpr, W, H, int(z.metric), g.data_ptr(), W,
+                                           gmin.data_ptr(), dist.data_ptr(), W, mm.data_ptr(), _stream()), "vsb_rec_dist_unbounded")
+    elif z.aniso_w > 0:
         # anisotropic branch (processing_core.py:357-377): nearest-resize the mask, transform there, resize back
         aw, ah = int(z.aniso_w), int(z.aniso_h)
         near = ResizePlan(W, H, aw, ah, N.INTER_NEAREST)

@@ -21,7 +21,7 @@ VSB_MAX_PRIORS = 16
 VSB_MAX_XY_OPS = 16
 VSB_FAST_REACH = 63
 
-Z_FIXED, Z_WEIGHTED, Z_CONST, Z_DIST, Z_ENHANCED, Z_NONE, Z_MINMAX, Z_FIXED_FAR = 0, 1, 2, 3, 4, 5, 6, 7
+Z_FIXED, Z_WEIGHTED, Z_CONST, Z_DIST, Z_ENHANCED, Z_NONE, Z_MINMAX, Z_FIXED_FAR, Z_WEIGHTED_FAR, Z_ENHANCED_FAR = 0, 1, 2, 3, 4, 5, 6, 7, 8, 9
 METRIC_CHAMFER5, METRIC_EXACT = 0, 1
 OP_NONE, OP_LUT, OP_GAUSSIAN, OP_BILATERAL, OP_MEDIAN, OP_UNSHARP, OP_RESIZE = 0, 1, 2, 3, 4, 5, 6
 INTER_NEAREST, INTER_LINEAR, INTER_CUBIC, INTER_LANCZOS4, INTER_AREA, INTER_LINEAR_F32 = 0, 1, 2, 3, 4, 5
@@ -94,6 +94,11 @@ _SIGS = {
     "vsb_zblend_unbounded": (c_int, [c_void_p, c_size_t, c_int, c_int, c_void_p, POINTER(c_void_p), c_int, c_int, c_int,
                                      c_int, c_float, c_float, c_void_p, c_size_t, c_void_p, c_void_p, c_size_t, c_void_p,
                                      c_void_p, c_void_p, c_size_t, c_void_p]),
+    "vsb_rec_dist_unbounded": (c_int, [c_void_p, POINTER(c_void_p), c_int, c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p,
+                                       c_void_p, c_size_t, c_void_p, c_void_p]),
+    "vsb_weighted_unbounded": (c_int, [c_void_p, c_size_t, c_int, c_int, c_void_p, POINTER(c_void_p), c_int, POINTER(ZParams),
+                                       c_void_p, c_size_t, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_size_t,
+                                       c_void_p]),
     "vsb_pack_flags": (c_int, [c_void_p, c_size_t, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     "vsb_layer_stats": (c_int, [c_int, c_void_p]),
     "vsb_layer_fused": (c_int, [c_void_p, c_size_t, c_int, c_int, c_void_p, POINTER(c_void_p), c_void_p, POINTER(c_void_p),

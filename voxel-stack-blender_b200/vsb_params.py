@@ -73,6 +73,9 @@ def zparams_from_config(cfg, metric: str = "chamfer5", width: Optional[int] = No
         z.reach = chamfer_reach(fmax)
         z.fade = f32(fmax)
         z.den = f32(1.0)
+        if z.reach > N.VSB_FAST_REACH:      # a fade distance beyond the tile kernels' reach: unbounded distances
+            z.mode = N.Z_WEIGHTED_FAR
+            z.reach = 0
     elif mode == "enhanced_edt":
         if getattr(getattr(cfg, "anisotropic_params", None), "enabled", False):
             ap = cfg.anisotropic_params
@@ -93,6 +96,9 @@ def zparams_from_config(cfg, metric: str = "chamfer5", width: Optional[int] = No
         z.fade = f32(F)
         z.den = f32(F) if F > 0 else f32(1.0)
         z.reach = chamfer_reach(F)
+        if z.reach > N.VSB_FAST_REACH and z.aniso_w == 0:
+            z.mode = N.Z_ENHANCED_FAR
+            z.reach = 0
     else:  # fixed_fade (the dispatcher's default branch, processing_core.py:434-440)
         z.n_priors = N.VSB_MAX_PRIORS
         if not cfg.use_fixed_fade_receding:
@@ -121,8 +127,7 @@ def zparams_from_config(cfg, metric: str = "chamfer5", width: Optional[int] = No
             z.fade = f32(F)
             z.den = f32(1.0)
     if z.reach > N.VSB_FAST_REACH:
-        raise UnsupportedOnDevice(f"{mode}: fade distance needs reach {z.reach} > {N.VSB_FAST_REACH} (only the fixed fade "
-                                  "has the unbounded path so far)")
+        raise UnsupportedOnDevice(f"{mode}: fade distance needs reach {z.reach} > {N.VSB_FAST_REACH}")
     return z
 
 
