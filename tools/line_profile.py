@@ -9,12 +9,13 @@ subprocess.run(f"cd {tmp} && cuobjdump -xelf all {ROOT}/voxel-stack-blender_b200
 src_csv = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(src_csv.splitlines()))
 blocks, cur = [], None
+want = "k_layer" if "k_layer" in kname else kname
 for r in rows:
     if r and r[0] == "Kernel Name":
-        cur = []; blocks.append(cur); continue
+        cur = []; blocks.append((r[1] if len(r) > 1 else "", cur)); continue
     if cur is not None:
         cur.append(r)
-b = blocks[0]; hdr = b[0]; data = b[1:]
+b = [blk for name, blk in blocks if want in name][-1]; hdr = b[0]; data = b[1:]   # last matching launch in the report
 ie, ss = hdr.index("Instructions Executed"), hdr.index("# Samples")
 txt = open(os.path.join(tmp, "all.txt")).read().split("\n")
 start = [i for i, l in enumerate(txt) if l.startswith(".text." + kname) and l.endswith(":")][0]
