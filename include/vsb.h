@@ -248,6 +248,21 @@ typedef struct {
 int vsb_pack_flags(const uint8_t *gray, size_t pitch, int W, int H, int thresh, uint32_t *bits, int wpr,
                    uint16_t *flags, vsb_stream_t stream);
 
+/* LUT-only pipelines (no XY filter): one pass over the gray layer writes the packed mask AND lut[gray] (the final
+ * value of every pixel that does not recede); vsb_layer_patch then computes the fade on the receding pixels alone and
+ * rewrites them with lut[max(gray, gradient)].  Same results as vsb_layer_fused without XY stage, the gray layer is
+ * read from HBM once and untouched tiles cost one look at their mask words. */
+int vsb_pack_flags_lut(const uint8_t *gray, size_t pitch, int W, int H, int thresh, uint32_t *bits, int wpr,
+                       uint16_t *flags, const uint8_t *lut256_dev /* NULL = identity */, uint8_t *out, size_t out_pitch,
+                       const uint32_t *const *prior_bits, int n_priors,
+                       int *rec_tiles /* NULL, or int[1 + tiles]: [0] receives the number of 128x32 tiles holding a
+                                         receding pixel w.r.t. the given priors, [1..] their indices */,
+                       vsb_stream_t stream);
+int vsb_layer_patch(const uint8_t *in, size_t in_pitch, int W, int H, const uint32_t *cur_bits,
+                    const uint32_t *const *prior_bits, int wpr, const vsb_zparams *params, const float *T_dev,
+                    const uint8_t *lut1_dev, const int *rec_tiles /* from vsb_pack_flags_lut, or NULL = look at every tile */,
+                    uint8_t *out /* pre-filled by vsb_pack_flags_lut */, size_t out_pitch, vsb_stream_t stream);
+
 /* work counters of vsb_layer_fused (debugging / DESIGN.md numbers): op 1 = enable + clear, 2 = read 8 counters
  * (uniform tiles, worked tiles, tiles with receding pixels, receding pixels, bilateral pixels, Gaussian words,
  * 0, 0) and clear, 0 = disable */

@@ -615,3 +615,48 @@ def test_stack_engine_far_modes(E, mode):
     want = O.run_stack(layers, d)
     for i, (a, b) in enumerate(zip(outs, want)):
         assert np.array_equal(a, b), (mode, i, int((a != b).sum()))
+
+
+def test_pack_lut_and_patch_equal_fused_no_xy(E):
+    """LUT-only chains: vsb_pack_flags_lut + vsb_layer_patch (gray read once, receding tiles from a work list) ==
+    the oracle, with and without the work list, ragged sizes included."""
+    import ctypes
+    import vsb_native as N, vsb_params as P
+    t = E.torch()
+    lut = O.generate_lut("gamma", gamma_value=1.8)
+    for (W, H) in ((500, 301), (1024, 77), (130, 33)):
+        layers = small_stack(W=W, H=H, L=5, seed=21, raft=True, n_blobs=7)
+        for mode, F in (("fixed_fade", 12.0), ("weighted_stack", 9.0), ("fixed_fade", 0.0)):
+            d = {"blending_mode": mode, "receding_layers": 3, "use_fixed_fade_receding": True, "fixed_fade_distance_receding": F,
+                 "manual_weights": [4, 2, 1], "fade_distances_receding": [9.0, 6.0, 3.0]}
+            want = [O.apply_lut(o, lut) for o in O.run_stack(layers, d)]
+            from config import Config
+            z = P.zparams_from_config(Config.from_dict(d))
+            masks = []
+            for zi, g in enumerate(layers):
+                img = E.DevImage.from_numpy(g)
+                cur = E.DevBits(H, W)
+                pri = list(reversed(masks[-3:]))
+                for use_list in (True, False):
+                    out = E.DevImage(H, W)
+                    flags = t.empty(((H + 31) // 32) * ((W + 127) // 128), dtype=t.int16, device="cuda")
+                    rec = t.empty(1 + flags.numel(), dtype=t.int32, device="cuda")
+                    ld = E.lut_dev(lut)
+                    pa = N.ptr_array([p.ptr for p in pri])
+                    N.check(N.load().vsb_pack_flags_lut(img.ptr, img.pitch, W, H, 127, cur.ptr, cur.wpr, flags.data_ptr(), ld.data_ptr(),
+                                                        out.ptr, out.pitch, pa, len(pri), rec.data_ptr() if use_list else None,
+                                                        E._stream()), "vsb_pack_flags_lut")
+                    zz = N.ZParams.from_buffer_copy(z)
+                    if mode == "weighted_stack":
+                        k = min(len(pri), 3)
+                        zz.n_priors = k if k else 0
+                        zz.total_weight = float(sum([4, 2, 1][:k]))
+                    else:
+                        zz.n_priors = len(pri)
+                    N.check(N.load().vsb_layer_patch(img.ptr, img.pitch, W, H, cur.ptr, pa, cur.wpr, ctypes.byref(zz),
+                                                     E.table_dev(zz.reach).data_ptr(), ld.data_ptr(),
+                                                     rec.data_ptr() if use_list else None, out.ptr, out.pitch, E._stream()),
+                            "vsb_layer_patch")
+                    got = out.numpy()
+                    assert np.array_equal(got, want[zi]), (W, H, mode, zi, use_list, int((got != want[zi]).sum()))
+                masks.append(cur)

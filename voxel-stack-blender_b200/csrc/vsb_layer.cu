@@ -67,6 +67,8 @@ struct LayerParams {
     unsigned long long *stats; // optional work counters (vsb_layer_stats)
     struct { int T, raw, src, s1, s2, bits, list, raw_stride, src_stride; } sm; // dynamic shared memory carve (bytes / words)
     int ntiles;
+    const int *rec_list; // sparse: [0] = number of tiles with receding pixels, [1..] their indices (nullptr = all tiles)
+    int sparse;          // no-XY variant only: `out` already holds LUT1[gray]; rewrite just the receding pixels
     vsb_zparams z;
 };
 #define GL_OFF 1400 // Gaussian word list starts here in s_list (bilateral word list: at most 36*38 entries)
@@ -75,18 +77,28 @@ struct LayerParams {
 // One CTA = two vertically adjacent 128x32 tiles; a thread owns one mask word (32 pixels, two 128-bit loads, both
 // issued before first use), so there is no cross-lane combine; the uniformity flag of each tile is a warp vote per
 // 8 rows plus one shared-memory AND.
-template <bool ALIGNED>
+struct PackPriors { const uint32_t *p[VSB_MAX_PRIORS]; int n; };
+
+// LUTOUT: the same pass also writes lut[gray] (the layer as it leaves a LUT-only pipeline wherever nothing recedes;
+// vsb_layer_patch then rewrites the receding pixels), so the gray layer is read from HBM once.
+template <bool ALIGNED, bool LUTOUT>
 __global__ void __launch_bounds__(VSB_THREADS) k_pack_flags(const uint8_t *__restrict__ gray, size_t pitch, int W, int H,
                                                             uint32_t thr4, uint32_t *__restrict__ bits, int wpr,
-                                                            uint16_t *__restrict__ flags, int tiles_x, int tiles_y)
+                                                            uint16_t *__restrict__ flags, int tiles_x, int tiles_y,
+                                                            const uint8_t *__restrict__ lut, uint8_t *__restrict__ out,
+                                                            size_t opitch, int out_aligned, PackPriors pr,
+                                                            int *__restrict__ rec_list)
 {
     __shared__ int s_ok[2];
+    __shared__ int s_rec[2];
+    __shared__ __align__(4) uint8_t s_plut[256];
+    if (LUTOUT && lut && threadIdx.x < 64) ((uint32_t *)s_plut)[threadIdx.x] = ((const uint32_t *)lut)[threadIdx.x];
     const int t = threadIdx.x, half = t >> 7, u = t & 127;
     const int ty = blockIdx.y * 2 + half;
     const int x0 = blockIdx.x * VSB_TW, y0 = ty * VSB_TH;
     const int r = u >> 2, wq = u & 3;
     const int y = y0 + r, x = x0 + wq * 32;
-    if (t < 2) s_ok[t] = 1;
+    if (t < 2) { s_ok[t] = 1; s_rec[t] = 0; }
     const int n = (y < H) ? max(0, min(32, W - x)) : 0;
     uint4 a = make_uint4(0, 0, 0, 0), b = make_uint4(0, 0, 0, 0);
     uint32_t first = 0;
@@ -105,6 +117,21 @@ __global__ void __launch_bounds__(VSB_THREADS) k_pack_flags(const uint8_t *__res
     if (n < 32) word &= n > 0 ? ((1u << n) - 1u) : 0u;
     const int wx = (x0 >> 5) + wq;
     if (y < H && wx < wpr) bits[(size_t)y * wpr + wx] = word;
+    if (LUTOUT && rec_list) { // tiles with receding pixels (prior white, current black) go on the patch kernel's work list
+        uint32_t acc = 0;
+        if (y < H && wx < wpr) for (int j = 0; j < pr.n; ++j) acc |= pr.p[j][(size_t)y * wpr + wx];
+        if (__any_sync(0xffffffffu, (acc & ~word) != 0u) && (t & 31) == 0) s_rec[half] = 1;
+    }
+    if (LUTOUT && n > 0) {
+        VsbLut Lp;
+        Lp.s = lut ? s_plut : nullptr;
+        Lp.l0 = lut ? (uint32_t)s_plut[0] * 0x01010101u : 0u;
+        Lp.l255 = lut ? (uint32_t)s_plut[255] * 0x01010101u : 0xFFFFFFFFu;
+        uint8_t *dst = out + (size_t)y * opitch + x;
+        const uint4 oa = Lp.map16(a), ob = Lp.map16(b);
+        if (n == 32 && out_aligned) { vsb_st16_stream(dst, oa); vsb_st16_stream(dst + 16, ob); }
+        else { vsb_st_bytes(dst, oa, n); if (n > 16) vsb_st_bytes(dst + 16, ob, n - 16); }
+    }
     const uint32_t bc = first * 0x01010101u;
     bool ok = true;
     if (n == 32) ok = (a.x == bc) & (a.y == bc) & (a.z == bc) & (a.w == bc) & (b.x == bc) & (b.y == bc) & (b.z == bc) & (b.w == bc);
@@ -114,11 +141,15 @@ __global__ void __launch_bounds__(VSB_THREADS) k_pack_flags(const uint8_t *__res
     }
     if (!__all_sync(0xffffffffu, ok) && (t & 31) == 0) s_ok[half] = 0;
     __syncthreads();
-    if (u == 0 && ty < tiles_y) flags[ty * tiles_x + blockIdx.x] = (uint16_t)(s_ok[half] ? first : FLAG_MIXED);
+    if (u == 0 && ty < tiles_y) {
+        flags[ty * tiles_x + blockIdx.x] = (uint16_t)(s_ok[half] ? first : FLAG_MIXED);
+        if (LUTOUT && rec_list && s_rec[half]) rec_list[1 + atomicAdd(&rec_list[0], 1)] = ty * tiles_x + (int)blockIdx.x;
+    }
 }
 
-extern "C" int vsb_pack_flags(const uint8_t *gray, size_t pitch, int W, int H, int thresh, uint32_t *bits, int wpr,
-                              uint16_t *flags, vsb_stream_t stream)
+static int pack_flags_launch(const uint8_t *gray, size_t pitch, int W, int H, int thresh, uint32_t *bits, int wpr,
+                             uint16_t *flags, bool lutout, const uint8_t *lut, uint8_t *out, size_t opitch,
+                             const uint32_t *const *prior_bits, int n_priors, int *rec_list, vsb_stream_t stream)
 {
     VSB_REQUIRE(gray && bits && flags, "vsb_pack_flags: null pointer");
     VSB_REQUIRE(W > 0 && H > 0 && wpr >= ((W + 127) / 128) * 4 && pitch >= (size_t)W, "vsb_pack_flags: bad geometry");
@@ -127,9 +158,39 @@ extern "C" int vsb_pack_flags(const uint8_t *gray, size_t pitch, int W, int H, i
     dim3 grid(tiles_x, (tiles_y + 1) / 2);
     const uint32_t thr4 = (uint32_t)thresh * 0x01010101u;
     cudaStream_t s = (cudaStream_t)stream;
-    if (vsb_aligned16(gray, pitch)) k_pack_flags<true><<<grid, VSB_THREADS, 0, s>>>(gray, pitch, W, H, thr4, bits, wpr, flags, tiles_x, tiles_y);
-    else k_pack_flags<false><<<grid, VSB_THREADS, 0, s>>>(gray, pitch, W, H, thr4, bits, wpr, flags, tiles_x, tiles_y);
+    const int oal = out ? (vsb_aligned16(out, opitch) ? 1 : 0) : 0;
+    const bool al = vsb_aligned16(gray, pitch);
+    PackPriors pr;
+    memset(&pr, 0, sizeof pr);
+    if (rec_list) {
+        VSB_REQUIRE(n_priors >= 0 && n_priors <= VSB_MAX_PRIORS && (n_priors == 0 || prior_bits), "vsb_pack_flags_lut: priors");
+        pr.n = n_priors;
+        for (int i = 0; i < n_priors; ++i) pr.p[i] = prior_bits[i];
+        VSB_CUDA(cudaMemsetAsync(rec_list, 0, sizeof(int), s));
+    }
+    if (lutout) {
+        if (al) k_pack_flags<true, true><<<grid, VSB_THREADS, 0, s>>>(gray, pitch, W, H, thr4, bits, wpr, flags, tiles_x, tiles_y, lut, out, opitch, oal, pr, rec_list);
+        else k_pack_flags<false, true><<<grid, VSB_THREADS, 0, s>>>(gray, pitch, W, H, thr4, bits, wpr, flags, tiles_x, tiles_y, lut, out, opitch, oal, pr, rec_list);
+    } else {
+        if (al) k_pack_flags<true, false><<<grid, VSB_THREADS, 0, s>>>(gray, pitch, W, H, thr4, bits, wpr, flags, tiles_x, tiles_y, nullptr, nullptr, 0, 0, pr, nullptr);
+        else k_pack_flags<false, false><<<grid, VSB_THREADS, 0, s>>>(gray, pitch, W, H, thr4, bits, wpr, flags, tiles_x, tiles_y, nullptr, nullptr, 0, 0, pr, nullptr);
+    }
     return vsb_check_launch("k_pack_flags");
+}
+
+extern "C" int vsb_pack_flags(const uint8_t *gray, size_t pitch, int W, int H, int thresh, uint32_t *bits, int wpr,
+                              uint16_t *flags, vsb_stream_t stream)
+{
+    return pack_flags_launch(gray, pitch, W, H, thresh, bits, wpr, flags, false, nullptr, nullptr, 0, nullptr, 0, nullptr, stream);
+}
+
+extern "C" int vsb_pack_flags_lut(const uint8_t *gray, size_t pitch, int W, int H, int thresh, uint32_t *bits, int wpr,
+                                  uint16_t *flags, const uint8_t *lut256_dev, uint8_t *out, size_t out_pitch,
+                                  const uint32_t *const *prior_bits, int n_priors, int *rec_tiles, vsb_stream_t stream)
+{
+    VSB_REQUIRE(out && out != gray && out_pitch >= (size_t)W, "vsb_pack_flags_lut: output missing / in place / pitch < width");
+    return pack_flags_launch(gray, pitch, W, H, thresh, bits, wpr, flags, true, lut256_dev, out, out_pitch, prior_bits, n_priors,
+                             rec_tiles, stream);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -234,7 +295,7 @@ __global__ void __launch_bounds__(VSB_THREADS, XY ? VSB_LAYER_CTAS_XY : 6) k_lay
     VsbLut L1, L2;
     L1.s = p.lut1 ? s_lut1 : nullptr; L1.l0 = 0u; L1.l255 = 0xFFFFFFFFu; // broadcasts filled in after the first barrier
     L2.s = p.lut2 ? s_lut2 : nullptr; L2.l0 = 0u; L2.l255 = 0xFFFFFFFFu;
-    if (t < 64 && p.lut1) ((uint32_t *)s_lut1)[t] = ((const uint32_t *)p.lut1)[t];
+    if (t < 64 && p.lut1 && !(!XY && p.sparse)) ((uint32_t *)s_lut1)[t] = ((const uint32_t *)p.lut1)[t];
     bool late_staged = false; // trailing LUT and bilateral tables: staged by the first tile that is not trivially uniform
     bool t_staged = false; // chamfer table [(R+1) x (R+1)]: staged by the first tile that needs it
 
@@ -273,11 +334,17 @@ __global__ void __launch_bounds__(VSB_THREADS, XY ? VSB_LAYER_CTAS_XY : 6) k_lay
     };
 
     int tile = PERSIST ? (int)blockIdx.x : (int)(blockIdx.y * gridDim.x + blockIdx.x);
+    int wl_tx = (int)blockIdx.x, wl_ty = (int)blockIdx.y;
+    if (!PERSIST && !XY && p.rec_list) { // work list of the patch launch: CTA i takes the i-th listed tile
+        if (tile >= p.rec_list[0]) return;
+        tile = p.rec_list[1 + tile];
+        wl_tx = tile % p.tiles_x; wl_ty = tile / p.tiles_x;
+    }
     int buf = 0;
     if (PERSIST && tile < p.ntiles) prefetch(tile, 0);
 
     for (; tile < p.ntiles; tile += PERSIST ? (int)gridDim.x : p.ntiles) {
-        const int tx = PERSIST ? tile % p.tiles_x : (int)blockIdx.x, ty = PERSIST ? tile / p.tiles_x : (int)blockIdx.y; // 2-D grid: no division
+        const int tx = PERSIST ? tile % p.tiles_x : wl_tx, ty = PERSIST ? tile / p.tiles_x : wl_ty; // 2-D grid: no division
         const int x0 = tx * VSB_TW, y0 = ty * VSB_TH;
         const int oy = y0 + r, ox = x0 + c * 16;
         const int nvalid = (oy < H) ? max(0, min(16, W - ox)) : 0;
@@ -331,11 +398,13 @@ __global__ void __launch_bounds__(VSB_THREADS, XY ? VSB_LAYER_CTAS_XY : 6) k_lay
                     rwv[0] = acc & ~p.cur[o];
                 }
             }
-            if (nvalid == 16 && p.aligned) { gv[0] = vsb_ld16_stream(p.in + (size_t)oy * p.ipitch + ox); gstate[0] = 1; }
-            else if (nvalid > 0) gstate[0] = 2;
-            ref_raw = p.in[(size_t)y0 * p.ipitch + x0];
+            ref_raw = 0;
+            if (!p.sparse) {
+                if (nvalid == 16 && p.aligned) { gv[0] = vsb_ld16_stream(p.in + (size_t)oy * p.ipitch + ox); gstate[0] = 1; }
+                else if (nvalid > 0) gstate[0] = 2;
+                ref_raw = p.in[(size_t)y0 * p.ipitch + x0];
+            }
             if (t == 0) { s_cnt = 0; s_gcnt = 0; s_quiet = 0; }
-            if (XY && t < RH) { s_zpl[t] = 0ULL; s_wpl[t] = 0ULL; }
             __syncthreads();
         } else {
             if (ZMODE != ZL_NONE) {
@@ -382,9 +451,11 @@ __global__ void __launch_bounds__(VSB_THREADS, XY ? VSB_LAYER_CTAS_XY : 6) k_lay
         if (L1.s) { L1.l0 = (uint32_t)s_lut1[0] * 0x01010101u; L1.l255 = (uint32_t)s_lut1[255] * 0x01010101u; }
         const uint32_t ref = L1.map4(ref_raw * 0x01010101u);
         bool uni = true;
+        const bool sparse = !XY && p.sparse != 0;
 #pragma unroll
         for (int u = 0; u < (XY ? 2 : 1); ++u) {
             const int i = t + u * VSB_THREADS;
+            if (sparse) break;
             if (!XY || i < RH * RG_CH) {
                 const int rr = XY ? i / RG_CH : r, cc = XY ? i - rr * RG_CH : c + 1;
                 uint4 v = make_uint4(0, 0, 0, 0);
@@ -425,6 +496,10 @@ __global__ void __launch_bounds__(VSB_THREADS, XY ? VSB_LAYER_CTAS_XY : 6) k_lay
         if (p.stats && t == 0) atomicAdd(&p.stats[tile_state == 0 ? 0 : 1], 1ULL);
         PHASE(8);
         do { // one pass; `break` = tile finished
+        if (sparse) {
+            if (!any_rec) break; // the pre-filled output stands
+            if (t < 64 && p.lut1) ((uint32_t *)s_lut1)[t] = ((const uint32_t *)p.lut1)[t]; // visible after P2's barriers
+        }
         if (tile_state == 0) { // uniform region, nothing recedes: every filter of a constant is that constant
             if (nvalid > 0) {
                 const uint32_t cv = p.lut2 ? (uint32_t)p.lut2[ref & 255u] * 0x01010101u : ref;
@@ -508,12 +583,14 @@ __global__ void __launch_bounds__(VSB_THREADS, XY ? VSB_LAYER_CTAS_XY : 6) k_lay
                 }
                 const int graw = PERSIST ? (int)rawb[rr * RG_W + rc] : (int)p.in[(size_t)y * p.ipitch + x];
                 const int m = max(graw, g & 255); // merge with the raw gray value
+                if (sparse) { p.out[(size_t)y * p.opitch + x] = L1.s ? L1.s[m] : (uint8_t)m; continue; }
                 s1[rr][rc] = L1.s ? L1.s[m] : (uint8_t)m;
                 if (XY) { // the word no longer holds a known constant
                     atomicAnd(&s_zpl32[rr][rc >> 7], ~(1u << ((rc >> 2) & 31)));
                     atomicAnd(&s_wpl32[rr][rc >> 7], ~(1u << ((rc >> 2) & 31)));
                 }
             }
+            if (sparse) break; // receding pixels rewritten in place
             __syncthreads();
             if (t == 0) s_cnt = 0;
             PHASE(10);
@@ -735,11 +812,11 @@ extern "C" int vsb_layer_stats(int op, unsigned long long *out8)
     return VSB_OK;
 }
 
-extern "C" int vsb_layer_fused(const uint8_t *in, size_t in_pitch, int W, int H, const uint32_t *cur_bits,
-                               const uint32_t *const *prior_bits, const uint16_t *cur_flags,
-                               const uint16_t *const *prior_flags, int wpr, const vsb_zparams *zp, const float *T_dev,
-                               const uint8_t *lut1_dev, const vsb_xy_fused *xy, const uint8_t *lut2_dev, uint8_t *out,
-                               size_t out_pitch, vsb_stream_t stream)
+static int layer_launch(const uint8_t *in, size_t in_pitch, int W, int H, const uint32_t *cur_bits,
+                        const uint32_t *const *prior_bits, const uint16_t *cur_flags,
+                        const uint16_t *const *prior_flags, int wpr, const vsb_zparams *zp, const float *T_dev,
+                        const uint8_t *lut1_dev, const vsb_xy_fused *xy, const uint8_t *lut2_dev, uint8_t *out,
+                        size_t out_pitch, vsb_stream_t stream, int sparse, const int *rec_list = nullptr)
 {
     VSB_REQUIRE(in && out && zp && in != out, "vsb_layer_fused: null pointer / in-place");
     VSB_REQUIRE(W >= 8 && H >= 8 && in_pitch >= (size_t)W && out_pitch >= (size_t)W,
@@ -795,6 +872,8 @@ extern "C" int vsb_layer_fused(const uint8_t *in, size_t in_pitch, int W, int H,
     p.stats = g_layer_stats;
     VSB_REQUIRE(p.halo <= LH_MAX, "vsb_layer_fused: halo %d > %d", p.halo, LH_MAX);
     p.ntiles = p.tiles_x * p.tiles_y;
+    p.sparse = sparse;
+    p.rec_list = sparse ? rec_list : nullptr;
     const BilTapsL *taps_dev = nullptr;
     if (p.hb > 0) { const int rc = taps_on_device(taps, &taps_dev); if (rc) return rc; }
     // persistent + prefetch variant: whole 16-byte chunks only, at most 7 masks staged per tile
@@ -825,4 +904,26 @@ extern "C" int vsb_layer_fused(const uint8_t *in, size_t in_pitch, int W, int H,
     case VSB_Z_CONST: return launch_layer<VSB_Z_CONST, 0>(p, taps_dev, persist, smem, s);
     default: return launch_layer<ZL_NONE, 0>(p, taps_dev, persist, smem, s);
     }
+}
+
+extern "C" int vsb_layer_fused(const uint8_t *in, size_t in_pitch, int W, int H, const uint32_t *cur_bits,
+                               const uint32_t *const *prior_bits, const uint16_t *cur_flags,
+                               const uint16_t *const *prior_flags, int wpr, const vsb_zparams *zp, const float *T_dev,
+                               const uint8_t *lut1_dev, const vsb_xy_fused *xy, const uint8_t *lut2_dev, uint8_t *out,
+                               size_t out_pitch, vsb_stream_t stream)
+{
+    return layer_launch(in, in_pitch, W, H, cur_bits, prior_bits, cur_flags, prior_flags, wpr, zp, T_dev, lut1_dev, xy, lut2_dev,
+                        out, out_pitch, stream, 0);
+}
+
+extern "C" int vsb_layer_patch(const uint8_t *in, size_t in_pitch, int W, int H, const uint32_t *cur_bits,
+                               const uint32_t *const *prior_bits, int wpr, const vsb_zparams *zp, const float *T_dev,
+                               const uint8_t *lut1_dev, const int *rec_tiles, uint8_t *out, size_t out_pitch,
+                               vsb_stream_t stream)
+{
+    VSB_REQUIRE(zp && (zp->mode == VSB_Z_FIXED || zp->mode == VSB_Z_WEIGHTED || zp->mode == VSB_Z_CONST),
+                "vsb_layer_patch: fixed, weighted or constant fades only");
+    if (zp->n_priors == 0) return VSB_OK; // nothing can recede: the pre-filled output stands
+    return layer_launch(in, in_pitch, W, H, cur_bits, prior_bits, nullptr, nullptr, wpr, zp, T_dev, lut1_dev, nullptr, nullptr,
+                        out, out_pitch, stream, 1, rec_tiles);
 }

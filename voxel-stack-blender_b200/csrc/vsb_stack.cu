@@ -56,6 +56,7 @@ struct vsb_stack {
     vsb_xy_fused fx;
     uint8_t *lut2_dev;
     std::vector<uint16_t *> flag_ring;
+    int *rec_tiles;        // LUT-only chains: work list of the patch kernel (1 + tiles ints)
     // optional per-stage CUDA-event profiling (bench.py roofline leg)
     bool prof_on;
     struct ProfRec { int stage; int launches; cudaEvent_t a, b; };
@@ -94,6 +95,7 @@ extern "C" int vsb_stack_destroy(vsb_stack *s)
     cudaStreamSynchronize(s->s_h2d); cudaStreamSynchronize(s->s_comp); cudaStreamSynchronize(s->s_d2h);
     for (auto &o : s->ops) { if (o.lut_dev) cudaFree(o.lut_dev); if (o.plan) vsb_resize_plan_destroy(o.plan); }
     if (s->tmp_blur) cudaFree(s->tmp_blur);
+    if (s->rec_tiles) cudaFree(s->rec_tiles);
     if (s->an_near) vsb_resize_plan_destroy(s->an_near);
     if (s->an_lin) vsb_resize_plan_destroy(s->an_lin);
     if (s->an_bits) cudaFree(s->an_bits);
@@ -167,7 +169,7 @@ extern "C" int vsb_stack_create(int W, int H, int n_priors, const vsb_zparams *z
     s->rec_bits = nullptr; s->dist = nullptr; s->labels = nullptr; s->cmax = nullptr;
     s->ub_g = s->ub_gmin = nullptr; s->ub_dist = nullptr; s->ub_mm = nullptr;
     s->prof_on = false;
-    s->fused = false; s->lut2_dev = nullptr;
+    s->fused = false; s->lut2_dev = nullptr; s->rec_tiles = nullptr;
     memset(&s->fx, 0, sizeof s->fx);
 
     // XY chain: compose runs of apply_lut; a leading run is folded into the Z-blend epilogue
@@ -281,6 +283,7 @@ extern "C" int vsb_stack_create(int W, int H, int n_priors, const vsb_zparams *z
         const size_t ntiles = (size_t)((W + VSB_TW - 1) / VSB_TW) * ((H + VSB_TH - 1) / VSB_TH);
         s->flag_ring.assign((size_t)n_priors + 1, nullptr);
         for (auto &p : s->flag_ring) STACK_CUDA(cudaMalloc((void **)&p, ntiles * sizeof(uint16_t)));
+        STACK_CUDA(cudaMalloc((void **)&s->rec_tiles, (ntiles + 1) * sizeof(int)));
     }
     *out_stack = s;
     return VSB_OK;
@@ -354,7 +357,19 @@ static int run_layer(vsb_stack *s, const uint8_t *gray, size_t gpitch, uint8_t *
     const int nring = s->n_priors + 1;
     uint32_t *cur = s->ring[s->head];
     int rc;
-    if (s->fused) { ProfScope ps(s, ST_PACKF, 1); rc = vsb_pack_flags(gray, gpitch, s->W, s->H, 127, cur, s->wpr, s->flag_ring[s->head], st); }
+    // LUT-only chain with a tile-reach fade: the pack pass also writes lut[gray], the layer kernel only patches the
+    // receding pixels (the gray layer is read once)
+    const bool patch_path = s->fused && emit && s->ops.empty() && getenv("VSB_NO_PATCH") == nullptr &&
+                            (s->zp.mode == VSB_Z_FIXED || s->zp.mode == VSB_Z_WEIGHTED || s->zp.mode == VSB_Z_CONST);
+    if (patch_path) {
+        const uint32_t *ppri[VSB_MAX_PRIORS];
+        const int pnp = s->count < s->n_priors ? s->count : s->n_priors;
+        for (int i = 0; i < pnp; ++i) ppri[i] = s->ring[(s->head - 1 - i + 2 * nring) % nring];
+        ProfScope ps(s, ST_PACKF, 1);
+        rc = vsb_pack_flags_lut(gray, gpitch, s->W, s->H, 127, cur, s->wpr, s->flag_ring[s->head], s->lead_lut_dev, out, opitch,
+                                ppri, pnp, s->rec_tiles, st);
+    }
+    else if (s->fused) { ProfScope ps(s, ST_PACKF, 1); rc = vsb_pack_flags(gray, gpitch, s->W, s->H, 127, cur, s->wpr, s->flag_ring[s->head], st); }
     else { ProfScope ps(s, ST_PACK, 1); rc = vsb_threshold_pack(gray, gpitch, s->W, s->H, 127, cur, s->wpr, st); }
     if (rc) return rc;
     if (emit) {
@@ -379,7 +394,10 @@ static int run_layer(vsb_stack *s, const uint8_t *gray, size_t gpitch, uint8_t *
         if (s->fused && !enhanced && !far_mode) {
             const uint16_t *pfl[VSB_MAX_PRIORS];
             for (int i = 0; i < np; ++i) pfl[i] = s->flag_ring[(s->head - 1 - i + 2 * nring) % nring];
-            {
+            if (patch_path) {
+                ProfScope ps(s, ST_LAYER, 1);
+                rc = vsb_layer_patch(gray, gpitch, s->W, s->H, cur, pri, s->wpr, &zp, s->T_dev, s->lead_lut_dev, s->rec_tiles, out, opitch, st);
+            } else {
                 ProfScope ps(s, ST_LAYER, 1);
                 // the tile-flag shortcut saves the input read of quiet tiles; it only pays once the kernel is HBM bound
                 static const bool use_flags = getenv("VSB_TILE_FLAGS") != nullptr;
