@@ -19,6 +19,24 @@ def calculate_iou(boxA, boxB):
     return inter / float(smaller) if smaller != 0 else 0.0
 
 
+def _score_matrix(cur_boxes, prev_boxes):
+    """calculate_iou for every (current, previous) pair at once: the same integer intersections and the same
+    float64 division as the scalar function, so the matrix equals the reference's element for element (a stack with
+    thousands of supports makes this millions of pairs per layer)."""
+    n, m = len(cur_boxes), len(prev_boxes)
+    if n == 0 or m == 0:
+        return np.zeros((n, m))
+    c = np.asarray(cur_boxes, np.int64).reshape(n, 4)
+    q = np.asarray(prev_boxes, np.int64).reshape(m, 4)
+    iw = np.minimum((c[:, 0] + c[:, 2])[:, None], (q[:, 0] + q[:, 2])[None, :]) - np.maximum(c[:, 0][:, None], q[:, 0][None, :])
+    ih = np.minimum((c[:, 1] + c[:, 3])[:, None], (q[:, 1] + q[:, 3])[None, :]) - np.maximum(c[:, 1][:, None], q[:, 1][None, :])
+    inter = np.maximum(iw, 0) * np.maximum(ih, 0)
+    smaller = np.minimum((c[:, 2] * c[:, 3])[:, None], (q[:, 2] * q[:, 3])[None, :])
+    out = np.zeros((n, m))
+    np.divide(inter, smaller.astype(np.float64), out=out, where=smaller != 0)
+    return out
+
+
 class ROITracker:
     """reference :25-109.  State: next_roi_id and previous_rois {id: roi dict}."""
 
@@ -53,10 +71,7 @@ class ROITracker:
             return list(tracked.values())
 
         prev_ids = list(self.previous_rois)
-        scores = np.zeros((len(current_rois_raw), len(prev_ids)))
-        for ci, roi in enumerate(current_rois_raw):
-            for pj, pid in enumerate(prev_ids):
-                scores[ci, pj] = calculate_iou(roi["bbox"], self.previous_rois[pid]["bbox"])
+        scores = _score_matrix([r["bbox"] for r in current_rois_raw], [self.previous_rois[i]["bbox"] for i in prev_ids])
 
         # greedy one-to-one assignment, best score first; equal scores keep their flattened (row-major) order
         assigned, taken = {}, set()
