@@ -10,7 +10,7 @@ import dataclasses
 import enum
 import json
 import os
-from dataclasses import dataclass, field
+from dataclasses import field
 from typing import List, Optional
 
 DEFAULT_NUM_WORKERS = max(1, (os.cpu_count() or 2) - 1)
@@ -41,37 +41,10 @@ _LUT_LIMITS = {"gamma_value": (0.01, 10.0), "s_curve_contrast": (0.0, 1.0), "log
                "exp_param": (0.01, 10.0), "sqrt_param": (0.1, 50.0), "rodbard_param": (0.0, 2.0)}
 
 
-@dataclass
-class LutParameters:
-    lut_source: str = "generated"
-    lut_generation_type: str = "linear"
-    input_min: int = 0
-    input_max: int = 255
-    output_min: int = 0
-    output_max: int = 255
-    gamma_value: float = 1.0
-    s_curve_contrast: float = 0.5
-    log_param: float = 10.0
-    exp_param: float = 2.0
-    sqrt_param: float = 2.0
-    rodbard_param: float = 1.0
-    spline_points: List[List[int]] = field(default_factory=lambda: [[0, 0], [255, 255]])
-    fixed_lut_path: str = ""
-
-    def __post_init__(self):
-        self.lut_source = self.lut_source.lower()
-        if self.lut_source not in ("generated", "file"):
-            self.lut_source = "generated"
-        if self.lut_generation_type not in _LUT_KINDS:
-            self.lut_generation_type = "linear"
-        for lo_name, hi_name in (("input_min", "input_max"), ("output_min", "output_max")):
-            lo, hi = _clamp(getattr(self, lo_name), 0, 255), _clamp(getattr(self, hi_name), 0, 255)
-            if lo > hi:
-                lo, hi = hi, lo
-            setattr(self, lo_name, lo)
-            setattr(self, hi_name, hi)
-        for name, (lo, hi) in _LUT_LIMITS.items():
-            setattr(self, name, _clamp(getattr(self, name), lo, hi))
+def _record(name, spec, methods=None):
+    """A dataclass from a (field, type, default) table; callables are default factories."""
+    cols = [(n, t, field(default_factory=d) if callable(d) else field(default=d)) for n, t, d in spec]
+    return dataclasses.make_dataclass(name, cols, namespace=dict(methods or {}), module=__name__)
 
 
 def _only_fields(cls, data: dict) -> dict:
@@ -79,112 +52,107 @@ def _only_fields(cls, data: dict) -> dict:
     return {k: v for k, v in data.items() if k in names}
 
 
-@dataclass
-class XYBlendOperation:
-    type: str = "none"
-    gaussian_ksize_x: int = 3
-    gaussian_ksize_y: int = 3
-    gaussian_sigma_x: float = 0.0
-    gaussian_sigma_y: float = 0.0
-    bilateral_d: int = 9
-    bilateral_sigma_color: float = 75.0
-    bilateral_sigma_space: float = 75.0
-    median_ksize: int = 5
-    unsharp_amount: float = 1.0
-    unsharp_threshold: int = 0
-    unsharp_blur_ksize: int = 5
-    unsharp_blur_sigma: float = 0.0
-    resize_width: Optional[int] = None
-    resize_height: Optional[int] = None
-    resample_mode: str = "LANCZOS4"
-    lut_params: LutParameters = field(default_factory=LutParameters)
-
-    def __post_init__(self):
-        self.type = self.type.lower()
-        odd = self._ensure_odd_positive_ksize
-        if self.type == "gaussian_blur":
-            self.gaussian_ksize_x, self.gaussian_ksize_y = odd(self.gaussian_ksize_x), odd(self.gaussian_ksize_y)
-        elif self.type == "median_blur":
-            self.median_ksize = odd(self.median_ksize)
-        elif self.type == "unsharp_mask":
-            self.unsharp_blur_ksize = odd(self.unsharp_blur_ksize)
-        if self.type == "resize":
-            for name in ("resize_width", "resize_height"):
-                v = getattr(self, name)
-                if v is not None:
-                    v = max(0, v)
-                    setattr(self, name, v if v != 0 else None)
-        if isinstance(self.lut_params, dict):
-            self.lut_params = self.from_dict_to_lut_params(self.lut_params)
-
-    def _ensure_odd_positive_ksize(self, ksize: int) -> int:
-        if ksize <= 0:
-            return 1
-        return ksize if ksize % 2 else ksize + 1
-
-    @staticmethod
-    def from_dict_to_lut_params(data: dict) -> LutParameters:
-        return LutParameters(**_only_fields(LutParameters, data))
+# ---- LutParameters (reference config.py:44-84) --------------------------------------------------------------
+def _lut_post_init(self):
+    self.lut_source = self.lut_source.lower()
+    if self.lut_source not in ("generated", "file"):
+        self.lut_source = "generated"
+    if self.lut_generation_type not in _LUT_KINDS:
+        self.lut_generation_type = "linear"
+    for lo_name, hi_name in (("input_min", "input_max"), ("output_min", "output_max")):
+        lo, hi = _clamp(getattr(self, lo_name), 0, 255), _clamp(getattr(self, hi_name), 0, 255)
+        if lo > hi:
+            lo, hi = hi, lo
+        setattr(self, lo_name, lo)
+        setattr(self, hi_name, hi)
+    for name, (lo, hi) in _LUT_LIMITS.items():
+        setattr(self, name, _clamp(getattr(self, name), lo, hi))
 
 
-@dataclass
-class RoiParameters:
-    min_size: int = 100
-    enable_raft_support_handling: bool = False
-    raft_layer_count: int = 5
-    raft_min_size: int = 10000
-    support_max_size: int = 500
-    support_max_layer: int = 1000
-    support_max_growth: float = 2.5
+LutParameters = _record("LutParameters", [
+    ("lut_source", str, "generated"), ("lut_generation_type", str, "linear"),
+    ("input_min", int, 0), ("input_max", int, 255), ("output_min", int, 0), ("output_max", int, 255),
+    ("gamma_value", float, 1.0), ("s_curve_contrast", float, 0.5), ("log_param", float, 10.0), ("exp_param", float, 2.0),
+    ("sqrt_param", float, 2.0), ("rodbard_param", float, 1.0),
+    ("spline_points", List[List[int]], lambda: [[0, 0], [255, 255]]), ("fixed_lut_path", str, ""),
+], {"__post_init__": _lut_post_init})
 
 
-@dataclass
-class AnisotropicParams:
-    enabled: bool = False
-    x_factor: float = 1.0
-    y_factor: float = 1.0
+# ---- XYBlendOperation (reference config.py:86-135) ----------------------------------------------------------
+def _odd_positive(self, ksize: int) -> int:
+    if ksize <= 0:
+        return 1
+    return ksize if ksize % 2 else ksize + 1
 
 
-@dataclass
-class Config:
+def _lut_params_from_dict(data: dict):
+    return LutParameters(**_only_fields(LutParameters, data))
+
+
+def _xy_post_init(self):
+    self.type = self.type.lower()
+    odd = self._ensure_odd_positive_ksize
+    kernel_fields = {"gaussian_blur": ("gaussian_ksize_x", "gaussian_ksize_y"), "median_blur": ("median_ksize",),
+                     "unsharp_mask": ("unsharp_blur_ksize",)}
+    for name in kernel_fields.get(self.type, ()):
+        setattr(self, name, odd(getattr(self, name)))
+    if self.type == "resize":            # negative sizes clamp to 0, and 0 means "not given"
+        for name in ("resize_width", "resize_height"):
+            v = getattr(self, name)
+            if v is not None:
+                setattr(self, name, max(0, v) or None)
+    if isinstance(self.lut_params, dict):
+        self.lut_params = self.from_dict_to_lut_params(self.lut_params)
+
+
+XYBlendOperation = _record("XYBlendOperation", [
+    ("type", str, "none"),
+    ("gaussian_ksize_x", int, 3), ("gaussian_ksize_y", int, 3), ("gaussian_sigma_x", float, 0.0), ("gaussian_sigma_y", float, 0.0),
+    ("bilateral_d", int, 9), ("bilateral_sigma_color", float, 75.0), ("bilateral_sigma_space", float, 75.0),
+    ("median_ksize", int, 5),
+    ("unsharp_amount", float, 1.0), ("unsharp_threshold", int, 0), ("unsharp_blur_ksize", int, 5), ("unsharp_blur_sigma", float, 0.0),
+    ("resize_width", Optional[int], None), ("resize_height", Optional[int], None), ("resample_mode", str, "LANCZOS4"),
+    ("lut_params", LutParameters, LutParameters),
+], {"__post_init__": _xy_post_init, "_ensure_odd_positive_ksize": _odd_positive,
+    "from_dict_to_lut_params": staticmethod(_lut_params_from_dict)})
+
+RoiParameters = _record("RoiParameters", [
+    ("min_size", int, 100), ("enable_raft_support_handling", bool, False), ("raft_layer_count", int, 5),
+    ("raft_min_size", int, 10000), ("support_max_size", int, 500), ("support_max_layer", int, 1000),
+    ("support_max_growth", float, 2.5)])
+
+AnisotropicParams = _record("AnisotropicParams", [("enabled", bool, False), ("x_factor", float, 1.0), ("y_factor", float, 1.0)])
+
+_CONFIG_SCHEMA = [
     # I/O
-    output_file_prefix: str = "Voxel_Blend_Processed_"
-    input_mode: str = "folder"
-    input_folder: str = ""
-    output_folder: str = ""
-    start_index: Optional[int] = 0
-    stop_index: Optional[int] = None
+    ("output_file_prefix", str, "Voxel_Blend_Processed_"), ("input_mode", str, "folder"), ("input_folder", str, ""),
+    ("output_folder", str, ""), ("start_index", Optional[int], 0), ("stop_index", Optional[int], None),
     # UVTools mode
-    uvtools_path: str = "C:\\Program Files\\UVTools\\UVToolsCmd.exe"
-    uvtools_temp_folder: str = ""
-    uvtools_input_file: str = ""
-    uvtools_output_location: str = "working_folder"
-    uvtools_delete_temp_on_completion: bool = True
+    ("uvtools_path", str, "C:\\Program Files\\UVTools\\UVToolsCmd.exe"), ("uvtools_temp_folder", str, ""),
+    ("uvtools_input_file", str, ""), ("uvtools_output_location", str, "working_folder"),
+    ("uvtools_delete_temp_on_completion", bool, True),
     # stack blending
-    blending_mode: ProcessingMode = ProcessingMode.FIXED_FADE
-    receding_layers: int = 4
-    use_fixed_fade_receding: bool = False
-    fixed_fade_distance_receding: float = 10.0
-    anisotropic_params: AnisotropicParams = field(default_factory=AnisotropicParams)
+    ("blending_mode", ProcessingMode, ProcessingMode.FIXED_FADE), ("receding_layers", int, 4),
+    ("use_fixed_fade_receding", bool, False), ("fixed_fade_distance_receding", float, 10.0),
+    ("anisotropic_params", AnisotropicParams, AnisotropicParams),
     # weighted stack
-    weighted_falloff_type: WeightingFalloff = WeightingFalloff.LINEAR
-    manual_weights: List[int] = field(default_factory=lambda: [100, 75, 50, 25])
-    fade_distances_receding: List[float] = field(default_factory=lambda: [10.0, 10.0, 10.0, 10.0])
+    ("weighted_falloff_type", WeightingFalloff, WeightingFalloff.LINEAR),
+    ("manual_weights", List[int], lambda: [100, 75, 50, 25]),
+    ("fade_distances_receding", List[float], lambda: [10.0, 10.0, 10.0, 10.0]),
     # overhang (unused by the reference as well)
-    overhang_layers: int = 0
-    use_fixed_fade_overhang: bool = False
-    fixed_fade_distance_overhang: float = 10.0
+    ("overhang_layers", int, 0), ("use_fixed_fade_overhang", bool, False), ("fixed_fade_distance_overhang", float, 10.0),
     # ROI mode
-    roi_params: RoiParameters = field(default_factory=RoiParameters)
+    ("roi_params", RoiParameters, RoiParameters),
     # general
-    thread_count: int = DEFAULT_NUM_WORKERS
-    use_numba_jit: bool = False
-    debug_save: bool = False
-    xy_blend_pipeline: List[XYBlendOperation] = field(default_factory=lambda: [XYBlendOperation("none")])
-    # --- additive B200 engine keys (defaults = reference behaviour) ---
-    distance_metric: str = "chamfer5"   # "chamfer5" (cv2 DIST_L2 mask 5, bit parity) or "exact"
-    devices: Optional[List[int]] = None  # CUDA devices for Z-sharding; None = current device
+    ("thread_count", int, DEFAULT_NUM_WORKERS), ("use_numba_jit", bool, False), ("debug_save", bool, False),
+    ("xy_blend_pipeline", List[XYBlendOperation], lambda: [XYBlendOperation("none")]),
+    # additive B200 engine keys (defaults = reference behaviour)
+    ("distance_metric", str, "chamfer5"),      # "chamfer5" (cv2 DIST_L2 mask 5, bit parity) or "exact"
+    ("devices", Optional[List[int]], None),    # CUDA devices for Z-sharding; None = current device
+]
 
+
+class _ConfigMethods:
     def to_dict(self) -> dict:
         d = dataclasses.asdict(self)
         for k, v in list(d.items()):
@@ -255,7 +223,10 @@ class Config:
             return cls()
 
 
-def upgrade_config(cfg: Config):
+Config = _record("Config", _CONFIG_SCHEMA, {k: v for k, v in vars(_ConfigMethods).items() if not k.startswith("__")})
+
+
+def upgrade_config(cfg):
     """legacy attribute names (config.py:292-301)"""
     for old, new in (("n_layers", "receding_layers"), ("use_fixed_norm", "use_fixed_fade_receding"),
                      ("fixed_fade_distance", "fixed_fade_distance_receding")):

@@ -9,7 +9,7 @@ from __future__ import annotations
 
 import json
 import os
-from typing import Callable, List
+from typing import Callable
 
 import numpy as np
 
@@ -66,87 +66,79 @@ def load_lut(filepath: str) -> np.ndarray:
         raise IOError(f"Failed to load LUT from '{filepath}': {exc}")
 
 
-def generate_linear_lut(input_min: int, input_max: int, output_min: int, output_max: int) -> np.ndarray:
-    return _generate_curve_in_range(lambda x: x, input_min, input_max, output_min, output_max)
+# ---- curve families (reference lut_manager.py:92-169) ---------------------------------------------------------
+# Every family is "shape(ramp in [0, 1]) stretched onto [output_min, output_max] over [input_min, input_max]"; a
+# family is a function param -> shape.  The public generate_<family>_lut(param, in_min, in_max, out_min, out_max)
+# entry points the GUI and xy_blend_processor call positionally are stamped out of this table.
+def _power(exponent):
+    return lambda x: np.power(x, exponent)
 
 
-def _power_lut(exponent: float, rng) -> np.ndarray:
-    return _generate_curve_in_range(lambda x: np.power(x, exponent), *rng)
-
-
-def generate_gamma_lut(gamma_value: float, input_min: int, input_max: int, output_min: int, output_max: int) -> np.ndarray:
-    if gamma_value <= 0:
-        gamma_value = 0.01
-    return _power_lut(1.0 / gamma_value, (input_min, input_max, output_min, output_max))
-
-
-def generate_s_curve_lut(contrast: float, input_min: int, input_max: int, output_min: int, output_max: int) -> np.ndarray:
+def _s_curve(contrast):
     contrast = max(0.0, min(1.0, contrast))
-
-    def curve(x):
-        if contrast == 0.0:
-            return x
-        if contrast == 1.0:
-            return np.where(x < 0.5, 0.0, 1.0)
-        g = 1.0 / (1.0 + contrast * 4)
-        return np.where(x < 0.5, np.power(x / 0.5, g) * 0.5, 1.0 - np.power((1.0 - x) / 0.5, g) * 0.5)
-    return _generate_curve_in_range(curve, input_min, input_max, output_min, output_max)
+    if contrast == 0.0:
+        return lambda x: x
+    if contrast == 1.0:
+        return lambda x: np.where(x < 0.5, 0.0, 1.0)
+    g = 1.0 / (1.0 + contrast * 4)
+    return lambda x: np.where(x < 0.5, np.power(x / 0.5, g) * 0.5, 1.0 - np.power((1.0 - x) / 0.5, g) * 0.5)
 
 
-def generate_log_lut(param: float, input_min: int, input_max: int, output_min: int, output_max: int) -> np.ndarray:
-    if param <= 0:
-        param = 0.01
-    return _generate_curve_in_range(lambda x: np.log1p(x * param) / np.log1p(param), input_min, input_max,
-                                    output_min, output_max)
-
-
-def generate_exp_lut(param: float, input_min: int, input_max: int, output_min: int, output_max: int) -> np.ndarray:
-    if param <= 0:
-        param = 0.01
-    return _power_lut(param, (input_min, input_max, output_min, output_max))
-
-
-def generate_sqrt_lut(root_value: float, input_min: int, input_max: int, output_min: int, output_max: int) -> np.ndarray:
-    if root_value <= 0:
-        root_value = 0.1
-    return _power_lut(1.0 / root_value, (input_min, input_max, output_min, output_max))
-
-
-def generate_rodbard_lut(contrast: float, input_min: int, input_max: int, output_min: int, output_max: int) -> np.ndarray:
-    def curve(x):
+def _rodbard(contrast):
+    def shape(x):                      # blend of the identity with the ACES-style rational curve
         num = x * (2.51 * x + 0.03)
         den = x * (2.43 * x + 0.59) + 0.14
-        aces = np.divide(num, den, out=np.zeros_like(x), where=den != 0)
-        return (1 - contrast) * x + contrast * aces
-    return _generate_curve_in_range(curve, input_min, input_max, output_min, output_max)
+        return (1 - contrast) * x + contrast * np.divide(num, den, out=np.zeros_like(x), where=den != 0)
+    return shape
 
 
-def generate_spline_lut(control_points: List[List[int]], input_min: int, input_max: int, output_min: int,
-                        output_max: int) -> np.ndarray:
+def _spline(control_points):
     if len(control_points) < 2:
-        return generate_linear_lut(input_min, input_max, output_min, output_max)
+        return lambda x: x
     from scipy.interpolate import CubicSpline
     pts = sorted(control_points, key=lambda p: p[0])
     xs = np.array([p[0] for p in pts]) / 255.0
     ys = np.array([p[1] for p in pts]) / 255.0
-    if xs[0] > 0:
+    if xs[0] > 0:                      # hold the first / last value out to the ends of the ramp
         xs, ys = np.insert(xs, 0, 0), np.insert(ys, 0, ys[0])
     if xs[-1] < 1.0:
         xs, ys = np.append(xs, 1.0), np.append(ys, ys[-1])
-    return _generate_curve_in_range(CubicSpline(xs, ys, bc_type="clamped"), input_min, input_max, output_min,
-                                    output_max)
+    return CubicSpline(xs, ys, bc_type="clamped")
 
 
-_GENERATORS = {
-    "linear": lambda p, r: generate_linear_lut(*r),
-    "gamma": lambda p, r: generate_gamma_lut(p.gamma_value, *r),
-    "s_curve": lambda p, r: generate_s_curve_lut(p.s_curve_contrast, *r),
-    "log": lambda p, r: generate_log_lut(p.log_param, *r),
-    "exp": lambda p, r: generate_exp_lut(p.exp_param, *r),
-    "sqrt": lambda p, r: generate_sqrt_lut(p.sqrt_param, *r),
-    "rodbard": lambda p, r: generate_rodbard_lut(p.rodbard_param, *r),
-    "spline": lambda p, r: generate_spline_lut(p.spline_points, *r),
+def _floor(value, least):               # non-positive parameters fall back to a small positive one
+    return least if value <= 0 else value
+
+
+# family -> (LutParameters attribute carrying the parameter or None, param -> shape)
+_FAMILIES = {
+    "linear": (None, lambda _=None: (lambda x: x)),
+    "gamma": ("gamma_value", lambda g: _power(1.0 / _floor(g, 0.01))),
+    "s_curve": ("s_curve_contrast", _s_curve),
+    "log": ("log_param", lambda k: (lambda x, k=_floor(k, 0.01): np.log1p(x * k) / np.log1p(k))),
+    "exp": ("exp_param", lambda e: _power(_floor(e, 0.01))),
+    "sqrt": ("sqrt_param", lambda r: _power(1.0 / _floor(r, 0.1))),
+    "rodbard": ("rodbard_param", _rodbard),
+    "spline": ("spline_points", _spline),
 }
+
+
+def _entry_point(family):
+    _, shape_of = _FAMILIES[family]
+    if family == "linear":
+        def generate(input_min, input_max, output_min, output_max):
+            return _generate_curve_in_range(shape_of(), input_min, input_max, output_min, output_max)
+    else:
+        def generate(param, input_min, input_max, output_min, output_max):
+            return _generate_curve_in_range(shape_of(param), input_min, input_max, output_min, output_max)
+    generate.__name__ = f"generate_{family}_lut"
+    generate.__doc__ = f"uint8[256] table of the '{family}' family (reference lut_manager.py:92-169)."
+    return generate
+
+
+for _family in _FAMILIES:
+    globals()[f"generate_{_family}_lut"] = _entry_point(_family)
+del _family
 
 
 def lut_from_params(lut_params) -> np.ndarray:
@@ -155,10 +147,12 @@ def lut_from_params(lut_params) -> np.ndarray:
     table = None
     try:
         if lut_params.lut_source == "generated":
-            gen = _GENERATORS.get(lut_params.lut_generation_type)
-            if gen is not None:
-                table = gen(lut_params, (lut_params.input_min, lut_params.input_max, lut_params.output_min,
-                                         lut_params.output_max))
+            family = _FAMILIES.get(lut_params.lut_generation_type)
+            if family is not None:
+                attr, shape_of = family
+                shape = shape_of(getattr(lut_params, attr)) if attr else shape_of()
+                table = _generate_curve_in_range(shape, lut_params.input_min, lut_params.input_max, lut_params.output_min,
+                                                 lut_params.output_max)
         elif lut_params.lut_source == "file":
             if lut_params.fixed_lut_path and os.path.exists(lut_params.fixed_lut_path):
                 table = load_lut(lut_params.fixed_lut_path)
