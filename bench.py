@@ -184,7 +184,9 @@ def main():
     base_config = {"workload": wl if (W, H) == (W16, H16) else wl.replace("15120x6230", f"{W}x{H}"),
                    "width": W, "height": H, "batch_layers_per_gpu": args.batch, "resident_layers_per_gpu": args.resident,
                    "z_shard": f"{world} contiguous slabs, 4-layer mask halo, no collective", "metric_variant": "chamfer5",
-                   "l2": f"each step streams {args.batch} x {W * H / 1e6:.0f} MB of input per GPU (>> 126 MB L2)"}
+                   "l2": f"each step streams {args.batch} x {W * H / 1e6:.0f} MB of input per GPU (>> 126 MB L2)",
+                   "slab": f"layers z = 20 + 1000*rank .. +{args.resident} of the synthetic stack (steady state: supports + model blobs; "
+                           "the raft and the layers right after it ends, z < 16, are not in the slab)"}
 
     # ------------------------------------------------------------------ reference arm (CPU only)
     if args.impl == "reference":

@@ -660,3 +660,74 @@ def test_pack_lut_and_patch_equal_fused_no_xy(E):
                     got = out.numpy()
                     assert np.array_equal(got, want[zi]), (W, H, mode, zi, use_list, int((got != want[zi]).sum()))
                 masks.append(cur)
+
+
+# ---- randomised configurations: stack runtime vs the oracle's stack loop --------------------------------------------
+def _random_case(rng):
+    W, H = int(rng.integers(130, 700)), int(rng.integers(40, 330))
+    mode = str(rng.choice(["fixed_fade", "fixed_minmax", "weighted_stack", "enhanced_edt", "fixed_far"]))
+    d = {"receding_layers": int(rng.integers(0, 6)), "use_fixed_fade_receding": True,
+         "fixed_fade_distance_receding": float(rng.choice([0.0, 3.5, 10.0, 27.25, 40.0, 63.0])),
+         "manual_weights": [int(v) for v in rng.integers(0, 100, int(rng.integers(1, 6)))],
+         "fade_distances_receding": [float(v) for v in rng.uniform(2.0, 50.0, int(rng.integers(0, 5)))],
+         "use_numba_jit": bool(rng.integers(0, 2))}
+    if mode == "fixed_minmax":
+        d.update(blending_mode="fixed_fade", use_fixed_fade_receding=False)
+    elif mode == "fixed_far":
+        d.update(blending_mode="fixed_fade", fixed_fade_distance_receding=float(rng.choice([90.0, 150.5])))
+    else:
+        d["blending_mode"] = mode
+    if mode == "enhanced_edt" and rng.random() < 0.35 and d["fixed_fade_distance_receding"] <= 40.0:
+        d["anisotropic_params"] = {"enabled": True, "x_factor": float(rng.choice([0.5, 1.0, 1.3, 2.0])),
+                                   "y_factor": float(rng.choice([0.7, 1.0, 1.6]))}
+    ops = []
+    cw, ch = W, H
+    for _ in range(int(rng.integers(0, 5))):
+        t = str(rng.choice(["apply_lut", "gaussian_blur", "bilateral_filter", "median_blur", "unsharp_mask", "resize"]))
+        if t == "apply_lut":
+            kind = str(rng.choice(["linear", "gamma", "s_curve", "log", "exp", "sqrt", "rodbard"]))
+            lo, hi = sorted(int(v) for v in rng.integers(0, 256, 2))
+            ops.append({"type": t, "lut_params": {"lut_source": "generated", "lut_generation_type": kind, "input_min": lo, "input_max": hi,
+                                                  "output_min": int(rng.integers(0, 128)), "output_max": int(rng.integers(128, 256)),
+                                                  "gamma_value": 1.7, "s_curve_contrast": 0.6, "log_param": 4.0, "exp_param": 1.5,
+                                                  "sqrt_param": 2.5, "rodbard_param": 0.8}})
+        elif t == "gaussian_blur":
+            ops.append({"type": t, "gaussian_ksize_x": int(rng.choice([1, 3, 5, 7, 9, 13])), "gaussian_ksize_y": int(rng.choice([1, 3, 5, 7, 11])),
+                        "gaussian_sigma_x": float(rng.choice([0.0, 0.8, 2.1])), "gaussian_sigma_y": float(rng.choice([0.0, 1.3]))})
+        elif t == "bilateral_filter":
+            ops.append({"type": t, "bilateral_d": int(rng.choice([7, 9, 11])), "bilateral_sigma_color": float(rng.choice([20.0, 60.0])),
+                        "bilateral_sigma_space": float(rng.choice([3.0, 60.0]))})
+        elif t == "median_blur":
+            ops.append({"type": t, "median_ksize": int(rng.choice([1, 3, 5]))})
+        elif t == "unsharp_mask":
+            ops.append({"type": t, "unsharp_amount": float(rng.choice([0.4, 1.0, 2.3])), "unsharp_threshold": int(rng.choice([0, 3, 10])),
+                        "unsharp_blur_ksize": int(rng.choice([3, 5, 9])), "unsharp_blur_sigma": float(rng.choice([0.0, 1.4]))})
+        else:
+            nw, nh = int(rng.integers(40, 500)), int(rng.integers(30, 300))
+            if rng.random() < 0.3:
+                nh = None
+            ops.append({"type": t, "resize_width": nw, "resize_height": nh,
+                        "resample_mode": str(rng.choice(["NEAREST", "BILINEAR", "LANCZOS4", "AREA"]))})
+    d["xy_blend_pipeline"] = ops
+    return W, H, d
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_stack_engine_random_configs_vs_oracle(E, seed):
+    """Random mode / fade / window / XY chain (all op types incl. size changes) on ragged sizes: the C++ stack runtime
+    equals the oracle's stack loop pixel for pixel (bilateral d >= 7 and no BICUBIC: the two places where the reference's
+    own library paths disagree by one grey level)."""
+    import lut_manager, vsb_params as P
+    from config import Config
+    rng = np.random.default_rng(1000 + seed)
+    W, H, d = _random_case(rng)
+    layers = small_stack(W=W, H=H, L=6, seed=seed, raft=bool(seed % 2), n_blobs=6)
+    cfg = Config.from_dict(d)
+    ops = P.xy_ops_from_pipeline(cfg.xy_blend_pipeline, lambda o: lut_manager.lut_from_params(o.lut_params), W, H)
+    eng = E.StackEngine(W, H, cfg, ops)
+    got = [eng.process(g) for g in layers]
+    eng.close()
+    want = O.run_stack(layers, d)
+    for zi, (a, b) in enumerate(zip(got, want)):
+        assert a.shape == b.shape, (seed, zi, a.shape, b.shape, d)
+        assert np.array_equal(a, b), (seed, zi, int((a != b).sum()), d)
