@@ -8,7 +8,8 @@ W, H, L = 15120, 6230, 40
 cfg = bench.workload_config(bench.write_lut_file())
 if len(sys.argv) > 1 and sys.argv[1] == "zlut":
     cfg.xy_blend_pipeline = cfg.xy_blend_pipeline[:1]
-stack = S.DeviceStack(W, H, L, seed=1)
+Z0 = int(os.environ.get('Z0', '0'))
+stack = S.DeviceStack(W, H, L, seed=1, z0=Z0, total_layers=Z0 + L)
 ops = P.xy_ops_from_pipeline(cfg.xy_blend_pipeline, lambda op: lut_manager.lut_from_params(op.lut_params))
 eng = E.StackEngine(W, H, cfg, ops)
 out = torch.empty((H, stack.pitch), dtype=torch.uint8, device='cuda')

@@ -264,6 +264,8 @@ template <int ZMODE, int METRIC, bool PERSIST, bool XY>
 __global__ void __launch_bounds__(VSB_THREADS, XY ? VSB_LAYER_CTAS_XY : 6) k_layer(const __grid_constant__ LayerParams p,
                                                        const BilTapsL *__restrict__ taps)
 {
+    // work list of the patch launch: CTAs beyond the number of listed tiles leave before any set-up
+    if (!PERSIST && !XY && p.rec_list && (int)(blockIdx.y * gridDim.x + blockIdx.x) >= p.rec_list[0]) return;
     extern __shared__ __align__(16) uint8_t dsm[];
     float *s_T = (float *)(dsm + p.sm.T);
     uint8_t *s_rawb = dsm + p.sm.raw;                             // PERSIST: [2][RH][RG_W] raw input region
@@ -336,7 +338,6 @@ __global__ void __launch_bounds__(VSB_THREADS, XY ? VSB_LAYER_CTAS_XY : 6) k_lay
     int tile = PERSIST ? (int)blockIdx.x : (int)(blockIdx.y * gridDim.x + blockIdx.x);
     int wl_tx = (int)blockIdx.x, wl_ty = (int)blockIdx.y;
     if (!PERSIST && !XY && p.rec_list) { // work list of the patch launch: CTA i takes the i-th listed tile
-        if (tile >= p.rec_list[0]) return;
         tile = p.rec_list[1 + tile];
         wl_tx = tile % p.tiles_x; wl_ty = tile / p.tiles_x;
     }
@@ -399,6 +400,18 @@ __global__ void __launch_bounds__(VSB_THREADS, XY ? VSB_LAYER_CTAS_XY : 6) k_lay
                 }
             }
             ref_raw = 0;
+            if (p.sparse && ZMODE != ZL_NONE && ZMODE != VSB_Z_CONST) {
+                // patch launch: every listed tile has receding pixels, so the search window and the chamfer table are
+                // requested together with the tile's mask words -- one memory round trip per tile instead of two
+                if (METRIC == VSB_METRIC_CHAMFER5 && !t_staged) {
+                    const int nT = (R + 1) * (R + 1);
+                    const int nfull = ((((size_t)p.T) & 15) == 0) ? (nT >> 2) : 0;
+                    for (int i = t; i < nfull; i += VSB_THREADS) ((float4 *)s_T)[i] = ((const float4 *)p.T)[i];
+                    for (int i = 4 * nfull + t; i < nT; i += VSB_THREADS) s_T[i] = p.T[i];
+                    t_staged = true;
+                }
+                stage_mask_rows<LBW>(s_bits, p.cur, wpr, H, (x0 >> 5) - 3, y0 - R, RH + 2 * R);
+            }
             if (!p.sparse) {
                 if (nvalid == 16 && p.aligned) { gv[0] = vsb_ld16_stream(p.in + (size_t)oy * p.ipitch + ox); gstate[0] = 1; }
                 else if (nvalid > 0) gstate[0] = 2;
@@ -523,7 +536,7 @@ __global__ void __launch_bounds__(VSB_THREADS, XY ? VSB_LAYER_CTAS_XY : 6) k_lay
         // ---- P2: distance search + gradient on the receding pixels of the region ----------------------------
         if (ZMODE != ZL_NONE && any_rec) {
             const int brows = RH + 2 * R;
-            if (ZMODE != VSB_Z_CONST) {
+            if (ZMODE != VSB_Z_CONST && !sparse) {
                 if (METRIC == VSB_METRIC_CHAMFER5 && !t_staged) {
                     const int nT = (R + 1) * (R + 1);
                     const int nfull = ((((size_t)p.T) & 15) == 0) ? (nT >> 2) : 0; // 16-byte groups when the table is aligned
@@ -533,6 +546,7 @@ __global__ void __launch_bounds__(VSB_THREADS, XY ? VSB_LAYER_CTAS_XY : 6) k_lay
                 }
                 stage_mask_rows<LBW>(s_bits, p.cur, wpr, H, (x0 >> 5) - 3, y0 - Hh - R, brows);
             }
+            if (ZMODE != VSB_Z_CONST && sparse) stage_rowany_rows<LBW>(s_rowany, s_bits, brows); // window staged before the first barrier
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
                 const int i = t + u * VSB_THREADS;
@@ -551,8 +565,10 @@ __global__ void __launch_bounds__(VSB_THREADS, XY ? VSB_LAYER_CTAS_XY : 6) k_lay
                 }
             }
             __syncthreads();
-            if (ZMODE != VSB_Z_CONST) stage_rowany_rows<LBW>(s_rowany, s_bits, brows);
-            __syncthreads();
+            if (!sparse) {
+                if (ZMODE != VSB_Z_CONST) stage_rowany_rows<LBW>(s_rowany, s_bits, brows);
+                __syncthreads();
+            }
             const int total = s_cnt;
             if (p.stats && t == 0) { atomicAdd(&p.stats[2], 1ULL); atomicAdd(&p.stats[3], (unsigned long long)total); }
             PHASE(9);
