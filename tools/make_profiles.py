@@ -23,7 +23,7 @@ def short(name):
     return re.sub(r"\(.*", "", name).strip()
 agg = collections.OrderedDict()
 with open(os.path.join(P, f"{tag}_launches.csv"), "w") as fh:
-    fh.write("# ncu --metrics gpu__time_duration.sum --clock-control none -s 8 -c 40, python bench.py --steps 1 --warmup 1 --batch 4 --resident 8 --no-e2e --no-cpu-baseline\n")
+    fh.write("# ncu --metrics gpu__time_duration.sum --clock-control none -s 8 -c 60, python bench.py --steps 1 --warmup 1 --batch 4 --resident 12 --no-e2e --no-cpu-baseline\n")
     fh.write("id,kernel,duration_us\n")
     for r in rows:
         v = float(r[mv].replace(",", "")) * {"ns": 1e-3, "us": 1.0, "ms": 1e3}.get(r[mu], 1.0)
