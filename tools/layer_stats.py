@@ -5,7 +5,7 @@ import numpy as np, torch
 import bench, vsb_engine as E, vsb_native as N, vsb_params as P, vsb_synth as S, lut_manager
 W,H,L=15120,6230,12
 cfg=bench.workload_config(bench.write_lut_file())
-stack=S.DeviceStack(W,H,L,seed=1,z0=20,total_layers=20+L)
+Z0=int(os.environ.get('Z0','20')); stack=S.DeviceStack(W,H,L,seed=1,z0=Z0,total_layers=max(436,Z0+L))
 ops=P.xy_ops_from_pipeline(cfg.xy_blend_pipeline, lambda op: lut_manager.lut_from_params(op.lut_params))
 eng=E.StackEngine(W,H,cfg,ops)
 outs=torch.empty((2,H,stack.pitch),dtype=torch.uint8,device='cuda')
