@@ -112,15 +112,16 @@ __global__ void __launch_bounds__(VSB_THREADS) k_pack_flags(const uint8_t *__res
         a = vsb_ld_bytes(src, n);
         if (n > 16) b = vsb_ld_bytes(src + 16, n - 16);
     }
+    const int wx = (x0 >> 5) + wq;
+    uint32_t pacc = 0; // OR of the prior masks' words: requested together with the gray chunks (one round trip)
+    if (LUTOUT && rec_list && y < H && wx < wpr)
+        for (int j = 0; j < pr.n; ++j) pacc |= pr.p[j][(size_t)y * wpr + wx];
     __syncthreads();
     uint32_t word = vsb_gt_bits16(a, thr4) | (vsb_gt_bits16(b, thr4) << 16);
     if (n < 32) word &= n > 0 ? ((1u << n) - 1u) : 0u;
-    const int wx = (x0 >> 5) + wq;
     if (y < H && wx < wpr) bits[(size_t)y * wpr + wx] = word;
     if (LUTOUT && rec_list) { // tiles with receding pixels (prior white, current black) go on the patch kernel's work list
-        uint32_t acc = 0;
-        if (y < H && wx < wpr) for (int j = 0; j < pr.n; ++j) acc |= pr.p[j][(size_t)y * wpr + wx];
-        if (__any_sync(0xffffffffu, (acc & ~word) != 0u) && (t & 31) == 0) s_rec[half] = 1;
+        if (__any_sync(0xffffffffu, (pacc & ~word) != 0u) && (t & 31) == 0) s_rec[half] = 1;
     }
     if (LUTOUT && n > 0) {
         VsbLut Lp;
