@@ -20,6 +20,18 @@ __device__ __forceinline__ int nearest_dx(const uint32_t *rowp, int px)
 }
 
 
+// the same over px-31 .. px+31 only (three words instead of five): enough once the running minimum is <= 32, because a
+// seed 32 or more columns away cannot undercut it (every metric here is >= max(|dx|, |dy|)); returns 64 when empty
+__device__ __forceinline__ int nearest_dx_narrow(const uint32_t *rowp, int px)
+{
+    const int wi = px >> 5, b = px & 31;
+    const uint32_t w1 = rowp[wi - 1], w2 = rowp[wi], w3 = rowp[wi + 1];
+    const uint32_t rlo = __funnelshift_r(w2, w3, b), ltop = __funnelshift_l(w1, w2, 31 - b);
+    const int dr = rlo ? (__ffs(rlo) - 1) : 64;
+    const int dl = ltop ? __clz(ltop) : 64;
+    return min(dl, dr);
+}
+
 // stage rows y0-R .. y0+TH-1+R, words (x0>>5)-2 .. (x0>>5)+5 of a packed mask; outside the image = 0
 __device__ __forceinline__ void stage_mask_tile(uint32_t (*s_cur)[ROW_WORDS], const uint32_t *__restrict__ bits,
                                                 int wpr, int H, int x0, int y0, int R)
@@ -84,11 +96,11 @@ __device__ __forceinline__ float tile_search(const uint32_t (*s_cur)[RW], const 
         for (int k = 1; k <= R && (float)k < best; ++k) {
             const int ha = hr0 - k, hb = hr0 + k;
             if ((s_rowany[ha >> 5] >> (ha & 31)) & 1u) {
-                const int dx = nearest_dx(s_cur[ha], px);
+                const int dx = best <= 32.0f ? nearest_dx_narrow(s_cur[ha], px) : nearest_dx(s_cur[ha], px);
                 if (dx <= R) { const int M = max(k, dx), m = min(k, dx); best = fminf(best, TRI ? s_T[((M * (M + 1)) >> 1) + m] : s_T[M * n1 + m]); }
             }
             if ((s_rowany[hb >> 5] >> (hb & 31)) & 1u) {
-                const int dx = nearest_dx(s_cur[hb], px);
+                const int dx = best <= 32.0f ? nearest_dx_narrow(s_cur[hb], px) : nearest_dx(s_cur[hb], px);
                 if (dx <= R) { const int M = max(k, dx), m = min(k, dx); best = fminf(best, TRI ? s_T[((M * (M + 1)) >> 1) + m] : s_T[M * n1 + m]); }
             }
         }
