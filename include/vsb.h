@@ -231,8 +231,9 @@ int vsb_median(const uint8_t *in, size_t in_pitch, int W, int H, int ksize, uint
  *                    flags: uint16 [ceil(H/32)][ceil(W/128)];  wpr must be 4*ceil(W/128).
  *   vsb_layer_fused: Z-blend (FIXED / WEIGHTED / CONST, or NONE) -> lut1 -> [bilateral] -> [Gaussian] -> lut2
  *                    in ONE kernel, intermediates in shared memory.  Same arithmetic, bit for bit, as the
- *                    separate entry points above.  cur_flags / prior_flags (optional, from vsb_pack_flags)
- *                    let tiles that are one uniform value with no receding pixel skip all work.
+ *                    separate entry points above.  cur_flags / prior_flags (from vsb_pack_flags) are optional and
+ *                    currently not consulted: the kernel decides "uniform region, nothing recedes" from the data it
+ *                    stages anyway (measured: the flag look-up neither helps nor hurts).
  *     replaces processing_pipeline.py:98-107 (process_z_blending, merge_to_output, process_xy_pipeline)
  *     for XY chains of the shape [apply_lut*] [bilateral_filter d<=9] [gaussian_blur k<=7] [apply_lut*].
  * ------------------------------------------------------------------------------------------- */
