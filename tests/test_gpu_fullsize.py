@@ -89,3 +89,25 @@ def test_fullsize_properties(env, monkeypatch):
             xa, xb = (0 if x0 == 0 else m), (x1 - x0 if x1 == W else x1 - x0 - m)
             d = np.abs(got[ya:yb, xa:xb].astype(int) - want[zi][ya:yb, xa:xb].astype(int))
             assert d.max() == 0, ((y0, x0), zi, int((d > 0).sum()), int(d.max()))
+
+
+def test_fullsize_lut_only_patch_path(env, monkeypatch, lut_file):
+    """BASELINE config 1's shape at 16K (fade + one LUT, no XY filter): the pack-with-LUT + patch launches equal the
+    single fused kernel (VSB_NO_PATCH) and the unfused chain (VSB_NO_FUSED), layer by layer, over the raft cliff."""
+    from config import Config
+    E, stack, _ = env
+    cfg = Config.from_dict({"blending_mode": "fixed_fade", "receding_layers": N, "use_fixed_fade_receding": True,
+                            "fixed_fade_distance_receding": F,
+                            "xy_blend_pipeline": [{"type": "apply_lut", "lut_params": {"lut_source": "file", "fixed_lut_path": lut_file}}]})
+    a = run(E, stack, cfg)
+    da = [digest(a[i]) for i in range(L)]
+    del a
+    monkeypatch.setenv("VSB_NO_PATCH", "1")
+    b = run(E, stack, cfg)
+    monkeypatch.delenv("VSB_NO_PATCH")
+    assert [digest(b[i]) for i in range(L)] == da
+    del b
+    monkeypatch.setenv("VSB_NO_FUSED", "1")
+    c = run(E, stack, cfg)
+    monkeypatch.delenv("VSB_NO_FUSED")
+    assert [digest(c[i]) for i in range(L)] == da
