@@ -69,17 +69,23 @@ __global__ void __launch_bounds__(256) k_ccl_merge(const uint32_t *__restrict__ 
     const uint32_t ul = wx > 0 ? (rec[o - wpr - 1] >> 31) : 0u;
     const uint32_t ur = wx + 1 < wpr ? (rec[o - wpr + 1] & 1u) : 0u;
     const unsigned long long up = (unsigned long long)ul | ((unsigned long long)u << 1) | ((unsigned long long)ur << 33);
+    // One union per pair of touching runs, not per pixel: the pixels of a horizontal run are already linked (inside the
+    // word by k_ccl_init, across words by the union above), so linking each run of this word once to every run of the
+    // row above that touches its one-pixel dilation connects exactly the 8-neighbours.
     uint32_t todo = m;
     while (todo) {
-        const int b = __ffs(todo) - 1;
-        todo &= todo - 1;
-        const uint32_t n3 = (uint32_t)(up >> b) & 7u; // up-left, up, up-right
-        if (!n3) continue;
-        const int p = base + b, q = p - W;
-        if (n3 & 2u) uf_union(L, p, q);
-        else {
-            if (n3 & 1u) uf_union(L, p, q - 1);
-            if (n3 & 4u) uf_union(L, p, q + 1);
+        const int a = __ffs(todo) - 1;                              // run [a, e) of this word
+        const uint32_t gaps = ~m & (0xFFFFFFFFu << a);
+        const int e = gaps ? __ffs(gaps) - 1 : 32;
+        todo = e >= 32 ? 0u : (todo & (0xFFFFFFFFu << e));
+        // pixels a-1 .. e of the row above = window bits a .. e+1
+        unsigned long long touch = up & (~0ULL << a) & ((1ULL << (e + 2)) - 1ULL);
+        while (touch) {
+            const int q = __ffsll((long long)touch) - 1;            // a pixel of a touching run above: x0 + q - 1
+            uf_union(L, base + a, base - W + q - 1);
+            const unsigned long long ugaps = ~up & (~0ULL << q);    // skip the rest of that run
+            const int ue = ugaps ? __ffsll((long long)ugaps) - 1 : 64;
+            touch = ue >= 64 ? 0ULL : (touch & (~0ULL << ue));
         }
     }
 }
