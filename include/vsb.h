@@ -249,6 +249,16 @@ typedef struct {
 int vsb_pack_flags(const uint8_t *gray, size_t pitch, int W, int H, int thresh, uint32_t *bits, int wpr,
                    uint16_t *flags, vsb_stream_t stream);
 
+/* Enhanced EDT, second half fused with the XY chain: the ROI-normalised fade (vsb_enhanced_fade's arithmetic, `arith` =
+ * params->enhanced_arith, limit = params->fade_limit) evaluated on the receding pixels from the distances, component
+ * roots and per-root maxima that vsb_zblend_fused(VSB_Z_DIST) + vsb_ccl8_max produced, then merge -> lut1 -> [bilateral]
+ * -> [Gaussian] -> lut2 exactly like vsb_layer_fused.   processing_core.py:287-336, :404, :458 + the XY chain. */
+int vsb_layer_fused_enhanced(const uint8_t *in, size_t in_pitch, int W, int H, const uint32_t *cur_bits,
+                             const uint32_t *const *prior_bits, int wpr, const vsb_zparams *params, const float *dist,
+                             size_t dist_pitch_elems, const int32_t *labels, const uint32_t *compmax,
+                             const uint8_t *lut1_dev, const vsb_xy_fused *xy /* host, may be NULL */,
+                             const uint8_t *lut2_dev, uint8_t *out, size_t out_pitch, vsb_stream_t stream);
+
 /* LUT-only pipelines (no XY filter): one pass over the gray layer writes the packed mask AND lut[gray] (the final
  * value of every pixel that does not recede); vsb_layer_patch then computes the fade on the receding pixels alone and
  * rewrites them with lut[max(gray, gradient)].  Same results as vsb_layer_fused without XY stage, the gray layer is

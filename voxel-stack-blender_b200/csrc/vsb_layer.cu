@@ -20,6 +20,7 @@
 #include "vsb_tile.cuh"
 
 #define ZL_NONE 5               // stage-1 image is the input itself (XY-only use)
+#define ZL_SEARCHES(Z) ((Z) != ZL_NONE && (Z) != VSB_Z_CONST && (Z) != VSB_Z_ENHANCED) // modes that run the row search
 #define LH_MAX 7                // max XY halo (bilateral radius + Gaussian radius)
 #define RG_W 160                // staged region: x0-16 .. x0+143
 #define RG_CH 10
@@ -68,6 +69,8 @@ struct LayerParams {
     struct { int T, raw, src, s1, s2, bits, list, raw_stride, src_stride; } sm; // dynamic shared memory carve (bytes / words)
     int ntiles;
     const int *rec_list; // sparse: [0] = number of tiles with receding pixels, [1..] their indices (nullptr = all tiles)
+    // VSB_Z_ENHANCED: distances at the receding pixels, their component roots and the per-root maxima (vsb_ccl8_max)
+    const float *enh_dist; size_t enh_dpitch; const int32_t *enh_labels; const uint32_t *enh_cmax;
     int sparse;          // no-XY variant only: `out` already holds LUT1[gray]; rewrite just the receding pixels
     vsb_zparams z;
 };
@@ -401,7 +404,7 @@ __global__ void __launch_bounds__(VSB_THREADS, XY ? VSB_LAYER_CTAS_XY : 6) k_lay
                 }
             }
             ref_raw = 0;
-            if (p.sparse && ZMODE != ZL_NONE && ZMODE != VSB_Z_CONST) {
+            if (p.sparse && ZL_SEARCHES(ZMODE)) {
                 // patch launch: every listed tile has receding pixels, so the search window and the chamfer table are
                 // requested together with the tile's mask words -- one memory round trip per tile instead of two
                 if (METRIC == VSB_METRIC_CHAMFER5 && !t_staged) {
@@ -537,7 +540,7 @@ __global__ void __launch_bounds__(VSB_THREADS, XY ? VSB_LAYER_CTAS_XY : 6) k_lay
         // ---- P2: distance search + gradient on the receding pixels of the region ----------------------------
         if (ZMODE != ZL_NONE && any_rec) {
             const int brows = RH + 2 * R;
-            if (ZMODE != VSB_Z_CONST && !sparse) {
+            if (ZL_SEARCHES(ZMODE) && !sparse) {
                 if (METRIC == VSB_METRIC_CHAMFER5 && !t_staged) {
                     const int nT = (R + 1) * (R + 1);
                     const int nfull = ((((size_t)p.T) & 15) == 0) ? (nT >> 2) : 0; // 16-byte groups when the table is aligned
@@ -547,7 +550,7 @@ __global__ void __launch_bounds__(VSB_THREADS, XY ? VSB_LAYER_CTAS_XY : 6) k_lay
                 }
                 stage_mask_rows<LBW>(s_bits, p.cur, wpr, H, (x0 >> 5) - 3, y0 - Hh - R, brows);
             }
-            if (ZMODE != VSB_Z_CONST && sparse) stage_rowany_rows<LBW>(s_rowany, s_bits, brows); // window staged before the first barrier
+            if (ZL_SEARCHES(ZMODE) && sparse) stage_rowany_rows<LBW>(s_rowany, s_bits, brows); // window staged before the first barrier
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
                 const int i = t + u * VSB_THREADS;
@@ -567,7 +570,7 @@ __global__ void __launch_bounds__(VSB_THREADS, XY ? VSB_LAYER_CTAS_XY : 6) k_lay
             }
             __syncthreads();
             if (!sparse) {
-                if (ZMODE != VSB_Z_CONST) stage_rowany_rows<LBW>(s_rowany, s_bits, brows);
+                if (ZL_SEARCHES(ZMODE)) stage_rowany_rows<LBW>(s_rowany, s_bits, brows);
                 __syncthreads();
             }
             const int total = s_cnt;
@@ -579,7 +582,7 @@ __global__ void __launch_bounds__(VSB_THREADS, XY ? VSB_LAYER_CTAS_XY : 6) k_lay
                 const int rr = code >> 8, rc = code & 255;
                 const int x = x0 - 16 + rc, y = y0 - Hh + rr;
                 float best = 0.0f;
-                if (ZMODE != VSB_Z_CONST) best = tile_search<METRIC, LBW, false>(s_bits, s_rowany, s_T, R, rr + R, rc + 80);
+                if (ZL_SEARCHES(ZMODE)) best = tile_search<METRIC, LBW, false>(s_bits, s_rowany, s_T, R, rr + R, rc + 80);
                 int g;
                 if (ZMODE == VSB_Z_FIXED) {
                     const float n = __fdiv_rn(fminf(best, Ff), p.z.den);
@@ -595,6 +598,21 @@ __global__ void __launch_bounds__(VSB_THREADS, XY ? VSB_LAYER_CTAS_XY : 6) k_lay
                         }
                     }
                     g = (int)__fmul_rn(255.0f, __fdiv_rn(acc, p.z.total_weight));
+                } else if (ZMODE == VSB_Z_ENHANCED) {
+                    // fade normalised by min(component maximum, F): the float32 (SciPy) or float64 (Numba) arithmetic of
+                    // processing_core.py:295-302 / :329-334
+                    const float d = p.enh_dist[(size_t)y * p.enh_dpitch + x];
+                    const float mx = __uint_as_float(p.enh_cmax[p.enh_labels[(size_t)y * W + x]]);
+                    if (p.z.enhanced_arith == 0) {
+                        float den = (float)fmin((double)mx, p.z.fade_limit);
+                        if (den <= 0.0f) den = 1.0f;
+                        const float nrm = __fdiv_rn(fminf(fmaxf(d, 0.0f), den), den);
+                        g = (int)__fmul_rn(255.0f, __fsub_rn(1.0f, nrm));
+                    } else {
+                        const double den = fmin((double)mx, p.z.fade_limit);
+                        g = 0;
+                        if (den > 0.0) g = (int)(long long)__dmul_rn(__dsub_rn(1.0, __ddiv_rn(fmin((double)d, den), den)), 255.0);
+                    }
                 } else {
                     g = p.z.const_val;
                 }
@@ -829,17 +847,21 @@ extern "C" int vsb_layer_stats(int op, unsigned long long *out8)
     return VSB_OK;
 }
 
+struct EnhInputs { const float *dist; size_t dpitch; const int32_t *labels; const uint32_t *cmax; };
+
 static int layer_launch(const uint8_t *in, size_t in_pitch, int W, int H, const uint32_t *cur_bits,
                         const uint32_t *const *prior_bits, const uint16_t *cur_flags,
                         const uint16_t *const *prior_flags, int wpr, const vsb_zparams *zp, const float *T_dev,
                         const uint8_t *lut1_dev, const vsb_xy_fused *xy, const uint8_t *lut2_dev, uint8_t *out,
-                        size_t out_pitch, vsb_stream_t stream, int sparse, const int *rec_list = nullptr)
+                        size_t out_pitch, vsb_stream_t stream, int sparse, const int *rec_list = nullptr,
+                        const EnhInputs *enh = nullptr)
 {
     VSB_REQUIRE(in && out && zp && in != out, "vsb_layer_fused: null pointer / in-place");
     VSB_REQUIRE(W >= 8 && H >= 8 && in_pitch >= (size_t)W && out_pitch >= (size_t)W,
                 "vsb_layer_fused: images smaller than 8x8 take the unfused kernels");
     const int mode = zp->mode;
-    VSB_REQUIRE(mode == VSB_Z_FIXED || mode == VSB_Z_WEIGHTED || mode == VSB_Z_CONST || mode == VSB_Z_NONE,
+    VSB_REQUIRE(mode == VSB_Z_FIXED || mode == VSB_Z_WEIGHTED || mode == VSB_Z_CONST || mode == VSB_Z_NONE ||
+                (mode == VSB_Z_ENHANCED && enh && enh->dist && enh->labels && enh->cmax && enh->dpitch >= (size_t)W),
                 "vsb_layer_fused: mode %d not fused", mode);
     VSB_REQUIRE(zp->metric == VSB_METRIC_CHAMFER5 || zp->metric == VSB_METRIC_EXACT, "vsb_layer_fused: unknown metric");
     if (mode != VSB_Z_NONE) {
@@ -847,7 +869,8 @@ static int layer_launch(const uint8_t *in, size_t in_pitch, int W, int H, const 
         VSB_REQUIRE(zp->n_priors >= 0 && zp->n_priors <= VSB_MAX_PRIORS && (zp->n_priors == 0 || prior_bits),
                     "vsb_layer_fused: priors");
         VSB_REQUIRE(zp->reach >= 0 && zp->reach <= VSB_FAST_REACH, "vsb_layer_fused: reach %d > %d", zp->reach, VSB_FAST_REACH);
-        VSB_REQUIRE(T_dev || mode == VSB_Z_CONST || zp->metric == VSB_METRIC_EXACT, "vsb_layer_fused: chamfer table missing");
+        VSB_REQUIRE(T_dev || mode == VSB_Z_CONST || mode == VSB_Z_ENHANCED || zp->metric == VSB_METRIC_EXACT,
+                    "vsb_layer_fused: chamfer table missing");
     }
     LayerParams p;
     memset(&p, 0, sizeof p);
@@ -857,7 +880,8 @@ static int layer_launch(const uint8_t *in, size_t in_pitch, int W, int H, const 
     p.cur = cur_bits; p.cur_flags = cur_flags;
     p.z = *zp;
     if (mode == VSB_Z_NONE) p.z.n_priors = 0;
-    if (mode == VSB_Z_CONST) p.z.reach = 0;
+    if (mode == VSB_Z_CONST || mode == VSB_Z_ENHANCED) p.z.reach = 0;
+    if (mode == VSB_Z_ENHANCED) { p.enh_dist = enh->dist; p.enh_dpitch = enh->dpitch; p.enh_labels = enh->labels; p.enh_cmax = enh->cmax; }
     for (int i = 0; i < p.z.n_priors; ++i) {
         p.prior[i] = prior_bits[i];
         p.prior_flags[i] = prior_flags ? prior_flags[i] : nullptr;
@@ -898,7 +922,7 @@ static int layer_launch(const uint8_t *in, size_t in_pitch, int W, int H, const 
     const int RH = VSB_TH + 2 * p.halo;
     const int n1 = p.z.reach + 1;
     auto up16 = [](size_t v) { return (v + 15) & ~(size_t)15; };
-    const bool searching = mode != VSB_Z_NONE && mode != VSB_Z_CONST;
+    const bool searching = mode != VSB_Z_NONE && mode != VSB_Z_CONST && mode != VSB_Z_ENHANCED;
     size_t off = 0;
     p.sm.T = (int)off; off += up16((searching && zp->metric == VSB_METRIC_CHAMFER5) ? (size_t)n1 * n1 * 4 : 16);
     p.sm.raw_stride = (int)up16((size_t)RH * RG_W);
@@ -919,6 +943,7 @@ static int layer_launch(const uint8_t *in, size_t in_pitch, int W, int H, const 
     case VSB_Z_FIXED: return ex ? launch_layer<VSB_Z_FIXED, 1>(p, taps_dev, persist, smem, s) : launch_layer<VSB_Z_FIXED, 0>(p, taps_dev, persist, smem, s);
     case VSB_Z_WEIGHTED: return ex ? launch_layer<VSB_Z_WEIGHTED, 1>(p, taps_dev, persist, smem, s) : launch_layer<VSB_Z_WEIGHTED, 0>(p, taps_dev, persist, smem, s);
     case VSB_Z_CONST: return launch_layer<VSB_Z_CONST, 0>(p, taps_dev, persist, smem, s);
+    case VSB_Z_ENHANCED: return launch_layer<VSB_Z_ENHANCED, 0>(p, taps_dev, false, smem, s);
     default: return launch_layer<ZL_NONE, 0>(p, taps_dev, persist, smem, s);
     }
 }
@@ -943,4 +968,18 @@ extern "C" int vsb_layer_patch(const uint8_t *in, size_t in_pitch, int W, int H,
     if (zp->n_priors == 0) return VSB_OK; // nothing can recede: the pre-filled output stands
     return layer_launch(in, in_pitch, W, H, cur_bits, prior_bits, nullptr, nullptr, wpr, zp, T_dev, lut1_dev, nullptr, nullptr,
                         out, out_pitch, stream, 1, rec_tiles);
+}
+
+extern "C" int vsb_layer_fused_enhanced(const uint8_t *in, size_t in_pitch, int W, int H, const uint32_t *cur_bits,
+                                        const uint32_t *const *prior_bits, int wpr, const vsb_zparams *zp, const float *dist,
+                                        size_t dist_pitch_elems, const int32_t *labels, const uint32_t *compmax,
+                                        const uint8_t *lut1_dev, const vsb_xy_fused *xy, const uint8_t *lut2_dev, uint8_t *out,
+                                        size_t out_pitch, vsb_stream_t stream)
+{
+    VSB_REQUIRE(zp, "vsb_layer_fused_enhanced: null parameters");
+    vsb_zparams z = *zp;
+    z.mode = VSB_Z_ENHANCED;
+    const EnhInputs enh = {dist, dist_pitch_elems, labels, compmax};
+    return layer_launch(in, in_pitch, W, H, cur_bits, prior_bits, nullptr, nullptr, wpr, &z, nullptr, lut1_dev, xy, lut2_dev, out,
+                        out_pitch, stream, 0, nullptr, &enh);
 }

@@ -456,6 +456,16 @@ static int run_layer(vsb_stack *s, const uint8_t *gray, size_t gpitch, uint8_t *
             if (rc) return rc;
             { ProfScope ps(s, ST_CCL, 3); rc = vsb_ccl8_max(s->rec_bits, s->wpr, s->W, s->H, s->dist, (size_t)s->W, s->labels, s->cmax, st); }
             if (rc) return rc;
+            if (s->fused && getenv("VSB_NO_FUSED_ENHANCED") == nullptr) {
+                // the fade itself runs inside the layer kernel, straight into the XY chain (no intermediate image)
+                ProfScope ps(s, ST_LAYER, 1);
+                rc = vsb_layer_fused_enhanced(gray, gpitch, s->W, s->H, cur, pri, s->wpr, &zp, s->dist, (size_t)s->W, s->labels,
+                                              s->cmax, s->lead_lut_dev, &s->fx, s->lut2_dev, out, opitch, st);
+                if (rc) return rc;
+                s->head = (s->head + 1) % nring;
+                if (s->count < s->n_priors) ++s->count;
+                return VSB_OK;
+            }
             { ProfScope ps(s, ST_EFADE, 1);
               rc = vsb_enhanced_fade(gray, gpitch, s->W, s->H, s->rec_bits, s->wpr, s->dist, (size_t)s->W, s->labels,
                                      s->cmax, zp.fade_limit, zp.enhanced_arith, s->lead_lut_dev, zdst, zpitch, st); }

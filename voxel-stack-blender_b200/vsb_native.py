@@ -104,6 +104,9 @@ _SIGS = {
                                    POINTER(c_void_p), c_int, c_void_p, c_void_p]),
     "vsb_layer_patch": (c_int, [c_void_p, c_size_t, c_int, c_int, c_void_p, POINTER(c_void_p), c_int, POINTER(ZParams), c_void_p,
                                 c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "vsb_layer_fused_enhanced": (c_int, [c_void_p, c_size_t, c_int, c_int, c_void_p, POINTER(c_void_p), c_int, POINTER(ZParams),
+                                         c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
+                                         c_void_p]),
     "vsb_layer_stats": (c_int, [c_int, c_void_p]),
     "vsb_layer_fused": (c_int, [c_void_p, c_size_t, c_int, c_int, c_void_p, POINTER(c_void_p), c_void_p, POINTER(c_void_p),
                                 c_int, POINTER(ZParams), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
