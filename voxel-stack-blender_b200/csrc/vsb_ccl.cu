@@ -101,21 +101,28 @@ __global__ void __launch_bounds__(256) k_ccl_flatten_max(const uint32_t *__restr
     uint32_t m = rec[(size_t)y * wpr + wx];
     if (!m) return;
     const int base = y * W + (wx << 5);
+    // one root look-up per horizontal run (its pixels all hang off the run's first pixel since k_ccl_init), one
+    // atomicMax per group of consecutive runs with the same root
     int last_root = -1;
-    uint32_t run_max = 0;
+    uint32_t acc_max = 0;
     while (m) {
-        const int b = __ffs(m) - 1;
-        m &= m - 1;
-        const int p = base + b;
-        const int root = uf_find(L, p);
-        L[p] = root;
-        const uint32_t d = __float_as_uint(dist[(size_t)y * dpitch + (wx << 5) + b]);
+        const int a = __ffs(m) - 1;
+        const uint32_t gaps = ~m & (0xFFFFFFFFu << a);
+        const int e = gaps ? __ffs(gaps) - 1 : 32;
+        m = e >= 32 ? 0u : (m & (0xFFFFFFFFu << e));
+        const int root = uf_find(L, base + a);
+        uint32_t run_max = 0;
+        const float *drow = dist + (size_t)y * dpitch + (wx << 5);
+        for (int b = a; b < e; ++b) {
+            L[base + b] = root;
+            run_max = max(run_max, __float_as_uint(drow[b]));
+        }
         if (root != last_root) {
-            if (last_root >= 0) atomicMax(&cmax[last_root], run_max);
-            last_root = root; run_max = d;
-        } else run_max = max(run_max, d);
+            if (last_root >= 0) atomicMax(&cmax[last_root], acc_max);
+            last_root = root; acc_max = run_max;
+        } else acc_max = max(acc_max, run_max);
     }
-    if (last_root >= 0) atomicMax(&cmax[last_root], run_max);
+    if (last_root >= 0) atomicMax(&cmax[last_root], acc_max);
 }
 
 extern "C" int vsb_ccl8_max(const uint32_t *rec_bits, int wpr, int W, int H, const float *dist,
