@@ -189,6 +189,12 @@ int vsb_enhanced_fade(const uint8_t *gray, size_t gray_pitch, int W, int H, cons
                       const uint32_t *compmax, double fade_limit, int arith /* 0 = float32 (SciPy), 1 = float64 (Numba) */,
                       const uint8_t *lut256_dev, uint8_t *out, size_t out_pitch, vsb_stream_t stream);
 
+/* Enhanced EDT stage 1 in one launch: the packed receding mask (= vsb_maskdiff) and min(d, fade) at its pixels
+ * (= vsb_zblend_fused in VSB_Z_DIST mode).   processing_core.py:350, :379-381 */
+int vsb_rec_dist(const uint32_t *cur_bits, const uint32_t *const *prior_bits, int wpr, int W, int H,
+                 const vsb_zparams *params, const float *T_dev, uint32_t *rec_bits_out, float *dist_out,
+                 size_t dist_pitch_elems, vsb_stream_t stream);
+
 /* the two per-label fades exactly as the reference exposes them to its tests (dense, contiguous
  * arrays; labels 1..num_labels-1 from any labelling, 0 = background):
  *     arith 0 = _calculate_receding_gradient_field_enhanced_edt_scipy  processing_core.py:287-303

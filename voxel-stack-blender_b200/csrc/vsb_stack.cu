@@ -427,8 +427,12 @@ static int run_layer(vsb_stack *s, const uint8_t *gray, size_t gpitch, uint8_t *
         } else if (enhanced) {
             rc = ensure_enhanced_scratch(s);
             if (rc) return rc;
-            { ProfScope ps(s, ST_MASKDIFF, 1); rc = vsb_maskdiff(cur, pri, np, s->wpr, s->H, s->rec_bits, nullptr, st); }
-            if (rc) return rc;
+            const bool plain_enh = zp.mode == VSB_Z_ENHANCED && zp.aniso_w == 0; // receding mask + distances in one launch
+            if (!plain_enh) {
+                ProfScope ps(s, ST_MASKDIFF, 1);
+                rc = vsb_maskdiff(cur, pri, np, s->wpr, s->H, s->rec_bits, nullptr, st);
+                if (rc) return rc;
+            }
             if (zp.mode == VSB_Z_ENHANCED_FAR) {
                 rc = ensure_unbounded_scratch(s);
                 if (rc) return rc;
@@ -448,10 +452,8 @@ static int run_layer(vsb_stack *s, const uint8_t *gray, size_t gpitch, uint8_t *
                                               (size_t)zp.aniso_w, st);
                 if (!rc) rc = vsb_resize_f32_linear(s->an_lin, s->an_dist, (size_t)zp.aniso_w, s->dist, (size_t)s->W, st);
             } else {
-                vsb_zparams zd = zp; zd.mode = VSB_Z_DIST;
                 ProfScope ps(s, ST_ZDIST, 1);
-                rc = vsb_zblend_fused(nullptr, 0, s->W, s->H, cur, pri, s->wpr, &zd, s->T_dev, nullptr, nullptr, 0, s->dist,
-                                      (size_t)s->W, st);
+                rc = vsb_rec_dist(cur, pri, s->wpr, s->W, s->H, &zp, s->T_dev, s->rec_bits, s->dist, (size_t)s->W, st);
             }
             if (rc) return rc;
             { ProfScope ps(s, ST_CCL, 3); rc = vsb_ccl8_max(s->rec_bits, s->wpr, s->W, s->H, s->dist, (size_t)s->W, s->labels, s->cmax, st); }

@@ -26,6 +26,7 @@ struct ZKParams {
     const uint8_t *lut;
     float *dist;
     size_t dpitch;
+    uint32_t *rec_out; // VSB_Z_DIST: optional packed receding mask (what vsb_maskdiff would write)
     int W, H, wpr;
     int aligned;
     vsb_zparams z;
@@ -74,6 +75,7 @@ __global__ void __launch_bounds__(VSB_THREADS) k_zblend(const __grid_constant__ 
                 acc |= pw;
             }
             recw = acc;
+            if (MODE == VSB_Z_DIST && p.rec_out) p.rec_out[o] = acc;
         } else if (MODE == VSB_Z_WEIGHTED) {
             for (int i = 0; i < np; ++i) s_recp[i][rr][wi] = 0;
         }
@@ -179,10 +181,10 @@ static void launch_mode(int mode, dim3 grid, size_t smem, cudaStream_t s, const 
     }
 }
 
-extern "C" int vsb_zblend_fused(const uint8_t *gray, size_t gray_pitch, int W, int H, const uint32_t *cur_bits,
-                                const uint32_t *const *prior_bits, int wpr, const vsb_zparams *zp,
-                                const float *T_dev, const uint8_t *lut256_dev, uint8_t *out, size_t out_pitch,
-                                float *dist_out, size_t dist_pitch_elems, vsb_stream_t stream)
+static int zblend_launch(const uint8_t *gray, size_t gray_pitch, int W, int H, const uint32_t *cur_bits,
+                         const uint32_t *const *prior_bits, int wpr, const vsb_zparams *zp,
+                         const float *T_dev, const uint8_t *lut256_dev, uint8_t *out, size_t out_pitch,
+                         float *dist_out, size_t dist_pitch_elems, uint32_t *rec_out, vsb_stream_t stream)
 {
     VSB_REQUIRE(zp && cur_bits, "vsb_zblend_fused: null pointer");
     VSB_REQUIRE(W > 0 && H > 0 && wpr >= (W + 31) / 32, "vsb_zblend_fused: bad geometry");
@@ -206,7 +208,7 @@ extern "C" int vsb_zblend_fused(const uint8_t *gray, size_t gray_pitch, int W, i
     k.gray = gray; k.gpitch = gray_pitch; k.out = out; k.opitch = out_pitch;
     k.cur = cur_bits;
     for (int i = 0; i < VSB_MAX_PRIORS; ++i) k.prior[i] = i < zp->n_priors ? prior_bits[i] : nullptr;
-    k.T = T_dev; k.lut = lut256_dev; k.dist = dist_out; k.dpitch = dist_pitch_elems;
+    k.T = T_dev; k.lut = lut256_dev; k.dist = dist_out; k.dpitch = dist_pitch_elems; k.rec_out = rec_out;
     k.W = W; k.H = H; k.wpr = wpr;
     k.aligned = (zp->mode == VSB_Z_DIST) ? 1 : (vsb_aligned16(gray, gray_pitch) && vsb_aligned16(out, out_pitch));
     k.z = *zp;
@@ -218,4 +220,25 @@ extern "C" int vsb_zblend_fused(const uint8_t *gray, size_t gray_pitch, int W, i
     if (zp->metric == VSB_METRIC_CHAMFER5) launch_mode<VSB_METRIC_CHAMFER5>(zp->mode, grid, smem, s, k);
     else launch_mode<VSB_METRIC_EXACT>(zp->mode, grid, smem, s, k);
     return vsb_check_launch("k_zblend");
+}
+
+extern "C" int vsb_zblend_fused(const uint8_t *gray, size_t gray_pitch, int W, int H, const uint32_t *cur_bits,
+                                const uint32_t *const *prior_bits, int wpr, const vsb_zparams *zp,
+                                const float *T_dev, const uint8_t *lut256_dev, uint8_t *out, size_t out_pitch,
+                                float *dist_out, size_t dist_pitch_elems, vsb_stream_t stream)
+{
+    return zblend_launch(gray, gray_pitch, W, H, cur_bits, prior_bits, wpr, zp, T_dev, lut256_dev, out, out_pitch, dist_out,
+                         dist_pitch_elems, nullptr, stream);
+}
+
+extern "C" int vsb_rec_dist(const uint32_t *cur_bits, const uint32_t *const *prior_bits, int wpr, int W, int H,
+                            const vsb_zparams *zp, const float *T_dev, uint32_t *rec_bits_out, float *dist_out,
+                            size_t dist_pitch_elems, vsb_stream_t stream)
+{
+    VSB_REQUIRE(zp && rec_bits_out, "vsb_rec_dist: null pointer");
+    VSB_REQUIRE(wpr >= ((W + 127) / 128) * 4, "vsb_rec_dist: wpr must be 4 words per 128 pixels (every mask word is written)");
+    vsb_zparams z = *zp;
+    z.mode = VSB_Z_DIST;
+    return zblend_launch(nullptr, 0, W, H, cur_bits, prior_bits, wpr, &z, T_dev, nullptr, nullptr, 0, dist_out, dist_pitch_elems,
+                         rec_bits_out, stream);
 }

@@ -75,6 +75,8 @@ _SIGS = {
     "vsb_zblend_fused": (c_int, [c_void_p, c_size_t, c_int, c_int, c_void_p, POINTER(c_void_p), c_int,
                                  POINTER(ZParams), c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_size_t,
                                  c_void_p]),
+    "vsb_rec_dist": (c_int, [c_void_p, POINTER(c_void_p), c_int, c_int, c_int, POINTER(ZParams), c_void_p, c_void_p, c_void_p, c_size_t,
+                             c_void_p]),
     "vsb_ccl8_max": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p]),
     "vsb_enhanced_fade": (c_int, [c_void_p, c_size_t, c_int, c_int, c_void_p, c_int, c_void_p, c_size_t, c_void_p,
                                   c_void_p, c_double, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
