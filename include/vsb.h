@@ -399,6 +399,9 @@ int vsb_stack_out_size(vsb_stack *s, int *out_W, int *out_H);
 int vsb_stack_reset(vsb_stack *s);
 /* feed a halo layer: thresholded and pushed into the window, no output */
 int vsb_stack_push_halo(vsb_stack *s, const uint8_t *gray_host, size_t pitch);
+/* the same for a halo layer that is already resident on the device (asynchronous on the stack's stream): what a Z-shard
+ * whose slab lives in HBM calls for the receding_layers layers below its first one */
+int vsb_stack_push_halo_device(vsb_stack *s, const uint8_t *gray_dev, size_t pitch);
 /* one layer, host in -> host out (H2D, kernels, D2H; synchronous on return) */
 int vsb_stack_process_host(vsb_stack *s, const uint8_t *gray_host, size_t in_pitch,
                            uint8_t *out_host, size_t out_pitch);

@@ -66,7 +66,7 @@ struct LayerParams {
     alignas(16) int tap_off[96];     // bilateral taps as byte offsets in the staged region, and their space weights: read through
     alignas(16) float tap_sw[96];    // the constant bank with a warp-uniform index, so they cost no vector instruction
     unsigned long long *stats; // optional work counters (vsb_layer_stats)
-    struct { int T, raw, src, s1, s2, bits, list, raw_stride, src_stride; } sm; // dynamic shared memory carve (bytes / words)
+    struct { int T, s1, s2, bits, list; } sm; // dynamic shared memory carve (bytes / words)
     int ntiles;
     const int *rec_list; // sparse: [0] = number of tiles with receding pixels, [1..] their indices (nullptr = all tiles)
     // VSB_Z_ENHANCED: distances at the receding pixels, their component roots and the per-root maxima (vsb_ccl8_max)
@@ -248,32 +248,14 @@ __device__ __forceinline__ uint32_t gauss_word_ry(const uint8_t (*S)[RG_W], int 
         }                                                                                               \
     } while (0)
 
-__device__ __forceinline__ void cp_async16(void *smem, const void *g)
-{
-    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(g) : "memory");
-}
-__device__ __forceinline__ void cp_async4(void *smem, const void *g)
-{
-    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(g) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-
-// PERSIST: CTAs stride over the tiles; while tile i is processed the input region and the mask words of tile i+1
-// are already in flight (cp.async into the other half of a double buffer), so the DRAM/L2 latency of the
-// prologue is off the critical path and LUTs / tap tables / chamfer table are staged once per CTA.
-template <int ZMODE, int METRIC, bool PERSIST, bool XY>
+template <int ZMODE, int METRIC, bool XY>
 __global__ void __launch_bounds__(VSB_THREADS, XY ? VSB_LAYER_CTAS_XY : 6) k_layer(const __grid_constant__ LayerParams p,
                                                        const BilTapsL *__restrict__ taps)
 {
     // work list of the patch launch: CTAs beyond the number of listed tiles leave before any set-up
-    if (!PERSIST && !XY && p.rec_list && (int)(blockIdx.y * gridDim.x + blockIdx.x) >= p.rec_list[0]) return;
+    if (!XY && p.rec_list && (int)(blockIdx.y * gridDim.x + blockIdx.x) >= p.rec_list[0]) return;
     extern __shared__ __align__(16) uint8_t dsm[];
     float *s_T = (float *)(dsm + p.sm.T);
-    uint8_t *s_rawb = dsm + p.sm.raw;                             // PERSIST: [2][RH][RG_W] raw input region
-    uint32_t *s_srcw = (uint32_t *)(dsm + p.sm.src);              // PERSIST: [2][np+1][RH*6] mask words
     uint8_t (*s1)[RG_W] = (uint8_t (*)[RG_W])(dsm + p.sm.s1);      // stage 1; later the Gaussian output
     uint8_t (*s2buf)[RG_W] = (uint8_t (*)[RG_W])(dsm + p.sm.s2);   // stage 2 (bilateral output)
     uint32_t (*s_bits)[LBW] = (uint32_t (*)[LBW])(dsm + p.sm.bits);
@@ -305,91 +287,24 @@ __global__ void __launch_bounds__(VSB_THREADS, XY ? VSB_LAYER_CTAS_XY : 6) k_lay
     bool late_staged = false; // trailing LUT and bilateral tables: staged by the first tile that is not trivially uniform
     bool t_staged = false; // chamfer table [(R+1) x (R+1)]: staged by the first tile that needs it
 
-    auto prefetch = [&](int tile, int b) {
-        const int px0 = (tile % p.tiles_x) * VSB_TW, py0 = (tile / p.tiles_x) * VSB_TH;
-        uint8_t *rawb = s_rawb + (size_t)b * p.sm.raw_stride;
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            const int i = t + u * VSB_THREADS;
-            if (i < RH * RG_CH) {
-                const int rr = i / RG_CH, cc = i - rr * RG_CH;
-                const int y = py0 - Hh + rr, x = px0 - 16 + cc * 16;
-                uint8_t *dst = rawb + rr * RG_W + cc * 16;
-                if (y >= 0 && y < H && x >= 0 && x < W) cp_async16(dst, p.in + (size_t)y * p.ipitch + x);
-                else *(uint4 *)dst = make_uint4(0, 0, 0, 0);
-            }
-        }
-        if (ZMODE != ZL_NONE) {
-            uint32_t *srcb = s_srcw + (size_t)b * p.sm.src_stride;
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const int i = t + u * VSB_THREADS;
-                if (i < nsrc) {
-                    const int rr = i / 6, k = i - rr * 6;
-                    const int y = py0 - Hh + rr, wx = (px0 >> 5) - 1 + k;
-                    const bool ok = y >= 0 && y < H && wx >= 0 && wx < wpr;
-                    const size_t o = (size_t)y * wpr + wx;
-                    if (ok) cp_async4(srcb + i, p.cur + o); else srcb[i] = 0u;
-                    for (int j = 0; j < np; ++j) {
-                        if (ok) cp_async4(srcb + (j + 1) * nsrc + i, p.prior[j] + o); else srcb[(j + 1) * nsrc + i] = 0u;
-                    }
-                }
-            }
-        }
-        cp_async_commit();
-    };
-
-    int tile = PERSIST ? (int)blockIdx.x : (int)(blockIdx.y * gridDim.x + blockIdx.x);
+    int tile = (int)(blockIdx.y * gridDim.x + blockIdx.x);
     int wl_tx = (int)blockIdx.x, wl_ty = (int)blockIdx.y;
-    if (!PERSIST && !XY && p.rec_list) { // work list of the patch launch: CTA i takes the i-th listed tile
+    if (!XY && p.rec_list) { // work list of the patch launch: CTA i takes the i-th listed tile
         tile = p.rec_list[1 + tile];
         wl_tx = tile % p.tiles_x; wl_ty = tile / p.tiles_x;
     }
-    int buf = 0;
-    if (PERSIST && tile < p.ntiles) prefetch(tile, 0);
-
-    for (; tile < p.ntiles; tile += PERSIST ? (int)gridDim.x : p.ntiles) {
-        const int tx = PERSIST ? tile % p.tiles_x : wl_tx, ty = PERSIST ? tile / p.tiles_x : wl_ty; // 2-D grid: no division
+    {
+        const int tx = wl_tx, ty = wl_ty; // 2-D grid: no division
         const int x0 = tx * VSB_TW, y0 = ty * VSB_TH;
         const int oy = y0 + r, ox = x0 + c * 16;
         const int nvalid = (oy < H) ? max(0, min(16, W - ox)) : 0;
-        const uint8_t *rawb = s_rawb + (size_t)buf * p.sm.raw_stride;
-        const uint32_t *srcb = s_srcw + (size_t)buf * p.sm.src_stride;
 
         // ---- P1: prologue ---------------------------------------------------------------------------------------
         uint32_t rwv[2] = {0, 0};
         uint4 gv[2];
-        int gstate[2]; // 0 = outside the image, 1 = full chunk, 2 = partial (byte path, non-persistent only)
+        int gstate[2]; // 0 = outside the image, 1 = full chunk, 2 = partial (byte path)
         uint32_t ref_raw;
-        if (PERSIST) {
-            if (t == 0) { s_cnt = 0; s_gcnt = 0; s_quiet = 0; }
-            if (XY && t < RH) { s_zpl[t] = 0ULL; s_wpl[t] = 0ULL; }
-            cp_async_wait_all();
-            __syncthreads(); // this tile's region has landed (it was requested one iteration ago)
-            const int nxt = tile + (int)gridDim.x;
-            if (nxt < p.ntiles) prefetch(nxt, buf ^ 1);
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const int i = t + u * VSB_THREADS;
-                gv[u] = make_uint4(0, 0, 0, 0);
-                gstate[u] = 0;
-                if (i < RH * RG_CH) {
-                    const int rr = i / RG_CH, cc = i - rr * RG_CH;
-                    const int y = y0 - Hh + rr, x = x0 - 16 + cc * 16;
-                    if (y >= 0 && y < H && x >= 0 && x < W) { gv[u] = *(const uint4 *)(rawb + rr * RG_W + cc * 16); gstate[u] = 1; }
-                }
-                if (ZMODE != ZL_NONE && i < nsrc) {
-                    const int k = i % 6;
-                    uint32_t acc = 0;
-                    for (int j = 0; j < np; ++j) acc |= srcb[(j + 1) * nsrc + i];
-                    uint32_t rw = acc & ~srcb[i];
-                    if (k == 0) rw &= Hh ? (0xFFFFFFFFu << (32 - Hh)) : 0u;
-                    if (k == 5) rw &= (1u << Hh) - 1u;
-                    rwv[u] = rw;
-                }
-            }
-            ref_raw = rawb[Hh * RG_W + 16];
-        } else if (!XY) {
+        if (!XY) {
             // no XY filter: the region is the tile itself -- thread t owns chunk (r, c), threads < 128 one mask word
             gv[0] = gv[1] = make_uint4(0, 0, 0, 0);
             gstate[0] = gstate[1] = 0;
@@ -616,7 +531,7 @@ __global__ void __launch_bounds__(VSB_THREADS, XY ? VSB_LAYER_CTAS_XY : 6) k_lay
                 } else {
                     g = p.z.const_val;
                 }
-                const int graw = PERSIST ? (int)rawb[rr * RG_W + rc] : (int)p.in[(size_t)y * p.ipitch + x];
+                const int graw = (int)p.in[(size_t)y * p.ipitch + x];
                 const int m = max(graw, g & 255); // merge with the raw gray value
                 if (sparse) { p.out[(size_t)y * p.opitch + x] = L1.s ? L1.s[m] : (uint8_t)m; continue; }
                 s1[rr][rc] = L1.s ? L1.s[m] : (uint8_t)m;
@@ -772,40 +687,27 @@ __global__ void __launch_bounds__(VSB_THREADS, XY ? VSB_LAYER_CTAS_XY : 6) k_lay
             else vsb_st_bytes(dst, o, nvalid);
         }
         } while (0);
-        if (PERSIST) { __syncthreads(); buf ^= 1; } // shared buffers are reused by the next tile
     }
 }
 
-template <int ZMODE, int METRIC, bool PERSIST, bool XY>
+template <int ZMODE, int METRIC, bool XY>
 static int launch_layer_v(LayerParams &p, const BilTapsL *taps, size_t smem, cudaStream_t s)
 {
-    static int n_sms = 0; // per instantiation
-    if (n_sms == 0) {
-        VSB_CUDA(cudaFuncSetAttribute(k_layer<ZMODE, METRIC, PERSIST, XY>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-        int dev = 0, sms = 0;
-        VSB_CUDA(cudaGetDevice(&dev));
-        VSB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        n_sms = sms > 0 ? sms : 148;
+    static bool configured = false; // per instantiation
+    if (!configured) {
+        VSB_CUDA(cudaFuncSetAttribute(k_layer<ZMODE, METRIC, XY>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        configured = true;
     }
-    if (PERSIST) {
-        int per_sm = 0;
-        VSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_layer<ZMODE, METRIC, PERSIST, XY>, VSB_THREADS, smem));
-        if (per_sm < 1) per_sm = 1;
-        const int grid = p.ntiles < n_sms * per_sm ? p.ntiles : n_sms * per_sm;
-        k_layer<ZMODE, METRIC, PERSIST, XY><<<grid, VSB_THREADS, smem, s>>>(p, taps);
-    } else {
-        dim3 grid(p.tiles_x, p.tiles_y);
-        k_layer<ZMODE, METRIC, PERSIST, XY><<<grid, VSB_THREADS, smem, s>>>(p, taps);
-    }
+    dim3 grid(p.tiles_x, p.tiles_y);
+    k_layer<ZMODE, METRIC, XY><<<grid, VSB_THREADS, smem, s>>>(p, taps);
     return vsb_check_launch("k_layer");
 }
 
 template <int ZMODE, int METRIC>
-static int launch_layer(LayerParams &p, const BilTapsL *taps, bool persist, size_t smem, cudaStream_t s)
+static int launch_layer(LayerParams &p, const BilTapsL *taps, size_t smem, cudaStream_t s)
 {
     const bool xy = p.hb > 0 || p.nkx > 0;
-    if (persist) return launch_layer_v<ZMODE, METRIC, true, true>(p, taps, smem, s); // the prefetching variant keeps the general body
-    return xy ? launch_layer_v<ZMODE, METRIC, false, true>(p, taps, smem, s) : launch_layer_v<ZMODE, METRIC, false, false>(p, taps, smem, s);
+    return xy ? launch_layer_v<ZMODE, METRIC, true>(p, taps, smem, s) : launch_layer_v<ZMODE, METRIC, false>(p, taps, smem, s);
 }
 
 // Device copies of bilateral tap tables, keyed by content (a handful of distinct filters per process).
@@ -917,18 +819,12 @@ static int layer_launch(const uint8_t *in, size_t in_pitch, int W, int H, const 
     p.rec_list = sparse ? rec_list : nullptr;
     const BilTapsL *taps_dev = nullptr;
     if (p.hb > 0) { const int rc = taps_on_device(taps, &taps_dev); if (rc) return rc; }
-    // persistent + prefetch variant: whole 16-byte chunks only, at most 7 masks staged per tile
-    const bool persist = getenv("VSB_PERSIST") != nullptr && p.aligned && (W % 16) == 0 && p.z.n_priors <= 7;
     const int RH = VSB_TH + 2 * p.halo;
     const int n1 = p.z.reach + 1;
     auto up16 = [](size_t v) { return (v + 15) & ~(size_t)15; };
     const bool searching = mode != VSB_Z_NONE && mode != VSB_Z_CONST && mode != VSB_Z_ENHANCED;
     size_t off = 0;
     p.sm.T = (int)off; off += up16((searching && zp->metric == VSB_METRIC_CHAMFER5) ? (size_t)n1 * n1 * 4 : 16);
-    p.sm.raw_stride = (int)up16((size_t)RH * RG_W);
-    p.sm.raw = (int)off; off += persist ? 2 * (size_t)p.sm.raw_stride : 0;
-    p.sm.src_stride = (p.z.n_priors + 1) * RH * 6;
-    p.sm.src = (int)off; off += (persist && mode != VSB_Z_NONE) ? up16(2 * (size_t)p.sm.src_stride * 4) : 0;
     p.sm.s1 = (int)off; off += up16((size_t)RH * RG_W);
     p.sm.bits = (int)off; off += searching ? up16((size_t)(RH + 2 * p.z.reach) * LBW * 4) : 16;
     const size_t s2bytes = up16((size_t)RH * RG_W);
@@ -940,11 +836,11 @@ static int layer_launch(const uint8_t *in, size_t in_pitch, int W, int H, const 
     cudaStream_t s = (cudaStream_t)stream;
     const bool ex = zp->metric == VSB_METRIC_EXACT;
     switch (mode) {
-    case VSB_Z_FIXED: return ex ? launch_layer<VSB_Z_FIXED, 1>(p, taps_dev, persist, smem, s) : launch_layer<VSB_Z_FIXED, 0>(p, taps_dev, persist, smem, s);
-    case VSB_Z_WEIGHTED: return ex ? launch_layer<VSB_Z_WEIGHTED, 1>(p, taps_dev, persist, smem, s) : launch_layer<VSB_Z_WEIGHTED, 0>(p, taps_dev, persist, smem, s);
-    case VSB_Z_CONST: return launch_layer<VSB_Z_CONST, 0>(p, taps_dev, persist, smem, s);
-    case VSB_Z_ENHANCED: return launch_layer<VSB_Z_ENHANCED, 0>(p, taps_dev, false, smem, s);
-    default: return launch_layer<ZL_NONE, 0>(p, taps_dev, persist, smem, s);
+    case VSB_Z_FIXED: return ex ? launch_layer<VSB_Z_FIXED, 1>(p, taps_dev, smem, s) : launch_layer<VSB_Z_FIXED, 0>(p, taps_dev, smem, s);
+    case VSB_Z_WEIGHTED: return ex ? launch_layer<VSB_Z_WEIGHTED, 1>(p, taps_dev, smem, s) : launch_layer<VSB_Z_WEIGHTED, 0>(p, taps_dev, smem, s);
+    case VSB_Z_CONST: return launch_layer<VSB_Z_CONST, 0>(p, taps_dev, smem, s);
+    case VSB_Z_ENHANCED: return launch_layer<VSB_Z_ENHANCED, 0>(p, taps_dev, smem, s);
+    default: return launch_layer<ZL_NONE, 0>(p, taps_dev, smem, s);
     }
 }
 

@@ -10,7 +10,8 @@
 #include <cstdlib>
 #include "vsb_common.cuh"
 
-#define STACK_SLOTS 3
+#define STACK_SLOTS 4
+#define STACK_MAX_WINDOW 128 // receding_layers the window can hold (the GUI offers 0..100, ui_components.py:168)
 
 struct DevOp {
     int type; // 1 lut, 2 gaussian, 3 bilateral, 4 median, 5 unsharp mask, 6 resize
@@ -35,6 +36,13 @@ struct vsb_stack {
     uint8_t *lead_lut_dev;       // leading apply_lut ops composed, or nullptr
     float *T_dev;
     cudaStream_t s_h2d, s_comp, s_d2h;
+    // Consecutive layers of a device batch alternate between s_comp (lane 0) and s_aux (lane 1): the bandwidth-bound
+    // pack pass of layer z+1 runs beside the issue- / latency-bound layer kernel of layer z.  The window ring holds
+    // n_priors + 2 masks so that the pack of z+1 never overwrites a mask layer z still reads.
+    cudaStream_t s_aux;
+    cudaEvent_t ev_fork, ev_join, ev_pack[2];
+    bool overlap_ok;             // the configured path keeps no per-layer scratch besides the per-lane one
+    uint32_t *or_scratch[2];     // more than VSB_MAX_PRIORS receding layers: OR of the window, per lane
     cudaEvent_t ev_h2d[STACK_SLOTS], ev_comp[STACK_SLOTS], ev_d2h[STACK_SLOTS];
     bool slot_used[STACK_SLOTS];
     uint8_t *gray_dev[STACK_SLOTS], *out_dev[STACK_SLOTS];
@@ -56,7 +64,9 @@ struct vsb_stack {
     vsb_xy_fused fx;
     uint8_t *lut2_dev;
     std::vector<uint16_t *> flag_ring;
-    int *rec_tiles;        // LUT-only chains: work list of the patch kernel (1 + tiles ints)
+    int *rec_tiles[2];     // LUT-only chains: work list of the patch kernel (1 + tiles ints), per lane
+    // environment switches, read once at creation
+    bool env_no_patch, env_no_fused_enh, env_tile_flags, env_no_overlap;
     // optional per-stage CUDA-event profiling (bench.py roofline leg)
     bool prof_on;
     struct ProfRec { int stage; int launches; cudaEvent_t a, b; };
@@ -70,16 +80,17 @@ static const char *kOpNames[] = {"none", "lut_apply", "gaussian_q88", "bilateral
 
 struct ProfScope {
     vsb_stack *s; size_t idx; bool on;
-    ProfScope(vsb_stack *st, int stage, int launches) : s(st), idx(0), on(st->prof_on)
+    cudaStream_t st_;
+    ProfScope(vsb_stack *st, int stage, int launches, cudaStream_t stream) : s(st), idx(0), on(st->prof_on), st_(stream)
     {
         if (!on) return;
         vsb_stack::ProfRec r; r.stage = stage; r.launches = launches; r.a = r.b = nullptr;
         if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) { on = false; return; }
-        cudaEventRecord(r.a, s->s_comp);
+        cudaEventRecord(r.a, st_);
         idx = s->prof.size();
         s->prof.push_back(r);
     }
-    ~ProfScope() { if (on) cudaEventRecord(s->prof[idx].b, s->s_comp); }
+    ~ProfScope() { if (on) cudaEventRecord(s->prof[idx].b, st_); }
 };
 
 static void compose(uint8_t *acc, const uint8_t *next)
@@ -92,10 +103,19 @@ static void compose(uint8_t *acc, const uint8_t *next)
 extern "C" int vsb_stack_destroy(vsb_stack *s)
 {
     if (!s) return VSB_OK;
-    cudaStreamSynchronize(s->s_h2d); cudaStreamSynchronize(s->s_comp); cudaStreamSynchronize(s->s_d2h);
+    if (s->s_h2d) cudaStreamSynchronize(s->s_h2d);
+    if (s->s_comp) cudaStreamSynchronize(s->s_comp);
+    if (s->s_aux) cudaStreamSynchronize(s->s_aux);
+    if (s->s_d2h) cudaStreamSynchronize(s->s_d2h);
     for (auto &o : s->ops) { if (o.lut_dev) cudaFree(o.lut_dev); if (o.plan) vsb_resize_plan_destroy(o.plan); }
     if (s->tmp_blur) cudaFree(s->tmp_blur);
-    if (s->rec_tiles) cudaFree(s->rec_tiles);
+    for (int i = 0; i < 2; ++i) {
+        if (s->rec_tiles[i]) cudaFree(s->rec_tiles[i]);
+        if (s->or_scratch[i]) cudaFree(s->or_scratch[i]);
+        if (s->ev_pack[i]) cudaEventDestroy(s->ev_pack[i]);
+    }
+    if (s->ev_fork) cudaEventDestroy(s->ev_fork);
+    if (s->ev_join) cudaEventDestroy(s->ev_join);
     if (s->an_near) vsb_resize_plan_destroy(s->an_near);
     if (s->an_lin) vsb_resize_plan_destroy(s->an_lin);
     if (s->an_bits) cudaFree(s->an_bits);
@@ -125,6 +145,7 @@ extern "C" int vsb_stack_destroy(vsb_stack *s)
     if (s->ub_mm) cudaFree(s->ub_mm);
     if (s->s_h2d) cudaStreamDestroy(s->s_h2d);
     if (s->s_comp) cudaStreamDestroy(s->s_comp);
+    if (s->s_aux) cudaStreamDestroy(s->s_aux);
     if (s->s_d2h) cudaStreamDestroy(s->s_d2h);
     delete s;
     return VSB_OK;
@@ -144,8 +165,8 @@ extern "C" int vsb_stack_create(int W, int H, int n_priors, const vsb_zparams *z
                                 vsb_stack **out_stack)
 {
     VSB_REQUIRE(out_stack && zp, "vsb_stack_create: null pointer");
-    VSB_REQUIRE(W > 0 && H > 0 && n_priors >= 0 && n_priors <= VSB_MAX_PRIORS,
-                "vsb_stack_create: bad geometry or more than %d receding layers", VSB_MAX_PRIORS);
+    VSB_REQUIRE(W > 0 && H > 0 && n_priors >= 0 && n_priors <= STACK_MAX_WINDOW,
+                "vsb_stack_create: bad geometry or more than %d receding layers", STACK_MAX_WINDOW);
     VSB_REQUIRE(n_ops >= 0 && n_ops <= VSB_MAX_XY_OPS && (n_ops == 0 || ops), "vsb_stack_create: bad op list");
     const bool far_mode = zp->mode == VSB_Z_MINMAX || zp->mode == VSB_Z_FIXED_FAR || zp->mode == VSB_Z_WEIGHTED_FAR ||
                           zp->mode == VSB_Z_ENHANCED_FAR;
@@ -157,7 +178,14 @@ extern "C" int vsb_stack_create(int W, int H, int n_priors, const vsb_zparams *z
     s->pitch = ((size_t)W + 127) & ~(size_t)127;
     s->zp = *zp;
     s->lead_lut_dev = nullptr; s->T_dev = nullptr;
-    s->s_h2d = s->s_comp = s->s_d2h = nullptr;
+    s->s_h2d = s->s_comp = s->s_d2h = s->s_aux = nullptr;
+    s->ev_fork = s->ev_join = nullptr;
+    for (int i = 0; i < 2; ++i) { s->ev_pack[i] = nullptr; s->rec_tiles[i] = nullptr; s->or_scratch[i] = nullptr; }
+    s->overlap_ok = false;
+    s->env_no_patch = getenv("VSB_NO_PATCH") != nullptr;
+    s->env_no_fused_enh = getenv("VSB_NO_FUSED_ENHANCED") != nullptr;
+    s->env_tile_flags = getenv("VSB_TILE_FLAGS") != nullptr;
+    s->env_no_overlap = getenv("VSB_NO_OVERLAP") != nullptr;
     for (int i = 0; i < STACK_SLOTS; ++i) {
         s->ev_h2d[i] = s->ev_comp[i] = s->ev_d2h[i] = nullptr;
         s->slot_used[i] = false; s->gray_dev[i] = s->out_dev[i] = nullptr;
@@ -169,7 +197,7 @@ extern "C" int vsb_stack_create(int W, int H, int n_priors, const vsb_zparams *z
     s->rec_bits = nullptr; s->dist = nullptr; s->labels = nullptr; s->cmax = nullptr;
     s->ub_g = s->ub_gmin = nullptr; s->ub_dist = nullptr; s->ub_mm = nullptr;
     s->prof_on = false;
-    s->fused = false; s->lut2_dev = nullptr; s->rec_tiles = nullptr;
+    s->fused = false; s->lut2_dev = nullptr;
     memset(&s->fx, 0, sizeof s->fx);
 
     // XY chain: compose runs of apply_lut; a leading run is folded into the Z-blend epilogue
@@ -245,6 +273,10 @@ extern "C" int vsb_stack_create(int W, int H, int n_priors, const vsb_zparams *z
     STACK_CUDA(cudaStreamCreateWithFlags(&s->s_h2d, cudaStreamNonBlocking));
     STACK_CUDA(cudaStreamCreateWithFlags(&s->s_comp, cudaStreamNonBlocking));
     STACK_CUDA(cudaStreamCreateWithFlags(&s->s_d2h, cudaStreamNonBlocking));
+    STACK_CUDA(cudaStreamCreateWithFlags(&s->s_aux, cudaStreamNonBlocking));
+    STACK_CUDA(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
+    STACK_CUDA(cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming));
+    for (int i = 0; i < 2; ++i) STACK_CUDA(cudaEventCreateWithFlags(&s->ev_pack[i], cudaEventDisableTiming));
     for (int i = 0; i < STACK_SLOTS; ++i) {
         STACK_CUDA(cudaEventCreateWithFlags(&s->ev_h2d[i], cudaEventDisableTiming));
         STACK_CUDA(cudaEventCreateWithFlags(&s->ev_comp[i], cudaEventDisableTiming));
@@ -277,14 +309,20 @@ extern "C" int vsb_stack_create(int W, int H, int n_priors, const vsb_zparams *z
         STACK_CUDA(cudaMalloc((void **)&s->T_dev, T.size() * sizeof(float)));
         STACK_CUDA(cudaMemcpy(s->T_dev, T.data(), T.size() * sizeof(float), cudaMemcpyHostToDevice));
     }
-    s->ring.assign((size_t)n_priors + 1, nullptr);
+    s->ring.assign((size_t)n_priors + 2, nullptr);
     for (auto &p : s->ring) STACK_CUDA(cudaMalloc((void **)&p, (size_t)s->wpr * H * sizeof(uint32_t)));
+    if (n_priors > VSB_MAX_PRIORS)
+        for (int i = 0; i < 2; ++i) STACK_CUDA(cudaMalloc((void **)&s->or_scratch[i], (size_t)s->wpr * H * sizeof(uint32_t)));
     if (s->fused) {
         const size_t ntiles = (size_t)((W + VSB_TW - 1) / VSB_TW) * ((H + VSB_TH - 1) / VSB_TH);
-        s->flag_ring.assign((size_t)n_priors + 1, nullptr);
+        s->flag_ring.assign((size_t)n_priors + 2, nullptr);
         for (auto &p : s->flag_ring) STACK_CUDA(cudaMalloc((void **)&p, ntiles * sizeof(uint16_t)));
-        STACK_CUDA(cudaMalloc((void **)&s->rec_tiles, (ntiles + 1) * sizeof(int)));
+        for (int i = 0; i < 2; ++i) STACK_CUDA(cudaMalloc((void **)&s->rec_tiles[i], (ntiles + 1) * sizeof(int)));
     }
+    // two-lane overlap: only the paths whose per-layer scratch is per lane (the fused layer kernel and the LUT-only
+    // patch path); Enhanced EDT / unbounded / unfused chains share scratch images and stay on one stream
+    s->overlap_ok = !s->env_no_overlap && s->fused &&
+                    (zp->mode == VSB_Z_FIXED || zp->mode == VSB_Z_WEIGHTED || zp->mode == VSB_Z_CONST);
     *out_stack = s;
     return VSB_OK;
 }
@@ -350,32 +388,63 @@ static int ensure_aniso_scratch(vsb_stack *s, const vsb_zparams &zp)
     return VSB_OK;
 }
 
-// all kernels of one layer on the compute stream; gray/out are device pointers
-static int run_layer(vsb_stack *s, const uint8_t *gray, size_t gpitch, uint8_t *out, size_t opitch, bool emit)
+// The window's prior masks for this layer, newest first.  More than VSB_MAX_PRIORS of them (the GUI allows 100): every
+// mode but the weighted stack only uses their OR (processing_core.py:61-65, :346), so they are OR-ed into the lane's
+// scratch mask in chunks and handed on as one prior; the weighted stack only ever reads the first len(weights) <= 16.
+static int window_priors(vsb_stack *s, int lane, vsb_stream_t st, const uint32_t **pri, int *np_out)
 {
-    vsb_stream_t st = (vsb_stream_t)s->s_comp;
-    const int nring = s->n_priors + 1;
+    const int nring = s->n_priors + 2;
+    const int np = s->count < s->n_priors ? s->count : s->n_priors;
+    const bool weighted = s->zp.mode == VSB_Z_WEIGHTED || s->zp.mode == VSB_Z_WEIGHTED_FAR;
+    if (np <= VSB_MAX_PRIORS || weighted) {
+        const int n = np < VSB_MAX_PRIORS ? np : VSB_MAX_PRIORS;
+        for (int i = 0; i < n; ++i) pri[i] = s->ring[(s->head - 1 - i + 2 * nring) % nring];
+        *np_out = n;
+        return VSB_OK;
+    }
+    uint32_t *acc = s->or_scratch[lane];
+    for (int done = 0; done < np;) {
+        const uint32_t *src[VSB_MAX_PRIORS];
+        int n = 0;
+        if (done > 0) src[n++] = acc;
+        while (n < VSB_MAX_PRIORS && done < np) { src[n++] = s->ring[(s->head - 1 - done + 2 * nring) % nring]; ++done; }
+        const int rc = vsb_bits_or(src, n, s->wpr, s->H, acc, st);
+        if (rc) return rc;
+    }
+    pri[0] = acc;
+    *np_out = 1;
+    return VSB_OK;
+}
+
+// all kernels of one layer on the lane's stream (lane 0 = s_comp, lane 1 = s_aux); gray/out are device pointers.
+// `signal_pack`: record ev_pack[lane] once the layer's mask (and tile flags) are written -- what the next layer,
+// running on the other lane, waits for.
+static int run_layer(vsb_stack *s, const uint8_t *gray, size_t gpitch, uint8_t *out, size_t opitch, bool emit, int lane = 0,
+                     bool signal_pack = false)
+{
+    cudaStream_t cst = lane ? s->s_aux : s->s_comp;
+    vsb_stream_t st = (vsb_stream_t)cst;
+    const int nring = s->n_priors + 2;
     uint32_t *cur = s->ring[s->head];
     int rc;
+    const uint32_t *pri[VSB_MAX_PRIORS];
+    int np = 0;
+    rc = window_priors(s, lane, st, pri, &np);
+    if (rc) return rc;
     // LUT-only chain with a tile-reach fade: the pack pass also writes lut[gray], the layer kernel only patches the
     // receding pixels (the gray layer is read once)
-    const bool patch_path = s->fused && emit && s->ops.empty() && getenv("VSB_NO_PATCH") == nullptr &&
+    const bool patch_path = s->fused && emit && s->ops.empty() && !s->env_no_patch &&
                             (s->zp.mode == VSB_Z_FIXED || s->zp.mode == VSB_Z_WEIGHTED || s->zp.mode == VSB_Z_CONST);
     if (patch_path) {
-        const uint32_t *ppri[VSB_MAX_PRIORS];
-        const int pnp = s->count < s->n_priors ? s->count : s->n_priors;
-        for (int i = 0; i < pnp; ++i) ppri[i] = s->ring[(s->head - 1 - i + 2 * nring) % nring];
-        ProfScope ps(s, ST_PACKF, 1);
+        ProfScope ps(s, ST_PACKF, 1, cst);
         rc = vsb_pack_flags_lut(gray, gpitch, s->W, s->H, 127, cur, s->wpr, s->flag_ring[s->head], s->lead_lut_dev, out, opitch,
-                                ppri, pnp, s->rec_tiles, st);
+                                pri, np, s->rec_tiles[lane], st);
     }
-    else if (s->fused) { ProfScope ps(s, ST_PACKF, 1); rc = vsb_pack_flags(gray, gpitch, s->W, s->H, 127, cur, s->wpr, s->flag_ring[s->head], st); }
-    else { ProfScope ps(s, ST_PACK, 1); rc = vsb_threshold_pack(gray, gpitch, s->W, s->H, 127, cur, s->wpr, st); }
+    else if (s->fused) { ProfScope ps(s, ST_PACKF, 1, cst); rc = vsb_pack_flags(gray, gpitch, s->W, s->H, 127, cur, s->wpr, s->flag_ring[s->head], st); }
+    else { ProfScope ps(s, ST_PACK, 1, cst); rc = vsb_threshold_pack(gray, gpitch, s->W, s->H, 127, cur, s->wpr, st); }
     if (rc) return rc;
+    if (signal_pack) VSB_CUDA(cudaEventRecord(s->ev_pack[lane], cst));
     if (emit) {
-        const uint32_t *pri[VSB_MAX_PRIORS];
-        const int np = s->count < s->n_priors ? s->count : s->n_priors;
-        for (int i = 0; i < np; ++i) pri[i] = s->ring[(s->head - 1 - i + 2 * nring) % nring]; // newest first
         vsb_zparams zp = s->zp;
         if (zp.mode == VSB_Z_WEIGHTED || zp.mode == VSB_Z_WEIGHTED_FAR) {
             // k = min(len(priors), len(weights)); total weight is over the k used weights (processing_core.py:231-238)
@@ -393,15 +462,15 @@ static int run_layer(vsb_stack *s, const uint8_t *gray, size_t gpitch, uint8_t *
         const bool enhanced = zp.mode == VSB_Z_ENHANCED || zp.mode == VSB_Z_ENHANCED_FAR;
         if (s->fused && !enhanced && !far_mode) {
             const uint16_t *pfl[VSB_MAX_PRIORS];
-            for (int i = 0; i < np; ++i) pfl[i] = s->flag_ring[(s->head - 1 - i + 2 * nring) % nring];
+            const bool window_flags = s->env_tile_flags && s->n_priors <= VSB_MAX_PRIORS; // an OR-ed window has no tile flags
+            for (int i = 0; i < np; ++i) pfl[i] = window_flags ? s->flag_ring[(s->head - 1 - i + 2 * nring) % nring] : nullptr;
             if (patch_path) {
-                ProfScope ps(s, ST_LAYER, 1);
-                rc = vsb_layer_patch(gray, gpitch, s->W, s->H, cur, pri, s->wpr, &zp, s->T_dev, s->lead_lut_dev, s->rec_tiles, out, opitch, st);
+                ProfScope ps(s, ST_LAYER, 1, cst);
+                rc = vsb_layer_patch(gray, gpitch, s->W, s->H, cur, pri, s->wpr, &zp, s->T_dev, s->lead_lut_dev, s->rec_tiles[lane], out, opitch, st);
             } else {
-                ProfScope ps(s, ST_LAYER, 1);
+                ProfScope ps(s, ST_LAYER, 1, cst);
                 // the tile-flag shortcut saves the input read of quiet tiles; it only pays once the kernel is HBM bound
-                static const bool use_flags = getenv("VSB_TILE_FLAGS") != nullptr;
-                rc = vsb_layer_fused(gray, gpitch, s->W, s->H, cur, pri, use_flags ? s->flag_ring[s->head] : nullptr, pfl, s->wpr, &zp, s->T_dev,
+                rc = vsb_layer_fused(gray, gpitch, s->W, s->H, cur, pri, window_flags ? s->flag_ring[s->head] : nullptr, pfl, s->wpr, &zp, s->T_dev,
                                      s->lead_lut_dev, &s->fx, s->lut2_dev, out, opitch, st);
             }
             if (rc) return rc;
@@ -415,7 +484,7 @@ static int run_layer(vsb_stack *s, const uint8_t *gray, size_t gpitch, uint8_t *
         if (far_mode) {
             rc = ensure_unbounded_scratch(s);
             if (rc) return rc;
-            ProfScope ps(s, ST_ZBLEND, 5);
+            ProfScope ps(s, ST_ZBLEND, 5, cst);
             if (zp.mode == VSB_Z_WEIGHTED_FAR)
                 rc = vsb_weighted_unbounded(gray, gpitch, s->W, s->H, cur, pri, s->wpr, &zp, s->ub_g, (size_t)s->W, s->ub_gmin,
                                             s->ub_dist, (size_t)s->W, s->ub_mm, s->lead_lut_dev, zdst, zpitch, st);
@@ -429,14 +498,14 @@ static int run_layer(vsb_stack *s, const uint8_t *gray, size_t gpitch, uint8_t *
             if (rc) return rc;
             const bool plain_enh = zp.mode == VSB_Z_ENHANCED && zp.aniso_w == 0; // receding mask + distances in one launch
             if (!plain_enh) {
-                ProfScope ps(s, ST_MASKDIFF, 1);
+                ProfScope ps(s, ST_MASKDIFF, 1, cst);
                 rc = vsb_maskdiff(cur, pri, np, s->wpr, s->H, s->rec_bits, nullptr, st);
                 if (rc) return rc;
             }
             if (zp.mode == VSB_Z_ENHANCED_FAR) {
                 rc = ensure_unbounded_scratch(s);
                 if (rc) return rc;
-                ProfScope ps(s, ST_ZDIST, 4);
+                ProfScope ps(s, ST_ZDIST, 4, cst);
                 rc = vsb_rec_dist_unbounded(cur, pri, np, s->wpr, s->W, s->H, zp.metric, s->ub_g, (size_t)s->W, s->ub_gmin, s->dist,
                                             (size_t)s->W, s->ub_mm, st);
             } else if (zp.aniso_w > 0) {
@@ -445,22 +514,22 @@ static int run_layer(vsb_stack *s, const uint8_t *gray, size_t gpitch, uint8_t *
                 // which fades to 0 exactly like the true distance (bilinear taps are adjacent pixels, reach covers +3)
                 rc = ensure_aniso_scratch(s, zp);
                 if (rc) return rc;
-                ProfScope ps(s, ST_ZDIST, 3);
+                ProfScope ps(s, ST_ZDIST, 3, cst);
                 const float far = (float)((zp.fade_limit > 0.0 ? zp.fade_limit : 0.0) + 4.0);
                 rc = vsb_resize_bits_nearest(s->an_near, cur, s->wpr, s->an_bits, s->an_wpr, st);
                 if (!rc) rc = vsb_dt_chamfer5(s->an_bits, s->an_wpr, zp.aniso_w, zp.aniso_h, zp.aniso_reach, s->an_T, far, s->an_dist,
                                               (size_t)zp.aniso_w, st);
                 if (!rc) rc = vsb_resize_f32_linear(s->an_lin, s->an_dist, (size_t)zp.aniso_w, s->dist, (size_t)s->W, st);
             } else {
-                ProfScope ps(s, ST_ZDIST, 1);
+                ProfScope ps(s, ST_ZDIST, 1, cst);
                 rc = vsb_rec_dist(cur, pri, s->wpr, s->W, s->H, &zp, s->T_dev, s->rec_bits, s->dist, (size_t)s->W, st);
             }
             if (rc) return rc;
-            { ProfScope ps(s, ST_CCL, 3); rc = vsb_ccl8_max(s->rec_bits, s->wpr, s->W, s->H, s->dist, (size_t)s->W, s->labels, s->cmax, st); }
+            { ProfScope ps(s, ST_CCL, 3, cst); rc = vsb_ccl8_max(s->rec_bits, s->wpr, s->W, s->H, s->dist, (size_t)s->W, s->labels, s->cmax, st); }
             if (rc) return rc;
-            if (s->fused && getenv("VSB_NO_FUSED_ENHANCED") == nullptr) {
+            if (s->fused && !s->env_no_fused_enh) {
                 // the fade itself runs inside the layer kernel, straight into the XY chain (no intermediate image)
-                ProfScope ps(s, ST_LAYER, 1);
+                ProfScope ps(s, ST_LAYER, 1, cst);
                 rc = vsb_layer_fused_enhanced(gray, gpitch, s->W, s->H, cur, pri, s->wpr, &zp, s->dist, (size_t)s->W, s->labels,
                                               s->cmax, s->lead_lut_dev, &s->fx, s->lut2_dev, out, opitch, st);
                 if (rc) return rc;
@@ -468,12 +537,12 @@ static int run_layer(vsb_stack *s, const uint8_t *gray, size_t gpitch, uint8_t *
                 if (s->count < s->n_priors) ++s->count;
                 return VSB_OK;
             }
-            { ProfScope ps(s, ST_EFADE, 1);
+            { ProfScope ps(s, ST_EFADE, 1, cst);
               rc = vsb_enhanced_fade(gray, gpitch, s->W, s->H, s->rec_bits, s->wpr, s->dist, (size_t)s->W, s->labels,
                                      s->cmax, zp.fade_limit, zp.enhanced_arith, s->lead_lut_dev, zdst, zpitch, st); }
             if (rc) return rc;
         } else {
-            { ProfScope ps(s, ST_ZBLEND, 1);
+            { ProfScope ps(s, ST_ZBLEND, 1, cst);
               rc = vsb_zblend_fused(gray, gpitch, s->W, s->H, cur, pri, s->wpr, &zp, s->T_dev, s->lead_lut_dev, zdst, zpitch,
                                     nullptr, 0, st); }
             if (rc) return rc;
@@ -482,7 +551,7 @@ static int run_layer(vsb_stack *s, const uint8_t *gray, size_t gpitch, uint8_t *
         size_t spitch = zpitch;
         if (s->fused && nops) { // Enhanced EDT: its own stage 1, then the fused XY chain
             vsb_zparams zn = zp; zn.mode = VSB_Z_NONE; zn.n_priors = 0;
-            ProfScope ps(s, ST_LAYER, 1);
+            ProfScope ps(s, ST_LAYER, 1, cst);
             rc = vsb_layer_fused(src, spitch, s->W, s->H, nullptr, nullptr, nullptr, nullptr, s->wpr, &zn, nullptr, nullptr,
                                  &s->fx, s->lut2_dev, out, opitch, st);
             if (rc) return rc;
@@ -495,7 +564,7 @@ static int run_layer(vsb_stack *s, const uint8_t *gray, size_t gpitch, uint8_t *
             uint8_t *dst = last ? out : s->tmp[(i + 1) & 1];
             const size_t dpitch = last ? opitch : s->tpitch;
             const DevOp &o = s->ops[i];
-            ProfScope ps(s, ST_OP0 + (int)i, o.type == 5 ? 3 : 1);
+            ProfScope ps(s, ST_OP0 + (int)i, o.type == 5 ? 3 : 1, cst);
             switch (o.type) {
             case 1: rc = vsb_lut_apply(src, spitch, o.iw, o.ih, o.lut_dev, dst, dpitch, st); break;
             case 2: rc = vsb_gaussian_q88(src, spitch, o.iw, o.ih, o.op.kx, o.op.nkx, o.op.ky, o.op.nky, dst, dpitch, st); break;
@@ -531,10 +600,24 @@ extern "C" int vsb_stack_process_device_batch(vsb_stack *s, const uint8_t *gray_
                                               long long out_layer_stride, int out_ring, int n_layers)
 {
     VSB_REQUIRE(s && gray_dev && out_dev && n_layers >= 0 && out_ring >= 1, "vsb_stack_process_device_batch: bad arguments");
+    // two lanes: layer i runs on lane i & 1 and starts once the previous layer's mask is written; everything is forked
+    // from and joined back to s_comp, so callers keep ordering their work on the one stream vsb_stack_stream() returns.
+    // Needs two distinct output buffers in flight and no per-stage timing (the events of two lanes would interleave).
+    const bool overlap = s->overlap_ok && !s->prof_on && n_layers > 1 && out_ring >= 2;
+    if (overlap) {
+        VSB_CUDA(cudaEventRecord(s->ev_fork, s->s_comp));
+        VSB_CUDA(cudaStreamWaitEvent(s->s_aux, s->ev_fork, 0));
+    }
     for (int i = 0; i < n_layers; ++i) {
+        const int lane = overlap ? (i & 1) : 0;
+        if (overlap && i > 0) VSB_CUDA(cudaStreamWaitEvent(lane ? s->s_aux : s->s_comp, s->ev_pack[lane ^ 1], 0));
         int rc = run_layer(s, gray_dev + (long long)i * in_layer_stride, in_pitch,
-                           out_dev + (long long)(i % out_ring) * out_layer_stride, out_pitch, true);
+                           out_dev + (long long)(i % out_ring) * out_layer_stride, out_pitch, true, lane, overlap);
         if (rc) return rc;
+    }
+    if (overlap) {
+        VSB_CUDA(cudaEventRecord(s->ev_join, s->s_aux));
+        VSB_CUDA(cudaStreamWaitEvent(s->s_comp, s->ev_join, 0));
     }
     return VSB_OK;
 }
@@ -544,6 +627,7 @@ extern "C" int vsb_stack_sync(vsb_stack *s)
     VSB_REQUIRE(s, "vsb_stack_sync: null stack");
     VSB_CUDA(cudaStreamSynchronize(s->s_h2d));
     VSB_CUDA(cudaStreamSynchronize(s->s_comp));
+    VSB_CUDA(cudaStreamSynchronize(s->s_aux));
     VSB_CUDA(cudaStreamSynchronize(s->s_d2h));
     return VSB_OK;
 }
@@ -595,6 +679,12 @@ extern "C" int vsb_stack_push_halo(vsb_stack *s, const uint8_t *gray_host, size_
     int t = submit(s, gray_host, pitch, nullptr, 0, false);
     if (t < 0) return t;
     return vsb_stack_wait(s, t);
+}
+
+extern "C" int vsb_stack_push_halo_device(vsb_stack *s, const uint8_t *gray_dev, size_t pitch)
+{
+    VSB_REQUIRE(s && gray_dev && pitch >= (size_t)s->W, "vsb_stack_push_halo_device: bad arguments");
+    return run_layer(s, gray_dev, pitch, nullptr, 0, false);
 }
 
 extern "C" int vsb_stack_process_host(vsb_stack *s, const uint8_t *gray_host, size_t in_pitch, uint8_t *out_host,

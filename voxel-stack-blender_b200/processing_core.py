@@ -109,7 +109,8 @@ def _calculate_weighted_receding_gradient_field(current_white_mask, prior_binary
         return _zeros_like(current_white_mask)
     if k > N.VSB_MAX_PRIORS:
         raise P.UnsupportedOnDevice(f"weighted stack over more than {N.VSB_MAX_PRIORS} layers")
-    z = P.zparams_from_config(_as_mode(config, ProcessingMode.WEIGHTED_STACK), getattr(config, "distance_metric", "chamfer5"))
+    z = P.zparams_from_config(_as_mode(config, ProcessingMode.WEIGHTED_STACK), getattr(config, "distance_metric", "chamfer5"),
+                              weighted_k=k)
     z.n_priors = k
     z.total_weight = np.float32(float(sum(weights[:k])))
     cur = _bits(current_white_mask)

@@ -15,6 +15,8 @@ import os
 import queue
 import re
 import shutil
+import threading
+import time
 import traceback
 
 import cv2
@@ -145,74 +147,109 @@ class ProcessingPipelineThread(QThread):
         done = 0
         workers = self.max_workers
         engine = None
-        with concurrent.futures.ThreadPoolExecutor(workers) as decoder, \
-                concurrent.futures.ThreadPoolExecutor(workers) as encoder:
-            pending = collections.deque()
-            it = iter(filenames)
+        try:
+            with concurrent.futures.ThreadPoolExecutor(workers) as decoder, \
+                    concurrent.futures.ThreadPoolExecutor(workers) as encoder:
+                pending = collections.deque()
+                it = iter(filenames)
 
-            def top_up():
-                while len(pending) < 2 * workers:
-                    name = next(it, None)
-                    if name is None:
-                        return
-                    pending.append((name, decoder.submit(cv2.imread, os.path.join(input_path, name), cv2.IMREAD_GRAYSCALE)))
+                def top_up():
+                    while len(pending) < 2 * workers:
+                        name = next(it, None)
+                        if name is None:
+                            return
+                        pending.append((name, decoder.submit(cv2.imread, os.path.join(input_path, name), cv2.IMREAD_GRAYSCALE)))
 
-            def write(path, image):
-                cv2.imwrite(path, image)
-                print(f"Successfully wrote output file: {path}")
+                def write(path, image):
+                    cv2.imwrite(path, image)
+                    print(f"Successfully wrote output file: {path}")
 
-            top_up()
-            jobs = []
-            index = 0
-            while pending:
-                if not self._is_running:
-                    self.logger.log("Processing stopped by user.")
-                    self.status_update.emit("Processing stopped by user.")
-                    break
-                name, fut = pending.popleft()
                 top_up()
-                index += 1
-                self.status_update.emit(f"Analyzing {name} ({index}/{total})")
-                gray = fut.result()
-                if gray is None:
-                    print(f"Warning: Could not load image at {os.path.join(input_path, name)}")
-                    self.status_update.emit(f"Skipping unloadable image: {name}")
-                    total = max(1, total - 1)
-                    continue
-                if engine is None:
-                    H, W = gray.shape
-                    ops = list(cfg.xy_blend_pipeline or [])
-                    chain = (lambda d: xy_blend_processor.process_xy_pipeline_dev(d, ops)[0]) if ops else None
-                    engine = E.RoiStackEngine(W, H, cfg, chain)
-                out = engine.process(gray, _layer_number(name))
-                jobs.append(encoder.submit(write, os.path.join(output_path, name), out))
-                while jobs and (jobs[0].done() or len(jobs) > 2 * workers):
-                    jobs.pop(0).result()
+                jobs = []
+                index = 0
+                while pending:
+                    if not self._is_running:
+                        self.logger.log("Processing stopped by user.")
+                        self.status_update.emit("Processing stopped by user.")
+                        break
+                    name, fut = pending.popleft()
+                    top_up()
+                    index += 1
+                    self.status_update.emit(f"Analyzing {name} ({index}/{total})")
+                    gray = fut.result()
+                    if gray is None:
+                        print(f"Warning: Could not load image at {os.path.join(input_path, name)}")
+                        self.status_update.emit(f"Skipping unloadable image: {name}")
+                        total = max(1, total - 1)
+                        continue
+                    if engine is None:
+                        H, W = gray.shape
+                        ops = list(cfg.xy_blend_pipeline or [])
+                        chain = (lambda d: xy_blend_processor.process_xy_pipeline_dev(d, ops)[0]) if ops else None
+                        engine = E.RoiStackEngine(W, H, cfg, chain)
+                    out = engine.process(gray, _layer_number(name))
+                    jobs.append(encoder.submit(write, os.path.join(output_path, name), out))
+                    while jobs and (jobs[0].done() or len(jobs) > 2 * workers):
+                        jobs.pop(0).result()
+                        done += 1
+                        self.status_update.emit(f"Completed processing images ({done}/{total})")
+                        self.progress_update.emit(int((done / total) * 100))
+                for j in jobs:
+                    j.result()
                     done += 1
                     self.status_update.emit(f"Completed processing images ({done}/{total})")
                     self.progress_update.emit(int((done / total) * 100))
-            for j in jobs:
-                j.result()
-                done += 1
-                self.status_update.emit(f"Completed processing images ({done}/{total})")
-                self.progress_update.emit(int((done / total) * 100))
-        if engine is not None:
-            engine.close()
+        finally:
+            if engine is not None:
+                E.torch().cuda.synchronize()
+                engine.close()
 
     def _blend_stack(self, input_path, filenames, output_path):
+        """The stack loop (processing_pipeline.py:141-223) on the device.  With `config.devices` naming several CUDA
+        devices the stack is Z-sharded: contiguous slabs, one engine and one host thread per device, each slab first
+        re-ingesting the `receding_layers` layers below it as a mask-only halo (no collective)."""
         if self.app_config.blending_mode == ProcessingMode.ROI_FADE:
             return self._blend_stack_roi(input_path, filenames, output_path)
-        total = len(filenames)
-        done = 0
+        cfg = self.app_config
+        devices = [int(d) for d in (getattr(cfg, "devices", None) or [])]
+        self._progress = {"done": 0, "total": len(filenames), "index": 0}
+        self._progress_lock = threading.Lock()
+        self.io_seconds = {"decode": 0.0, "device_wait": 0.0, "encode": 0.0, "layers": 0}
+        if len(devices) <= 1:
+            return self._blend_slab(input_path, filenames, [], output_path, devices[0] if devices else None)
+        halo = max(0, int(cfg.receding_layers))
+        plan = [p for p in E.zshard_plan(len(filenames), len(devices), halo) if p["z1"] > p["z0"]]
+        errors = []
+
+        def slab(p):
+            try:
+                self._blend_slab(input_path, filenames[p["z0"]:p["z1"]], filenames[p["halo0"]:p["z0"]], output_path,
+                                 devices[p["rank"]])
+            except Exception as exc:  # surfaced by run() exactly like a failed worker future (:179-185)
+                errors.append(exc)
+                self._is_running = False
+
+        threads = [threading.Thread(target=slab, args=(p,), daemon=True) for p in plan]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        if errors:
+            raise errors[0]
+
+    def _blend_slab(self, input_path, filenames, halo_files, output_path, device=None):
+        prog, lock = self._progress, self._progress_lock
         torch = E.torch()
+        if device is not None:
+            torch.cuda.set_device(device)
         workers = self.max_workers
         engine = None
         free_bufs: "queue.Queue" = queue.Queue()
         inflight = collections.deque()
         encode_jobs = set()
+        io = self.io_seconds
 
         def finish_encodes(block_all=False):
-            nonlocal done
             if not encode_jobs:
                 return
             if block_all:
@@ -222,13 +259,26 @@ class ProcessingPipelineThread(QThread):
             for job in ready:
                 encode_jobs.discard(job)
                 job.result()
-                done += 1
+                with lock:
+                    prog["done"] += 1
+                    done, total = prog["done"], prog["total"]
                 self.status_update.emit(f"Completed processing images ({done}/{total})")
                 self.progress_update.emit(int((done / total) * 100))
 
+        def decode(path):
+            t0 = time.perf_counter()
+            img = cv2.imread(path, cv2.IMREAD_GRAYSCALE)
+            with lock:
+                io["decode"] += time.perf_counter() - t0
+            return img
+
         def encode(buf, path, W):
             try:
+                t0 = time.perf_counter()
                 cv2.imwrite(path, buf[1][:, :W])
+                with lock:
+                    io["encode"] += time.perf_counter() - t0
+                    io["layers"] += 1
                 print(f"Successfully wrote output file: {path}")
             finally:
                 free_bufs.put(buf)
@@ -236,62 +286,86 @@ class ProcessingPipelineThread(QThread):
 
         def retire(encoder):
             ticket, buf, path = inflight.popleft()
+            t0 = time.perf_counter()
             engine.wait(ticket)
+            with lock:
+                io["device_wait"] += time.perf_counter() - t0
             encode_jobs.add(encoder.submit(encode, buf, path, engine.out_W))
 
-        with concurrent.futures.ThreadPoolExecutor(workers) as decoder, \
-                concurrent.futures.ThreadPoolExecutor(workers) as encoder:
-            lookahead = 2 * workers                                   # same back-pressure bound as :169
-            pending = collections.deque()
-            it = iter(filenames)
+        try:
+            with concurrent.futures.ThreadPoolExecutor(workers) as decoder, \
+                    concurrent.futures.ThreadPoolExecutor(workers) as encoder:
+                lookahead = 2 * workers                                   # same back-pressure bound as :169
+                pending = collections.deque()
+                it = iter([(n, True) for n in halo_files] + [(n, False) for n in filenames])
 
-            def top_up():
-                while len(pending) < lookahead:
-                    name = next(it, None)
-                    if name is None:
-                        return
-                    path = os.path.join(input_path, name)
-                    pending.append((name, decoder.submit(cv2.imread, path, cv2.IMREAD_GRAYSCALE)))
+                def top_up():
+                    while len(pending) < lookahead:
+                        item = next(it, None)
+                        if item is None:
+                            return
+                        name, is_halo = item
+                        pending.append((name, is_halo, decoder.submit(decode, os.path.join(input_path, name))))
 
-            top_up()
-            index = 0
-            while pending:
-                if not self._is_running:
-                    self.logger.log("Processing stopped by user.")
-                    self.status_update.emit("Processing stopped by user.")
-                    break
-                name, fut = pending.popleft()
                 top_up()
-                index += 1
-                self.status_update.emit(f"Analyzing {name} ({index}/{total})")
-                gray = fut.result()
-                if gray is None:
-                    print(f"Warning: Could not load image at {os.path.join(input_path, name)}")
-                    self.status_update.emit(f"Skipping unloadable image: {name}")
-                    total = max(1, total - 1)
-                    continue
-                if engine is None:
-                    H, W = gray.shape
-                    engine = self._make_engine(H, W)
-                    for _ in range(engine.slots + workers):
-                        pin_in = torch.empty((H, engine.pitch), dtype=torch.uint8, pin_memory=True)
-                        pin_out = torch.empty((engine.out_H, E.pitch_for(engine.out_W)), dtype=torch.uint8, pin_memory=True)
-                        free_bufs.put((pin_in.numpy(), pin_out.numpy(), pin_in, pin_out))
-                if gray.shape != (engine.H, engine.W):
-                    raise ValueError(f"{name}: layer size {gray.shape[::-1]} differs from the stack's "
-                                     f"{(engine.W, engine.H)}")
-                finish_encodes()
-                buf = free_bufs.get()
-                np.copyto(buf[0][:, : engine.W], gray)
-                ticket = engine.submit(buf[2].data_ptr(), engine.pitch, buf[3].data_ptr(), E.pitch_for(engine.out_W))
-                inflight.append((ticket, buf, os.path.join(output_path, name)))
-                while len(inflight) >= engine.slots:
+                while pending:
+                    if not self._is_running:
+                        self.logger.log("Processing stopped by user.")
+                        self.status_update.emit("Processing stopped by user.")
+                        break
+                    name, is_halo, fut = pending.popleft()
+                    top_up()
+                    if not is_halo:
+                        with lock:
+                            prog["index"] += 1
+                            index, total = prog["index"], prog["total"]
+                        self.status_update.emit(f"Analyzing {name} ({index}/{total})")
+                    gray = fut.result()
+                    if gray is None:
+                        print(f"Warning: Could not load image at {os.path.join(input_path, name)}")
+                        if not is_halo:
+                            self.status_update.emit(f"Skipping unloadable image: {name}")
+                            with lock:
+                                prog["total"] = max(1, prog["total"] - 1)
+                        continue
+                    if engine is None:
+                        H, W = gray.shape
+                        engine = self._make_engine(H, W)
+                        for _ in range(engine.slots + workers):
+                            pin_in = torch.empty((H, engine.pitch), dtype=torch.uint8, pin_memory=True)
+                            pin_out = torch.empty((engine.out_H, E.pitch_for(engine.out_W)), dtype=torch.uint8, pin_memory=True)
+                            free_bufs.put((pin_in.numpy(), pin_out.numpy(), pin_in, pin_out))
+                    if gray.shape != (engine.H, engine.W):
+                        raise ValueError(f"{name}: layer size {gray.shape[::-1]} differs from the stack's "
+                                         f"{(engine.W, engine.H)}")
+                    if is_halo:                                           # masks only: thresholded, pushed, no output
+                        while inflight:
+                            retire(encoder)
+                        engine.push_halo(gray)
+                        continue
+                    finish_encodes()
+                    buf = free_bufs.get()
+                    np.copyto(buf[0][:, : engine.W], gray)
+                    ticket = engine.submit(buf[2].data_ptr(), engine.pitch, buf[3].data_ptr(), E.pitch_for(engine.out_W))
+                    inflight.append((ticket, buf, os.path.join(output_path, name)))
+                    while len(inflight) >= engine.slots:
+                        retire(encoder)
+                while inflight:
                     retire(encoder)
-            while inflight:
-                retire(encoder)
-            finish_encodes(block_all=True)
-        if engine is not None:
-            engine.close()
+                finish_encodes(block_all=True)
+        finally:
+            # a failure above may leave copies in flight between pinned host buffers and the device: drain the streams
+            # before those buffers (and the engine's staging slots) are released
+            if engine is not None:
+                try:
+                    engine.sync()
+                finally:
+                    engine.close()
+            for job in list(encode_jobs):
+                try:
+                    job.result()
+                except Exception:
+                    pass
 
     def run(self):
         self.logger.log("Run started.")
@@ -315,8 +389,10 @@ class ProcessingPipelineThread(QThread):
                 return
             self.logger.log(f"Found {len(filenames)} images to process.")
             if cfg.debug_save:
-                self.logger.log("debug_save: intermediate dumps are only produced by the per-call API "
-                                "(processing_core), not by the device stack engine.")
+                note = ("debug_save: the device stack engine keeps intermediates on the GPU and writes no debug_03a/03b "
+                        "images; call processing_core.process_z_blending(..., debug_info=...) per layer for the dumps.")
+                self.logger.log(note)
+                self.status_update.emit(note)
             try:
                 self._blend_stack(input_path, filenames, output_path)
             except Exception as exc:

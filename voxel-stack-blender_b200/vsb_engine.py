@@ -439,8 +439,8 @@ class RoiStackEngine:
         self.tracker = roi_tracker.ROITracker()
         self.window: List[DevBits] = []
         self.n_priors = max(0, int(cfg.receding_layers))
-        if self.n_priors > N.VSB_MAX_PRIORS:
-            raise P.UnsupportedOnDevice(f"more than {N.VSB_MAX_PRIORS} receding layers")
+        if self.n_priors > N.VSB_MAX_WINDOW:
+            raise P.UnsupportedOnDevice(f"more than {N.VSB_MAX_WINDOW} receding layers")
         self.xy_chain = xy_chain          # callable DevImage -> DevImage, or None
         self.last_rois: List[dict] = []
 
@@ -466,6 +466,8 @@ class RoiStackEngine:
             if not (skip and r["classification"] in ("raft", "support")):
                 eligible[r["component"]] = 1
         priors = list(reversed(self.window))     # newest first (only their OR matters here)
+        if len(priors) > N.VSB_MAX_PRIORS:
+            priors = [or_bits(priors)]
         out = roi_fade(img, cur, priors, comp.cid, comp.n if (classified and priors) else 0, eligible,
                        float(cfg.fixed_fade_distance_receding), bool(cfg.use_fixed_fade_receding))
         if self.xy_chain is not None:
@@ -557,8 +559,8 @@ class StackEngine:
         self.pitch = pitch_for(W)
         z = P.zparams_from_config(cfg, metric, self.W, self.H)
         n_priors = max(0, int(cfg.receding_layers))
-        if n_priors > N.VSB_MAX_PRIORS:
-            raise P.UnsupportedOnDevice(f"more than {N.VSB_MAX_PRIORS} receding layers")
+        if n_priors > N.VSB_MAX_WINDOW:   # the GUI offers 0..100 (ui_components.py:168)
+            raise P.UnsupportedOnDevice(f"more than {N.VSB_MAX_WINDOW} receding layers")
         ops = list(xy_ops or [])
         if len(ops) > N.VSB_MAX_XY_OPS:
             raise P.UnsupportedOnDevice(f"more than {N.VSB_MAX_XY_OPS} XY operations")
@@ -589,6 +591,10 @@ class StackEngine:
     def push_halo(self, gray: np.ndarray):
         gray = np.ascontiguousarray(gray, np.uint8)
         N.check(N.load().vsb_stack_push_halo(self._h, gray.ctypes.data_as(c_void_p), gray.strides[0]), "vsb_stack_push_halo")
+
+    def push_halo_device(self, gray_ptr: int, pitch: int):
+        """Halo layer already in HBM (a Z-shard of a device-resident stack): thresholded into the window, no output."""
+        N.check(N.load().vsb_stack_push_halo_device(self._h, gray_ptr, pitch), "vsb_stack_push_halo_device")
 
     def process(self, gray: np.ndarray) -> np.ndarray:
         gray = np.ascontiguousarray(gray, np.uint8)

@@ -18,6 +18,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("VSB_B200_LIB") or os.path.join(_HERE, "libvsb_b200.so")  # override: A/B builds of the same ABI
 
 VSB_MAX_PRIORS = 16
+VSB_MAX_WINDOW = 128     # receding_layers a stack engine can hold (csrc/vsb_stack.cu STACK_MAX_WINDOW)
 VSB_MAX_XY_OPS = 16
 VSB_FAST_REACH = 63
 
@@ -129,6 +130,7 @@ _SIGS = {
     "vsb_resize_bits_nearest": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p]),
     "vsb_stack_reset": (c_int, [c_void_p]),
     "vsb_stack_push_halo": (c_int, [c_void_p, c_void_p, c_size_t]),
+    "vsb_stack_push_halo_device": (c_int, [c_void_p, c_void_p, c_size_t]),
     "vsb_stack_process_host": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_size_t]),
     "vsb_stack_submit_host": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_size_t]),
     "vsb_stack_wait": (c_int, [c_void_p, c_int]),

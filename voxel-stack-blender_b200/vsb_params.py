@@ -19,7 +19,7 @@ f32 = np.float32
 
 
 class UnsupportedOnDevice(NotImplementedError):
-    """A configuration SURVEY.md section 8(f) lists as 'next' -- not built on the B200 path yet."""
+    """A parameter combination outside what the device kernels cover ("Not built")."""
 
 
 def _mode_name(cfg) -> str:
@@ -41,10 +41,12 @@ def anisotropic_dims(width: int, height: int, x_factor: float, y_factor: float):
     return int(width * xf), int(height * yf)
 
 
-def zparams_from_config(cfg, metric: str = "chamfer5", width: Optional[int] = None, height: Optional[int] = None) -> N.ZParams:
+def zparams_from_config(cfg, metric: str = "chamfer5", width: Optional[int] = None, height: Optional[int] = None,
+                        weighted_k: Optional[int] = None) -> N.ZParams:
     """Fade parameters as the reference derives them from Config (processing_core.py:112-113,
-    :138-140, :227-257, :387).  `width`/`height` (the layer size) are needed by the anisotropic Enhanced EDT only.
-    Raises UnsupportedOnDevice for the section-8(f) configurations that are not on the device yet."""
+    :138-140, :227-257, :387).  `width`/`height` (the layer size) are needed by the anisotropic Enhanced EDT only;
+    `weighted_k` = number of prior masks a per-call weighted blend was handed (default: config.receding_layers, what
+    a stack holds).  Raises UnsupportedOnDevice for the combinations DESIGN.md lists as not built."""
     z = N.ZParams()
     z.metric = N.METRIC_EXACT if metric == "exact" else N.METRIC_CHAMFER5
     mode = _mode_name(cfg)
@@ -52,12 +54,16 @@ def zparams_from_config(cfg, metric: str = "chamfer5", width: Optional[int] = No
     z.fade_limit = F
     z.enhanced_arith = 1 if getattr(cfg, "use_numba_jit", False) else 0
     if mode == "roi_fade":
-        raise UnsupportedOnDevice("ROI_FADE (stateful tracker, per-ROI transforms) is outside the B200 hot path "
-                                  "(SURVEY.md 8f rank 3)")
+        raise UnsupportedOnDevice("ROI_FADE carries tracker state from layer to layer: drive it through "
+                                  "vsb_engine.RoiStackEngine (what ProcessingPipelineThread does), not StackEngine")
     if mode == "weighted_stack":
-        weights = list(cfg.manual_weights)[:N.VSB_MAX_PRIORS]
-        if len(cfg.manual_weights) > N.VSB_MAX_PRIORS and cfg.receding_layers > N.VSB_MAX_PRIORS:
+        # the reference only ever reads the first min(len(priors), len(weights)) entries (processing_core.py:231-233);
+        # a stack never holds more than receding_layers priors
+        held = weighted_k if weighted_k is not None else getattr(cfg, "receding_layers", len(cfg.manual_weights))
+        k_max = min(len(cfg.manual_weights), max(0, int(held)))
+        if k_max > N.VSB_MAX_PRIORS:
             raise UnsupportedOnDevice(f"weighted stack over more than {N.VSB_MAX_PRIORS} layers")
+        weights = list(cfg.manual_weights)[:k_max]
         fades = list(cfg.fade_distances_receding)
         z.mode = N.Z_WEIGHTED
         z.n_priors = len(weights)
