@@ -25,6 +25,7 @@ digests against a single-GPU pass of the whole stack.
   --workload zlut|cfg2|cfg3|edt : make that configuration the main line instead of the headline
 """
 import argparse
+import contextlib
 import json
 import os
 import shutil
@@ -750,7 +751,8 @@ def main():
             errs = []
             th.error_signal.connect(errs.append)
             t0 = time.perf_counter()
-            th.run()
+            with contextlib.redirect_stdout(sys.stderr):        # run() prints one line per written file, like the reference
+                th.run()
             dtp = time.perf_counter() - t0
             nout = len([f for f in os.listdir(outd) if f.endswith(".png")])
             io = getattr(th, "io_seconds", {})

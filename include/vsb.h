@@ -233,8 +233,12 @@ int vsb_median(const uint8_t *in, size_t in_pitch, int W, int H, int ksize, uint
 
 /* ---------------------------------------------------------------------------------------------
  * The fused per-layer path (two launches per layer).
- *   vsb_pack_flags : K1 plus one uint16 per 128x32 tile: the tile's single gray value, or 0x100 = mixed.
+ *   vsb_pack_flags : K1 plus one uint16 per 128x32 tile: the tile's single gray value, or 0x100 = mixed; bit 0x200 is
+ *                    set when every byte of the tile is 0 or 255 (the input the reference asks for, README.md:25).
  *                    flags: uint16 [ceil(H/32)][ceil(W/128)];  wpr must be 4*ceil(W/128).
+ *                    With threshold 127 and 16-byte aligned rows this is the persistent TMA-fed kernel of
+ *                    csrc/vsb_pack_tma.cu (cp.async.bulk.tensor loads into per-warp mbarrier rings, bulk tensor
+ *                    stores for lut[gray]); other thresholds / alignments take the plain-load kernel.
  *   vsb_layer_fused: Z-blend (FIXED / WEIGHTED / CONST, or NONE) -> lut1 -> [bilateral] -> [Gaussian] -> lut2
  *                    in ONE kernel, intermediates in shared memory.  Same arithmetic, bit for bit, as the
  *                    separate entry points above.  cur_flags / prior_flags (from vsb_pack_flags) are optional and
@@ -271,7 +275,10 @@ int vsb_layer_fused_enhanced(const uint8_t *in, size_t in_pitch, int W, int H, c
  * read from HBM once and untouched tiles cost one look at their mask words. */
 int vsb_pack_flags_lut(const uint8_t *gray, size_t pitch, int W, int H, int thresh, uint32_t *bits, int wpr,
                        uint16_t *flags, const uint8_t *lut256_dev /* NULL = identity */, uint8_t *out, size_t out_pitch,
-                       const uint32_t *const *prior_bits, int n_priors,
+                       const uint32_t *const *prior_bits,
+                       const uint16_t *const *prior_flags /* NULL, or the priors' tile flags (vsb_pack_flags*): tiles
+                                         where every prior is uniformly black skip the prior-mask reads */,
+                       int n_priors,
                        int *rec_tiles /* NULL, or int[1 + tiles]: [0] receives the number of 128x32 tiles holding a
                                          receding pixel w.r.t. the given priors, [1..] their indices */,
                        vsb_stream_t stream);

@@ -461,6 +461,82 @@ def test_synth_raster_device_equals_numpy(E):
         assert np.array_equal(got, S.raster_numpy(table, raft, z, W, H)), z
 
 
+# ---- K1 as the TMA-fed streaming kernel (csrc/vsb_pack_tma.cu) -----------------------------------------------------------
+def _tile_flags_numpy(g):
+    H, W = g.shape
+    ty, tx = (H + 31) // 32, (W + 127) // 128
+    f = np.zeros((ty, tx), np.uint16)
+    for j in range(ty):
+        for i in range(tx):
+            t = g[j * 32:(j + 1) * 32, i * 128:(i + 1) * 128]
+            v = 0x100 if (t != t[0, 0]).any() else int(t[0, 0])
+            if ((t == 0) | (t == 255)).all():
+                v |= 0x200
+            f[j, i] = v
+    return f
+
+
+@pytest.mark.parametrize("shape", [(8, 16), (33, 128), (70, 300), (301, 517), (64, 1040), (97, 2049)])
+@pytest.mark.parametrize("kind", ["binary", "gray"])
+def test_pack_flags_streaming_kernel(E, shape, kind):
+    """vsb_pack_flags / vsb_pack_flags_lut (threshold 127, aligned rows -> the persistent TMA kernel): mask bits, tile
+    flags (uniform value / MIXED / BINARY), lut[gray] and the receding-tile list, ragged right and bottom tiles included,
+    against NumPy.  processing_core.py:44, lut_manager.py:63."""
+    import vsb_native as N
+    t = E.torch()
+    H, W = shape
+    rng = np.random.default_rng(H * 1000 + W)
+    if kind == "binary":
+        g = (rng.random((H, W)) < 0.5).astype(np.uint8) * np.uint8(255)
+        g[: H // 2, : W // 3] = 255
+        g[H // 2:, W // 2:] = 0
+    else:
+        g = rng.integers(0, 256, (H, W), dtype=np.uint8)
+        g[: H // 2, : W // 2] = 37          # uniform gray tiles
+        g[0, 0] = 127; g[-1, -1] = 128
+    pri_np = [(rng.random((H, W)) < 0.3).astype(np.uint8) * np.uint8(255) for _ in range(3)]
+    pri_np[0][:, : W // 2] = 0
+    pri_np[1][:, : W // 2] = 0
+    pri_np[2][:, : W // 2] = 0             # left half: every prior uniformly black -> gated tiles
+    lut = rng.permutation(256).astype(np.uint8)
+    img = E.DevImage.from_numpy(g)
+    ntiles = ((H + 31) // 32) * ((W + 127) // 128)
+    pri, pfl = [], []
+    for pn in pri_np:
+        b = E.DevBits(H, W)
+        f = t.zeros(ntiles, dtype=t.int16, device="cuda")
+        N.check(N.load().vsb_pack_flags(E.DevImage.from_numpy(pn).ptr, E.pitch_for(W), W, H, 127, b.ptr, b.wpr, f.data_ptr(),
+                                        E._stream()), "vsb_pack_flags")
+        assert np.array_equal(f.cpu().numpy().view(np.uint16).reshape(-1), _tile_flags_numpy(pn).reshape(-1))
+        pri.append(b); pfl.append(f)
+    want_bits = O.threshold(g)
+    want_flags = _tile_flags_numpy(g).reshape(-1)
+    prior_or = np.zeros((H, W), bool)
+    for pn in pri_np:
+        prior_or |= pn > 127
+    rec = prior_or & ~(g > 127)
+    want_rec = sorted(j * ((W + 127) // 128) + i for j in range((H + 31) // 32) for i in range((W + 127) // 128)
+                      if rec[j * 32:(j + 1) * 32, i * 128:(i + 1) * 128].any())
+    for gated in (False, True):
+        cur = E.DevBits(H, W)
+        cur.t.fill_(-1)
+        flags = t.zeros(ntiles, dtype=t.int16, device="cuda")
+        out = E.DevImage(H, W, zero=True)
+        rl = t.zeros(1 + ntiles, dtype=t.int32, device="cuda")
+        N.check(N.load().vsb_pack_flags_lut(img.ptr, img.pitch, W, H, 127, cur.ptr, cur.wpr, flags.data_ptr(),
+                                            E.lut_dev(lut).data_ptr(), out.ptr, out.pitch, N.ptr_array([p.ptr for p in pri]),
+                                            N.ptr_array([f.data_ptr() for f in pfl]) if gated else None, len(pri),
+                                            rl.data_ptr(), E._stream()), "vsb_pack_flags_lut")
+        assert np.array_equal(E.unpack(cur).numpy(), want_bits)
+        raw = np.unpackbits(cur.t.cpu().numpy().view(np.uint8), axis=1, bitorder="little")
+        assert not raw[:, W:].any()                                # bits at x >= W stay 0
+        assert np.array_equal(flags.cpu().numpy().view(np.uint16), want_flags)
+        assert np.array_equal(out.numpy(), lut[g])
+        assert not out.t[:, W:].any()                              # the pitch padding is never written
+        r = rl.cpu().numpy()
+        assert sorted(r[1:1 + r[0]].tolist()) == want_rec
+
+
 # ---- the fused per-layer kernel (vsb_pack_flags + vsb_layer_fused) --------------------------------------------------
 FUSED_CHAINS = {
     "lut_bil7_g3_lut": [{"type": "apply_lut", "lut_params": {"lut_generation_type": "gamma", "gamma_value": 2.2}},
@@ -644,7 +720,7 @@ def test_pack_lut_and_patch_equal_fused_no_xy(E):
                     ld = E.lut_dev(lut)
                     pa = N.ptr_array([p.ptr for p in pri])
                     N.check(N.load().vsb_pack_flags_lut(img.ptr, img.pitch, W, H, 127, cur.ptr, cur.wpr, flags.data_ptr(), ld.data_ptr(),
-                                                        out.ptr, out.pitch, pa, len(pri), rec.data_ptr() if use_list else None,
+                                                        out.ptr, out.pitch, pa, None, len(pri), rec.data_ptr() if use_list else None,
                                                         E._stream()), "vsb_pack_flags_lut")
                     zz = N.ZParams.from_buffer_copy(z)
                     if mode == "weighted_stack":

@@ -28,6 +28,7 @@
 #define LBW 10                  // mask words per staged row: x0-96 .. x0+223
 #define LB_ROWS_MAX (RG_ROWS_MAX + 2 * VSB_FAST_REACH)
 #define FLAG_MIXED 0x100
+#define FLAG_BINARY 0x200 // every byte of the tile is 0 or 255
 
 static __device__ __forceinline__ float lds_f32(uint32_t a)
 {
@@ -93,6 +94,7 @@ __global__ void __launch_bounds__(VSB_THREADS) k_pack_flags(const uint8_t *__res
                                                             int *__restrict__ rec_list)
 {
     __shared__ int s_ok[2];
+    __shared__ int s_bin[2];
     __shared__ int s_rec[2];
     __shared__ __align__(4) uint8_t s_plut[256];
     if (LUTOUT && lut && threadIdx.x < 64) ((uint32_t *)s_plut)[threadIdx.x] = ((const uint32_t *)lut)[threadIdx.x];
@@ -101,7 +103,7 @@ __global__ void __launch_bounds__(VSB_THREADS) k_pack_flags(const uint8_t *__res
     const int x0 = blockIdx.x * VSB_TW, y0 = ty * VSB_TH;
     const int r = u >> 2, wq = u & 3;
     const int y = y0 + r, x = x0 + wq * 32;
-    if (t < 2) { s_ok[t] = 1; s_rec[t] = 0; }
+    if (t < 2) { s_ok[t] = 1; s_bin[t] = 1; s_rec[t] = 0; }
     const int n = (y < H) ? max(0, min(32, W - x)) : 0;
     uint4 a = make_uint4(0, 0, 0, 0), b = make_uint4(0, 0, 0, 0);
     uint32_t first = 0;
@@ -144,16 +146,28 @@ __global__ void __launch_bounds__(VSB_THREADS) k_pack_flags(const uint8_t *__res
         for (int i = 0; i < n; ++i) ok = ok && (((w[i >> 2] >> ((i & 3) * 8)) & 255u) == first);
     }
     if (!__all_sync(0xffffffffu, ok) && (t & 31) == 0) s_ok[half] = 0;
+    {   // strictly binary tile (every byte 0 or 255; zero-filled bytes outside the image count as 0)
+        const uint32_t w8[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        uint32_t nb = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) nb |= w8[i] ^ (((w8[i] >> 7) & 0x01010101u) * 0xFFu);
+        if (!__all_sync(0xffffffffu, nb == 0u) && (t & 31) == 0) s_bin[half] = 0;
+    }
     __syncthreads();
     if (u == 0 && ty < tiles_y) {
-        flags[ty * tiles_x + blockIdx.x] = (uint16_t)(s_ok[half] ? first : FLAG_MIXED);
+        flags[ty * tiles_x + blockIdx.x] = (uint16_t)((s_ok[half] ? first : FLAG_MIXED) | (s_bin[half] ? FLAG_BINARY : 0));
         if (LUTOUT && rec_list && s_rec[half]) rec_list[1 + atomicAdd(&rec_list[0], 1)] = ty * tiles_x + (int)blockIdx.x;
     }
 }
 
+int vsb_pack_tma_launch(const uint8_t *gray, size_t pitch, int W, int H, uint32_t *bits, int wpr, uint16_t *flags, bool lutout,
+                        const uint8_t *lut, uint8_t *out, size_t opitch, const uint32_t *const *prior_bits,
+                        const uint16_t *const *prior_flags, int n_priors, int *rec_list, cudaStream_t s); // vsb_pack_tma.cu
+
 static int pack_flags_launch(const uint8_t *gray, size_t pitch, int W, int H, int thresh, uint32_t *bits, int wpr,
                              uint16_t *flags, bool lutout, const uint8_t *lut, uint8_t *out, size_t opitch,
-                             const uint32_t *const *prior_bits, int n_priors, int *rec_list, vsb_stream_t stream)
+                             const uint32_t *const *prior_bits, const uint16_t *const *prior_flags, int n_priors, int *rec_list,
+                             vsb_stream_t stream)
 {
     VSB_REQUIRE(gray && bits && flags, "vsb_pack_flags: null pointer");
     VSB_REQUIRE(W > 0 && H > 0 && wpr >= ((W + 127) / 128) * 4 && pitch >= (size_t)W, "vsb_pack_flags: bad geometry");
@@ -172,6 +186,11 @@ static int pack_flags_launch(const uint8_t *gray, size_t pitch, int W, int H, in
         for (int i = 0; i < n_priors; ++i) pr.p[i] = prior_bits[i];
         VSB_CUDA(cudaMemsetAsync(rec_list, 0, sizeof(int), s));
     }
+    // the streaming kernel (TMA-fed, one warp per tile): threshold 127, 16-byte aligned rows
+    static const bool no_tma = getenv("VSB_NO_TMA") != nullptr;
+    if (!no_tma && thresh == 127 && al && (!lutout || oal))
+        return vsb_pack_tma_launch(gray, pitch, W, H, bits, wpr, flags, lutout, lut, out, opitch, prior_bits, prior_flags, n_priors,
+                                   rec_list, s);
     if (lutout) {
         if (al) k_pack_flags<true, true><<<grid, VSB_THREADS, 0, s>>>(gray, pitch, W, H, thr4, bits, wpr, flags, tiles_x, tiles_y, lut, out, opitch, oal, pr, rec_list);
         else k_pack_flags<false, true><<<grid, VSB_THREADS, 0, s>>>(gray, pitch, W, H, thr4, bits, wpr, flags, tiles_x, tiles_y, lut, out, opitch, oal, pr, rec_list);
@@ -185,16 +204,17 @@ static int pack_flags_launch(const uint8_t *gray, size_t pitch, int W, int H, in
 extern "C" int vsb_pack_flags(const uint8_t *gray, size_t pitch, int W, int H, int thresh, uint32_t *bits, int wpr,
                               uint16_t *flags, vsb_stream_t stream)
 {
-    return pack_flags_launch(gray, pitch, W, H, thresh, bits, wpr, flags, false, nullptr, nullptr, 0, nullptr, 0, nullptr, stream);
+    return pack_flags_launch(gray, pitch, W, H, thresh, bits, wpr, flags, false, nullptr, nullptr, 0, nullptr, nullptr, 0, nullptr, stream);
 }
 
 extern "C" int vsb_pack_flags_lut(const uint8_t *gray, size_t pitch, int W, int H, int thresh, uint32_t *bits, int wpr,
                                   uint16_t *flags, const uint8_t *lut256_dev, uint8_t *out, size_t out_pitch,
-                                  const uint32_t *const *prior_bits, int n_priors, int *rec_tiles, vsb_stream_t stream)
+                                  const uint32_t *const *prior_bits, const uint16_t *const *prior_flags, int n_priors,
+                                  int *rec_tiles, vsb_stream_t stream)
 {
     VSB_REQUIRE(out && out != gray && out_pitch >= (size_t)W, "vsb_pack_flags_lut: output missing / in place / pitch < width");
-    return pack_flags_launch(gray, pitch, W, H, thresh, bits, wpr, flags, true, lut256_dev, out, out_pitch, prior_bits, n_priors,
-                             rec_tiles, stream);
+    return pack_flags_launch(gray, pitch, W, H, thresh, bits, wpr, flags, true, lut256_dev, out, out_pitch, prior_bits, prior_flags,
+                             n_priors, rec_tiles, stream);
 }
 
 // ------------------------------------------------------------------------------------------------------

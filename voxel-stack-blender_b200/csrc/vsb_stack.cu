@@ -437,8 +437,11 @@ static int run_layer(vsb_stack *s, const uint8_t *gray, size_t gpitch, uint8_t *
                             (s->zp.mode == VSB_Z_FIXED || s->zp.mode == VSB_Z_WEIGHTED || s->zp.mode == VSB_Z_CONST);
     if (patch_path) {
         ProfScope ps(s, ST_PACKF, 1, cst);
+        const uint16_t *pfl[VSB_MAX_PRIORS];
+        const bool have_flags = s->n_priors <= VSB_MAX_PRIORS; // an OR-ed window has no tile flags
+        for (int i = 0; i < np; ++i) pfl[i] = have_flags ? s->flag_ring[(s->head - 1 - i + 2 * nring) % nring] : nullptr;
         rc = vsb_pack_flags_lut(gray, gpitch, s->W, s->H, 127, cur, s->wpr, s->flag_ring[s->head], s->lead_lut_dev, out, opitch,
-                                pri, np, s->rec_tiles[lane], st);
+                                pri, have_flags ? pfl : nullptr, np, s->rec_tiles[lane], st);
     }
     else if (s->fused) { ProfScope ps(s, ST_PACKF, 1, cst); rc = vsb_pack_flags(gray, gpitch, s->W, s->H, 127, cur, s->wpr, s->flag_ring[s->head], st); }
     else { ProfScope ps(s, ST_PACK, 1, cst); rc = vsb_threshold_pack(gray, gpitch, s->W, s->H, 127, cur, s->wpr, st); }

@@ -104,7 +104,7 @@ _SIGS = {
                                        c_void_p]),
     "vsb_pack_flags": (c_int, [c_void_p, c_size_t, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     "vsb_pack_flags_lut": (c_int, [c_void_p, c_size_t, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_size_t,
-                                   POINTER(c_void_p), c_int, c_void_p, c_void_p]),
+                                   POINTER(c_void_p), POINTER(c_void_p), c_int, c_void_p, c_void_p]),
     "vsb_layer_patch": (c_int, [c_void_p, c_size_t, c_int, c_int, c_void_p, POINTER(c_void_p), c_int, POINTER(ZParams), c_void_p,
                                 c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "vsb_layer_fused_enhanced": (c_int, [c_void_p, c_size_t, c_int, c_int, c_void_p, POINTER(c_void_p), c_int, POINTER(ZParams),
