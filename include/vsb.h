@@ -87,13 +87,17 @@ int vsb_dt_chamfer5(const uint32_t *seed_bits, int wpr, int W, int H, int R, con
 int vsb_dt_exact_windowed(const uint32_t *seed_bits, int wpr, int W, int H, int R, float clip,
                           float *dist, size_t dist_pitch_elems, vsb_stream_t stream);
 
-/* K2' exact Euclidean distance transform, unbounded reach (cv2.DIST_MASK_PRECISE analogue):
- *     separable -- column pass (vertical distance to the nearest set bit, uint16 scratch
- *     `colnear` [H][pitch_elems], 0xFFFF = none) then a row pass over the lower envelope of
- *     parabolas.  d2_out (optional) = exact integer squared distance (INT32_MAX if no seed);
- *     dist_out (optional) = sqrtf(d2). */
-int vsb_dt_exact(const uint32_t *seed_bits, int wpr, int W, int H, uint16_t *colnear,
-                 int32_t *d2_out, float *dist_out, size_t pitch_elems, vsb_stream_t stream);
+/* K2' exact Euclidean distance transform, unbounded reach (cv2.DIST_MASK_PRECISE analogue), csrc/vsb_edt.cu:
+ *     separable lower-envelope algorithm -- row pass (distance to the nearest set bit of the same row, uint16, the
+ *     packed row staged with one bulk copy and the finished row stored with one) then, along every column, the
+ *     lower envelope of the parabolas (y - y')^2 + h(x,y')^2 by Meijster's integer two-scan method on the runs between
+ *     set bits.  Cost is O(W*H) whatever the distances are.
+ *     d2_out (optional) = exact integer squared distance (INT32_MAX if the image holds no set bit);
+ *     dist_out (optional) = sqrtf(d2) (3e38 there).  W, H <= 32767; wpr a multiple of 4; scratch: device buffer of
+ *     vsb_edt_exact_scratch_bytes(W, H) bytes, 128-byte aligned. */
+size_t vsb_edt_exact_scratch_bytes(int W, int H);
+int vsb_edt_exact(const uint32_t *seed_bits, int wpr, int W, int H, void *scratch, int32_t *d2_out, float *dist_out,
+                  size_t pitch_elems, vsb_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Unbounded reach (csrc/vsb_unbounded.cu): column distances + pruned row search.
@@ -241,9 +245,8 @@ int vsb_median(const uint8_t *in, size_t in_pitch, int W, int H, int ksize, uint
  *                    stores for lut[gray]); other thresholds / alignments take the plain-load kernel.
  *   vsb_layer_fused: Z-blend (FIXED / WEIGHTED / CONST, or NONE) -> lut1 -> [bilateral] -> [Gaussian] -> lut2
  *                    in ONE kernel, intermediates in shared memory.  Same arithmetic, bit for bit, as the
- *                    separate entry points above.  cur_flags / prior_flags (from vsb_pack_flags) are optional and
- *                    currently not consulted: the kernel decides "uniform region, nothing recedes" from the data it
- *                    stages anyway (measured: the flag look-up neither helps nor hurts).
+ *                    separate entry points above.  cur_flags / prior_flags (from vsb_pack_flags) are optional: they
+ *                    select the binary fast path (see general_tiles) and let uniform neighbourhoods leave early.
  *     replaces processing_pipeline.py:98-107 (process_z_blending, merge_to_output, process_xy_pipeline)
  *     for XY chains of the shape [apply_lut*] [bilateral_filter d<=9] [gaussian_blur k<=7] [apply_lut*].
  * ------------------------------------------------------------------------------------------- */
@@ -254,7 +257,16 @@ typedef struct {
     float cw[256];
     int nkx, nky;                     /* 0 = no Gaussian; odd, <= 7 */
     int32_t kx[7], ky[7];
+    /* bilateral shortcut of the binary fast path (vsb_bilateral_two_valued_min_same): a window that holds only
+     * lut1[0] / lut1[255] with at least this many taps equal to the centre rounds to the centre; 0 = never assume it */
+    int two_valued_min_same;
 } vsb_xy_fused;
+
+/* Smallest number m of taps (centre included) equal to the centre value for which cv2.bilateralFilter, on a window
+ * holding only the two values v0 and v1, provably returns the centre: worst case over tap placements of
+ * |v1 - v0| * Wo * cw[|v1-v0|] / (Ws + Wo * cw[|v1-v0|]) < 0.49 (float32 accumulation error is < 1e-3).  Returns 0 if no
+ * m <= ntaps gives that.  Host helper, no device work.     xy_blend_processor.py:35-40 */
+int vsb_bilateral_two_valued_min_same(const float *tap_sw, int ntaps, const float *cw256, int v0, int v1);
 
 int vsb_pack_flags(const uint8_t *gray, size_t pitch, int W, int H, int thresh, uint32_t *bits, int wpr,
                    uint16_t *flags, vsb_stream_t stream);
@@ -267,7 +279,10 @@ int vsb_layer_fused_enhanced(const uint8_t *in, size_t in_pitch, int W, int H, c
                              const uint32_t *const *prior_bits, int wpr, const vsb_zparams *params, const float *dist,
                              size_t dist_pitch_elems, const int32_t *labels, const uint32_t *compmax,
                              const uint8_t *lut1_dev, const vsb_xy_fused *xy /* host, may be NULL */,
-                             const uint8_t *lut2_dev, uint8_t *out, size_t out_pitch, vsb_stream_t stream);
+                             const uint8_t *lut2_dev, uint8_t *out, size_t out_pitch,
+                             const uint16_t *cur_flags /* NULL, or the layer's tile flags */,
+                             int *general_tiles /* NULL, or int[1 + tiles] scratch: see vsb_layer_fused */,
+                             vsb_stream_t stream);
 
 /* LUT-only pipelines (no XY filter): one pass over the gray layer writes the packed mask AND lut[gray] (the final
  * value of every pixel that does not recede); vsb_layer_patch then computes the fade on the receding pixels alone and
@@ -296,7 +311,12 @@ int vsb_layer_fused(const uint8_t *in, size_t in_pitch, int W, int H, const uint
                     const uint32_t *const *prior_bits, const uint16_t *cur_flags,
                     const uint16_t *const *prior_flags, int wpr, const vsb_zparams *params, const float *T_dev,
                     const uint8_t *lut1_dev, const vsb_xy_fused *xy /* host, may be NULL */,
-                    const uint8_t *lut2_dev, uint8_t *out, size_t out_pitch, vsb_stream_t stream);
+                    const uint8_t *lut2_dev, uint8_t *out, size_t out_pitch,
+                    int *general_tiles /* NULL, or int[1 + tiles] device scratch.  With it and cur_flags, tiles whose
+                                          3x3 tile neighbourhood is strictly binary (flag bit 0x200) run in k_layer2, which
+                                          derives everything from the packed masks and never reads `in`; the other
+                                          tiles are listed here and taken by the general kernel */,
+                    vsb_stream_t stream);
 
 /* vsb_zblend_unbounded's two halves, for the other modes with fade distances beyond VSB_FAST_REACH:
  * distances at the receding pixels only (dist is untouched elsewhere; minmax2 receives their min / max float bits) */

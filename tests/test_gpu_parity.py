@@ -118,6 +118,44 @@ def test_exact_edt(E, slices, ref_dist):
     assert (d2 == 0x7fffffff).all()
 
 
+@pytest.mark.parametrize("case", ["one_seed", "corner_seeds", "all_white", "sparse", "dense", "columns", "rows", "ragged", "tall"])
+def test_exact_edt_envelope_cases(E, case):
+    """vsb_edt_exact (row pass + Meijster lower envelope along the columns): integer d2 equal to the oracle's
+    Felzenszwalb transform on inputs whose runs are long (a single seed: every column is one run over the whole height),
+    empty rows, seeds only on the border, widths that are not a multiple of 32 / 64, and images taller than several bands."""
+    rng = np.random.default_rng(len(case))
+    shapes = {"one_seed": (300, 700), "corner_seeds": (257, 513), "all_white": (65, 130), "sparse": (400, 1000),
+              "dense": (200, 333), "columns": (190, 260), "rows": (260, 190), "ragged": (131, 1001), "tall": (1500, 96)}
+    H, W = shapes[case]
+    seed = np.zeros((H, W), np.uint8)
+    if case == "one_seed":
+        seed[211, 40] = 255
+    elif case == "corner_seeds":
+        seed[0, 0] = seed[-1, -1] = seed[0, -1] = 255
+    elif case == "all_white":
+        seed[:] = 255
+    elif case == "sparse":
+        seed[rng.random((H, W)) < 0.0005] = 255
+    elif case == "dense":
+        seed[rng.random((H, W)) < 0.4] = 255
+    elif case == "columns":
+        seed[:, ::37] = 255
+        seed[100:, 74] = 0
+    elif case == "rows":
+        seed[::41, :] = 255
+        seed[82, 50:] = 0
+    elif case == "ragged":
+        seed[rng.random((H, W)) < 0.003] = 255
+        seed[:, -1] = 0
+    else:
+        seed[rng.random((H, W)) < 0.002] = 255
+        seed[700:1300, :] = 0
+    d2o = O.edt_exact_sq(seed)
+    d2, dist = E.edt_exact_np(seed)
+    assert np.array_equal(d2, d2o), int((d2 != d2o).sum())
+    assert np.array_equal(dist, np.sqrt(d2o.astype(np.float32)))
+
+
 # ---- fused Z-blend ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("F,N", [(10.0, 3), (40.0, 4), (7.5, 2), (64.0, 4), (0.5, 1), (1.0, 3), (23.25, 6)])
 def test_fixed_fade_synthetic(E, F, N):
@@ -476,7 +514,7 @@ def _tile_flags_numpy(g):
     return f
 
 
-@pytest.mark.parametrize("shape", [(8, 16), (33, 128), (70, 300), (301, 517), (64, 1040), (97, 2049)])
+@pytest.mark.parametrize("shape", [(8, 16), (33, 128), (70, 300), (301, 517), (64, 1040), (97, 2049), (310, 2064), (2006, 8208)])
 @pytest.mark.parametrize("kind", ["binary", "gray"])
 def test_pack_flags_streaming_kernel(E, shape, kind):
     """vsb_pack_flags / vsb_pack_flags_lut (threshold 127, aligned rows -> the persistent TMA kernel): mask bits, tile
@@ -568,22 +606,30 @@ def test_fused_layer_kernel_vs_oracle(E, chain, mode, F, metric, size):
     if size != (500, 301) and chain in ("bil9", "none") and mode != "fixed_fade":
         pytest.skip("covered at the first size")
     layers = small_stack(W=W, H=H, L=L, seed=13, raft=True, n_blobs=9)
-    gray_aa = [l.copy() for l in layers]
-    rng = np.random.default_rng(3)
-    for g in gray_aa:                                      # a few anti-aliased pixels: gray is not strictly binary
-        ys, xs = rng.integers(0, H, 200), rng.integers(0, W, 200)
-        g[ys, xs] = rng.integers(0, 256, 200)
     base = {"blending_mode": mode, "receding_layers": 3, "use_fixed_fade_receding": True,
             "fixed_fade_distance_receding": F, "manual_weights": [5, 3, 1], "fade_distances_receding": [14.0, 9.0, 5.0],
             "xy_blend_pipeline": FUSED_CHAINS[chain]}
     cfg = Config.from_dict(dict(base, distance_metric=metric))
-    want = O.run_stack(gray_aa, dict(base, metric=metric))
-    eng = engine_for_metric(E, cfg, W, H, metric)
-    got = [eng.process(g) for g in gray_aa]
-    eng.close()
-    for zi, (a, b) in enumerate(zip(got, want)):
-        d = np.abs(a.astype(int) - b.astype(int))
-        assert d.max() == 0, (chain, mode, zi, int((d > 0).sum()), int(d.max()), np.argwhere(d > 0)[:5].tolist())
+    # gray input three ways: strictly binary (every tile takes the mask-only kernel k_layer2), anti-aliased pixels in one
+    # corner (binary and general tiles side by side, halos crossing between them), anti-aliased pixels everywhere
+    for aa in (("none", "corner", "spread") if size == (500, 301) else ("corner",)):
+        gray_aa = [l.copy() for l in layers]
+        rng = np.random.default_rng(3)
+        for g in gray_aa:
+            if aa == "spread":
+                ys, xs = rng.integers(0, H, 200), rng.integers(0, W, 200)
+            elif aa == "corner":
+                ys, xs = rng.integers(H // 2, H, 80), rng.integers(0, W // 3, 80)
+            else:
+                continue
+            g[ys, xs] = rng.integers(0, 256, len(ys))
+        want = O.run_stack(gray_aa, dict(base, metric=metric))
+        eng = engine_for_metric(E, cfg, W, H, metric)
+        got = [eng.process(g) for g in gray_aa]
+        eng.close()
+        for zi, (a, b) in enumerate(zip(got, want)):
+            d = np.abs(a.astype(int) - b.astype(int))
+            assert d.max() == 0, (aa, chain, mode, zi, int((d > 0).sum()), int(d.max()), np.argwhere(d > 0)[:5].tolist())
 
 
 def engine_for_metric(E, cfg, W, H, metric):

@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libvsb_b200.so")
 OBJ = os.path.join(HERE, "build")
-SOURCES = ["vsb_api.cu", "vsb_mask.cu", "vsb_zblend.cu", "vsb_dt.cu", "vsb_ccl.cu", "vsb_xy.cu", "vsb_layer.cu", "vsb_pack_tma.cu", "vsb_unbounded.cu", "vsb_geom.cu", "vsb_roi.cu", "vsb_synth.cu",
+SOURCES = ["vsb_api.cu", "vsb_mask.cu", "vsb_zblend.cu", "vsb_dt.cu", "vsb_edt.cu", "vsb_ccl.cu", "vsb_xy.cu", "vsb_layer.cu", "vsb_pack_tma.cu", "vsb_unbounded.cu", "vsb_geom.cu", "vsb_roi.cu", "vsb_synth.cu",
            "vsb_stack.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 # -fmad=false: the float32 fade arithmetic must round after every operation exactly like NumPy does

@@ -6,7 +6,7 @@
 //     row probe is hoisted: h[row][col] = nearest set bit of the staged row (one probe per staged row
 //     and column, shared by the 32 tile rows), then D(p) = min_k N(k, h[row+-k][col]).
 //     replaces cv2.distanceTransform(~cur, DIST_L2, 5)      processing_core.py:129,250,379
-//   vsb_dt_exact: unbounded exact EDT, separable (column scan, then row pass pruned by k^2 < best).
+//   (the unbounded exact transform is csrc/vsb_edt.cu)
 #include "vsb_tile.cuh"
 
 template <int METRIC>
@@ -91,71 +91,4 @@ extern "C" int vsb_dt_exact_windowed(const uint32_t *seed_bits, int wpr, int W, 
                                      float *dist, size_t dist_pitch_elems, vsb_stream_t stream)
 {
     return launch_dense(VSB_METRIC_EXACT, seed_bits, wpr, W, H, R, nullptr, clip, dist, dist_pitch_elems, stream);
-}
-
-// ---- unbounded exact EDT ---------------------------------------------------------------------------
-#define COL_NONE 0xFFFFu
-
-// thread per column; rows are walked in order so each warp writes 64 contiguous bytes per step
-__global__ void __launch_bounds__(128) k_edt_columns(const uint32_t *__restrict__ bits, int wpr, int W, int H,
-                                                     uint16_t *__restrict__ col, size_t pitch)
-{
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    if (x >= W) return;
-    const int wi = x >> 5, b = x & 31;
-    uint32_t run = COL_NONE;
-    for (int y = 0; y < H; ++y) {
-        const uint32_t bit = (bits[(size_t)y * wpr + wi] >> b) & 1u;
-        run = bit ? 0u : (run == COL_NONE ? COL_NONE : min(run + 1u, 0xFFFEu));
-        col[(size_t)y * pitch + x] = (uint16_t)run;
-    }
-    run = COL_NONE;
-    for (int y = H - 1; y >= 0; --y) {
-        const uint32_t bit = (bits[(size_t)y * wpr + wi] >> b) & 1u;
-        run = bit ? 0u : (run == COL_NONE ? COL_NONE : min(run + 1u, 0xFFFEu));
-        const uint32_t prev = col[(size_t)y * pitch + x];
-        if (run < prev) col[(size_t)y * pitch + x] = (uint16_t)run;
-    }
-}
-
-// D2(x,y) = min_k (x-k)^2 + col[y][k]^2, scanned outwards from x while k^2 < best
-__global__ void __launch_bounds__(256) k_edt_rows(const uint16_t *__restrict__ col, size_t pitch, int W, int H,
-                                                  int32_t *__restrict__ d2_out, float *__restrict__ dist_out)
-{
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y;
-    if (x >= W) return;
-    const uint16_t *row = col + (size_t)y * pitch;
-    long long best = 0x7fffffffLL;
-    uint32_t g = row[x];
-    if (g != COL_NONE) best = (long long)g * g;
-    const int kmax = max(x, W - 1 - x);
-    for (int k = 1; k <= kmax && (long long)k * k < best; ++k) {
-        if (x - k >= 0) {
-            g = row[x - k];
-            if (g != COL_NONE) best = min(best, (long long)k * k + (long long)g * g);
-        }
-        if (x + k < W) {
-            g = row[x + k];
-            if (g != COL_NONE) best = min(best, (long long)k * k + (long long)g * g);
-        }
-    }
-    const int32_t v = best >= 0x7fffffffLL ? 0x7fffffff : (int32_t)best;
-    if (d2_out) d2_out[(size_t)y * pitch + x] = v;
-    if (dist_out) dist_out[(size_t)y * pitch + x] = v == 0x7fffffff ? 3.0e38f : __fsqrt_rn((float)v);
-}
-
-extern "C" int vsb_dt_exact(const uint32_t *seed_bits, int wpr, int W, int H, uint16_t *colnear, int32_t *d2_out,
-                            float *dist_out, size_t pitch_elems, vsb_stream_t stream)
-{
-    VSB_REQUIRE(seed_bits && colnear && (d2_out || dist_out), "vsb_dt_exact: null pointer");
-    VSB_REQUIRE(W > 0 && H > 0 && H < 65534 && wpr >= (W + 31) / 32 && pitch_elems >= (size_t)W,
-                "vsb_dt_exact: bad geometry");
-    cudaStream_t s = (cudaStream_t)stream;
-    k_edt_columns<<<(W + 127) / 128, 128, 0, s>>>(seed_bits, wpr, W, H, colnear, pitch_elems);
-    int rc = vsb_check_launch("k_edt_columns");
-    if (rc) return rc;
-    dim3 grid((W + 255) / 256, H);
-    k_edt_rows<<<grid, 256, 0, s>>>(colnear, pitch_elems, W, H, d2_out, dist_out);
-    return vsb_check_launch("k_edt_rows");
 }

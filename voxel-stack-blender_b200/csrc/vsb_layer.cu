@@ -67,9 +67,12 @@ struct LayerParams {
     alignas(16) int tap_off[96];     // bilateral taps as byte offsets in the staged region, and their space weights: read through
     alignas(16) float tap_sw[96];    // the constant bank with a warp-uniform index, so they cost no vector instruction
     unsigned long long *stats; // optional work counters (vsb_layer_stats)
-    struct { int T, s1, s2, bits, list; } sm; // dynamic shared memory carve (bytes / words)
+    struct { int T, s1, s2, bits, list, glist; } sm; // dynamic shared memory carve (bytes / words)
     int ntiles;
     const int *rec_list; // sparse: [0] = number of tiles with receding pixels, [1..] their indices (nullptr = all tiles)
+    int gen_grid;        // CTAs of the list-mode launch
+    int *gen_list;       // XY: k_layer2 appends the tiles it leaves to the general kernel; k_layer then walks that list
+    int two_valued;      // k_layer2: a window holding only LUT1[0] / LUT1[255] with >= 3 taps equal to the centre keeps the centre
     // VSB_Z_ENHANCED: distances at the receding pixels, their component roots and the per-root maxima (vsb_ccl8_max)
     const float *enh_dist; size_t enh_dpitch; const int32_t *enh_labels; const uint32_t *enh_cmax;
     int sparse;          // no-XY variant only: `out` already holds LUT1[gray]; rewrite just the receding pixels
@@ -186,9 +189,10 @@ static int pack_flags_launch(const uint8_t *gray, size_t pitch, int W, int H, in
         for (int i = 0; i < n_priors; ++i) pr.p[i] = prior_bits[i];
         VSB_CUDA(cudaMemsetAsync(rec_list, 0, sizeof(int), s));
     }
-    // the streaming kernel (TMA-fed, one warp per tile): threshold 127, 16-byte aligned rows
+    // the streaming kernel (TMA-fed, one warp per tile): threshold 127, 16-byte aligned rows, width a multiple of 16
+    // (the TMA unit bounds-checks the innermost dimension in 16-byte units)
     static const bool no_tma = getenv("VSB_NO_TMA") != nullptr;
-    if (!no_tma && thresh == 127 && al && (!lutout || oal))
+    if (!no_tma && thresh == 127 && al && (W & 15) == 0 && (!lutout || oal))
         return vsb_pack_tma_launch(gray, pitch, W, H, bits, wpr, flags, lutout, lut, out, opitch, prior_bits, prior_flags, n_priors,
                                    rec_list, s);
     if (lutout) {
@@ -307,13 +311,20 @@ __global__ void __launch_bounds__(VSB_THREADS, XY ? VSB_LAYER_CTAS_XY : 6) k_lay
     bool late_staged = false; // trailing LUT and bilateral tables: staged by the first tile that is not trivially uniform
     bool t_staged = false; // chamfer table [(R+1) x (R+1)]: staged by the first tile that needs it
 
-    int tile = (int)(blockIdx.y * gridDim.x + blockIdx.x);
-    int wl_tx = (int)blockIdx.x, wl_ty = (int)blockIdx.y;
-    if (!XY && p.rec_list) { // work list of the patch launch: CTA i takes the i-th listed tile
-        tile = p.rec_list[1 + tile];
-        wl_tx = tile % p.tiles_x; wl_ty = tile / p.tiles_x;
-    }
-    {
+    // gen_list (XY launches that follow k_layer2): a 1-D grid of CTAs strides over the listed tiles -- the tiles whose
+    // region is not strictly binary; the list is empty for the input the reference asks for
+    const int *glist = XY ? p.gen_list : nullptr;
+    const int n_listed = glist ? glist[0] : 1;
+    for (int li = glist ? (int)blockIdx.x : 0; li < n_listed; li += glist ? (int)gridDim.x : 1) {
+        int tile = (int)(blockIdx.y * gridDim.x + blockIdx.x);
+        int wl_tx = (int)blockIdx.x, wl_ty = (int)blockIdx.y;
+        if (glist) {
+            tile = glist[1 + li];
+            wl_tx = tile % p.tiles_x; wl_ty = tile / p.tiles_x;
+        } else if (!XY && p.rec_list) { // work list of the patch launch: CTA i takes the i-th listed tile
+            tile = p.rec_list[1 + tile];
+            wl_tx = tile % p.tiles_x; wl_ty = tile / p.tiles_x;
+        }
         const int tx = wl_tx, ty = wl_ty; // 2-D grid: no division
         const int x0 = tx * VSB_TW, y0 = ty * VSB_TH;
         const int oy = y0 + r, ox = x0 + c * 16;
@@ -707,8 +718,11 @@ __global__ void __launch_bounds__(VSB_THREADS, XY ? VSB_LAYER_CTAS_XY : 6) k_lay
             else vsb_st_bytes(dst, o, nvalid);
         }
         } while (0);
+        if (glist) __syncthreads(); // shared buffers are reused by the next listed tile
     }
 }
+
+#include "vsb_layer2.cuh"
 
 template <int ZMODE, int METRIC, bool XY>
 static int launch_layer_v(LayerParams &p, const BilTapsL *taps, size_t smem, cudaStream_t s)
@@ -719,8 +733,31 @@ static int launch_layer_v(LayerParams &p, const BilTapsL *taps, size_t smem, cud
         configured = true;
     }
     dim3 grid(p.tiles_x, p.tiles_y);
+    if (XY && p.gen_list) grid = dim3(p.gen_grid, 1);
     k_layer<ZMODE, METRIC, XY><<<grid, VSB_THREADS, smem, s>>>(p, taps);
     return vsb_check_launch("k_layer");
+}
+
+// binary fast path: k_layer2 over all tiles (it lists the tiles it does not take), then k_layer over that list
+template <int ZMODE, int METRIC>
+static int launch_layer2(LayerParams &p, const BilTapsL *taps, size_t smem2, size_t smem, int *gen_list, cudaStream_t s)
+{
+    static int n_sms = 0; // per instantiation
+    if (n_sms == 0) {
+        VSB_CUDA(cudaFuncSetAttribute(k_layer2<ZMODE, METRIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        int dev = 0, sms = 0;
+        VSB_CUDA(cudaGetDevice(&dev));
+        VSB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        n_sms = sms > 0 ? sms : 148;
+    }
+    VSB_CUDA(cudaMemsetAsync(gen_list, 0, sizeof(int), s));
+    p.gen_list = gen_list;
+    dim3 grid(p.tiles_x, p.tiles_y);
+    k_layer2<ZMODE, METRIC><<<grid, VSB_THREADS, smem2, s>>>(p, taps);
+    int rc = vsb_check_launch("k_layer2");
+    if (rc) return rc;
+    p.gen_grid = p.ntiles < 2 * n_sms ? p.ntiles : 2 * n_sms;
+    return launch_layer_v<ZMODE, METRIC, true>(p, taps, smem, s);
 }
 
 template <int ZMODE, int METRIC>
@@ -731,6 +768,7 @@ static int launch_layer(LayerParams &p, const BilTapsL *taps, size_t smem, cudaS
 }
 
 // Device copies of bilateral tap tables, keyed by content (a handful of distinct filters per process).
+#include <algorithm>
 #include <mutex>
 #include <vector>
 struct TapCacheEntry { unsigned long long hash; int dev; BilTapsL *d; };
@@ -776,7 +814,7 @@ static int layer_launch(const uint8_t *in, size_t in_pitch, int W, int H, const 
                         const uint16_t *const *prior_flags, int wpr, const vsb_zparams *zp, const float *T_dev,
                         const uint8_t *lut1_dev, const vsb_xy_fused *xy, const uint8_t *lut2_dev, uint8_t *out,
                         size_t out_pitch, vsb_stream_t stream, int sparse, const int *rec_list = nullptr,
-                        const EnhInputs *enh = nullptr)
+                        const EnhInputs *enh = nullptr, int *general_tiles = nullptr)
 {
     VSB_REQUIRE(in && out && zp && in != out, "vsb_layer_fused: null pointer / in-place");
     VSB_REQUIRE(W >= 8 && H >= 8 && in_pitch >= (size_t)W && out_pitch >= (size_t)W,
@@ -807,7 +845,6 @@ static int layer_launch(const uint8_t *in, size_t in_pitch, int W, int H, const 
     for (int i = 0; i < p.z.n_priors; ++i) {
         p.prior[i] = prior_bits[i];
         p.prior_flags[i] = prior_flags ? prior_flags[i] : nullptr;
-        if (cur_flags && !p.prior_flags[i]) p.cur_flags = nullptr; // no shortcut without all flags
     }
     p.T = T_dev; p.lut1 = lut1_dev; p.lut2 = lut2_dev;
     p.tiles_x = (W + VSB_TW - 1) / VSB_TW; p.tiles_y = (H + VSB_TH - 1) / VSB_TH;
@@ -855,6 +892,30 @@ static int layer_launch(const uint8_t *in, size_t in_pitch, int W, int H, const 
     const size_t smem = off;
     cudaStream_t s = (cudaStream_t)stream;
     const bool ex = zp->metric == VSB_METRIC_EXACT;
+    // strictly binary regions (certified per tile by the pack pass) take k_layer2, which works from the masks alone
+    static const bool no_layer2 = getenv("VSB_NO_LAYER2") != nullptr;
+    const bool has_xy = p.hb > 0 || p.nkx > 0;
+    if (!no_layer2 && has_xy && !sparse && general_tiles && cur_flags && cur_bits &&
+        (mode == VSB_Z_FIXED || mode == VSB_Z_WEIGHTED || mode == VSB_Z_CONST || mode == VSB_Z_ENHANCED)) {
+        p.two_valued = (xy && p.hb >= 1 && xy->two_valued_min_same >= 1 && xy->two_valued_min_same <= 3) ? 1 : 0;
+        LayerParams p2 = p; // same carve for T / s1 / s2 / bits, then the three lists
+        size_t o2 = 0;
+        p2.sm.T = (int)o2; o2 += up16((searching && zp->metric == VSB_METRIC_CHAMFER5) ? (size_t)n1 * n1 * 4 : 16);
+        p2.sm.s1 = (int)o2; o2 += up16((size_t)RH * RG_W);
+        p2.sm.s2 = (int)o2; o2 += up16((size_t)RH * RG_W);
+        p2.sm.bits = (int)o2; o2 += searching ? up16((size_t)(RH + 2 * p.z.reach) * LBW * 4) : 16;
+        p2.sm.list = (int)o2; p2.sm.glist = 4480; // 34 x 130 bilateral pixels at most, 1024 Gaussian words, 46 x 142 receding pixels
+        o2 += (size_t)(4480 + 1024 + 6656) * 2;
+        const size_t smem2 = o2;
+        int rc2;
+        switch (mode) {
+        case VSB_Z_FIXED: rc2 = ex ? launch_layer2<VSB_Z_FIXED, 1>(p2, taps_dev, smem2, smem, general_tiles, s) : launch_layer2<VSB_Z_FIXED, 0>(p2, taps_dev, smem2, smem, general_tiles, s); break;
+        case VSB_Z_WEIGHTED: rc2 = ex ? launch_layer2<VSB_Z_WEIGHTED, 1>(p2, taps_dev, smem2, smem, general_tiles, s) : launch_layer2<VSB_Z_WEIGHTED, 0>(p2, taps_dev, smem2, smem, general_tiles, s); break;
+        case VSB_Z_CONST: rc2 = launch_layer2<VSB_Z_CONST, 0>(p2, taps_dev, smem2, smem, general_tiles, s); break;
+        default: rc2 = launch_layer2<VSB_Z_ENHANCED, 0>(p2, taps_dev, smem2, smem, general_tiles, s); break;
+        }
+        return rc2;
+    }
     switch (mode) {
     case VSB_Z_FIXED: return ex ? launch_layer<VSB_Z_FIXED, 1>(p, taps_dev, smem, s) : launch_layer<VSB_Z_FIXED, 0>(p, taps_dev, smem, s);
     case VSB_Z_WEIGHTED: return ex ? launch_layer<VSB_Z_WEIGHTED, 1>(p, taps_dev, smem, s) : launch_layer<VSB_Z_WEIGHTED, 0>(p, taps_dev, smem, s);
@@ -864,14 +925,31 @@ static int layer_launch(const uint8_t *in, size_t in_pitch, int W, int H, const 
     }
 }
 
+extern "C" int vsb_bilateral_two_valued_min_same(const float *tap_sw, int ntaps, const float *cw256, int v0, int v1)
+{
+    if (!tap_sw || !cw256 || ntaps < 1 || ntaps > 1024 || v0 < 0 || v0 > 255 || v1 < 0 || v1 > 255) return 0;
+    if (v0 == v1) return 1;
+    std::vector<double> sw(tap_sw, tap_sw + ntaps);
+    std::sort(sw.begin(), sw.end());
+    const double d = (double)abs(v1 - v0), k = (double)cw256[abs(v1 - v0)], k0 = (double)cw256[0];
+    for (int m = 1; m <= ntaps; ++m) {
+        // worst case: the m taps that equal the centre carry the smallest space weights, the others the largest
+        double ws = 0.0, wo = 0.0;
+        for (int i = 0; i < m; ++i) ws += sw[i] * k0;
+        for (int i = m; i < ntaps; ++i) wo += sw[i] * k;
+        if (ws > 0.0 && d * wo / (ws + wo) < 0.49) return m;
+    }
+    return 0;
+}
+
 extern "C" int vsb_layer_fused(const uint8_t *in, size_t in_pitch, int W, int H, const uint32_t *cur_bits,
                                const uint32_t *const *prior_bits, const uint16_t *cur_flags,
                                const uint16_t *const *prior_flags, int wpr, const vsb_zparams *zp, const float *T_dev,
                                const uint8_t *lut1_dev, const vsb_xy_fused *xy, const uint8_t *lut2_dev, uint8_t *out,
-                               size_t out_pitch, vsb_stream_t stream)
+                               size_t out_pitch, int *general_tiles, vsb_stream_t stream)
 {
     return layer_launch(in, in_pitch, W, H, cur_bits, prior_bits, cur_flags, prior_flags, wpr, zp, T_dev, lut1_dev, xy, lut2_dev,
-                        out, out_pitch, stream, 0);
+                        out, out_pitch, stream, 0, nullptr, nullptr, general_tiles);
 }
 
 extern "C" int vsb_layer_patch(const uint8_t *in, size_t in_pitch, int W, int H, const uint32_t *cur_bits,
@@ -890,12 +968,12 @@ extern "C" int vsb_layer_fused_enhanced(const uint8_t *in, size_t in_pitch, int 
                                         const uint32_t *const *prior_bits, int wpr, const vsb_zparams *zp, const float *dist,
                                         size_t dist_pitch_elems, const int32_t *labels, const uint32_t *compmax,
                                         const uint8_t *lut1_dev, const vsb_xy_fused *xy, const uint8_t *lut2_dev, uint8_t *out,
-                                        size_t out_pitch, vsb_stream_t stream)
+                                        size_t out_pitch, const uint16_t *cur_flags, int *general_tiles, vsb_stream_t stream)
 {
     VSB_REQUIRE(zp, "vsb_layer_fused_enhanced: null parameters");
     vsb_zparams z = *zp;
     z.mode = VSB_Z_ENHANCED;
     const EnhInputs enh = {dist, dist_pitch_elems, labels, compmax};
-    return layer_launch(in, in_pitch, W, H, cur_bits, prior_bits, nullptr, nullptr, wpr, &z, nullptr, lut1_dev, xy, lut2_dev, out,
-                        out_pitch, stream, 0, nullptr, &enh);
+    return layer_launch(in, in_pitch, W, H, cur_bits, prior_bits, cur_flags, nullptr, wpr, &z, nullptr, lut1_dev, xy, lut2_dev, out,
+                        out_pitch, stream, 0, nullptr, &enh, general_tiles);
 }

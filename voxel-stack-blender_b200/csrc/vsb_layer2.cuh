@@ -1,0 +1,418 @@
+// vsb_layer2.cuh -- k_layer2: the fused per-layer kernel for STRICTLY BINARY regions (every input byte 0 or 255 -- what
+// the reference asks of its input, README.md:25,68-70, and what k_pack_flags certifies per tile with FLAG_BINARY).
+// Included by vsb_layer.cu; same arithmetic, bit for bit, as k_layer.
+//
+// In a binary region the stage-1 image (merge + leading LUT) is a function of the packed masks alone: LUT1[0] where the
+// current mask is black, LUT1[255] where it is white, LUT1[gradient] on the receding pixels.  So this kernel never reads
+// the gray layer.  Per 128x32 tile:
+//   1. tile flags of the 3x3 neighbourhood: a non-binary neighbour hands the tile to the general kernel (gen_list);
+//      nine equal uniform flags with nothing that can recede give the constant output at once;
+//   2. the region's mask words (tile + XY halo, 6 words per row: current, and OR(priors) & ~current);
+//   3. bit-plane morphology decides, per pixel, which filters can be skipped exactly:
+//        - bilateral: a window without a receding pixel holds only the two values LUT1[0] / LUT1[255]; with at least three
+//          taps equal to the centre (centre + two of its 4-neighbours, one LOP3 network) the host-checked bound says the
+//          rounded result IS the centre (two_valued); everything else goes on the pixel list;
+//        - Gaussian: words whose (bilateral + Gaussian)-radius window is one constant keep their value;
+//   4. bits -> bytes for both stage buffers (4 pixels per PRMT-free multiply/select), receding pixels: row search, fade,
+//      LUT1; then the listed bilateral pixels, the listed Gaussian words, trailing LUT, 128-bit stores.
+#pragma once
+
+#define L2W 6                        // mask words per region row: x0-32 .. x0+159
+#define L2_PLANES 7                  // and_b, or_b, rec_b, and_h, or_h, rec_h, safe
+
+// bits [lo, hi) of the 192-bit region span that fall into word k
+__device__ __forceinline__ uint32_t span_mask(int k, int lo, int hi)
+{
+    const int a = max(lo - 32 * k, 0), b = min(hi - 32 * k, 32);
+    if (a >= b) return 0u;
+    const uint32_t upto_b = b >= 32 ? 0xFFFFFFFFu : ((1u << b) - 1u);
+    return upto_b & ~((1u << a) - 1u);
+}
+
+// horizontal OR / AND of a bit row over |d| <= k (wl, w, wr = left neighbour word, the word, right neighbour word)
+template <bool IS_AND>
+__device__ __forceinline__ uint32_t hwin(uint32_t wl, uint32_t w, uint32_t wr, int k)
+{
+    uint32_t acc = w;
+    for (int d = 1; d <= k; ++d) {
+        const uint32_t a = __funnelshift_r(w, wr, d), b = __funnelshift_l(wl, w, d);
+        acc = IS_AND ? (acc & a & b) : (acc | a | b);
+    }
+    return acc;
+}
+
+// 4 mask bits -> 4 bytes, K1 where the bit is set, K0 elsewhere (K0 / K1 replicated over the word)
+__device__ __forceinline__ uint32_t expand4(uint32_t nib, uint32_t K0, uint32_t K1)
+{
+    const uint32_t m = ((nib * 0x00204081u) & 0x01010101u) * 0xFFu;
+    return (m & K1) | (~m & K0);
+}
+
+template <int ZMODE, int METRIC>
+__global__ void __launch_bounds__(VSB_THREADS, 3) k_layer2(const __grid_constant__ LayerParams p, const BilTapsL *__restrict__ taps)
+{
+    extern __shared__ __align__(16) uint8_t dsm[];
+    float *s_T = (float *)(dsm + p.sm.T);
+    uint8_t (*s1)[RG_W] = (uint8_t (*)[RG_W])(dsm + p.sm.s1);
+    uint8_t (*s2buf)[RG_W] = (uint8_t (*)[RG_W])(dsm + p.sm.s2);
+    uint32_t (*s_bits)[LBW] = (uint32_t (*)[LBW])(dsm + p.sm.bits);
+    uint16_t *s_list = (uint16_t *)(dsm + p.sm.list);   // bilateral pixel list; Gaussian word list behind it
+    uint16_t *s_glist = s_list + p.sm.glist;
+    uint16_t *s_rlist = s_glist + 1024;                  // receding pixel list
+    __shared__ uint32_t s_c[RG_ROWS_MAX][8], s_r[RG_ROWS_MAX][8];      // region words: current mask, receding mask
+    __shared__ uint32_t s_pl[L2_PLANES][RG_ROWS_MAX][8];
+    __shared__ uint32_t s_rowany[(LB_ROWS_MAX + 31) / 32];
+    __shared__ float s_cw2[512];
+    __shared__ __align__(4) uint8_t s_lut1[256];
+    __shared__ __align__(4) uint8_t s_lut2[256];
+    __shared__ int s_cnt, s_gcnt, s_rcnt, s_state, s_decision;
+
+    const int t = threadIdx.x, lane = t & 31;
+    const int W = p.W, H = p.H, wpr = p.wpr;
+    const int np = p.z.n_priors;
+    const int r = t >> 3, c = t & 7;
+    const int Hh = p.halo, hb = p.hb;
+    const int rx = p.nkx >> 1, ry = p.nky >> 1, hg = max(rx, ry);
+    const bool gauss = p.nkx > 0;
+    const int RH = VSB_TH + 2 * Hh;
+    const int R = p.z.reach;
+    const int tx = (int)blockIdx.x, ty = (int)blockIdx.y;
+    const int x0 = tx * VSB_TW, y0 = ty * VSB_TH;
+    const int oy = y0 + r, ox = x0 + c * 16;
+    const int nvalid = (oy < H) ? max(0, min(16, W - ox)) : 0;
+
+    // ---- 1. tile flags of the 3x3 neighbourhood --------------------------------------------------------------------------
+    if (t < 32) {
+        bool all_bin = true, same = true, pri_black = true;
+        uint32_t f0 = 0;
+        if (lane < 9) {
+            const int ny = min(max(ty + lane / 3 - 1, 0), p.tiles_y - 1), nx = min(max(tx + lane % 3 - 1, 0), p.tiles_x - 1);
+            const uint32_t f = p.cur_flags[ny * p.tiles_x + nx];
+            f0 = f;
+            all_bin = (f & FLAG_BINARY) != 0u;
+            for (int j = 0; j < np; ++j) {
+                const uint16_t *pf = p.prior_flags[j];
+                const uint32_t g = pf ? pf[ny * p.tiles_x + nx] : FLAG_MIXED;
+                pri_black = pri_black && !(g & FLAG_MIXED) && (g & 0xFFu) <= 127u;
+            }
+        }
+        const uint32_t fc = __shfl_sync(0xffffffffu, f0, 4); // the tile itself
+        if (lane < 9) same = (f0 == fc) && !(f0 & FLAG_MIXED);
+        all_bin = __all_sync(0xffffffffu, all_bin);
+        same = __all_sync(0xffffffffu, same);
+        pri_black = __all_sync(0xffffffffu, pri_black);
+        int dec = 0; // 0 = work, 1 = not binary -> general kernel, 2 = constant output
+        if (!all_bin) dec = 1;
+        else if (same && ((fc & 0xFFu) > 127u || pri_black || np == 0)) dec = 2 | (int)((fc & 0xFFu) << 8);
+        if (lane == 0) {
+            s_decision = dec;
+            s_cnt = 0; s_gcnt = 0; s_rcnt = 0; s_state = 0;
+            if (dec == 1) p.gen_list[1 + atomicAdd(&p.gen_list[0], 1)] = ty * p.tiles_x + tx;
+        }
+    }
+    if (t < 64 && p.lut1) ((uint32_t *)s_lut1)[t] = ((const uint32_t *)p.lut1)[t];
+    if (t >= 64 && t < 128 && p.lut2) ((uint32_t *)s_lut2)[t - 64] = ((const uint32_t *)p.lut2)[t - 64];
+    __syncthreads();
+    const int dec = s_decision;
+    if (dec == 1) return;
+    const uint32_t k0b = p.lut1 ? s_lut1[0] : 0u, k1b = p.lut1 ? s_lut1[255] : 255u;
+    const uint32_t K0 = k0b * 0x01010101u, K1 = k1b * 0x01010101u;
+    auto constant_out = [&](uint32_t s1val) {
+        if (nvalid > 0) {
+            const uint32_t cv = (p.lut2 ? (uint32_t)s_lut2[s1val] : s1val) * 0x01010101u;
+            uint8_t *dst = p.out + (size_t)oy * p.opitch + ox;
+            const uint4 o = make_uint4(cv, cv, cv, cv);
+            if (nvalid == 16 && p.aligned) vsb_st16_stream(dst, o);
+            else vsb_st_bytes(dst, o, nvalid);
+        }
+    };
+    if (dec & 2) { constant_out(((dec >> 8) & 0xFF) > 127 ? k1b : k0b); return; }
+
+    // ---- 2. region mask words --------------------------------------------------------------------------------------------
+    const int wx0 = (x0 >> 5) - 1;               // word column of region word 0
+    const int img_lo = 32 - x0, img_hi = W - x0 + 32; // image columns in span coordinates
+    const bool border = (x0 - Hh < 0) || (x0 + VSB_TW + Hh > W) || (y0 - Hh < 0) || (y0 + VSB_TH + Hh > H);
+    const bool searching = ZL_SEARCHES(ZMODE);
+    uint32_t code = 0;
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        const int i = t + u * VSB_THREADS;
+        if (i < RH * L2W) {
+            const int rr = i / L2W, k = i - rr * L2W;
+            int y = y0 - Hh + rr;
+            const bool row_in = y >= 0 && y < H;
+            if (!row_in) y = vsb_reflect101(y, H); // BORDER_REFLECT_101 rows: the mirrored row's bits
+            const int wx = wx0 + k;
+            uint32_t cw = 0, rw = 0;
+            if (wx >= 0 && wx < wpr) {
+                const size_t o = (size_t)y * wpr + wx;
+                cw = p.cur[o];
+                uint32_t acc = 0;
+                for (int j = 0; j < np; ++j) acc |= p.prior[j][o];
+                rw = acc & ~cw & span_mask(k, max(32 - Hh, img_lo), min(160 + Hh, img_hi));
+            }
+            s_c[rr][k] = cw;
+            s_r[rr][k] = rw;
+            const uint32_t rm = span_mask(k, max(32 - Hh, img_lo), min(160 + Hh, img_hi));
+            code |= (rw ? 1u : 0u) | ((cw & rm) ? 2u : 0u) | ((~cw & rm) ? 4u : 0u);
+        }
+    }
+    code = __reduce_or_sync(0xffffffffu, code);
+    if (lane == 0 && code) atomicOr(&s_state, (int)code);
+    if (searching && METRIC == VSB_METRIC_CHAMFER5) { // the chamfer table rides along with the first round trip
+        const int nT = (R + 1) * (R + 1);
+        const int nfull = ((((size_t)p.T) & 15) == 0) ? (nT >> 2) : 0;
+        for (int i = t; i < nfull; i += VSB_THREADS) ((float4 *)s_T)[i] = ((const float4 *)p.T)[i];
+        for (int i = 4 * nfull + t; i < nT; i += VSB_THREADS) s_T[i] = p.T[i];
+    }
+    if (hb > 0) {
+        const float cwt = taps->cw[t];
+        s_cw2[255 + t] = cwt; s_cw2[255 - t] = cwt;
+    }
+    __syncthreads();
+    const int state = s_state;
+    const bool any_rec = (state & 1) != 0;
+    if (!any_rec && (state & 6) != 6) { constant_out((state & 2) ? k1b : k0b); return; } // one value, nothing recedes
+
+    // out-of-image columns (left / right border tiles): mirrored bits, one thread per region row
+    if (border && t < RH && ((x0 - Hh < 0) || (x0 + VSB_TW + Hh > W))) {
+        auto getb = [&](const uint32_t *row, int sx) -> uint32_t { return (row[sx >> 5] >> (sx & 31)) & 1u; };
+        auto setb = [&](uint32_t *row, int sx, uint32_t v) { row[sx >> 5] = (row[sx >> 5] & ~(1u << (sx & 31))) | (v << (sx & 31)); };
+        for (int j = 1; j <= Hh; ++j) {
+            if (x0 - Hh < 0) { // x = -j  <-  x = +j
+                const int sd = img_lo - j, ss = img_lo + j;
+                if (sd >= 0 && ss < 192) { setb(s_c[t], sd, getb(s_c[t], ss)); setb(s_r[t], sd, getb(s_r[t], ss)); }
+            }
+            if (x0 + VSB_TW + Hh > W) { // x = W-1+j  <-  x = W-1-j
+                const int sd = img_hi - 1 + j, ss = img_hi - 1 - j;
+                if (sd < 192 && ss >= 0) { setb(s_c[t], sd, getb(s_c[t], ss)); setb(s_r[t], sd, getb(s_r[t], ss)); }
+            }
+        }
+    }
+    if (border) __syncthreads();
+
+    // ---- 3a. horizontal pass of the morphology + bits -> bytes + receding pixel list + search window -----------------------
+    if (any_rec && searching) stage_mask_rows<LBW>(s_bits, p.cur, wpr, H, (x0 >> 5) - 3, y0 - Hh - R, RH + 2 * R);
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        const int i = t + u * VSB_THREADS;
+        if (i < RH * L2W) {
+            const int rr = i / L2W, k = i - rr * L2W;
+            const uint32_t cl = k > 0 ? s_c[rr][k - 1] : 0u, cc = s_c[rr][k], cr = k < L2W - 1 ? s_c[rr][k + 1] : 0u;
+            const uint32_t rl = k > 0 ? s_r[rr][k - 1] : 0u, rc = s_r[rr][k], rq = k < L2W - 1 ? s_r[rr][k + 1] : 0u;
+            s_pl[0][rr][k] = hwin<true>(cl, cc, cr, hb);
+            s_pl[1][rr][k] = hwin<false>(cl, cc, cr, hb);
+            s_pl[2][rr][k] = hwin<false>(rl, rc, rq, hb);
+            s_pl[3][rr][k] = hwin<true>(cl, cc, cr, hb + rx);
+            s_pl[4][rr][k] = hwin<false>(cl, cc, cr, hb + rx);
+            s_pl[5][rr][k] = hwin<false>(rl, rc, rq, hb + rx);
+            uint32_t safe = 0u;
+            if (p.two_valued && rr > 0 && rr < RH - 1) { // centre + at least two of its 4-neighbours hold the same value
+                const uint32_t sl = ~(cc ^ __funnelshift_l(cl, cc, 1)), sr = ~(cc ^ __funnelshift_r(cc, cr, 1));
+                const uint32_t su = ~(cc ^ s_c[rr - 1][k]), sd = ~(cc ^ s_c[rr + 1][k]);
+                safe = (sl & sr) | (su & sd) | ((sl | sr) & (su | sd));
+            }
+            s_pl[6][rr][k] = safe;
+            if (rc) { // receding pixels of this word -> list
+                uint32_t rw = rc;
+                int base = atomicAdd(&s_rcnt, __popc(rw));
+                while (rw) {
+                    const int bq = __ffs(rw) - 1;
+                    rw &= rw - 1;
+                    s_rlist[base++] = (uint16_t)((rr << 8) | (32 * k + bq - 16));
+                }
+            }
+        }
+        if (i < RH * RG_CH) { // bytes of chunk (rr, cc): span bits 16*cc+16 .. +15
+            const int rr = i / RG_CH, cc = i - rr * RG_CH;
+            const uint32_t hw = (s_c[rr][(cc + 1) >> 1] >> (((cc + 1) & 1) * 16)) & 0xFFFFu;
+            const uint4 v = make_uint4(expand4(hw & 15u, K0, K1), expand4((hw >> 4) & 15u, K0, K1),
+                                       expand4((hw >> 8) & 15u, K0, K1), expand4(hw >> 12, K0, K1));
+            *(uint4 *)&s1[rr][cc * 16] = v;
+            *(uint4 *)&s2buf[rr][cc * 16] = v;
+        }
+    }
+    __syncthreads();
+
+    // ---- 3b. vertical pass: which pixels need the bilateral, which words the Gaussian ---------------------------------------
+    if (any_rec && searching) stage_rowany_rows<LBW>(s_rowany, s_bits, RH + 2 * R);
+    {
+        const int nb_lo = Hh - hg, nb_hi = Hh + VSB_TH + hg; // region rows on which stage 2 is needed
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int i = t + u * VSB_THREADS;
+            if (i < RH * L2W) {
+                const int rr = i / L2W, k = i - rr * L2W;
+                const int y = y0 - Hh + rr;
+                const bool row_in = y >= 0 && y < H;
+                if (hb > 0 && rr >= nb_lo && rr < nb_hi && row_in) {
+                    uint32_t A = 0xFFFFFFFFu, O = 0u, Rr = 0u;
+                    for (int d = -hb; d <= hb; ++d) { A &= s_pl[0][rr + d][k]; O |= s_pl[1][rr + d][k]; Rr |= s_pl[2][rr + d][k]; }
+                    uint32_t nb = Rr | ((O & ~A) & ~s_pl[6][rr][k]);
+                    nb &= span_mask(k, max(32 - hg, img_lo), min(160 + hg, img_hi));
+                    if (nb) {
+                        int base = atomicAdd(&s_cnt, __popc(nb));
+                        while (nb) {
+                            const int bq = __ffs(nb) - 1;
+                            nb &= nb - 1;
+                            s_list[base++] = (uint16_t)((rr << 8) | (32 * k + bq - 16));
+                        }
+                    }
+                }
+                if (gauss && rr >= Hh && rr < Hh + VSB_TH && row_in) {
+                    uint32_t A = 0xFFFFFFFFu, O = 0u, Rr = 0u;
+                    const int vr = hb + ry;
+                    for (int d = -vr; d <= vr; ++d) { A &= s_pl[3][rr + d][k]; O |= s_pl[4][rr + d][k]; Rr |= s_pl[5][rr + d][k]; }
+                    uint32_t ng = (Rr | (O & ~A)) & span_mask(k, max(32, img_lo), min(160, img_hi));
+                    ng = (ng | (ng >> 1) | (ng >> 2) | (ng >> 3)) & 0x11111111u; // one bit per 4-pixel word
+                    if (ng) {
+                        int base = atomicAdd(&s_gcnt, __popc(ng));
+                        while (ng) {
+                            const int bq = __ffs(ng) - 1;
+                            ng &= ng - 1;
+                            s_glist[base++] = (uint16_t)((rr << 8) | ((32 * k + bq - 16) >> 2));
+                        }
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- 4. receding pixels: distance, fade, leading LUT -> both stage buffers ------------------------------------------------
+    if (any_rec) {
+        const int total = s_rcnt;
+        const float Ff = p.z.fade;
+        for (int i = t; i < total; i += VSB_THREADS) {
+            const int codev = s_rlist[i];
+            const int rr = codev >> 8, rc = codev & 255;
+            const int x = x0 - 16 + rc, y = y0 - Hh + rr;
+            if (y < 0 || y >= H || x < 0 || x >= W) continue; // mirrored positions are filled in below
+            float best = 0.0f;
+            if (ZL_SEARCHES(ZMODE)) best = tile_search<METRIC, LBW, false>(s_bits, s_rowany, s_T, R, rr + R, rc + 80);
+            int g;
+            if (ZMODE == VSB_Z_FIXED) {
+                const float n = __fdiv_rn(fminf(best, Ff), p.z.den);
+                g = (int)__fmul_rn(255.0f, __fsub_rn(1.0f, n));
+            } else if (ZMODE == VSB_Z_WEIGHTED) {
+                float acc = 0.0f;
+                const size_t o = (size_t)y * wpr + (x >> 5);
+                const uint32_t ncur = ~p.cur[o];
+                for (int j = 0; j < np; ++j) {
+                    if (p.z.weights[j] > 0.0f && (((p.prior[j][o] & ncur) >> (x & 31)) & 1u)) {
+                        const float n = __fsub_rn(1.0f, __fdiv_rn(fminf(best, p.z.fades[j]), p.z.dens[j]));
+                        acc = __fadd_rn(acc, __fmul_rn(n, p.z.weights[j]));
+                    }
+                }
+                g = (int)__fmul_rn(255.0f, __fdiv_rn(acc, p.z.total_weight));
+            } else if (ZMODE == VSB_Z_ENHANCED) {
+                const float d = p.enh_dist[(size_t)y * p.enh_dpitch + x];
+                const float mx = __uint_as_float(p.enh_cmax[p.enh_labels[(size_t)y * W + x]]);
+                if (p.z.enhanced_arith == 0) {
+                    float den = (float)fmin((double)mx, p.z.fade_limit);
+                    if (den <= 0.0f) den = 1.0f;
+                    const float nrm = __fdiv_rn(fminf(fmaxf(d, 0.0f), den), den);
+                    g = (int)__fmul_rn(255.0f, __fsub_rn(1.0f, nrm));
+                } else {
+                    const double den = fmin((double)mx, p.z.fade_limit);
+                    g = 0;
+                    if (den > 0.0) g = (int)(long long)__dmul_rn(__dsub_rn(1.0, __ddiv_rn(fmin((double)d, den), den)), 255.0);
+                }
+            } else {
+                g = p.z.const_val;
+            }
+            const int m = g & 255; // merge with the raw gray value: a receding pixel is black, its gray value is 0
+            const uint8_t v = p.lut1 ? s_lut1[m] : (uint8_t)m;
+            s1[rr][rc] = v;
+            s2buf[rr][rc] = v;
+        }
+        __syncthreads();
+        // REFLECT_101 of the gradient values into the out-of-image halo (border tiles): mirror the stage-1 bytes
+        if (border) {
+            for (int i = t; i < total; i += VSB_THREADS) {
+                const int codev = s_rlist[i];
+                const int rr = codev >> 8, rc = codev & 255;
+                const int x = x0 - 16 + rc, y = y0 - Hh + rr;
+                if (y >= 0 && y < H && x >= 0 && x < W) continue;
+                const int ys = vsb_reflect101(y, H), xs = vsb_reflect101(x, W);
+                const uint8_t v = s1[ys - (y0 - Hh)][xs - (x0 - 16)];
+                s1[rr][rc] = v;
+                s2buf[rr][rc] = v;
+            }
+            __syncthreads();
+        }
+    }
+
+    uint8_t (*S2)[RG_W] = hb > 0 ? s2buf : s1;                  // Gaussian input
+    uint8_t (*OUT)[RG_W] = gauss ? (hb > 0 ? s1 : s2buf) : S2;  // what the store phase reads
+
+    // ---- 5. bilateral on the listed pixels ------------------------------------------------------------------------------------
+    if (hb > 0) {
+        const int total = s_cnt;
+        if (total > 0) {
+            const int ntaps = p.ntaps;
+            for (int i = t; i < total; i += VSB_THREADS) {
+                const int codev = s_list[i];
+                const int rr = codev >> 8, rc = codev & 255;
+                const uint8_t *ctr = &s1[rr][rc];
+                const int v0 = *ctr;
+                uint32_t cwa = (uint32_t)__cvta_generic_to_shared(s_cw2) + 4u * (uint32_t)(255 - v0);
+                asm volatile("" : "+r"(cwa)); // opaque: keeps the per-tap address at one IMAD
+                float sacc = 0.0f, ws = 0.0f;
+#pragma unroll 4
+                for (int k = 0; k < ntaps; ++k) {
+                    const int v = ctr[p.tap_off[k]];
+                    const float w = __fmul_rn(p.tap_sw[k], lds_f32(cwa + 4u * (uint32_t)v));
+                    sacc = __fmaf_rn((float)v, w, sacc);
+                    ws = __fadd_rn(ws, w);
+                }
+                const int o = __float2int_rn(__fdiv_rn(sacc, ws));
+                s2buf[rr][rc] = (uint8_t)min(max(o, 0), 255);
+            }
+        }
+        __syncthreads();
+        if (border && hg > 0) { // stage-2 values of the out-of-image halo: mirror
+            const int r_lo = Hh - hg, nr = VSB_TH + 2 * hg;
+            for (int i = t; i < nr * RG_W; i += VSB_THREADS) {
+                const int rr = r_lo + i / RG_W, rc = i % RG_W;
+                const int y = y0 - Hh + rr, x = x0 - 16 + rc;
+                if (x < -hg || x >= W + hg || y < -hg || y >= H + hg) continue;
+                if (y < 0 || y >= H || x < 0 || x >= W) {
+                    const int ys = vsb_reflect101(y, H), xs = vsb_reflect101(x, W);
+                    s2buf[rr][rc] = s2buf[ys - (y0 - Hh)][xs - (x0 - 16)];
+                }
+            }
+            __syncthreads();
+        }
+    }
+
+    // ---- 6. Gaussian on the listed words -----------------------------------------------------------------------------------------
+    if (gauss) {
+        const int gtotal = s_gcnt;
+        for (int i = t; i < gtotal; i += VSB_THREADS) {
+            const int codev = s_glist[i];
+            const int rr = codev >> 8, w = codev & 255;
+            uint32_t o;
+            switch (rx) {
+            case 0: o = gauss_word_ry<0>(S2, rr, w, p.kx, p.ky, ry); break;
+            case 1: o = gauss_word_ry<1>(S2, rr, w, p.kx, p.ky, ry); break;
+            case 2: o = gauss_word_ry<2>(S2, rr, w, p.kx, p.ky, ry); break;
+            default: o = gauss_word_ry<3>(S2, rr, w, p.kx, p.ky, ry); break;
+            }
+            *(uint32_t *)&OUT[rr][4 * w] = o;
+        }
+        __syncthreads();
+    }
+
+    // ---- 7. trailing LUT, store ------------------------------------------------------------------------------------------------------
+    if (nvalid > 0) {
+        VsbLut L2;
+        L2.s = p.lut2 ? s_lut2 : nullptr;
+        L2.l0 = (uint32_t)s_lut2[0] * 0x01010101u; L2.l255 = (uint32_t)s_lut2[255] * 0x01010101u;
+        uint4 o = *(const uint4 *)&OUT[r + Hh][16 + 16 * c];
+        o = L2.map16(o);
+        uint8_t *dst = p.out + (size_t)oy * p.opitch + ox;
+        if (nvalid == 16 && p.aligned) vsb_st16_stream(dst, o);
+        else vsb_st_bytes(dst, o, nvalid);
+    }
+}

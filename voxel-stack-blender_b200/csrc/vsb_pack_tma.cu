@@ -3,8 +3,8 @@
 // One WARP owns one 128x32 tile at a time and runs its own pipeline: lane 0 keeps PK_STAGES bulk tensor loads
 // (cp.async.bulk.tensor.2d, 4 KB boxes) in flight into the warp's private shared-memory ring and waits on the stage's
 // mbarrier; the 32 lanes then read the tile with conflict-free 128-bit shared loads (a quarter warp = one 128-byte row),
-// derive the mask words, the tile flag and -- for LUT-only pipelines -- lut[gray], which leaves through a bulk tensor
-// store from a double-buffered staging tile.  No block-level barrier anywhere: warps never wait for each other, the tile
+// derive the mask words, the tile flag and -- for LUT-only pipelines -- lut[gray], which is written back into the same
+// stage and leaves from there through a bulk tensor store.  No block-level barrier anywhere: warps never wait for each other, the tile
 // flag is a warp vote.  Out-of-image bytes arrive as zeros (TMA bounds handling) and out-of-image stores are dropped,
 // so ragged right / bottom tiles need no byte loops.
 //
@@ -77,6 +77,8 @@ __device__ __forceinline__ uint32_t msb_bytes(uint32_t w)
     return d;
 }
 
+#define PK_HELD 4 // prior masks whose words stay un-ORed in registers across one tile (the window of the usual N <= 4)
+
 template <bool LUTOUT>
 __global__ void __launch_bounds__(PK_WARPS * 32) k_pack_tma(const __grid_constant__ CUtensorMap tm_in,
                                                             const __grid_constant__ CUtensorMap tm_out,
@@ -87,9 +89,8 @@ __global__ void __launch_bounds__(PK_WARPS * 32) k_pack_tma(const __grid_constan
     __shared__ __align__(4) uint8_t s_lut[256];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int S = p.stages;
-    uint8_t *dsm = (uint8_t *)(((uintptr_t)dsm_raw + 127) & ~(uintptr_t)127);
-    uint8_t *in_ring = dsm + (size_t)warp * (S + (LUTOUT ? 2 : 0)) * PK_TILE_BYTES;
-    uint8_t *out_ring = in_ring + (size_t)S * PK_TILE_BYTES;
+    // 128-byte aligned ring, addressed by pointer arithmetic on the shared array (keeps the accesses LDS / STS)
+    uint8_t *ring = dsm_raw + ((128u - (vsb_smem_u32(dsm_raw) & 127u)) & 127u) + (size_t)warp * S * PK_TILE_BYTES;
     uint64_t *bar = s_bar[warp];
 
     if (LUTOUT && p.lut && threadIdx.x < 64) ((uint32_t *)s_lut)[threadIdx.x] = ((const uint32_t *)p.lut)[threadIdx.x];
@@ -103,13 +104,15 @@ __global__ void __launch_bounds__(PK_WARPS * 32) k_pack_tma(const __grid_constan
     const int count = gw < p.ntiles ? (p.ntiles - gw + nw - 1) / nw : 0;
     const uint32_t K0 = (LUTOUT && p.lut) ? (uint32_t)s_lut[0] * 0x01010101u : 0u;
     const uint32_t K1 = (LUTOUT && p.lut) ? (uint32_t)s_lut[255] * 0x01010101u : 0xFFFFFFFFu;
+    // LUTOUT: lut[gray] is written back into the stage it was read from and leaves from there with a bulk tensor store;
+    // the stage is refilled once that store has drained it, i.e. two tiles later -> S - 2 loads in flight per warp
 
     auto issue = [&](int k) { // lane 0: tile k of this warp -> stage k % S
         const int tile = gw + k * nw;
-        const int ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
+        const int ty = (int)((unsigned)tile / (unsigned)p.tiles_x), tx = tile - ty * p.tiles_x;
         const int st = k % S;
         vsb_mbar_expect_tx(&bar[st], PK_TILE_BYTES);
-        vsb_tma_load_2d(in_ring + (size_t)st * PK_TILE_BYTES, &tm_in, tx * VSB_TW, ty * VSB_TH, &bar[st]);
+        vsb_tma_load_2d(ring + (size_t)st * PK_TILE_BYTES, &tm_in, tx * VSB_TW, ty * VSB_TH, &bar[st]);
     };
     if (lane == 0)
         for (int k = 0; k < S && k < count; ++k) issue(k);
@@ -119,10 +122,14 @@ __global__ void __launch_bounds__(PK_WARPS * 32) k_pack_tma(const __grid_constan
     const int c = lane & 7, rb = lane >> 3, odd = lane & 1, wq = c >> 1;
     const bool want_rec = LUTOUT && p.rec_list != nullptr && p.np > 0;
 
-    // receding-tile detection needs OR(priors) at this lane's four words.  Those loads are requested one tile ahead,
-    // and whether a tile needs them at all (some prior is not uniformly black there) two tiles ahead, so neither
-    // latency is on the critical path.
-    uint32_t pacc_next[4] = {0, 0, 0, 0};
+    // receding-tile detection needs OR(priors) at this lane's four words.  Those loads are requested one tile ahead and
+    // stay un-combined in registers until they are used, and whether a tile needs them at all (some prior is not
+    // uniformly black there) is looked up two tiles ahead, so neither latency is on the critical path.
+    uint32_t held[PK_HELD][4];
+#pragma unroll
+    for (int j = 0; j < PK_HELD; ++j)
+#pragma unroll
+        for (int m = 0; m < 4; ++m) held[j][m] = 0u;
     uint32_t gate_flag_next = 0; // this lane's prior flag of the tile after next
     auto load_gate = [&](int k) -> uint32_t {
         if (!want_rec || !p.gate || k >= count || lane >= p.np) return 0u;
@@ -134,78 +141,97 @@ __global__ void __launch_bounds__(PK_WARPS * 32) k_pack_tma(const __grid_constan
         const bool mine = lane < p.np && ((f & FLAG_MIXED) || (f & 0xFFu) > 127u);
         return __any_sync(0xffffffffu, mine);
     };
-    auto load_priors = [&](int k, uint32_t (&acc)[4]) {
-        const int tile = gw + k * nw;
-        const int ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
+    auto load_priors = [&](int ty, int tx) {
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
             const int y = ty * VSB_TH + rb + 4 * (2 * m + odd);
-            uint32_t a = 0;
             if (y < p.H) {
                 const size_t o = (size_t)y * p.wpr + tx * 4 + wq;
-                for (int j = 0; j < p.np; ++j) a |= p.prior[j][o];
+#pragma unroll
+                for (int j = 0; j < PK_HELD; ++j)
+                    if (j < p.np) held[j][m] = p.prior[j][o];
+                for (int j = PK_HELD; j < p.np; ++j) held[0][m] |= p.prior[j][o]; // longer windows: combined right away
             }
-            acc[m] = a;
         }
     };
+    // tile coordinates advance by nw tiles per step: (dty, dtx) with a carry instead of a division
+    const int dty = nw / p.tiles_x, dtx = nw - dty * p.tiles_x;
+    int ty = gw / p.tiles_x, tx = gw - ty * p.tiles_x;
     if (want_rec && count > 0) {
-        if (needs_priors(load_gate(0))) load_priors(0, pacc_next);
+        if (needs_priors(load_gate(0))) load_priors(ty, tx);
         gate_flag_next = load_gate(1);
     }
 
     for (int k = 0; k < count; ++k) {
         const int tile = gw + k * nw;
-        const int ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
         const int x0 = tx * VSB_TW, y0 = ty * VSB_TH;
+        int ty1 = ty + dty, tx1 = tx + dtx; // the warp's next tile
+        if (tx1 >= p.tiles_x) { tx1 -= p.tiles_x; ++ty1; }
         const int st = k % S;
-        uint32_t pacc[4] = {pacc_next[0], pacc_next[1], pacc_next[2], pacc_next[3]};
-        if (want_rec) { // requests for the tiles ahead
-#pragma unroll
-            for (int m = 0; m < 4; ++m) pacc_next[m] = 0;
-            if (k + 1 < count && needs_priors(gate_flag_next)) load_priors(k + 1, pacc_next);
-            gate_flag_next = load_gate(k + 2);
+        if (LUTOUT && lane == 0 && k >= 2 && k - 2 + S < count) { // the store of tile k-2 has drained its stage: refill it
+            vsb_tma_wait_read<1>();
+            issue(k - 2 + S);
         }
         vsb_mbar_wait(&bar[st], (uint32_t)((k / S) & 1));
-        const uint8_t *src = in_ring + (size_t)st * PK_TILE_BYTES;
+        uint8_t *src = ring + (size_t)st * PK_TILE_BYTES;
         uint4 v[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = *(const uint4 *)(src + (rb + 4 * j) * VSB_TW + c * 16);
         const uint32_t first = src[0];
 
-        // ---- mask halves, uniformity, binarity, lut[gray] ----------------------------------------------------------------
+        // ---- mask halves, uniformity, binarity ------------------------------------------------------------------------
+        // (rows / 16-byte chunks outside the image arrive as zeros: they yield 0 bits, count as binary, and are left out of
+        // the uniformity test; W is a multiple of 16 on this path, so a chunk is either inside or outside)
         const uint32_t bc = first * 0x01010101u;
+        const bool col_in = x0 + c * 16 < p.W;
+        const int rows_in = p.H - y0;
         uint32_t diff = 0, nonbin = 0, half[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const uint32_t w[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
-            uint32_t m[4];
+            uint32_t m[4], dj = 0;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 m[i] = msb_bytes(w[i]);
-                diff |= w[i] ^ bc;
+                dj |= w[i] ^ bc;
                 nonbin |= w[i] ^ m[i];
             }
+            if (col_in && rb + 4 * j < rows_in) diff |= dj;
             // four mask bits per word: bytes 0x00/0xFF -> one bit each, summed into the top byte by a multiply
             const uint32_t u01 = ((m[0] & 0x08040201u) | (m[1] & 0x80402010u)) * 0x01010101u;
             const uint32_t u23 = ((m[2] & 0x08040201u) | (m[3] & 0x80402010u)) * 0x01010101u;
             half[j] = (u01 >> 24) | ((u23 >> 16) & 0xFF00u);
-            if (LUTOUT) {
-                uint32_t o[4];
+        }
+        const bool binary = __all_sync(0xffffffffu, nonbin == 0u);
+        if (!LUTOUT) {
+            // the stage has been consumed (every value above depends on the loads): refill it
+            __syncwarp();
+            if (lane == 0 && k + S < count) issue(k + S);
+        } else {
+            // ---- lut[gray], in place, then out through the tensor store ---------------------------------------------------
+            if (binary) { // every byte is 0 or 255: select between lut[0] and lut[255] by the sign mask, no look-ups
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    o[i] = (m[i] & K1) | (~m[i] & K0); // exact wherever the byte is 0 or 255
-                    if (w[i] != m[i]) {               // a gray byte in the word: real table look-ups
-                        o[i] = p.lut ? ((uint32_t)s_lut[w[i] & 255u] | ((uint32_t)s_lut[(w[i] >> 8) & 255u] << 8) |
-                                        ((uint32_t)s_lut[(w[i] >> 16) & 255u] << 16) | ((uint32_t)s_lut[w[i] >> 24] << 24))
-                                     : w[i];
-                    }
+                for (int j = 0; j < 8; ++j) {
+                    const uint32_t m0 = msb_bytes(v[j].x), m1 = msb_bytes(v[j].y), m2 = msb_bytes(v[j].z), m3 = msb_bytes(v[j].w);
+                    v[j] = make_uint4((m0 & K1) | (~m0 & K0), (m1 & K1) | (~m1 & K0), (m2 & K1) | (~m2 & K0), (m3 & K1) | (~m3 & K0));
                 }
-                v[j] = make_uint4(o[0], o[1], o[2], o[3]);
+            } else if (p.lut) { // gray bytes in the tile: real table look-ups
+                auto look = [&](uint32_t w) -> uint32_t {
+                    return (uint32_t)s_lut[w & 255u] | ((uint32_t)s_lut[(w >> 8) & 255u] << 8) |
+                           ((uint32_t)s_lut[(w >> 16) & 255u] << 16) | ((uint32_t)s_lut[w >> 24] << 24);
+                };
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = make_uint4(look(v[j].x), look(v[j].y), look(v[j].z), look(v[j].w));
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) *(uint4 *)(src + (rb + 4 * j) * VSB_TW + c * 16) = v[j];
+            vsb_fence_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                vsb_tma_store_2d(&tm_out, x0, y0, src);
+                vsb_tma_commit();
             }
         }
-        // the stage has been consumed (every value above depends on the loads): refill it
-        __syncwarp();
-        if (lane == 0 && k + S < count) issue(k + S);
 
         // ---- pair exchange -> four full mask words per lane -------------------------------------------------------------
         const uint32_t s0 = odd ? (half[0] | (half[2] << 16)) : (half[1] | (half[3] << 16));
@@ -228,46 +254,30 @@ __global__ void __launch_bounds__(PK_WARPS * 32) k_pack_tma(const __grid_constan
         for (int m = 0; m < 4; ++m) {
             const int y = y0 + rb + 4 * (2 * m + odd);
             if (y < p.H) p.bits[(size_t)y * p.wpr + tx * 4 + wq] = word[m];
-            rec = rec || (pacc[m] & ~word[m]) != 0u;
+            if (want_rec) { // first use of the words requested one tile ago
+                uint32_t pa = held[0][m];
+#pragma unroll
+                for (int j = 1; j < PK_HELD; ++j) pa |= held[j][m];
+                rec = rec || (pa & ~word[m]) != 0u;
+            }
         }
 
         // ---- tile flag: uniform value | MIXED, BINARY --------------------------------------------------------------------
-        bool uni;
-        if (x0 + VSB_TW <= p.W && y0 + VSB_TH <= p.H) {
-            uni = __all_sync(0xffffffffu, diff == 0u);
-        } else { // ragged tile: out-of-image bytes (zeros) do not count
-            bool ok = true;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int y = y0 + rb + 4 * j, nv = min(16, p.W - (x0 + c * 16));
-                if (y < p.H && nv > 0) {
-                    const uint8_t *q = src + (rb + 4 * j) * VSB_TW + c * 16;
-                    for (int i = 0; i < nv; ++i) ok = ok && q[i] == first;
-                }
-            }
-            uni = __all_sync(0xffffffffu, ok);
-        }
-        const bool binary = __all_sync(0xffffffffu, nonbin == 0u);
+        const bool uni = __all_sync(0xffffffffu, diff == 0u);
         const bool any_rec = want_rec && __any_sync(0xffffffffu, rec);
         if (lane == 0) {
             p.flags[tile] = (uint16_t)((uni ? first : FLAG_MIXED) | (binary ? FLAG_BINARY : 0));
             if (any_rec) p.rec_list[1 + atomicAdd(&p.rec_list[0], 1)] = tile;
         }
-
-        // ---- lut[gray] leaves through the staging tile -------------------------------------------------------------------
-        if (LUTOUT) {
-            uint8_t *dst = out_ring + (size_t)(k & 1) * PK_TILE_BYTES;
-            if (lane == 0) vsb_tma_wait_read<1>(); // the store issued two tiles ago has drained this buffer
-            __syncwarp();
+        if (want_rec) { // requests for the tiles ahead (consumed at the end of the next iteration)
 #pragma unroll
-            for (int j = 0; j < 8; ++j) *(uint4 *)(dst + (rb + 4 * j) * VSB_TW + c * 16) = v[j];
-            vsb_fence_async_smem();
-            __syncwarp();
-            if (lane == 0) {
-                vsb_tma_store_2d(&tm_out, x0, y0, dst);
-                vsb_tma_commit();
-            }
+            for (int j = 0; j < PK_HELD; ++j)
+#pragma unroll
+                for (int m = 0; m < 4; ++m) held[j][m] = 0u;
+            if (k + 1 < count && needs_priors(gate_flag_next)) load_priors(ty1, tx1);
+            gate_flag_next = load_gate(k + 2);
         }
+        ty = ty1; tx = tx1;
     }
     if (LUTOUT && lane == 0) vsb_tma_wait_all<0>();
 }
@@ -303,7 +313,7 @@ int vsb_pack_tma_launch(const uint8_t *gray, size_t pitch, int W, int H, uint32_
     p.wpr = wpr; p.tiles_x = (W + VSB_TW - 1) / VSB_TW;
     const int tiles_y = (H + VSB_TH - 1) / VSB_TH;
     p.ntiles = p.tiles_x * tiles_y; p.W = W; p.H = H;
-    p.stages = stages_env >= 2 && stages_env <= 8 ? stages_env : (lutout ? 4 : 6);
+    p.stages = stages_env >= 3 && stages_env <= 8 ? stages_env : (lutout ? 4 : 3);
     CUtensorMap tm_in, tm_out;
     int rc = vsb_make_tmap_2d(&tm_in, gray, 1, (size_t)W, (size_t)H, pitch, VSB_TW, VSB_TH);
     if (rc) return rc;
@@ -313,7 +323,7 @@ int vsb_pack_tma_launch(const uint8_t *gray, size_t pitch, int W, int H, uint32_
     } else {
         tm_out = tm_in;
     }
-    const size_t smem = (size_t)PK_WARPS * (p.stages + (lutout ? 2 : 0)) * PK_TILE_BYTES + 128;
+    const size_t smem = (size_t)PK_WARPS * p.stages * PK_TILE_BYTES + 128;
     int per_sm = ctas_env > 0 ? ctas_env : (int)((220 * 1024) / (smem + 1024));
     if (per_sm < 1) per_sm = 1;
     if (per_sm > 4) per_sm = 4;

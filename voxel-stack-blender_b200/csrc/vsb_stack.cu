@@ -65,6 +65,7 @@ struct vsb_stack {
     uint8_t *lut2_dev;
     std::vector<uint16_t *> flag_ring;
     int *rec_tiles[2];     // LUT-only chains: work list of the patch kernel (1 + tiles ints), per lane
+    int *gen_tiles[2];     // XY chains: tiles k_layer2 leaves to the general kernel (1 + tiles ints), per lane
     // environment switches, read once at creation
     bool env_no_patch, env_no_fused_enh, env_tile_flags, env_no_overlap;
     // optional per-stage CUDA-event profiling (bench.py roofline leg)
@@ -111,6 +112,7 @@ extern "C" int vsb_stack_destroy(vsb_stack *s)
     if (s->tmp_blur) cudaFree(s->tmp_blur);
     for (int i = 0; i < 2; ++i) {
         if (s->rec_tiles[i]) cudaFree(s->rec_tiles[i]);
+        if (s->gen_tiles[i]) cudaFree(s->gen_tiles[i]);
         if (s->or_scratch[i]) cudaFree(s->or_scratch[i]);
         if (s->ev_pack[i]) cudaEventDestroy(s->ev_pack[i]);
     }
@@ -180,7 +182,7 @@ extern "C" int vsb_stack_create(int W, int H, int n_priors, const vsb_zparams *z
     s->lead_lut_dev = nullptr; s->T_dev = nullptr;
     s->s_h2d = s->s_comp = s->s_d2h = s->s_aux = nullptr;
     s->ev_fork = s->ev_join = nullptr;
-    for (int i = 0; i < 2; ++i) { s->ev_pack[i] = nullptr; s->rec_tiles[i] = nullptr; s->or_scratch[i] = nullptr; }
+    for (int i = 0; i < 2; ++i) { s->ev_pack[i] = nullptr; s->rec_tiles[i] = nullptr; s->gen_tiles[i] = nullptr; s->or_scratch[i] = nullptr; }
     s->overlap_ok = false;
     s->env_no_patch = getenv("VSB_NO_PATCH") != nullptr;
     s->env_no_fused_enh = getenv("VSB_NO_FUSED_ENHANCED") != nullptr;
@@ -317,7 +319,14 @@ extern "C" int vsb_stack_create(int W, int H, int n_priors, const vsb_zparams *z
         const size_t ntiles = (size_t)((W + VSB_TW - 1) / VSB_TW) * ((H + VSB_TH - 1) / VSB_TH);
         s->flag_ring.assign((size_t)n_priors + 2, nullptr);
         for (auto &p : s->flag_ring) STACK_CUDA(cudaMalloc((void **)&p, ntiles * sizeof(uint16_t)));
-        for (int i = 0; i < 2; ++i) STACK_CUDA(cudaMalloc((void **)&s->rec_tiles[i], (ntiles + 1) * sizeof(int)));
+        for (int i = 0; i < 2; ++i) {
+            STACK_CUDA(cudaMalloc((void **)&s->rec_tiles[i], (ntiles + 1) * sizeof(int)));
+            STACK_CUDA(cudaMalloc((void **)&s->gen_tiles[i], (ntiles + 1) * sizeof(int)));
+        }
+        if (s->fx.has_bilateral) { // may a two-valued window be taken as the identity?  (values after the leading LUT)
+            const int v0 = have_lead ? lead[0] : 0, v1 = have_lead ? lead[255] : 255;
+            s->fx.two_valued_min_same = vsb_bilateral_two_valued_min_same(s->fx.tap_sw, s->fx.ntaps, s->fx.cw, v0, v1);
+        }
     }
     // two-lane overlap: only the paths whose per-layer scratch is per lane (the fused layer kernel and the LUT-only
     // patch path); Enhanced EDT / unbounded / unfused chains share scratch images and stay on one stream
@@ -465,7 +474,7 @@ static int run_layer(vsb_stack *s, const uint8_t *gray, size_t gpitch, uint8_t *
         const bool enhanced = zp.mode == VSB_Z_ENHANCED || zp.mode == VSB_Z_ENHANCED_FAR;
         if (s->fused && !enhanced && !far_mode) {
             const uint16_t *pfl[VSB_MAX_PRIORS];
-            const bool window_flags = s->env_tile_flags && s->n_priors <= VSB_MAX_PRIORS; // an OR-ed window has no tile flags
+            const bool window_flags = s->n_priors <= VSB_MAX_PRIORS; // an OR-ed window has no tile flags
             for (int i = 0; i < np; ++i) pfl[i] = window_flags ? s->flag_ring[(s->head - 1 - i + 2 * nring) % nring] : nullptr;
             if (patch_path) {
                 ProfScope ps(s, ST_LAYER, 1, cst);
@@ -473,8 +482,8 @@ static int run_layer(vsb_stack *s, const uint8_t *gray, size_t gpitch, uint8_t *
             } else {
                 ProfScope ps(s, ST_LAYER, 1, cst);
                 // the tile-flag shortcut saves the input read of quiet tiles; it only pays once the kernel is HBM bound
-                rc = vsb_layer_fused(gray, gpitch, s->W, s->H, cur, pri, window_flags ? s->flag_ring[s->head] : nullptr, pfl, s->wpr, &zp, s->T_dev,
-                                     s->lead_lut_dev, &s->fx, s->lut2_dev, out, opitch, st);
+                rc = vsb_layer_fused(gray, gpitch, s->W, s->H, cur, pri, s->flag_ring[s->head], pfl, s->wpr, &zp, s->T_dev,
+                                     s->lead_lut_dev, &s->fx, s->lut2_dev, out, opitch, s->gen_tiles[lane], st);
             }
             if (rc) return rc;
             s->head = (s->head + 1) % nring;
@@ -534,7 +543,8 @@ static int run_layer(vsb_stack *s, const uint8_t *gray, size_t gpitch, uint8_t *
                 // the fade itself runs inside the layer kernel, straight into the XY chain (no intermediate image)
                 ProfScope ps(s, ST_LAYER, 1, cst);
                 rc = vsb_layer_fused_enhanced(gray, gpitch, s->W, s->H, cur, pri, s->wpr, &zp, s->dist, (size_t)s->W, s->labels,
-                                              s->cmax, s->lead_lut_dev, &s->fx, s->lut2_dev, out, opitch, st);
+                                              s->cmax, s->lead_lut_dev, &s->fx, s->lut2_dev, out, opitch, s->flag_ring[s->head],
+                                              s->gen_tiles[lane], st);
                 if (rc) return rc;
                 s->head = (s->head + 1) % nring;
                 if (s->count < s->n_priors) ++s->count;
@@ -556,7 +566,7 @@ static int run_layer(vsb_stack *s, const uint8_t *gray, size_t gpitch, uint8_t *
             vsb_zparams zn = zp; zn.mode = VSB_Z_NONE; zn.n_priors = 0;
             ProfScope ps(s, ST_LAYER, 1, cst);
             rc = vsb_layer_fused(src, spitch, s->W, s->H, nullptr, nullptr, nullptr, nullptr, s->wpr, &zn, nullptr, nullptr,
-                                 &s->fx, s->lut2_dev, out, opitch, st);
+                                 &s->fx, s->lut2_dev, out, opitch, nullptr, st);
             if (rc) return rc;
             s->head = (s->head + 1) % nring;
             if (s->count < s->n_priors) ++s->count;

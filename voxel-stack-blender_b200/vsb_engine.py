@@ -304,16 +304,16 @@ def distance_np(cur_white: np.ndarray, R: int, clip: float, metric: str = "chamf
 
 
 def edt_exact_np(cur_white: np.ndarray):
-    """Unbounded exact EDT: (squared distances int32, distances float32)."""
+    """Unbounded exact EDT (lower-envelope algorithm, csrc/vsb_edt.cu): (squared distances int32, distances float32)."""
     t = torch()
     img = DevImage.from_numpy(cur_white)
     b = pack(img)
     H, W = img.H, img.W
-    col = t.empty((H, W), dtype=t.int16, device="cuda")
+    scratch = t.empty(int(N.load().vsb_edt_exact_scratch_bytes(W, H)), dtype=t.uint8, device="cuda")
     d2 = t.empty((H, W), dtype=t.int32, device="cuda")
     dist = t.empty((H, W), dtype=t.float32, device="cuda")
-    N.check(N.load().vsb_dt_exact(b.ptr, b.wpr, W, H, col.data_ptr(), d2.data_ptr(), dist.data_ptr(), W, _stream()),
-            "vsb_dt_exact")
+    N.check(N.load().vsb_edt_exact(b.ptr, b.wpr, W, H, scratch.data_ptr(), d2.data_ptr(), dist.data_ptr(), W, _stream()),
+            "vsb_edt_exact")
     return d2.cpu().numpy(), dist.cpu().numpy()
 
 

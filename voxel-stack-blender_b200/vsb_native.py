@@ -58,7 +58,7 @@ class RoiStat(ctypes.Structure):
 class XYFused(ctypes.Structure):
     _fields_ = [("has_bilateral", c_int), ("radius", c_int), ("ntaps", c_int), ("tap_dy", c_int8 * 96),
                 ("tap_dx", c_int8 * 96), ("tap_sw", c_float * 96), ("cw", c_float * 256), ("nkx", c_int), ("nky", c_int),
-                ("kx", c_int32 * 7), ("ky", c_int32 * 7)]
+                ("kx", c_int32 * 7), ("ky", c_int32 * 7), ("two_valued_min_same", c_int)]
 
 
 _SIGS = {
@@ -72,7 +72,8 @@ _SIGS = {
     "vsb_chamfer_table": (c_int, [c_void_p, c_int]),
     "vsb_dt_chamfer5": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_float, c_void_p, c_size_t, c_void_p]),
     "vsb_dt_exact_windowed": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_size_t, c_void_p]),
-    "vsb_dt_exact": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "vsb_edt_exact_scratch_bytes": (c_size_t, [c_int, c_int]),
+    "vsb_edt_exact": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "vsb_zblend_fused": (c_int, [c_void_p, c_size_t, c_int, c_int, c_void_p, POINTER(c_void_p), c_int,
                                  POINTER(ZParams), c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_size_t,
                                  c_void_p]),
@@ -109,10 +110,12 @@ _SIGS = {
                                 c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "vsb_layer_fused_enhanced": (c_int, [c_void_p, c_size_t, c_int, c_int, c_void_p, POINTER(c_void_p), c_int, POINTER(ZParams),
                                          c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
-                                         c_void_p]),
+                                         c_void_p, c_void_p, c_void_p]),
+    "vsb_bilateral_two_valued_min_same": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int]),
     "vsb_layer_stats": (c_int, [c_int, c_void_p]),
     "vsb_layer_fused": (c_int, [c_void_p, c_size_t, c_int, c_int, c_void_p, POINTER(c_void_p), c_void_p, POINTER(c_void_p),
-                                c_int, POINTER(ZParams), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+                                c_int, POINTER(ZParams), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p,
+                                c_void_p]),
     "vsb_stack_create": (c_int, [c_int, c_int, c_int, POINTER(ZParams), POINTER(XYOp), c_int, POINTER(c_void_p)]),
     "vsb_roi_components": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "vsb_roi_fade": (c_int, [c_void_p, c_size_t, c_int, c_int, c_void_p, POINTER(c_void_p), c_int, c_int, c_void_p, c_void_p,
