@@ -3,231 +3,250 @@
 //   replaces cv2.distanceTransform(src, DIST_L2, DIST_MASK_PRECISE)  (the `exact` metric; the reference's own call sites
 //   processing_core.py:129,250,379 use mask size 5 -- SURVEY.md finding 1)
 //
-// Separable lower-envelope algorithm (Felzenszwalb & Huttenlocher; the integer formulation of Meijster, Roerdink &
-// Hesselink), two launches:
+// Separable lower-envelope formulation (Felzenszwalb & Huttenlocher / Meijster et al.):
 //
-//   k_edt_rows : h(x,y) = distance from (x,y) to the nearest white pixel of ROW y (uint16, 0xFFFF = none).  One CTA per
-//                row: the row's packed mask arrives with one bulk copy (cp.async.bulk + mbarrier), a block-wide
-//                prefix-max / suffix-min over the words gives every word its nearest white column on either side, each
-//                lane then resolves one pixel with clz / ffs, and the finished row leaves with one bulk store.
-//   k_edt_cols : D2(x,y) = min_y' (y - y')^2 + h(x,y')^2 along every column.  A white pixel ends the influence of
-//                everything above it on everything below it, so columns split into independent runs of black pixels; a
-//                thread owns the runs that START in its 64-row band (lanes = 32 adjacent columns: the band's mask rows are
-//                transposed with warp ballots so that run starts fall out of two 32-bit words per lane, and the loads of
-//                lanes working on the same rows coalesce) and for each run does Meijster's two scans: downwards, the stack of
-//                parabolas on the lower envelope (integer `Sep`, the stack lives in a global scratch array indexed like
-//                the image -- entry q of a run sits q rows below the run's first candidate, which never collides with
-//                the run above or below); upwards, the evaluation.  Every candidate is pushed and popped at most once:
-//                O(run length), whatever the distances are.  White pixels get their zeros from the thread that scans
-//                over them.
+//     g(x,y)  = distance from (x,y) to the nearest white pixel of COLUMN x                       (column pass)
+//     D2(x,y) = min over x' of (x - x')^2 + g(x',y)^2   -- the lower envelope of W parabolas     (row pass)
 //
-// d2 is the exact integer squared distance (INT32_MAX where the image holds no white pixel in reach of the column's run,
-// i.e. nowhere), dist = sqrtf(d2) correctly rounded.  Limits: W, H <= 32767 (d2 and the envelope arithmetic stay in int32).
+// Both passes are laid out for the GPU instead of for a scan line:
+//
+//   column pass (k_edt_colsum, k_edt_colscan, k_edt_coldist).  The packed mask is cut into blocks of 32 rows; a warp takes a
+//   32 x 32 pixel square (one mask word column), transposes it with 32 ballots so that every lane holds ITS column as one
+//   32-bit word, and answers "nearest white pixel above / below inside the block" with clz / ffs.  A first launch records per
+//   (block, column) the first and last white row, a second one carries them down and up the (few) blocks, the third writes g
+//   as uint16 rows (EDT_GNONE where the column holds no white pixel at all).
+//
+//   row pass (k_edt_rowdc).  One CTA per image row, the row of g staged in shared memory with one bulk copy.  The stack of
+//   Meijster's scan is a chain of dependent steps as long as the row; here the envelope is evaluated by bisection instead:
+//   the column A(x) of the parabola that rules at x is non-decreasing in x (the cost (x-x')^2 + g(x')^2 is a Monge array), so
+//   once A is known at the multiples of 2S, every pixel x = S (2k+1) only has to look at the candidates A(x-S) .. A(x+S).
+//   Levels S = 2^k, ..., 2, 1 -- all pixels of a level are independent, the ranges of a level add up to about W, and a
+//   candidate further away than the best distance known so far is never looked at, so pixels close to white cost a few
+//   evaluations and nothing costs more than O(log W) per pixel whatever the distances are.  Short ranges are scanned by the
+//   pixel's own thread; long ones (the coarse levels, and pixels where A jumps) go to a work list in shared memory, cut
+//   into chunks that the warps scan cooperatively (redux.sync min + a 64-bit shared-memory atomicMin per chunk).
+//   The results leave the CTA in one coalesced pass (d2 and / or sqrtf).
+//
+// d2 is the exact integer squared distance (INT32_MAX where the image holds no white pixel), dist = sqrtf(d2) correctly
+// rounded (3e38 there).  Limits: W, H <= 32767 (all costs fit 32 bits: 46341^2 + 32766^2 < 2^32).
 #include "vsb_tma.cuh"
 
-#define EDT_NONE 0xFFFFu
-#define EDT_BAND 64
-#define EDT_INF_POS 0x3fffffff
+#define EDT_GNONE 46341u // g of a column without white pixels: its square exceeds INT32_MAX, every real candidate beats it
+#define EDT_BIG (1 << 20)
 
-// ---- row pass -------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_edt_rows(const uint32_t *__restrict__ bits, int wpr, int W, uint16_t *__restrict__ h,
-                                                  size_t hpitch)
+// ---- column pass ------------------------------------------------------------------------------------------------------
+// The warp's 32 x 32 square, transposed: bit r of the returned word = pixel (32 wc + lane, y0 + r).
+__device__ __forceinline__ uint32_t edt_column_word(const uint32_t *__restrict__ bits, int wpr, int H, int wc, int y0, int lane)
+{
+    const int y = y0 + lane;
+    const uint32_t roww = y < H ? bits[(size_t)y * wpr + wc] : 0u;
+    uint32_t col = 0;
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+        const uint32_t b = __ballot_sync(0xffffffffu, (roww >> c) & 1u);
+        if (c == lane) col = b;
+    }
+    return col;
+}
+
+// first / last white row of every (block of 32 rows, column): 0..31, 0xFF = none
+__global__ void __launch_bounds__(256) k_edt_colsum(const uint32_t *__restrict__ bits, int wpr, int H, uint8_t *__restrict__ first8,
+                                                    uint8_t *__restrict__ last8)
+{
+    const int lane = threadIdx.x & 31, wc = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (wc >= wpr) return;
+    const uint32_t col = edt_column_word(bits, wpr, H, wc, blockIdx.y * 32, lane);
+    const size_t o = (size_t)blockIdx.y * (32 * (size_t)wpr) + 32 * wc + lane;
+    first8[o] = col ? (uint8_t)(__ffs(col) - 1) : (uint8_t)0xFF;
+    last8[o] = col ? (uint8_t)(31 - __clz(col)) : (uint8_t)0xFF;
+}
+
+// blockIdx.y == 0: up[b][x] = last white row above block b; == 1: dn[b][x] = first white row below block b (0xFFFF = none)
+__global__ void __launch_bounds__(128) k_edt_colscan(const uint8_t *__restrict__ first8, const uint8_t *__restrict__ last8, int Wp, int nb,
+                                                     uint16_t *__restrict__ up, uint16_t *__restrict__ dn)
+{
+    const int x = blockIdx.x * 128 + threadIdx.x;
+    if (x >= Wp) return;
+    uint32_t run = 0xFFFFu;
+    if (blockIdx.y == 0) {
+#pragma unroll 8
+        for (int b = 0; b < nb; ++b) {
+            const uint32_t l = last8[(size_t)b * Wp + x];
+            up[(size_t)b * Wp + x] = (uint16_t)run;
+            if (l != 0xFFu) run = 32u * b + l;
+        }
+    } else {
+#pragma unroll 8
+        for (int b = nb - 1; b >= 0; --b) {
+            const uint32_t f = first8[(size_t)b * Wp + x];
+            dn[(size_t)b * Wp + x] = (uint16_t)run;
+            if (f != 0xFFu) run = 32u * b + f;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_edt_coldist(const uint32_t *__restrict__ bits, int wpr, int H, const uint16_t *__restrict__ up,
+                                                     const uint16_t *__restrict__ dn, uint16_t *__restrict__ g, size_t gpitch)
+{
+    const int lane = threadIdx.x & 31, wc = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (wc >= wpr) return;
+    const int y0 = blockIdx.y * 32;
+    const size_t o = (size_t)blockIdx.y * (32 * (size_t)wpr) + 32 * wc + lane;
+    const uint32_t u = up[o], d = dn[o];
+    const uint32_t col = edt_column_word(bits, wpr, H, wc, y0, lane);
+    const int up0 = u != 0xFFFFu ? y0 - (int)u : EDT_BIG;        // from row y0 to the nearest white row above the block
+    const int dn0 = d != 0xFFFFu ? (int)d - (y0 + 31) : EDT_BIG; // from row y0 + 31 to the nearest white row below it
+    if ((size_t)(32 * wc + lane) >= gpitch) return;
+    uint16_t *gp = g + (size_t)y0 * gpitch + 32 * wc + lane;
+    const int rows = min(32, H - y0);
+#pragma unroll 8
+    for (int r = 0; r < rows; ++r) {
+        const uint32_t above = col << (31 - r), below = col >> r;
+        const int du = above ? __clz(above) : up0 + r;
+        const int dd = below ? __ffs(below) - 1 : dn0 + 31 - r;
+        gp[(size_t)r * gpitch] = (uint16_t)min(min(du, dd), (int)EDT_GNONE);
+    }
+}
+
+// ---- row pass ---------------------------------------------------------------------------------------------------------
+#define DC_THREADS 256
+#define DC_INLINE 40     // candidates a pixel's own thread scans; longer ranges go to the warps' work list
+#define DC_CHUNK 512     // candidates per work-list chunk (one warp, 16 strides)
+#define DC_MAXPIX 512    // work-list pixels per level  (more than fit: scanned inline -- slower, still exact)
+#define DC_MAXCHUNK 768  // work-list chunks per level
+
+struct EdtRowSmem {
+    uint16_t *g, *a;           // the row of column distances; the ruling candidate per pixel
+    unsigned long long *key;   // work list: best (cost << 16 | candidate) per listed pixel
+    uint16_t *px;              //            the listed pixel
+    uint2 *chunk;              //            {slot | x << 16, lo | hi << 16}
+};
+
+__device__ __forceinline__ void edt_scan(const uint16_t *__restrict__ s_g, int x, int a, int b, int step, uint32_t &best, int &arg)
+{
+    for (int xp = a; xp <= b; xp += step) {
+        const uint32_t gg = s_g[xp];
+        const int d = x - xp;
+        const uint32_t c = (uint32_t)(d * d) + gg * gg;
+        if (c < best) { best = c; arg = xp; }
+    }
+}
+
+__global__ void __launch_bounds__(DC_THREADS, 3) k_edt_rowdc(const uint16_t *__restrict__ g, size_t gpitch, int W, int Wa, int top_S,
+                                                             int32_t *__restrict__ d2_out, float *__restrict__ dist_out, size_t opitch)
 {
     extern __shared__ __align__(128) uint8_t dsm[];
     __shared__ __align__(8) uint64_t s_bar;
-    __shared__ int s_wmax[8], s_wmin[8];
-    uint32_t *s_bits = (uint32_t *)dsm;                                   // wpr words
-    int *s_left = (int *)(dsm + (((size_t)wpr * 4 + 127) & ~(size_t)127)); // nearest white column at or before the END of word w
-    int *s_right = s_left + wpr;                                          // nearest white column at or after the START of word w
-    uint16_t *s_h = (uint16_t *)(s_right + wpr + ((32 - (2 * wpr) % 32) % 32)); // 128-byte aligned row of distances
-    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    __shared__ int s_cnt[2][2]; // [level parity][pixels, chunks]
+    EdtRowSmem S;
+    S.g = (uint16_t *)dsm;
+    S.a = S.g + Wa;
+    S.key = (unsigned long long *)(S.a + Wa);
+    S.chunk = (uint2 *)(S.key + DC_MAXPIX);
+    S.px = (uint16_t *)(S.chunk + DC_MAXCHUNK);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int y = blockIdx.x;
-    const uint32_t row_bytes = (uint32_t)wpr * 4u;
-    if (t == 0) {
+    if (tid == 0) {
         vsb_mbar_init(&s_bar, 1);
         vsb_fence_barrier_init();
+        s_cnt[0][0] = s_cnt[0][1] = s_cnt[1][0] = s_cnt[1][1] = 0;
     }
     __syncthreads();
-    if (t == 0) {
+    if (tid == 0) {
+        const uint32_t row_bytes = (uint32_t)(((size_t)W * 2 + 15) & ~(size_t)15);
         vsb_mbar_expect_tx(&s_bar, row_bytes);
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(vsb_smem_u32(s_bits)),
-                     "l"(bits + (size_t)y * wpr), "r"(row_bytes), "r"(vsb_smem_u32(&s_bar))
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(vsb_smem_u32(S.g)),
+                     "l"(g + (size_t)y * gpitch), "r"(row_bytes), "r"(vsb_smem_u32(&s_bar))
                      : "memory");
     }
     vsb_mbar_wait(&s_bar, 0);
 
-    // per word: last / first white column inside it; then an inclusive prefix-max and suffix-min over the row's words.
-    // Thread t owns the contiguous chunk of words [t*per, (t+1)*per).
-    const int per = (wpr + 255) / 256;
-    const int w0 = t * per, w1 = min(wpr, w0 + per);
-    int mx = -1, mn = EDT_INF_POS;
-    for (int w = w0; w < w1; ++w) {
-        const uint32_t v = s_bits[w];
-        if (v) { mx = 32 * w + 31 - __clz(v); mn = min(mn, 32 * w + __ffs(v) - 1); }
-    }
-    int pmx = mx, smn = mn; // inclusive scans of the per-thread values across the block
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int a = __shfl_up_sync(0xffffffffu, pmx, o), b = __shfl_down_sync(0xffffffffu, smn, o);
-        if (lane >= o) pmx = max(pmx, a);
-        if (lane + o < 32) smn = min(smn, b);
-    }
-    if (lane == 31) s_wmax[warp] = pmx;
-    if (lane == 0) s_wmin[warp] = smn;
-    __syncthreads();
-    int before = -1, after = EDT_INF_POS; // over the warps before / after mine
-    for (int k = 0; k < 8; ++k) {
-        if (k < warp) before = max(before, s_wmax[k]);
-        if (k > warp) after = min(after, s_wmin[k]);
-    }
-    {   // exclusive values for my chunk, then the per-word tables
-        int run = max(before, __shfl_up_sync(0xffffffffu, pmx, 1));
-        if (lane == 0) run = before;
-        for (int w = w0; w < w1; ++w) {
-            const uint32_t v = s_bits[w];
-            if (v) run = 32 * w + 31 - __clz(v);
-            s_left[w] = run;
-        }
-        int rr = min(after, __shfl_down_sync(0xffffffffu, smn, 1));
-        if (lane == 31) rr = after;
-        for (int w = w1 - 1; w >= w0; --w) {
-            const uint32_t v = s_bits[w];
-            if (v) rr = 32 * w + __ffs(v) - 1;
-            s_right[w] = rr;
-        }
-    }
-    __syncthreads();
-    for (int w = warp; w < wpr; w += 8) {
-        const uint32_t v = s_bits[w];
-        const int x = 32 * w + lane;
-        const uint32_t le = v & (0xFFFFFFFFu >> (31 - lane)), ge = v & (0xFFFFFFFFu << lane);
-        const int pl = le ? 32 * w + 31 - __clz(le) : (w > 0 ? s_left[w - 1] : -1);
-        const int pr = ge ? 32 * w + __ffs(ge) - 1 : (w + 1 < wpr ? s_right[w + 1] : EDT_INF_POS);
-        uint32_t d = EDT_NONE;
-        if (pl >= 0) d = (uint32_t)(x - pl);
-        if (pr < EDT_INF_POS) d = min(d, (uint32_t)(pr - x));
-        s_h[x] = (uint16_t)min(d, 0xFFFEu + (d == EDT_NONE));
-    }
-    vsb_fence_async_smem();
-    __syncthreads();
-    if (t == 0) {
-        const uint32_t out_bytes = (uint32_t)(((size_t)W * 2 + 15) & ~(size_t)15);
-        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(h + (size_t)y * hpitch), "r"(vsb_smem_u32(s_h)),
-                     "r"(out_bytes)
-                     : "memory");
-        vsb_tma_commit();
-        vsb_tma_wait_all<0>();
-    }
-}
-
-// ---- column pass ----------------------------------------------------------------------------------------------------
-#define EDT_PF 8 // rows of h requested ahead of the envelope scan (independent loads; the scan itself is a dependent chain)
-
-__global__ void __launch_bounds__(128) k_edt_cols(const uint32_t *__restrict__ bits, int wpr, int W, int H,
-                                                  const uint16_t *__restrict__ h, size_t hpitch, uint2 *__restrict__ stack,
-                                                  size_t spitch, int32_t *__restrict__ d2_out, float *__restrict__ dist_out,
-                                                  size_t opitch)
-{
-    const int lane = threadIdx.x & 31;
-    const int x = blockIdx.x * 128 + threadIdx.x;
-    const int wc = (blockIdx.x * 128 + (threadIdx.x & ~31)) >> 5; // the warp's mask word column (warp-uniform)
-    if (wc >= wpr) return;
-    const int yb0 = blockIdx.y * EDT_BAND, yb1 = min(H, yb0 + EDT_BAND);
-    // ---- the band's 64 rows of this warp's mask word, transposed: every lane gets its column as two 32-bit words ----------
-    uint32_t col[2];
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-        const int yy = yb0 + 32 * q + lane;
-        const uint32_t roww = yy < yb1 ? bits[(size_t)yy * wpr + wc] : 0xFFFFFFFFu; // rows below the image end a run like white
-        uint32_t mine = 0;
-#pragma unroll
-        for (int cidx = 0; cidx < 32; ++cidx) {
-            const uint32_t b = __ballot_sync(0xffffffffu, (roww >> cidx) & 1u);
-            if (cidx == lane) mine = b;
-        }
-        col[q] = mine;
-    }
-    const bool above = (yb0 == 0) ? true : ((bits[(size_t)(yb0 - 1) * wpr + wc] >> lane) & 1u); // top edge starts a run too
-    // zeros for the band's white pixels (coalesced: the warp walks the rows together)
-    for (int r = 0; r < yb1 - yb0; ++r) {
-        const bool wht = (col[r >> 5] >> (r & 31)) & 1u;
-        if (wht && x < W) {
-            if (d2_out) d2_out[(size_t)(yb0 + r) * opitch + x] = 0;
-            if (dist_out) dist_out[(size_t)(yb0 + r) * opitch + x] = 0.0f;
-        }
-    }
-    if (x >= W) return;
-    // run starts of my column inside the band: black pixel whose upper neighbour is white (or the image's top edge)
-    const unsigned long long c64 = (unsigned long long)col[0] | ((unsigned long long)col[1] << 32);
-    unsigned long long starts = ~c64 & ((c64 << 1) | (above ? 1ULL : 0ULL));
-    if (yb1 - yb0 < 64) starts &= (1ULL << (yb1 - yb0)) - 1ULL;
-
-    while (starts) {
-        const int ys = yb0 + __ffsll((long long)starts) - 1;
-        starts &= starts - 1ULL;
-        // ---- downward scan: lower envelope of the parabolas (y - s)^2 + f_s over the candidates of this run --------------
-        // candidates: the white pixel above the run (f = 0), the run's black pixels whose row holds a white pixel, and the
-        // white pixel that ends the run (f = 0; h == 0 marks it)
-        const int base = ys > 0 ? ys - 1 : 0;                    // row of the first possible candidate = stack slot 0
-        int q = -1, s_top = 0, t_top = 0, f_top = 0;            // the stack's top entry lives in registers
-        if (ys > 0) { q = 0; s_top = ys - 1; t_top = ys; f_top = 0; }
-        int ye = H - 1;
-        bool open = true;
-        for (int u0 = ys; u0 < H && open; u0 += EDT_PF) {
-            uint32_t hv[EDT_PF];
-#pragma unroll
-            for (int i = 0; i < EDT_PF; ++i) hv[i] = (u0 + i < H) ? (uint32_t)h[(size_t)(u0 + i) * hpitch + x] : EDT_NONE;
-#pragma unroll
-            for (int i = 0; i < EDT_PF; ++i) {
-                const int u = u0 + i;
-                if (!open || u >= H) break;
-                if (hv[i] != EDT_NONE) {
-                    const int fu = (int)(hv[i] * hv[i]);
-                    while (q >= 0) { // pop while the new parabola is already lower where the top one starts to rule
-                        const int da = t_top - s_top, db = t_top - u;
-                        if (da * da + f_top <= db * db + fu) break;
-                        if (--q >= 0) {
-                            const uint2 e = stack[(size_t)(base + q) * spitch + x];
-                            s_top = (int)(e.x & 0xFFFFu); t_top = (int)(e.x >> 16); f_top = (int)e.y;
-                        }
+    int parity = 0;
+    // level -1 is pixel 0 on its own (every other pixel has a solved neighbour on its left), then S = top_S .. 1
+    for (int Sx = -1; Sx != 0; Sx = (Sx < 0 ? top_S : Sx >> 1)) {
+        const int n = Sx < 0 ? 1 : (W - Sx + 2 * Sx - 1) / (2 * Sx); // pixels x = S (2k+1) < W
+        int *cnt = s_cnt[parity];
+        if (tid == 0) { s_cnt[parity ^ 1][0] = 0; s_cnt[parity ^ 1][1] = 0; }
+        bool listed = false;
+        for (int k = tid; k < n; k += DC_THREADS) {
+            int x, lo, hi;
+            if (Sx < 0) { x = 0; lo = 0; hi = W - 1; }
+            else { x = Sx * (2 * k + 1); lo = S.a[x - Sx]; hi = x + Sx < W ? (int)S.a[x + Sx] : W - 1; }
+            const uint32_t gx = S.g[x];
+            if (gx == 0u) { S.a[x] = (uint16_t)x; continue; }
+            uint32_t best = gx * gx;
+            int arg = x;
+            edt_scan(S.g, x, lo, lo, 1, best, arg);
+            edt_scan(S.g, x, hi, hi, 1, best, arg);
+            const int r = (int)__fsqrt_rn((float)best) + 1;      // no candidate further away than this can win (over-estimates are fine)
+            const int a = max(lo + 1, x - r), b = min(hi - 1, x + r);
+            const int len = b - a + 1;
+            bool inl = len <= DC_INLINE;
+            if (!inl) {
+                const int nch = (len + DC_CHUNK - 1) / DC_CHUNK;
+                const int slot = atomicAdd(&cnt[0], 1);
+                inl = slot >= DC_MAXPIX;
+                if (!inl) {
+                    const int e0 = atomicAdd(&cnt[1], nch);
+                    const bool fits = e0 + nch <= DC_MAXCHUNK;
+                    S.px[slot] = fits ? (uint16_t)x : (uint16_t)0xFFFFu;
+                    S.key[slot] = ((unsigned long long)best << 16) | (unsigned long long)arg;
+                    for (int c = 0; c < nch && e0 + c < DC_MAXCHUNK; ++c) {
+                        const int ca = a + c * DC_CHUNK, cb = min(b, ca + DC_CHUNK - 1);
+                        S.chunk[e0 + c] = make_uint2(fits ? ((uint32_t)slot | ((uint32_t)x << 16)) : 0xFFFFu, (uint32_t)ca | ((uint32_t)cb << 16));
                     }
-                    if (q < 0) {
-                        q = 0; s_top = u; t_top = ys; f_top = fu;
-                    } else {
-                        // first row where the new parabola is strictly lower: 1 + floor((u^2 - s^2 + fu - fs) / (2 (u - s)))
-                        const unsigned num = (unsigned)((u * u - s_top * s_top) + (fu - f_top));
-                        const int wst = 1 + (int)(num / (unsigned)(2 * (u - s_top)));
-                        if (wst < H) {
-                            stack[(size_t)(base + q) * spitch + x] = make_uint2((uint32_t)s_top | ((uint32_t)t_top << 16), (uint32_t)f_top);
-                            ++q; s_top = u; t_top = wst; f_top = fu;
-                        }
-                    }
-                    if (hv[i] == 0u) { ye = u - 1; open = false; } // the white pixel that ends the run
+                    inl = !fits;
+                    listed = true;
                 }
             }
-        }
-        // ---- upward scan: evaluate ---------------------------------------------------------------------------------------
-        for (int yq = ye; yq >= ys; --yq) {
-            while (q > 0 && t_top > yq) {
-                --q;
-                const uint2 e = stack[(size_t)(base + q) * spitch + x];
-                s_top = (int)(e.x & 0xFFFFu); t_top = (int)(e.x >> 16); f_top = (int)e.y;
+            if (inl) {
+                edt_scan(S.g, x, a, b, 1, best, arg);
+                S.a[x] = (uint16_t)arg;
             }
-            int d2 = 0x7fffffff;
-            if (q >= 0) { const int dy = yq - s_top; d2 = dy * dy + f_top; }
-            if (d2_out) d2_out[(size_t)yq * opitch + x] = d2;
-            if (dist_out) dist_out[(size_t)yq * opitch + x] = d2 == 0x7fffffff ? 3.0e38f : __fsqrt_rn((float)d2);
         }
+        if (__syncthreads_or(listed)) {
+            const int npix = min(cnt[0], DC_MAXPIX), nchunk = min(cnt[1], DC_MAXCHUNK);
+            for (int e = warp; e < nchunk; e += DC_THREADS / 32) {
+                const uint2 ch = S.chunk[e];
+                const uint32_t slot = ch.x & 0xFFFFu;
+                if (slot == 0xFFFFu) continue;
+                uint32_t best = 0xFFFFFFFFu;
+                int arg = 0xFFFF;
+                edt_scan(S.g, (int)(ch.x >> 16), (int)(ch.y & 0xFFFFu) + lane, (int)(ch.y >> 16), 32, best, arg);
+                const uint32_t m = __reduce_min_sync(0xffffffffu, best);
+                const uint32_t am = __reduce_min_sync(0xffffffffu, best == m ? (uint32_t)arg : 0xFFFFu);
+                if (lane == 0 && m != 0xFFFFFFFFu) atomicMin(&S.key[slot], ((unsigned long long)m << 16) | (unsigned long long)am);
+            }
+            __syncthreads();
+            for (int s = tid; s < npix; s += DC_THREADS) {
+                const uint32_t x = S.px[s];
+                if (x != 0xFFFFu) S.a[x] = (uint16_t)(S.key[s] & 0xFFFFull);
+            }
+            __syncthreads();
+        }
+        parity ^= 1;
+    }
+
+    for (int x = tid; x < W; x += DC_THREADS) {
+        const int a = S.a[x];
+        const uint32_t gg = S.g[a];
+        const int d = x - a;
+        const uint32_t c = (uint32_t)(d * d) + gg * gg;
+        const bool none = c >= 0x80000000u;
+        if (d2_out) d2_out[(size_t)y * opitch + x] = none ? 0x7fffffff : (int32_t)c;
+        if (dist_out) dist_out[(size_t)y * opitch + x] = none ? 3.0e38f : __fsqrt_rn((float)c);
     }
 }
 
 // ---- C-ABI ----------------------------------------------------------------------------------------------------------------
-static size_t edt_hpitch(int W) { return ((size_t)W + 63) & ~(size_t)63; }
+static size_t edt_gpitch(int W) { return ((size_t)W + 63) & ~(size_t)63; }
+static size_t edt_align(size_t v) { return (v + 255) & ~(size_t)255; }
 
 extern "C" size_t vsb_edt_exact_scratch_bytes(int W, int H)
 {
     if (W <= 0 || H <= 0) return 0;
-    return edt_hpitch(W) * (size_t)H * sizeof(uint16_t) + (size_t)W * (size_t)H * sizeof(uint2) + 256;
+    const size_t Wp = edt_gpitch(W) + 128, nb = ((size_t)H + 31) / 32; // Wp >= 32 * wpr for wpr = 4 * ceil(W / 128)
+    return edt_align(edt_gpitch(W) * (size_t)H * 2) + 2 * edt_align(nb * Wp) + 2 * edt_align(nb * Wp * 2) + 256;
 }
 
 extern "C" int vsb_edt_exact(const uint32_t *seed_bits, int wpr, int W, int H, void *scratch, int32_t *d2_out, float *dist_out,
@@ -237,22 +256,36 @@ extern "C" int vsb_edt_exact(const uint32_t *seed_bits, int wpr, int W, int H, v
     VSB_REQUIRE(W > 0 && H > 0 && W <= 32767 && H <= 32767 && wpr >= (W + 31) / 32 && (wpr & 3) == 0 && pitch_elems >= (size_t)W,
                 "vsb_edt_exact: bad geometry (W, H <= 32767; wpr a multiple of 4 words)");
     VSB_REQUIRE((((uintptr_t)seed_bits) & 15u) == 0 && (((uintptr_t)scratch) & 127u) == 0, "vsb_edt_exact: mask / scratch alignment");
+    const size_t gpitch = edt_gpitch(W), Wp = (size_t)32 * wpr, nb = ((size_t)H + 31) / 32;
+    VSB_REQUIRE(Wp <= gpitch + 128, "vsb_edt_exact: wpr = %d is wider than the scratch layout allows for W = %d", wpr, W);
     cudaStream_t s = (cudaStream_t)stream;
-    const size_t hpitch = edt_hpitch(W);
-    uint16_t *h = (uint16_t *)scratch;
-    uint2 *stack = (uint2 *)((uint8_t *)scratch + ((hpitch * (size_t)H * sizeof(uint16_t) + 127) & ~(size_t)127));
-    const size_t hrow = hpitch > (size_t)32 * wpr ? hpitch : (size_t)32 * wpr; // the row kernel resolves every bit of every word
-    const size_t smem = (((size_t)wpr * 4 + 127) & ~(size_t)127) + (size_t)2 * wpr * 4 + 128 + hrow * 2 + 128;
+    uint8_t *p = (uint8_t *)scratch;
+    uint16_t *g = (uint16_t *)p;             p += edt_align(gpitch * (size_t)H * 2);
+    uint8_t *first8 = p;                     p += edt_align(nb * Wp);
+    uint8_t *last8 = p;                      p += edt_align(nb * Wp);
+    uint16_t *up = (uint16_t *)p;            p += edt_align(nb * Wp * 2);
+    uint16_t *dn = (uint16_t *)p;
+
+    const dim3 gsq((wpr + 7) / 8, (unsigned)nb);
+    k_edt_colsum<<<gsq, 256, 0, s>>>(seed_bits, wpr, H, first8, last8);
+    int rc = vsb_check_launch("k_edt_colsum");
+    if (rc) return rc;
+    k_edt_colscan<<<dim3((unsigned)((Wp + 127) / 128), 2), 128, 0, s>>>(first8, last8, (int)Wp, (int)nb, up, dn);
+    if ((rc = vsb_check_launch("k_edt_colscan"))) return rc;
+    k_edt_coldist<<<gsq, 256, 0, s>>>(seed_bits, wpr, H, up, dn, g, gpitch);
+    if ((rc = vsb_check_launch("k_edt_coldist"))) return rc;
+
+    const int Wa = (int)gpitch;
+    const size_t smem = (size_t)Wa * 4 + DC_MAXPIX * 8 + DC_MAXCHUNK * 8 + DC_MAXPIX * 2;
     static bool configured = false;
     if (!configured) {
-        VSB_CUDA(cudaFuncSetAttribute(k_edt_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        VSB_CUDA(cudaFuncSetAttribute(k_edt_rowdc, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         configured = true;
     }
-    VSB_REQUIRE(smem <= 200 * 1024, "vsb_edt_exact: row of %d pixels does not fit the row kernel's shared memory", W);
-    k_edt_rows<<<H, 256, smem, s>>>(seed_bits, wpr, W, h, hpitch);
-    int rc = vsb_check_launch("k_edt_rows");
-    if (rc) return rc;
-    dim3 grid((W + 127) / 128, (H + EDT_BAND - 1) / EDT_BAND);
-    k_edt_cols<<<grid, 128, 0, s>>>(seed_bits, wpr, W, H, h, hpitch, stack, (size_t)W, d2_out, dist_out, pitch_elems);
-    return vsb_check_launch("k_edt_cols");
+    VSB_REQUIRE(smem <= 200 * 1024, "vsb_edt_exact: a row of %d pixels does not fit the row kernel's shared memory", W);
+    int top_S = 1;
+    while (top_S * 2 < W) top_S *= 2;
+    if (W == 1) top_S = 0;
+    k_edt_rowdc<<<H, DC_THREADS, smem, s>>>(g, gpitch, W, Wa, top_S, d2_out, dist_out, pitch_elems);
+    return vsb_check_launch("k_edt_rowdc");
 }
