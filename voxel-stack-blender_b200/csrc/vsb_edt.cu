@@ -11,10 +11,10 @@
 // Both passes are laid out for the GPU instead of for a scan line:
 //
 //   column pass (k_edt_colsum, k_edt_colscan, k_edt_coldist).  The packed mask is cut into blocks of 32 rows; a warp takes a
-//   32 x 32 pixel square (one mask word column), transposes it with 32 ballots so that every lane holds ITS column as one
-//   32-bit word, and answers "nearest white pixel above / below inside the block" with clz / ffs.  A first launch records per
-//   (block, column) the first and last white row, a second one carries them down and up the (few) blocks, the third writes g
-//   as uint16 rows (EDT_GNONE where the column holds no white pixel at all).
+//   32 x 32 pixel square (one mask word column) and transposes it with five shuffle butterflies so that every lane holds ITS
+//   column as one 32-bit word.  A first launch records per (block, column) the first and last white row (ffs / clz), a second
+//   one carries them down and up the (few) blocks, the third runs the two distance recurrences over the lane's word in
+//   registers and writes g as uint16 rows (EDT_GNONE where the column holds no white pixel at all).
 //
 //   row pass (k_edt_rowdc).  One CTA per image row, the row of g staged in shared memory with one bulk copy.  The stack of
 //   Meijster's scan is a chain of dependent steps as long as the row; here the envelope is evaluated by bisection instead:
@@ -23,9 +23,9 @@
 //   Levels S = 2^k, ..., 2, 1 -- all pixels of a level are independent, the ranges of a level add up to about W, and a
 //   candidate further away than the best distance known so far is never looked at, so pixels close to white cost a few
 //   evaluations and nothing costs more than O(log W) per pixel whatever the distances are.  Short ranges are scanned by the
-//   pixel's own thread; long ones (the coarse levels, and pixels where A jumps) go to a work list in shared memory, cut
-//   into chunks that the warps scan cooperatively (redux.sync min + a 64-bit shared-memory atomicMin per chunk).
-//   The results leave the CTA in one coalesced pass (d2 and / or sqrtf).
+//   pixel's own lane; long ones (the coarse levels, and pixels where A jumps) by the pixel's whole warp, 32 candidates per
+//   step, merged with redux.sync.  The last level (the odd pixels) is fused with the output: every lane stores a pair of
+//   results (d2 and / or sqrtf), 8 bytes wide and coalesced; pairs of white pixels skip the arithmetic altogether.
 //
 // d2 is the exact integer squared distance (INT32_MAX where the image holds no white pixel), dist = sqrtf(d2) correctly
 // rounded (3e38 there).  Limits: W, H <= 32767 (all costs fit 32 bits: 46341^2 + 32766^2 < 2^32).
@@ -35,18 +35,19 @@
 #define EDT_BIG (1 << 20)
 
 // ---- column pass ------------------------------------------------------------------------------------------------------
-// The warp's 32 x 32 square, transposed: bit r of the returned word = pixel (32 wc + lane, y0 + r).
+// The warp's 32 x 32 square, transposed: bit r of the returned word = pixel (32 wc + lane, y0 + r).  Five butterfly stages:
+// lanes k and k ^ j swap the off-diagonal j x j blocks of the bit matrix.
 __device__ __forceinline__ uint32_t edt_column_word(const uint32_t *__restrict__ bits, int wpr, int H, int wc, int y0, int lane)
 {
     const int y = y0 + lane;
-    const uint32_t roww = y < H ? bits[(size_t)y * wpr + wc] : 0u;
-    uint32_t col = 0;
+    uint32_t v = y < H ? bits[(size_t)y * wpr + wc] : 0u;
 #pragma unroll
-    for (int c = 0; c < 32; ++c) {
-        const uint32_t b = __ballot_sync(0xffffffffu, (roww >> c) & 1u);
-        if (c == lane) col = b;
+    for (int j = 16; j >= 1; j >>= 1) {
+        const uint32_t m = j == 16 ? 0x0000FFFFu : (j == 8 ? 0x00FF00FFu : (j == 4 ? 0x0F0F0F0Fu : (j == 2 ? 0x33333333u : 0x55555555u)));
+        const uint32_t o = __shfl_xor_sync(0xffffffffu, v, j);
+        v = (lane & j) ? ((v & ~m) | ((o >> j) & m)) : ((v & m) | ((o << j) & ~m));
     }
-    return col;
+    return v;
 }
 
 // first / last white row of every (block of 32 rows, column): 0..31, 0xFF = none
@@ -61,26 +62,32 @@ __global__ void __launch_bounds__(256) k_edt_colsum(const uint32_t *__restrict__
     last8[o] = col ? (uint8_t)(31 - __clz(col)) : (uint8_t)0xFF;
 }
 
-// blockIdx.y == 0: up[b][x] = last white row above block b; == 1: dn[b][x] = first white row below block b (0xFFFF = none)
-__global__ void __launch_bounds__(128) k_edt_colscan(const uint8_t *__restrict__ first8, const uint8_t *__restrict__ last8, int Wp, int nb,
-                                                     uint16_t *__restrict__ up, uint16_t *__restrict__ dn)
+// blockIdx.y == 0: up[b][x] = last white row above block b; == 1: dn[b][x] = first white row below block b (0xFFFF = none).
+// One thread per column; the block records are requested 16 at a time, the running value is the only dependent chain.
+#define EDT_SCAN_BATCH 16
+__global__ void __launch_bounds__(64) k_edt_colscan(const uint8_t *__restrict__ first8, const uint8_t *__restrict__ last8, int Wp, int nb,
+                                                    uint16_t *__restrict__ up, uint16_t *__restrict__ dn)
 {
-    const int x = blockIdx.x * 128 + threadIdx.x;
+    const int x = blockIdx.x * 64 + threadIdx.x;
     if (x >= Wp) return;
     uint32_t run = 0xFFFFu;
-    if (blockIdx.y == 0) {
-#pragma unroll 8
-        for (int b = 0; b < nb; ++b) {
-            const uint32_t l = last8[(size_t)b * Wp + x];
-            up[(size_t)b * Wp + x] = (uint16_t)run;
-            if (l != 0xFFu) run = 32u * b + l;
+    const bool down = blockIdx.y == 0;
+    const uint8_t *src = down ? last8 : first8;
+    uint16_t *dst = down ? up : dn;
+    for (int i0 = 0; i0 < nb; i0 += EDT_SCAN_BATCH) {
+        uint32_t v[EDT_SCAN_BATCH];
+#pragma unroll
+        for (int i = 0; i < EDT_SCAN_BATCH; ++i) {
+            const int b = down ? i0 + i : nb - 1 - (i0 + i);
+            v[i] = (i0 + i < nb) ? (uint32_t)src[(size_t)b * Wp + x] : 0xFFu;
         }
-    } else {
-#pragma unroll 8
-        for (int b = nb - 1; b >= 0; --b) {
-            const uint32_t f = first8[(size_t)b * Wp + x];
-            dn[(size_t)b * Wp + x] = (uint16_t)run;
-            if (f != 0xFFu) run = 32u * b + f;
+#pragma unroll
+        for (int i = 0; i < EDT_SCAN_BATCH; ++i) {
+            const int b = down ? i0 + i : nb - 1 - (i0 + i);
+            if (i0 + i < nb) {
+                dst[(size_t)b * Wp + x] = (uint16_t)run;
+                if (v[i] != 0xFFu) run = 32u * b + v[i];
+            }
         }
     }
 }
@@ -94,147 +101,189 @@ __global__ void __launch_bounds__(256) k_edt_coldist(const uint32_t *__restrict_
     const size_t o = (size_t)blockIdx.y * (32 * (size_t)wpr) + 32 * wc + lane;
     const uint32_t u = up[o], d = dn[o];
     const uint32_t col = edt_column_word(bits, wpr, H, wc, y0, lane);
-    const int up0 = u != 0xFFFFu ? y0 - (int)u : EDT_BIG;        // from row y0 to the nearest white row above the block
-    const int dn0 = d != 0xFFFFu ? (int)d - (y0 + 31) : EDT_BIG; // from row y0 + 31 to the nearest white row below it
     if ((size_t)(32 * wc + lane) >= gpitch) return;
     uint16_t *gp = g + (size_t)y0 * gpitch + 32 * wc + lane;
-    const int rows = min(32, H - y0);
-#pragma unroll 8
-    for (int r = 0; r < rows; ++r) {
-        const uint32_t above = col << (31 - r), below = col >> r;
-        const int du = above ? __clz(above) : up0 + r;
-        const int dd = below ? __ffs(below) - 1 : dn0 + 31 - r;
-        gp[(size_t)r * gpitch] = (uint16_t)min(min(du, dd), (int)EDT_GNONE);
+    // downwards: distance to the nearest white pixel at or above the row; upwards: at or below it, and the minimum leaves
+    int du[32];
+    int run = u != 0xFFFFu ? y0 - 1 - (int)u : EDT_BIG; // at "row -1" of the block
+#pragma unroll
+    for (int r = 0; r < 32; ++r) {
+        run = (col >> r) & 1u ? 0 : run + 1;
+        du[r] = run;
+    }
+    run = d != 0xFFFFu ? (int)d - (y0 + 32) : EDT_BIG;  // at "row 32" of the block
+    if (y0 + 32 <= H) {
+#pragma unroll
+        for (int r = 31; r >= 0; --r) {
+            run = (col >> r) & 1u ? 0 : run + 1;
+            gp[(size_t)r * gpitch] = (uint16_t)min(min(du[r], run), (int)EDT_GNONE);
+        }
+    } else {
+#pragma unroll
+        for (int r = 31; r >= 0; --r) {
+            run = (col >> r) & 1u ? 0 : run + 1;
+            if (y0 + r < H) gp[(size_t)r * gpitch] = (uint16_t)min(min(du[r], run), (int)EDT_GNONE);
+        }
     }
 }
 
 // ---- row pass ---------------------------------------------------------------------------------------------------------
 #define DC_THREADS 256
-#define DC_INLINE 40     // candidates a pixel's own thread scans; longer ranges go to the warps' work list
-#define DC_CHUNK 512     // candidates per work-list chunk (one warp, 16 strides)
-#define DC_MAXPIX 512    // work-list pixels per level  (more than fit: scanned inline -- slower, still exact)
-#define DC_MAXCHUNK 768  // work-list chunks per level
+#define DC_INLINE 24 // candidates a pixel's own lane scans; a longer range is scanned by the pixel's whole warp
 
-struct EdtRowSmem {
-    uint16_t *g, *a;           // the row of column distances; the ruling candidate per pixel
-    unsigned long long *key;   // work list: best (cost << 16 | candidate) per listed pixel
-    uint16_t *px;              //            the listed pixel
-    uint2 *chunk;              //            {slot | x << 16, lo | hi << 16}
-};
-
-__device__ __forceinline__ void edt_scan(const uint16_t *__restrict__ s_g, int x, int a, int b, int step, uint32_t &best, int &arg)
+__device__ __forceinline__ void edt_one(const uint16_t *__restrict__ s_g, int x, int xp, uint32_t &best, int &arg)
 {
-    for (int xp = a; xp <= b; xp += step) {
-        const uint32_t gg = s_g[xp];
-        const int d = x - xp;
-        const uint32_t c = (uint32_t)(d * d) + gg * gg;
-        if (c < best) { best = c; arg = xp; }
+    const uint32_t gg = s_g[xp];
+    const int d = x - xp;
+    const uint32_t c = (uint32_t)(d * d) + gg * gg;
+    if (c < best) { best = c; arg = xp; }
+}
+// candidates a, a + STEP, ... <= b of pixel x, two per trip (an index past b repeats b)
+template <int STEP>
+__device__ __forceinline__ void edt_scan(const uint16_t *__restrict__ s_g, int x, int a, int b, uint32_t &best, int &arg)
+{
+    for (int xp = a; xp <= b; xp += 2 * STEP) {
+        const int x1 = min(xp + STEP, b);
+        const uint32_t g0 = s_g[xp], g1 = s_g[x1];
+        const int d0 = x - xp, d1 = x - x1;
+        const uint32_t c0 = (uint32_t)(d0 * d0) + g0 * g0, c1 = (uint32_t)(d1 * d1) + g1 * g1;
+        if (c0 < best) { best = c0; arg = xp; }
+        if (c1 < best) { best = c1; arg = x1; }
     }
 }
 
-__global__ void __launch_bounds__(DC_THREADS, 3) k_edt_rowdc(const uint16_t *__restrict__ g, size_t gpitch, int W, int Wa, int top_S,
+// One pixel per lane (x < 0: the lane has none).  Pixel x lies between two solved pixels whose ruling candidates lo <= hi
+// bracket its own.  Start from the pixel's own column and the two bracket ends; only candidates closer than the square root
+// of that value can do better, which leaves the range [a, b].  Short ranges are scanned by the lane, long ones (coarse
+// levels; pixels where the ruling candidate jumps) by the whole warp, one after the other.  Returns the cost, sets arg.
+__device__ __forceinline__ uint32_t edt_solve(const uint16_t *__restrict__ s_g, int lane, int x, int lo, int hi, int &arg)
+{
+    uint32_t best = 0u;
+    int a = 1, b = 0;
+    arg = x;
+    if (x >= 0) {
+        const uint32_t gx = s_g[x];
+        if (gx != 0u) {
+            best = gx * gx;
+            edt_one(s_g, x, lo, best, arg);
+            edt_one(s_g, x, hi, best, arg);
+            if (hi - lo > 1) {
+                const int r = (int)__fsqrt_rn((float)best) + 1; // an over-estimate is fine
+                a = max(lo + 1, x - r);
+                b = min(hi - 1, x + r);
+                if (b - a < DC_INLINE) {
+                    edt_scan<1>(s_g, x, a, b, best, arg);
+                    b = a - 1;
+                }
+            }
+        }
+    }
+    uint32_t pend = __ballot_sync(0xffffffffu, b >= a);
+    while (pend) {
+        const int src = __ffs(pend) - 1;
+        pend &= pend - 1u;
+        const int X = __shfl_sync(0xffffffffu, x, src), A = __shfl_sync(0xffffffffu, a, src), B = __shfl_sync(0xffffffffu, b, src);
+        uint32_t wb = 0xFFFFFFFFu;
+        int wa = 0x7FFF;
+        edt_scan<32>(s_g, X, A + lane, B, wb, wa);
+        const uint32_t m = __reduce_min_sync(0xffffffffu, wb);
+        if (m < __shfl_sync(0xffffffffu, best, src)) {                       // warp-uniform
+            const uint32_t am = __reduce_min_sync(0xffffffffu, wb == m ? (uint32_t)wa : 0x7FFFu);
+            if (lane == src) { best = m; arg = (int)am; }
+        }
+    }
+    return best;
+}
+
+__global__ void __launch_bounds__(DC_THREADS, 4) k_edt_rowdc(const uint16_t *__restrict__ g, size_t gpitch, int W, int Wa, int top_log2,
                                                              int32_t *__restrict__ d2_out, float *__restrict__ dist_out, size_t opitch)
 {
     extern __shared__ __align__(128) uint8_t dsm[];
     __shared__ __align__(8) uint64_t s_bar;
-    __shared__ int s_cnt[2][2]; // [level parity][pixels, chunks]
-    EdtRowSmem S;
-    S.g = (uint16_t *)dsm;
-    S.a = S.g + Wa;
-    S.key = (unsigned long long *)(S.a + Wa);
-    S.chunk = (uint2 *)(S.key + DC_MAXPIX);
-    S.px = (uint16_t *)(S.chunk + DC_MAXCHUNK);
+    uint16_t *s_g = (uint16_t *)dsm; // the row of column distances
+    uint16_t *s_a = s_g + Wa;        // ruling candidate of the EVEN pixels (index x / 2)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int y = blockIdx.x;
     if (tid == 0) {
         vsb_mbar_init(&s_bar, 1);
         vsb_fence_barrier_init();
-        s_cnt[0][0] = s_cnt[0][1] = s_cnt[1][0] = s_cnt[1][1] = 0;
     }
     __syncthreads();
     if (tid == 0) {
         const uint32_t row_bytes = (uint32_t)(((size_t)W * 2 + 15) & ~(size_t)15);
         vsb_mbar_expect_tx(&s_bar, row_bytes);
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(vsb_smem_u32(S.g)),
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(vsb_smem_u32(s_g)),
                      "l"(g + (size_t)y * gpitch), "r"(row_bytes), "r"(vsb_smem_u32(&s_bar))
                      : "memory");
     }
     vsb_mbar_wait(&s_bar, 0);
 
-    int parity = 0;
-    // level -1 is pixel 0 on its own (every other pixel has a solved neighbour on its left), then S = top_S .. 1
-    for (int Sx = -1; Sx != 0; Sx = (Sx < 0 ? top_S : Sx >> 1)) {
-        const int n = Sx < 0 ? 1 : (W - Sx + 2 * Sx - 1) / (2 * Sx); // pixels x = S (2k+1) < W
-        int *cnt = s_cnt[parity];
-        if (tid == 0) { s_cnt[parity ^ 1][0] = 0; s_cnt[parity ^ 1][1] = 0; }
-        bool listed = false;
-        for (int k = tid; k < n; k += DC_THREADS) {
-            int x, lo, hi;
-            if (Sx < 0) { x = 0; lo = 0; hi = W - 1; }
-            else { x = Sx * (2 * k + 1); lo = S.a[x - Sx]; hi = x + Sx < W ? (int)S.a[x + Sx] : W - 1; }
-            const uint32_t gx = S.g[x];
-            if (gx == 0u) { S.a[x] = (uint16_t)x; continue; }
-            uint32_t best = gx * gx;
-            int arg = x;
-            edt_scan(S.g, x, lo, lo, 1, best, arg);
-            edt_scan(S.g, x, hi, hi, 1, best, arg);
-            const int r = (int)__fsqrt_rn((float)best) + 1;      // no candidate further away than this can win (over-estimates are fine)
-            const int a = max(lo + 1, x - r), b = min(hi - 1, x + r);
-            const int len = b - a + 1;
-            bool inl = len <= DC_INLINE;
-            if (!inl) {
-                const int nch = (len + DC_CHUNK - 1) / DC_CHUNK;
-                const int slot = atomicAdd(&cnt[0], 1);
-                inl = slot >= DC_MAXPIX;
-                if (!inl) {
-                    const int e0 = atomicAdd(&cnt[1], nch);
-                    const bool fits = e0 + nch <= DC_MAXCHUNK;
-                    S.px[slot] = fits ? (uint16_t)x : (uint16_t)0xFFFFu;
-                    S.key[slot] = ((unsigned long long)best << 16) | (unsigned long long)arg;
-                    for (int c = 0; c < nch && e0 + c < DC_MAXCHUNK; ++c) {
-                        const int ca = a + c * DC_CHUNK, cb = min(b, ca + DC_CHUNK - 1);
-                        S.chunk[e0 + c] = make_uint2(fits ? ((uint32_t)slot | ((uint32_t)x << 16)) : 0xFFFFu, (uint32_t)ca | ((uint32_t)cb << 16));
-                    }
-                    inl = !fits;
-                    listed = true;
-                }
+    // ---- pixel 0 on its own (every other pixel has a solved neighbour on its left)
+    if (warp == 0) {
+        int arg;
+        edt_solve(s_g, lane, lane == 0 ? 0 : -1, 0, W - 1, arg);
+        if (lane == 0) s_a[0] = (uint16_t)arg;
+    }
+    __syncthreads();
+    // ---- levels S = 2^top_log2 .. 2: the pixels x = S (2k+1).  Level S = 1 (the odd pixels) is fused with the output below.
+    for (int lv = top_log2; lv >= 1; --lv) {
+        const int Sx = 1 << lv;
+        const int n = (W + Sx - 1) >> (lv + 1);
+        // coarse levels hold few pixels and nearly all of them need their whole warp: deal them out in small groups so that
+        // all warps get some (C pixels per warp and trip, the lanes above C idle)
+        const int C = n >= 512 ? 32 : 1 << (31 - __clz(max(n >> 4, 1)));
+        for (int k0 = warp * C; k0 < n; k0 += (DC_THREADS / 32) * C) {
+            const int k = k0 + lane;
+            int x = -1, lo = 0, hi = 0;
+            if (lane < C && k < n) {
+                x = Sx * (2 * k + 1);
+                lo = s_a[(x - Sx) >> 1];
+                hi = x + Sx < W ? (int)s_a[(x + Sx) >> 1] : W - 1;
             }
-            if (inl) {
-                edt_scan(S.g, x, a, b, 1, best, arg);
-                S.a[x] = (uint16_t)arg;
-            }
+            int arg;
+            edt_solve(s_g, lane, x, lo, hi, arg);
+            if (x >= 0) s_a[x >> 1] = (uint16_t)arg;
         }
-        if (__syncthreads_or(listed)) {
-            const int npix = min(cnt[0], DC_MAXPIX), nchunk = min(cnt[1], DC_MAXCHUNK);
-            for (int e = warp; e < nchunk; e += DC_THREADS / 32) {
-                const uint2 ch = S.chunk[e];
-                const uint32_t slot = ch.x & 0xFFFFu;
-                if (slot == 0xFFFFu) continue;
-                uint32_t best = 0xFFFFFFFFu;
-                int arg = 0xFFFF;
-                edt_scan(S.g, (int)(ch.x >> 16), (int)(ch.y & 0xFFFFu) + lane, (int)(ch.y >> 16), 32, best, arg);
-                const uint32_t m = __reduce_min_sync(0xffffffffu, best);
-                const uint32_t am = __reduce_min_sync(0xffffffffu, best == m ? (uint32_t)arg : 0xFFFFu);
-                if (lane == 0 && m != 0xFFFFFFFFu) atomicMin(&S.key[slot], ((unsigned long long)m << 16) | (unsigned long long)am);
-            }
-            __syncthreads();
-            for (int s = tid; s < npix; s += DC_THREADS) {
-                const uint32_t x = S.px[s];
-                if (x != 0xFFFFu) S.a[x] = (uint16_t)(S.key[s] & 0xFFFFull);
-            }
-            __syncthreads();
-        }
-        parity ^= 1;
+        __syncthreads();
     }
 
-    for (int x = tid; x < W; x += DC_THREADS) {
-        const int a = S.a[x];
-        const uint32_t gg = S.g[a];
-        const int d = x - a;
-        const uint32_t c = (uint32_t)(d * d) + gg * gg;
-        const bool none = c >= 0x80000000u;
-        if (d2_out) d2_out[(size_t)y * opitch + x] = none ? 0x7fffffff : (int32_t)c;
-        if (dist_out) dist_out[(size_t)y * opitch + x] = none ? 3.0e38f : __fsqrt_rn((float)c);
+    // ---- level S = 1 and the output: lane k takes the pixel pair (2k, 2k+1) -- the even one is solved, the odd one sits
+    //      between two solved pixels -- and stores both results side by side.
+    int32_t *d2_row = d2_out ? d2_out + (size_t)y * opitch : nullptr;
+    float *dist_row = dist_out ? dist_out + (size_t)y * opitch : nullptr;
+    const bool pair_d2 = (((uintptr_t)d2_row) & 7u) == 0, pair_dist = (((uintptr_t)dist_row) & 7u) == 0;
+    for (int k0 = warp * 32; 2 * k0 < W; k0 += DC_THREADS) {
+        const int k = k0 + lane, xe = 2 * k, xo = xe + 1;
+        const bool ve = xe < W, vo = xo < W;
+        const int ae = ve ? (int)s_a[k] : 0;
+        uint32_t ce = 0u, co = 0u;
+        const uint32_t gpair = ve ? *(const uint32_t *)(s_g + xe) : 0u;      // g of both pixels (the row buffer is padded)
+        if (__any_sync(0xffffffffu, gpair != 0u)) {
+            int arg;
+            co = edt_solve(s_g, lane, vo ? xo : -1, ae, xo + 1 < W ? (int)s_a[k + 1] : W - 1, arg);
+            if (ve) {
+                const uint32_t gg = s_g[ae];
+                const int d = xe - ae;
+                ce = (uint32_t)(d * d) + gg * gg;
+            }
+        }
+        if (d2_row) {
+            const int32_t ie = ce >= 0x80000000u ? 0x7fffffff : (int32_t)ce, io = co >= 0x80000000u ? 0x7fffffff : (int32_t)co;
+            if (pair_d2 && vo) *(int2 *)(d2_row + xe) = make_int2(ie, io);
+            else {
+                if (ve) d2_row[xe] = ie;
+                if (vo) d2_row[xo] = io;
+            }
+        }
+        if (dist_row) {
+            const float fe = ce == 0u ? 0.0f : (ce >= 0x80000000u ? 3.0e38f : __fsqrt_rn((float)ce));
+            const float fo = co == 0u ? 0.0f : (co >= 0x80000000u ? 3.0e38f : __fsqrt_rn((float)co));
+            if (pair_dist && vo) *(float2 *)(dist_row + xe) = make_float2(fe, fo);
+            else {
+                if (ve) dist_row[xe] = fe;
+                if (vo) dist_row[xo] = fo;
+            }
+        }
     }
 }
 
@@ -270,22 +319,21 @@ extern "C" int vsb_edt_exact(const uint32_t *seed_bits, int wpr, int W, int H, v
     k_edt_colsum<<<gsq, 256, 0, s>>>(seed_bits, wpr, H, first8, last8);
     int rc = vsb_check_launch("k_edt_colsum");
     if (rc) return rc;
-    k_edt_colscan<<<dim3((unsigned)((Wp + 127) / 128), 2), 128, 0, s>>>(first8, last8, (int)Wp, (int)nb, up, dn);
+    k_edt_colscan<<<dim3((unsigned)((Wp + 63) / 64), 2), 64, 0, s>>>(first8, last8, (int)Wp, (int)nb, up, dn);
     if ((rc = vsb_check_launch("k_edt_colscan"))) return rc;
     k_edt_coldist<<<gsq, 256, 0, s>>>(seed_bits, wpr, H, up, dn, g, gpitch);
     if ((rc = vsb_check_launch("k_edt_coldist"))) return rc;
 
     const int Wa = (int)gpitch;
-    const size_t smem = (size_t)Wa * 4 + DC_MAXPIX * 8 + DC_MAXCHUNK * 8 + DC_MAXPIX * 2;
+    const size_t smem = (size_t)Wa * 3;
     static bool configured = false;
     if (!configured) {
         VSB_CUDA(cudaFuncSetAttribute(k_edt_rowdc, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         configured = true;
     }
     VSB_REQUIRE(smem <= 200 * 1024, "vsb_edt_exact: a row of %d pixels does not fit the row kernel's shared memory", W);
-    int top_S = 1;
-    while (top_S * 2 < W) top_S *= 2;
-    if (W == 1) top_S = 0;
-    k_edt_rowdc<<<H, DC_THREADS, smem, s>>>(g, gpitch, W, Wa, top_S, d2_out, dist_out, pitch_elems);
+    int top_log2 = 0; // levels S = 2^top_log2 .. 2 (the largest power of two below W), none for W <= 2; S = 1 always runs
+    while ((2 << top_log2) < W) ++top_log2;
+    k_edt_rowdc<<<H, DC_THREADS, smem, s>>>(g, gpitch, W, Wa, top_log2, d2_out, dist_out, pitch_elems);
     return vsb_check_launch("k_edt_rowdc");
 }
