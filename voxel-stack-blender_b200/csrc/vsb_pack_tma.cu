@@ -313,7 +313,7 @@ int vsb_pack_tma_launch(const uint8_t *gray, size_t pitch, int W, int H, uint32_
     p.wpr = wpr; p.tiles_x = (W + VSB_TW - 1) / VSB_TW;
     const int tiles_y = (H + VSB_TH - 1) / VSB_TH;
     p.ntiles = p.tiles_x * tiles_y; p.W = W; p.H = H;
-    p.stages = stages_env >= 3 && stages_env <= 8 ? stages_env : (lutout ? 4 : 3);
+    p.stages = stages_env >= 3 && stages_env <= 8 ? stages_env : (lutout ? 5 : 3);
     CUtensorMap tm_in, tm_out;
     int rc = vsb_make_tmap_2d(&tm_in, gray, 1, (size_t)W, (size_t)H, pitch, VSB_TW, VSB_TH);
     if (rc) return rc;
