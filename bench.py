@@ -302,7 +302,8 @@ def main():
     numa = pin_rank_to_gpu_numa(local_rank)                  # pinned staging buffers land next to this rank's GPU
     if world > 1:
         # NCCL's init lines (rank / nranks) go to stderr; stdout stays the one JSON line
-        os.environ.setdefault("NCCL_DEBUG", "INFO")
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() in ("VERSION", "WARN"):   # the image presets VERSION
+            os.environ["NCCL_DEBUG"] = "INFO"
         os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch.distributed as dist
