@@ -195,7 +195,7 @@ __device__ __forceinline__ uint32_t edt_solve(const uint16_t *__restrict__ s_g, 
     return best;
 }
 
-__global__ void __launch_bounds__(DC_THREADS, 4) k_edt_rowdc(const uint16_t *__restrict__ g, size_t gpitch, int W, int Wa, int top_log2,
+__global__ void __launch_bounds__(DC_THREADS, 5) k_edt_rowdc(const uint16_t *__restrict__ g, size_t gpitch, int W, int Wa, int top_log2,
                                                              int32_t *__restrict__ d2_out, float *__restrict__ dist_out, size_t opitch)
 {
     extern __shared__ __align__(128) uint8_t dsm[];
@@ -324,11 +324,12 @@ extern "C" int vsb_edt_exact(const uint32_t *seed_bits, int wpr, int W, int H, v
     k_edt_coldist<<<gsq, 256, 0, s>>>(seed_bits, wpr, H, up, dn, g, gpitch);
     if ((rc = vsb_check_launch("k_edt_coldist"))) return rc;
 
-    const int Wa = (int)gpitch;
+    const int Wa = (W + 15) & ~15; // row buffer: 2 Wa bytes of g + Wa bytes of A; at 16K five CTAs share an SM's shared memory
     const size_t smem = (size_t)Wa * 3;
     static bool configured = false;
     if (!configured) {
         VSB_CUDA(cudaFuncSetAttribute(k_edt_rowdc, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        VSB_CUDA(cudaFuncSetAttribute(k_edt_rowdc, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         configured = true;
     }
     VSB_REQUIRE(smem <= 200 * 1024, "vsb_edt_exact: a row of %d pixels does not fit the row kernel's shared memory", W);
