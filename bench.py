@@ -465,7 +465,7 @@ def main():
                               "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32/f32",
                               "data": "synthetic", "config": {"workload": WORKLOAD_TEXT["edt"]}, "impl": "b200",
                               "clocks": blk["clocks"], "edt_only": blk,
-                              "roofline": {"bound": "hbm", "kernel": "exact EDT (column + envelope row pass)",
+                              "roofline": {"bound": "hbm", "kernel": "exact EDT (k_edt_col* + k_edt_rowdc)",
                                            "achieved": best["gbs_algorithmic"], "peak": peak, "unit": "GB/s",
                                            "frac": best["frac_of_measured_peak"], "traffic": None, "peak_source": peak_src}}))
         return 0

@@ -88,10 +88,10 @@ int vsb_dt_exact_windowed(const uint32_t *seed_bits, int wpr, int W, int H, int 
                           float *dist, size_t dist_pitch_elems, vsb_stream_t stream);
 
 /* K2' exact Euclidean distance transform, unbounded reach (cv2.DIST_MASK_PRECISE analogue), csrc/vsb_edt.cu:
- *     separable lower-envelope algorithm -- row pass (distance to the nearest set bit of the same row, uint16, the
- *     packed row staged with one bulk copy and the finished row stored with one) then, along every column, the
- *     lower envelope of the parabolas (y - y')^2 + h(x,y')^2 by Meijster's integer two-scan method on the runs between
- *     set bits.  Cost is O(W*H) whatever the distances are.
+ *     separable lower-envelope formulation -- column pass (distance to the nearest set bit of the same column, uint16:
+ *     32x32 bit squares transposed with warp shuffles, block carries) then, along every row, the lower envelope of the
+ *     parabolas (x - x')^2 + g(x',y)^2, evaluated by bisection on the monotone column of the ruling parabola (one CTA
+ *     per row, the row of g staged with one bulk copy).  O(log W) per pixel at worst, whatever the distances are.
  *     d2_out (optional) = exact integer squared distance (INT32_MAX if the image holds no set bit);
  *     dist_out (optional) = sqrtf(d2) (3e38 there).  W, H <= 32767; wpr a multiple of 4; scratch: device buffer of
  *     vsb_edt_exact_scratch_bytes(W, H) bytes, 128-byte aligned. */

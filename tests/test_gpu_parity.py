@@ -120,8 +120,8 @@ def test_exact_edt(E, slices, ref_dist):
 
 @pytest.mark.parametrize("case", ["one_seed", "corner_seeds", "all_white", "sparse", "dense", "columns", "rows", "ragged", "tall"])
 def test_exact_edt_envelope_cases(E, case):
-    """vsb_edt_exact (row pass + Meijster lower envelope along the columns): integer d2 equal to the oracle's
-    Felzenszwalb transform on inputs whose runs are long (a single seed: every column is one run over the whole height),
+    """vsb_edt_exact (column distances + bisection on the lower envelope along the rows): integer d2 equal to the oracle's
+    Felzenszwalb transform on inputs whose envelopes are long (a single seed: every row is ruled by one far parabola),
     empty rows, seeds only on the border, widths that are not a multiple of 32 / 64, and images taller than several bands."""
     rng = np.random.default_rng(len(case))
     shapes = {"one_seed": (300, 700), "corner_seeds": (257, 513), "all_white": (65, 130), "sparse": (400, 1000),

@@ -37,10 +37,17 @@
 // ---- column pass ------------------------------------------------------------------------------------------------------
 // The warp's 32 x 32 square, transposed: bit r of the returned word = pixel (32 wc + lane, y0 + r).  Five butterfly stages:
 // lanes k and k ^ j swap the off-diagonal j x j blocks of the bit matrix.
-__device__ __forceinline__ uint32_t edt_column_word(const uint32_t *__restrict__ bits, int wpr, int H, int wc, int y0, int lane)
+__device__ __forceinline__ uint32_t edt_column_word(const uint32_t *__restrict__ bits, int wpr, int H, int wc0, int y0, uint32_t (*s_sq)[8])
 {
-    const int y = y0 + lane;
-    uint32_t v = y < H ? bits[(size_t)y * wpr + wc] : 0u;
+    // the CTA's eight squares side by side are 32 rows x 32 bytes: one coalesced pass into shared memory (a sector per row),
+    // then every warp picks up its word column
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    {
+        const int y = y0 + (t >> 3), wx = wc0 + (t & 7);
+        s_sq[t >> 3][t & 7] = (y < H && wx < wpr) ? bits[(size_t)y * wpr + wx] : 0u;
+    }
+    __syncthreads();
+    uint32_t v = s_sq[lane][warp];
 #pragma unroll
     for (int j = 16; j >= 1; j >>= 1) {
         const uint32_t m = j == 16 ? 0x0000FFFFu : (j == 8 ? 0x00FF00FFu : (j == 4 ? 0x0F0F0F0Fu : (j == 2 ? 0x33333333u : 0x55555555u)));
@@ -54,9 +61,10 @@ __device__ __forceinline__ uint32_t edt_column_word(const uint32_t *__restrict__
 __global__ void __launch_bounds__(256) k_edt_colsum(const uint32_t *__restrict__ bits, int wpr, int H, uint8_t *__restrict__ first8,
                                                     uint8_t *__restrict__ last8)
 {
+    __shared__ uint32_t s_sq[32][8];
     const int lane = threadIdx.x & 31, wc = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const uint32_t col = edt_column_word(bits, wpr, H, blockIdx.x * 8, blockIdx.y * 32, s_sq);
     if (wc >= wpr) return;
-    const uint32_t col = edt_column_word(bits, wpr, H, wc, blockIdx.y * 32, lane);
     const size_t o = (size_t)blockIdx.y * (32 * (size_t)wpr) + 32 * wc + lane;
     first8[o] = col ? (uint8_t)(__ffs(col) - 1) : (uint8_t)0xFF;
     last8[o] = col ? (uint8_t)(31 - __clz(col)) : (uint8_t)0xFF;
@@ -92,38 +100,29 @@ __global__ void __launch_bounds__(64) k_edt_colscan(const uint8_t *__restrict__ 
     }
 }
 
-__global__ void __launch_bounds__(256) k_edt_coldist(const uint32_t *__restrict__ bits, int wpr, int H, const uint16_t *__restrict__ up,
+__global__ void __launch_bounds__(256, 6) k_edt_coldist(const uint32_t *__restrict__ bits, int wpr, int H, const uint16_t *__restrict__ up,
                                                      const uint16_t *__restrict__ dn, uint16_t *__restrict__ g, size_t gpitch)
 {
+    __shared__ uint32_t s_sq[32][8];
     const int lane = threadIdx.x & 31, wc = blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (wc >= wpr) return;
     const int y0 = blockIdx.y * 32;
+    const uint32_t col = edt_column_word(bits, wpr, H, blockIdx.x * 8, y0, s_sq);
+    if (wc >= wpr) return;
     const size_t o = (size_t)blockIdx.y * (32 * (size_t)wpr) + 32 * wc + lane;
     const uint32_t u = up[o], d = dn[o];
-    const uint32_t col = edt_column_word(bits, wpr, H, wc, y0, lane);
     if ((size_t)(32 * wc + lane) >= gpitch) return;
     uint16_t *gp = g + (size_t)y0 * gpitch + 32 * wc + lane;
-    // downwards: distance to the nearest white pixel at or above the row; upwards: at or below it, and the minimum leaves
-    int du[32];
-    int run = u != 0xFFFFu ? y0 - 1 - (int)u : EDT_BIG; // at "row -1" of the block
+    // per row: the nearest white pixel at or above it from a clz of the word's low part (or the block above), at or below it
+    // from a running count walked upwards; the minimum leaves
+    const int up1 = u != 0xFFFFu ? y0 - (int)u : EDT_BIG;       // from row y0 to the nearest white row above the block
+    int run = d != 0xFFFFu ? (int)d - (y0 + 32) : EDT_BIG;      // at "row 32" of the block
+    const int rows = min(32, H - y0);
 #pragma unroll
-    for (int r = 0; r < 32; ++r) {
+    for (int r = 31; r >= 0; --r) {
         run = (col >> r) & 1u ? 0 : run + 1;
-        du[r] = run;
-    }
-    run = d != 0xFFFFu ? (int)d - (y0 + 32) : EDT_BIG;  // at "row 32" of the block
-    if (y0 + 32 <= H) {
-#pragma unroll
-        for (int r = 31; r >= 0; --r) {
-            run = (col >> r) & 1u ? 0 : run + 1;
-            gp[(size_t)r * gpitch] = (uint16_t)min(min(du[r], run), (int)EDT_GNONE);
-        }
-    } else {
-#pragma unroll
-        for (int r = 31; r >= 0; --r) {
-            run = (col >> r) & 1u ? 0 : run + 1;
-            if (y0 + r < H) gp[(size_t)r * gpitch] = (uint16_t)min(min(du[r], run), (int)EDT_GNONE);
-        }
+        const uint32_t low = col & (0xFFFFFFFFu >> (31 - r));   // rows 0 .. r
+        const int du = low ? r - (31 - __clz(low)) : up1 + r;
+        if (r < rows) gp[(size_t)r * gpitch] = (uint16_t)min(min(du, run), (int)EDT_GNONE);
     }
 }
 

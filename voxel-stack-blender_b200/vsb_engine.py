@@ -304,7 +304,7 @@ def distance_np(cur_white: np.ndarray, R: int, clip: float, metric: str = "chamf
 
 
 def edt_exact_np(cur_white: np.ndarray):
-    """Unbounded exact EDT (lower-envelope algorithm, csrc/vsb_edt.cu): (squared distances int32, distances float32)."""
+    """Unbounded exact EDT (separable lower-envelope formulation, csrc/vsb_edt.cu): (squared distances int32, distances float32)."""
     t = torch()
     img = DevImage.from_numpy(cur_white)
     b = pack(img)
