@@ -19,6 +19,12 @@
 
 #define L2W 6                        // mask words per region row: x0-32 .. x0+159
 #define L2_PLANES 7                  // and_b, or_b, rec_b, and_h, or_h, rec_h, safe
+#define L2_DENSE_MIN 2560            // receding pixels from which a tile takes the row-distance table
+#define L2_HCOLS 142                 // table columns: region columns L2_HC0 .. L2_HC0 + 141 (receding pixels lie in 9 .. 150)
+#define L2_HC0 9
+#define EDT_FAR (1 << 20)
+#define L2_HS 164                    // bytes per table column (the listed rows side by side; 41 words: conflict-free across columns)
+#define L2_DENSE_ROWS 164            // 142 x 164 bytes fit the space of the three lists (4480 + 1024 + 6656 entries)
 
 // bits [lo, hi) of the 192-bit region span that fall into word k
 __device__ __forceinline__ uint32_t span_mask(int k, int lo, int hi)
@@ -59,13 +65,15 @@ __global__ void __launch_bounds__(VSB_THREADS, 3) k_layer2(const __grid_constant
     uint16_t *s_list = (uint16_t *)(dsm + p.sm.list);   // bilateral pixel list; Gaussian word list behind it
     uint16_t *s_glist = s_list + p.sm.glist;
     uint16_t *s_rlist = s_glist + 1024;                  // receding pixel list
+    uint8_t *s_h = (uint8_t *)s_list;                    // dense tiles: row-distance table [column][L2_HS], in the space of the lists
     __shared__ uint32_t s_c[RG_ROWS_MAX][8], s_r[RG_ROWS_MAX][8];      // region words: current mask, receding mask
     __shared__ uint32_t s_pl[L2_PLANES][RG_ROWS_MAX][8];
     __shared__ uint32_t s_rowany[(LB_ROWS_MAX + 31) / 32];
     __shared__ float s_cw2[512];
     __shared__ __align__(4) uint8_t s_lut1[256];
     __shared__ __align__(4) uint8_t s_lut2[256];
-    __shared__ int s_cnt, s_gcnt, s_rcnt, s_state, s_decision;
+    __shared__ int s_cnt, s_gcnt, s_rcnt, s_state, s_decision, s_nact;
+    __shared__ uint8_t s_act[LB_ROWS_MAX + 4], s_lo[RG_ROWS_MAX], s_hi[RG_ROWS_MAX], s_mid[RG_ROWS_MAX]; // dense tiles: non-empty window rows, and per region row the ones in reach
 
     const int t = threadIdx.x, lane = t & 31;
     const int W = p.W, H = p.H, wpr = p.wpr;
@@ -234,8 +242,194 @@ __global__ void __launch_bounds__(VSB_THREADS, 3) k_layer2(const __grid_constant
     }
     __syncthreads();
 
+    // ---- dense tiles (hundreds of receding pixels: wide rims, and whole tiles right after a raft ends): the per-pixel row walk
+    //      probes the same window rows over and over, and most of them hold no white pixel.  List the non-empty window rows, take
+    //      the nearest-white distance of every (column, listed row) once -- one byte each, rows of a column side by side -- and
+    //      let the pixels read them four rows at a time.  The table borrows the space of the three lists (the receding pixels are
+    //      then taken from the mask words), so this runs BEFORE the filter lists are built.
+    bool use_h = false;
+    if (any_rec && searching && s_rcnt >= L2_DENSE_MIN) {
+        const int brows = RH + 2 * R;
+        stage_rowany_rows<LBW>(s_rowany, s_bits, brows);
+        __syncthreads();
+        if (t < 32) {
+            int n = 0;
+            for (int b0 = 0; b0 < brows; b0 += 32) {
+                const uint32_t w = s_rowany[b0 >> 5];
+                if ((w >> lane) & 1u) s_act[n + __popc(w & ((1u << lane) - 1u))] = (uint8_t)(b0 + lane);
+                n += __popc(w);
+            }
+            if (lane < 4) s_act[min(n + lane, LB_ROWS_MAX + 3)] = 255; // padding of the last group of four: never in reach
+            if (lane == 0) s_nact = n;
+        }
+        __syncthreads();
+        const int nact = s_nact;
+        use_h = nact <= L2_DENSE_ROWS && border == false;
+        if (use_h) {
+            if (t < RH) { // the listed rows within reach of region row t
+                const int hr0 = t + R;
+                int lo = 0;
+                while (lo < nact && (int)s_act[lo] < hr0 - R) ++lo;
+                int hi = lo;
+                while (hi < nact && (int)s_act[hi] <= hr0 + R) ++hi;
+                int mid = lo;
+                while (mid < hi && (int)s_act[mid] <= hr0) ++mid;
+                s_lo[t] = (uint8_t)lo; s_hi[t] = (uint8_t)hi; s_mid[t] = (uint8_t)mid; // [lo, mid): rows at or above, [mid, hi): below
+            }
+            const int nact4 = (nact + 3) & ~3;
+            for (int i = t; i < nact4 * L2_HCOLS; i += VSB_THREADS) {
+                const int a = i / L2_HCOLS, c = i - a * L2_HCOLS;
+                s_h[c * L2_HS + a] = a < nact ? (uint8_t)nearest_dx(s_bits[s_act[a]], c + L2_HC0 + 80) : (uint8_t)255;
+            }
+            __syncthreads();
+        }
+    }
+    // ---- 4. receding pixels: distance, fade, leading LUT -> both stage buffers ------------------------------------------------
+    // (after 3b for ordinary tiles, from the list; before it for dense tiles, from the mask words and the table)
+    const float Ff = p.z.fade;
+    auto fade_pixel = [&](const int rr, const int rc, const float best) -> uint8_t {
+        const int x = x0 - 16 + rc, y = y0 - Hh + rr;
+        int g;
+        if (ZMODE == VSB_Z_FIXED) {
+            const float n = __fdiv_rn(fminf(best, Ff), p.z.den);
+            g = (int)__fmul_rn(255.0f, __fsub_rn(1.0f, n));
+        } else if (ZMODE == VSB_Z_WEIGHTED) {
+            float acc = 0.0f;
+            const size_t o = (size_t)y * wpr + (x >> 5);
+            const uint32_t ncur = ~p.cur[o];
+            for (int j = 0; j < np; ++j) {
+                if (p.z.weights[j] > 0.0f && (((p.prior[j][o] & ncur) >> (x & 31)) & 1u)) {
+                    const float n = __fsub_rn(1.0f, __fdiv_rn(fminf(best, p.z.fades[j]), p.z.dens[j]));
+                    acc = __fadd_rn(acc, __fmul_rn(n, p.z.weights[j]));
+                }
+            }
+            g = (int)__fmul_rn(255.0f, __fdiv_rn(acc, p.z.total_weight));
+        } else if (ZMODE == VSB_Z_ENHANCED) {
+            const float d = p.enh_dist[(size_t)y * p.enh_dpitch + x];
+            const float mx = __uint_as_float(p.enh_cmax[p.enh_labels[(size_t)y * W + x]]);
+            if (p.z.enhanced_arith == 0) {
+                float den = (float)fmin((double)mx, p.z.fade_limit);
+                if (den <= 0.0f) den = 1.0f;
+                const float nrm = __fdiv_rn(fminf(fmaxf(d, 0.0f), den), den);
+                g = (int)__fmul_rn(255.0f, __fsub_rn(1.0f, nrm));
+            } else {
+                const double den = fmin((double)mx, p.z.fade_limit);
+                g = 0;
+                if (den > 0.0) g = (int)(long long)__dmul_rn(__dsub_rn(1.0, __ddiv_rn(fmin((double)d, den), den)), 255.0);
+            }
+        } else {
+            g = p.z.const_val;
+        }
+        const int m = g & 255; // merge with the raw gray value: a receding pixel is black, its gray value is 0
+        const uint8_t v = p.lut1 ? s_lut1[m] : (uint8_t)m;
+        s1[rr][rc] = v;
+        s2buf[rr][rc] = v;
+        return v;
+    };
+    if (use_h) { // dense, interior tile: a warp per mask word, a lane per pixel, distances from the table
+        const int n1 = R + 1;
+        for (int item = t >> 5; item < RH * L2W; item += VSB_THREADS / 32) {
+            const int rr = item / L2W, k = item - rr * L2W;
+            const uint32_t rw = s_r[rr][k];
+            if (rw == 0u) continue; // warp-uniform
+            const bool mine = (rw >> lane) & 1u;
+            const int rc = 32 * k + lane - 16;
+            const int hr0 = rr + R;
+            const uint8_t *hp = s_h + min(max(rc - L2_HC0, 0), L2_HCOLS - 1) * L2_HS;
+            // the listed rows in groups of four (one 32-bit read of the table each), outwards from the pixel's own row, first
+            // upwards then downwards; a SIMD byte compare picks the rows that hold a white pixel closer than the best distance
+            // so far, and a direction ends once no lane can do better than the group's smallest |dy|
+            float best = mine ? 3.0e38f : 0.0f;
+            int best2 = mine ? 0x7fffffff : 0;
+            uint32_t thr4 = (uint32_t)R * 0x01010101u; // per byte: dx <= thr can still improve this lane's best
+            const int lo = s_lo[rr], hi = s_hi[rr], mid = s_mid[rr];
+            auto group = [&](const int g4) { // rows g4 .. g4 + 3 of the list
+                const uint32_t w4 = *(const uint32_t *)(hp + g4);
+                uint32_t hit = mine ? __vcmpleu4(w4, thr4) : 0u;
+                while (hit) {
+                    const int q = (__ffs(hit) - 1) >> 3;
+                    hit &= ~(0xFFu << (8 * q));
+                    const int dx = (w4 >> (8 * q)) & 255, kk = abs((int)s_act[g4 + q] - hr0);
+                    if (kk <= R) {
+                        if (METRIC == VSB_METRIC_CHAMFER5) {
+                            const int M = max(kk, dx);
+                            if ((float)M < best) {
+                                best = fminf(best, s_T[M * n1 + min(kk, dx)]);
+                                thr4 = (uint32_t)min(R, (int)best) * 0x01010101u; // dx > floor(best) gives T >= dx > best... never better
+                            }
+                        } else {
+                            const int c2 = kk * kk + dx * dx;
+                            if (c2 < best2) {
+                                best2 = c2;
+                                thr4 = (uint32_t)min(R, (int)__fsqrt_ru((float)c2)) * 0x01010101u;
+                            }
+                        }
+                    }
+                }
+            };
+            for (int g4 = (mid - 1) & ~3; g4 >= (lo & ~3) && mid > lo; g4 -= 4) { // upwards: the group's nearest row is its last
+                const int kmin = max(hr0 - (int)s_act[min(g4 + 3, mid - 1)], 0);
+                if (METRIC == VSB_METRIC_CHAMFER5 ? __all_sync(0xffffffffu, best <= (float)kmin) : __all_sync(0xffffffffu, best2 <= kmin * kmin)) break;
+                group(g4);
+            }
+            for (int g4 = mid & ~3; g4 < hi; g4 += 4) {                           // downwards: its first
+                const int kmin = max((int)s_act[max(g4, mid)] - hr0, 0);
+                if (METRIC == VSB_METRIC_CHAMFER5 ? __all_sync(0xffffffffu, best <= (float)kmin) : __all_sync(0xffffffffu, best2 <= kmin * kmin)) break;
+                group(g4);
+            }
+            bool graded = false;
+            if (mine) {
+                if (METRIC != VSB_METRIC_CHAMFER5) best = best2 == 0x7fffffff ? 3.0e38f : __fsqrt_rn((float)best2);
+                graded = fade_pixel(rr, rc, best) != (uint8_t)k0b;
+            }
+            // a receding pixel whose value came out as black's (beyond the fade distance) IS a black pixel for the filters:
+            // only the others keep their mark, so the bypass planes below see a plain two-valued region there
+            const uint32_t nw = __ballot_sync(0xffffffffu, graded);
+            if (lane == 0) s_r[rr][k] = nw;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < 2; ++u) { // the receding planes of 3a, again, from the marks that are left
+            const int i = t + u * VSB_THREADS;
+            if (i < RH * L2W) {
+                const int rr = i / L2W, k = i - rr * L2W;
+                const uint32_t rl = k > 0 ? s_r[rr][k - 1] : 0u, rc = s_r[rr][k], rq = k < L2W - 1 ? s_r[rr][k + 1] : 0u;
+                s_pl[2][rr][k] = hwin<false>(rl, rc, rq, hb);
+                s_pl[5][rr][k] = hwin<false>(rl, rc, rq, hb + rx);
+            }
+        }
+        __syncthreads();
+    }
+    auto receding_listed = [&]() {
+        const int total = s_rcnt;
+        for (int i = t; i < total; i += VSB_THREADS) {
+            const int codev = s_rlist[i];
+            const int rr = codev >> 8, rc = codev & 255;
+            const int x = x0 - 16 + rc, y = y0 - Hh + rr;
+            if (y < 0 || y >= H || x < 0 || x >= W) continue; // mirrored positions are filled in below
+            float best = 0.0f;
+            if (ZL_SEARCHES(ZMODE)) best = tile_search<METRIC, LBW, false>(s_bits, s_rowany, s_T, R, rr + R, rc + 80);
+            fade_pixel(rr, rc, best);
+        }
+        __syncthreads();
+        // REFLECT_101 of the gradient values into the out-of-image halo (border tiles): mirror the stage-1 bytes
+        if (border) {
+            for (int i = t; i < total; i += VSB_THREADS) {
+                const int codev = s_rlist[i];
+                const int rr = codev >> 8, rc = codev & 255;
+                const int x = x0 - 16 + rc, y = y0 - Hh + rr;
+                if (y >= 0 && y < H && x >= 0 && x < W) continue;
+                const int ys = vsb_reflect101(y, H), xs = vsb_reflect101(x, W);
+                const uint8_t v = s1[ys - (y0 - Hh)][xs - (x0 - 16)];
+                s1[rr][rc] = v;
+                s2buf[rr][rc] = v;
+            }
+            __syncthreads();
+        }
+    };
+
     // ---- 3b. vertical pass: which pixels need the bilateral, which words the Gaussian ---------------------------------------
-    if (any_rec && searching) stage_rowany_rows<LBW>(s_rowany, s_bits, RH + 2 * R);
+    if (any_rec && searching && !use_h) stage_rowany_rows<LBW>(s_rowany, s_bits, RH + 2 * R);
     {
         const int nb_lo = Hh - hg, nb_hi = Hh + VSB_TH + hg; // region rows on which stage 2 is needed
 #pragma unroll
@@ -279,69 +473,7 @@ __global__ void __launch_bounds__(VSB_THREADS, 3) k_layer2(const __grid_constant
     }
     __syncthreads();
 
-    // ---- 4. receding pixels: distance, fade, leading LUT -> both stage buffers ------------------------------------------------
-    if (any_rec) {
-        const int total = s_rcnt;
-        const float Ff = p.z.fade;
-        for (int i = t; i < total; i += VSB_THREADS) {
-            const int codev = s_rlist[i];
-            const int rr = codev >> 8, rc = codev & 255;
-            const int x = x0 - 16 + rc, y = y0 - Hh + rr;
-            if (y < 0 || y >= H || x < 0 || x >= W) continue; // mirrored positions are filled in below
-            float best = 0.0f;
-            if (ZL_SEARCHES(ZMODE)) best = tile_search<METRIC, LBW, false>(s_bits, s_rowany, s_T, R, rr + R, rc + 80);
-            int g;
-            if (ZMODE == VSB_Z_FIXED) {
-                const float n = __fdiv_rn(fminf(best, Ff), p.z.den);
-                g = (int)__fmul_rn(255.0f, __fsub_rn(1.0f, n));
-            } else if (ZMODE == VSB_Z_WEIGHTED) {
-                float acc = 0.0f;
-                const size_t o = (size_t)y * wpr + (x >> 5);
-                const uint32_t ncur = ~p.cur[o];
-                for (int j = 0; j < np; ++j) {
-                    if (p.z.weights[j] > 0.0f && (((p.prior[j][o] & ncur) >> (x & 31)) & 1u)) {
-                        const float n = __fsub_rn(1.0f, __fdiv_rn(fminf(best, p.z.fades[j]), p.z.dens[j]));
-                        acc = __fadd_rn(acc, __fmul_rn(n, p.z.weights[j]));
-                    }
-                }
-                g = (int)__fmul_rn(255.0f, __fdiv_rn(acc, p.z.total_weight));
-            } else if (ZMODE == VSB_Z_ENHANCED) {
-                const float d = p.enh_dist[(size_t)y * p.enh_dpitch + x];
-                const float mx = __uint_as_float(p.enh_cmax[p.enh_labels[(size_t)y * W + x]]);
-                if (p.z.enhanced_arith == 0) {
-                    float den = (float)fmin((double)mx, p.z.fade_limit);
-                    if (den <= 0.0f) den = 1.0f;
-                    const float nrm = __fdiv_rn(fminf(fmaxf(d, 0.0f), den), den);
-                    g = (int)__fmul_rn(255.0f, __fsub_rn(1.0f, nrm));
-                } else {
-                    const double den = fmin((double)mx, p.z.fade_limit);
-                    g = 0;
-                    if (den > 0.0) g = (int)(long long)__dmul_rn(__dsub_rn(1.0, __ddiv_rn(fmin((double)d, den), den)), 255.0);
-                }
-            } else {
-                g = p.z.const_val;
-            }
-            const int m = g & 255; // merge with the raw gray value: a receding pixel is black, its gray value is 0
-            const uint8_t v = p.lut1 ? s_lut1[m] : (uint8_t)m;
-            s1[rr][rc] = v;
-            s2buf[rr][rc] = v;
-        }
-        __syncthreads();
-        // REFLECT_101 of the gradient values into the out-of-image halo (border tiles): mirror the stage-1 bytes
-        if (border) {
-            for (int i = t; i < total; i += VSB_THREADS) {
-                const int codev = s_rlist[i];
-                const int rr = codev >> 8, rc = codev & 255;
-                const int x = x0 - 16 + rc, y = y0 - Hh + rr;
-                if (y >= 0 && y < H && x >= 0 && x < W) continue;
-                const int ys = vsb_reflect101(y, H), xs = vsb_reflect101(x, W);
-                const uint8_t v = s1[ys - (y0 - Hh)][xs - (x0 - 16)];
-                s1[rr][rc] = v;
-                s2buf[rr][rc] = v;
-            }
-            __syncthreads();
-        }
-    }
+    if (any_rec && !use_h) receding_listed();
 
     uint8_t (*S2)[RG_W] = hb > 0 ? s2buf : s1;                  // Gaussian input
     uint8_t (*OUT)[RG_W] = gauss ? (hb > 0 ? s1 : s2buf) : S2;  // what the store phase reads
