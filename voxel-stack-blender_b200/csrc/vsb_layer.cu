@@ -72,6 +72,7 @@ struct LayerParams {
     const int *rec_list; // sparse: [0] = number of tiles with receding pixels, [1..] their indices (nullptr = all tiles)
     int gen_grid;        // CTAs of the list-mode launch
     int *gen_list;       // XY: k_layer2 appends the tiles it leaves to the general kernel; k_layer then walks that list
+    int *dense_list;     // XY: interior tiles with thousands of receding pixels, set aside for k_layer2_dense
     int two_valued;      // k_layer2: a window holding only LUT1[0] / LUT1[255] with >= 3 taps equal to the centre keeps the centre
     // VSB_Z_ENHANCED: distances at the receding pixels, their component roots and the per-root maxima (vsb_ccl8_max)
     const float *enh_dist; size_t enh_dpitch; const int32_t *enh_labels; const uint32_t *enh_cmax;
@@ -745,18 +746,26 @@ static int launch_layer2(LayerParams &p, const BilTapsL *taps, size_t smem2, siz
     static int n_sms = 0; // per instantiation
     if (n_sms == 0) {
         VSB_CUDA(cudaFuncSetAttribute(k_layer2<ZMODE, METRIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        VSB_CUDA(cudaFuncSetAttribute(k_layer2_dense<ZMODE, METRIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
         int dev = 0, sms = 0;
         VSB_CUDA(cudaGetDevice(&dev));
         VSB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         n_sms = sms > 0 ? sms : 148;
     }
-    VSB_CUDA(cudaMemsetAsync(gen_list, 0, sizeof(int), s));
+    // two lists in the scratch: the general kernel's, and behind it the dense launch's
     p.gen_list = gen_list;
+    p.dense_list = gen_list + 1 + p.ntiles;
+    VSB_CUDA(cudaMemsetAsync(p.gen_list, 0, sizeof(int), s));
+    VSB_CUDA(cudaMemsetAsync(p.dense_list, 0, sizeof(int), s));
     dim3 grid(p.tiles_x, p.tiles_y);
     k_layer2<ZMODE, METRIC><<<grid, VSB_THREADS, smem2, s>>>(p, taps);
     int rc = vsb_check_launch("k_layer2");
     if (rc) return rc;
     p.gen_grid = p.ntiles < 2 * n_sms ? p.ntiles : 2 * n_sms;
+    if (ZL_SEARCHES(ZMODE)) {
+        k_layer2_dense<ZMODE, METRIC><<<p.ntiles < 3 * n_sms ? p.ntiles : 3 * n_sms, VSB_THREADS, smem2, s>>>(p, taps);
+        if ((rc = vsb_check_launch("k_layer2_dense"))) return rc;
+    }
     return launch_layer_v<ZMODE, METRIC, true>(p, taps, smem, s);
 }
 

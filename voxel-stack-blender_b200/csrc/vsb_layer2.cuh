@@ -54,8 +54,10 @@ __device__ __forceinline__ uint32_t expand4(uint32_t nib, uint32_t K0, uint32_t 
     return (m & K1) | (~m & K0);
 }
 
-template <int ZMODE, int METRIC>
-__global__ void __launch_bounds__(VSB_THREADS, 3) k_layer2(const __grid_constant__ LayerParams p, const BilTapsL *__restrict__ taps)
+// one tile.  DENSE: the instantiation of the second launch, which holds the row-distance-table path for the tiles the first one
+// sets aside (interior tiles with thousands of receding pixels) -- kept out of the first launch's code
+template <int ZMODE, int METRIC, bool DENSE>
+__device__ __forceinline__ void layer2_tile(const LayerParams &p, const BilTapsL *__restrict__ taps, const int tx, const int ty)
 {
     extern __shared__ __align__(16) uint8_t dsm[];
     float *s_T = (float *)(dsm + p.sm.T);
@@ -84,7 +86,6 @@ __global__ void __launch_bounds__(VSB_THREADS, 3) k_layer2(const __grid_constant
     const bool gauss = p.nkx > 0;
     const int RH = VSB_TH + 2 * Hh;
     const int R = p.z.reach;
-    const int tx = (int)blockIdx.x, ty = (int)blockIdx.y;
     const int x0 = tx * VSB_TW, y0 = ty * VSB_TH;
     const int oy = y0 + r, ox = x0 + c * 16;
     const int nvalid = (oy < H) ? max(0, min(16, W - ox)) : 0;
@@ -115,7 +116,7 @@ __global__ void __launch_bounds__(VSB_THREADS, 3) k_layer2(const __grid_constant
         if (lane == 0) {
             s_decision = dec;
             s_cnt = 0; s_gcnt = 0; s_rcnt = 0; s_state = 0;
-            if (dec == 1) p.gen_list[1 + atomicAdd(&p.gen_list[0], 1)] = ty * p.tiles_x + tx;
+            if (dec == 1 && !DENSE) p.gen_list[1 + atomicAdd(&p.gen_list[0], 1)] = ty * p.tiles_x + tx;
         }
     }
     if (t < 64 && p.lut1) ((uint32_t *)s_lut1)[t] = ((const uint32_t *)p.lut1)[t];
@@ -248,7 +249,11 @@ __global__ void __launch_bounds__(VSB_THREADS, 3) k_layer2(const __grid_constant
     //      let the pixels read them four rows at a time.  The table borrows the space of the three lists (the receding pixels are
     //      then taken from the mask words), so this runs BEFORE the filter lists are built.
     bool use_h = false;
-    if (any_rec && searching && s_rcnt >= L2_DENSE_MIN) {
+    if (!DENSE && any_rec && searching && !border && s_rcnt >= L2_DENSE_MIN) { // set aside for the dense launch
+        if (t == 0) p.dense_list[1 + atomicAdd(&p.dense_list[0], 1)] = ty * p.tiles_x + tx;
+        return;
+    }
+    if (DENSE && any_rec && searching && s_rcnt >= L2_DENSE_MIN) {
         const int brows = RH + 2 * R;
         stage_rowany_rows<LBW>(s_rowany, s_bits, brows);
         __syncthreads();
@@ -326,7 +331,7 @@ __global__ void __launch_bounds__(VSB_THREADS, 3) k_layer2(const __grid_constant
         s2buf[rr][rc] = v;
         return v;
     };
-    if (use_h) { // dense, interior tile: a warp per mask word, a lane per pixel, distances from the table
+    if (DENSE && use_h) { // dense, interior tile: a warp per mask word, a lane per pixel, distances from the table
         const int n1 = R + 1;
         for (int item = t >> 5; item < RH * L2W; item += VSB_THREADS / 32) {
             const int rr = item / L2W, k = item - rr * L2W;
@@ -546,5 +551,24 @@ __global__ void __launch_bounds__(VSB_THREADS, 3) k_layer2(const __grid_constant
         uint8_t *dst = p.out + (size_t)oy * p.opitch + ox;
         if (nvalid == 16 && p.aligned) vsb_st16_stream(dst, o);
         else vsb_st_bytes(dst, o, nvalid);
+    }
+}
+
+template <int ZMODE, int METRIC>
+__global__ void __launch_bounds__(VSB_THREADS, 3) k_layer2(const __grid_constant__ LayerParams p, const BilTapsL *__restrict__ taps)
+{
+    layer2_tile<ZMODE, METRIC, false>(p, taps, (int)blockIdx.x, (int)blockIdx.y);
+}
+
+// the tiles set aside by k_layer2: a few CTAs per SM stride over the list (empty on ordinary layers)
+template <int ZMODE, int METRIC>
+__global__ void __launch_bounds__(VSB_THREADS, 3) k_layer2_dense(const __grid_constant__ LayerParams p, const BilTapsL *__restrict__ taps)
+{
+    const int n = p.dense_list[0];
+    for (int li = (int)blockIdx.x; li < n; li += (int)gridDim.x) {
+        const int tile = p.dense_list[1 + li];
+        const int ty = tile / p.tiles_x;
+        layer2_tile<ZMODE, METRIC, true>(p, taps, tile - ty * p.tiles_x, ty);
+        __syncthreads(); // the next tile re-initialises the shared state
     }
 }
