@@ -10,11 +10,12 @@
 //
 // Both passes are laid out for the GPU instead of for a scan line:
 //
-//   column pass (k_edt_colsum, k_edt_colscan, k_edt_coldist).  The packed mask is cut into blocks of 32 rows; a warp takes a
-//   32 x 32 pixel square (one mask word column) and transposes it with five shuffle butterflies so that every lane holds ITS
-//   column as one 32-bit word.  A first launch records per (block, column) the first and last white row (ffs / clz), a second
-//   one carries them down and up the (few) blocks, the third runs the two distance recurrences over the lane's word in
-//   registers and writes g as uint16 rows (EDT_GNONE where the column holds no white pixel at all).
+//   column pass (k_edt_colsum, k_edt_colscan, k_edt_coldist).  The packed mask is cut into blocks of 32 rows; a CTA brings a
+//   32-row x 8-word tile in with one bulk tensor load (cp.async.bulk.tensor.2d + mbarrier), a warp takes one 32 x 32 pixel
+//   square of it and transposes it with five shuffle butterflies so that every lane holds ITS column as one 32-bit word.
+//   A first launch records per (block, column) the first and last white row (ffs / clz), a second one carries them down
+//   and up the (few) blocks, the third runs the two distance recurrences over the lane's word in registers and writes g
+//   as uint16 rows (EDT_GNONE where the column holds no white pixel at all).
 //
 //   row pass (k_edt_rowdc).  One CTA per image row, the row of g staged in shared memory with one bulk copy.  The stack of
 //   Meijster's scan is a chain of dependent steps as long as the row; here the envelope is evaluated by bisection instead:
@@ -37,16 +38,22 @@
 // ---- column pass ------------------------------------------------------------------------------------------------------
 // The warp's 32 x 32 square, transposed: bit r of the returned word = pixel (32 wc + lane, y0 + r).  Five butterfly stages:
 // lanes k and k ^ j swap the off-diagonal j x j blocks of the bit matrix.
-__device__ __forceinline__ uint32_t edt_column_word(const uint32_t *__restrict__ bits, int wpr, int H, int wc0, int y0, uint32_t (*s_sq)[8])
+template <int NW>
+__device__ __forceinline__ uint32_t edt_column_word(const CUtensorMap *tm, int wc0, int y0, uint32_t (*s_sq)[NW], uint64_t *s_bar)
 {
-    // the CTA's eight squares side by side are 32 rows x 32 bytes: one coalesced pass into shared memory (a sector per row),
-    // then every warp picks up its word column
+    // the CTA's eight squares side by side are a 32-row x 32-byte tile of the packed mask: one bulk tensor load (rows and
+    // words outside the mask arrive as zeros), then every warp picks up its word column
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    {
-        const int y = y0 + (t >> 3), wx = wc0 + (t & 7);
-        s_sq[t >> 3][t & 7] = (y < H && wx < wpr) ? bits[(size_t)y * wpr + wx] : 0u;
+    if (t == 0) {
+        vsb_mbar_init(s_bar, 1);
+        vsb_fence_barrier_init();
     }
     __syncthreads();
+    if (t == 0) {
+        vsb_mbar_expect_tx(s_bar, 32 * NW * 4);
+        vsb_tma_load_2d(s_sq, tm, wc0, y0, s_bar);
+    }
+    vsb_mbar_wait(s_bar, 0);
     uint32_t v = s_sq[lane][warp];
 #pragma unroll
     for (int j = 16; j >= 1; j >>= 1) {
@@ -58,12 +65,13 @@ __device__ __forceinline__ uint32_t edt_column_word(const uint32_t *__restrict__
 }
 
 // first / last white row of every (block of 32 rows, column): 0..31, 0xFF = none
-__global__ void __launch_bounds__(256) k_edt_colsum(const uint32_t *__restrict__ bits, int wpr, int H, uint8_t *__restrict__ first8,
+__global__ void __launch_bounds__(256) k_edt_colsum(const __grid_constant__ CUtensorMap tm_bits, int wpr, uint8_t *__restrict__ first8,
                                                     uint8_t *__restrict__ last8)
 {
-    __shared__ uint32_t s_sq[32][8];
+    __shared__ __align__(128) uint32_t s_sq[32][8];
+    __shared__ __align__(8) uint64_t s_bar;
     const int lane = threadIdx.x & 31, wc = blockIdx.x * 8 + (threadIdx.x >> 5);
-    const uint32_t col = edt_column_word(bits, wpr, H, blockIdx.x * 8, blockIdx.y * 32, s_sq);
+    const uint32_t col = edt_column_word<8>(&tm_bits, blockIdx.x * 8, blockIdx.y * 32, s_sq, &s_bar);
     if (wc >= wpr) return;
     const size_t o = (size_t)blockIdx.y * (32 * (size_t)wpr) + 32 * wc + lane;
     first8[o] = col ? (uint8_t)(__ffs(col) - 1) : (uint8_t)0xFF;
@@ -100,29 +108,40 @@ __global__ void __launch_bounds__(64) k_edt_colscan(const uint8_t *__restrict__ 
     }
 }
 
-__global__ void __launch_bounds__(256, 6) k_edt_coldist(const uint32_t *__restrict__ bits, int wpr, int H, const uint16_t *__restrict__ up,
-                                                     const uint16_t *__restrict__ dn, uint16_t *__restrict__ g, size_t gpitch)
+#define EDT_CD_WARPS 8 // word columns per CTA of k_edt_coldist (wider CTAs were measured slower: 94 vs 79 us)
+__global__ void __launch_bounds__(EDT_CD_WARPS * 32, 6) k_edt_coldist(const __grid_constant__ CUtensorMap tm_bits, int wpr, int H,
+                                                                      const uint16_t *__restrict__ up, const uint16_t *__restrict__ dn,
+                                                                      uint16_t *__restrict__ g, size_t gpitch)
 {
-    __shared__ uint32_t s_sq[32][8];
-    const int lane = threadIdx.x & 31, wc = blockIdx.x * 8 + (threadIdx.x >> 5);
+    __shared__ __align__(128) uint32_t s_sq[32][EDT_CD_WARPS];
+    __shared__ __align__(8) uint64_t s_bar;
+    const int lane = threadIdx.x & 31, wc = blockIdx.x * EDT_CD_WARPS + (threadIdx.x >> 5);
     const int y0 = blockIdx.y * 32;
-    const uint32_t col = edt_column_word(bits, wpr, H, blockIdx.x * 8, y0, s_sq);
+    const uint32_t col = edt_column_word<EDT_CD_WARPS>(&tm_bits, blockIdx.x * EDT_CD_WARPS, y0, s_sq, &s_bar);
     if (wc >= wpr) return;
     const size_t o = (size_t)blockIdx.y * (32 * (size_t)wpr) + 32 * wc + lane;
     const uint32_t u = up[o], d = dn[o];
-    if ((size_t)(32 * wc + lane) >= gpitch) return;
-    uint16_t *gp = g + (size_t)y0 * gpitch + 32 * wc + lane;
+    if ((size_t)(32 * wc) >= gpitch) return; // (gpitch is a multiple of 64: a word column is inside or outside as a whole)
     // per row: the nearest white pixel at or above it from a clz of the word's low part (or the block above), at or below it
     // from a running count walked upwards; the minimum leaves
     const int up1 = u != 0xFFFFu ? y0 - (int)u : EDT_BIG;       // from row y0 to the nearest white row above the block
     int run = d != 0xFFFFu ? (int)d - (y0 + 32) : EDT_BIG;      // at "row 32" of the block
     const int rows = min(32, H - y0);
-#pragma unroll
-    for (int r = 31; r >= 0; --r) {
+    // two rows per trip; neighbouring lanes swap one value each so that every lane stores a pair of columns (32 bits) of one row
+    uint32_t *gw = (uint32_t *)(g + (size_t)y0 * gpitch + 32 * wc + (lane & ~1));
+    auto dist_at = [&](const int r) -> uint32_t {
         run = (col >> r) & 1u ? 0 : run + 1;
-        const uint32_t low = col & (0xFFFFFFFFu >> (31 - r));   // rows 0 .. r
+        const uint32_t low = col & (0xFFFFFFFFu >> (31 - r)); // rows 0 .. r
         const int du = low ? r - (31 - __clz(low)) : up1 + r;
-        if (r < rows) gp[(size_t)r * gpitch] = (uint16_t)min(min(du, run), (int)EDT_GNONE);
+        return (uint32_t)min(min(du, run), (int)EDT_GNONE);
+    };
+#pragma unroll
+    for (int r = 31; r >= 1; r -= 2) {
+        const uint32_t hi_row = dist_at(r), lo_row = dist_at(r - 1);
+        const uint32_t got = __shfl_xor_sync(0xffffffffu, (lane & 1) ? lo_row : hi_row, 1);
+        const int row = (lane & 1) ? r : r - 1; // odd lanes store row r, even lanes row r - 1
+        const uint32_t word = (lane & 1) ? (got | (hi_row << 16)) : (lo_row | (got << 16));
+        if (row < rows) gw[(size_t)row * (gpitch / 2)] = word;
     }
 }
 
@@ -315,12 +334,16 @@ extern "C" int vsb_edt_exact(const uint32_t *seed_bits, int wpr, int W, int H, v
     uint16_t *dn = (uint16_t *)p;
 
     const dim3 gsq((wpr + 7) / 8, (unsigned)nb);
-    k_edt_colsum<<<gsq, 256, 0, s>>>(seed_bits, wpr, H, first8, last8);
-    int rc = vsb_check_launch("k_edt_colsum");
+    CUtensorMap tm_bits; // the packed mask as a 2-D tensor of words: boxes of 8 words x 32 rows = the eight squares of a CTA
+    int rc = vsb_make_tmap_2d(&tm_bits, seed_bits, 4, (size_t)wpr, (size_t)H, (size_t)wpr * 4, 8, 32);
     if (rc) return rc;
+    k_edt_colsum<<<gsq, 256, 0, s>>>(tm_bits, wpr, first8, last8);
+    if ((rc = vsb_check_launch("k_edt_colsum"))) return rc;
     k_edt_colscan<<<dim3((unsigned)((Wp + 63) / 64), 2), 64, 0, s>>>(first8, last8, (int)Wp, (int)nb, up, dn);
     if ((rc = vsb_check_launch("k_edt_colscan"))) return rc;
-    k_edt_coldist<<<gsq, 256, 0, s>>>(seed_bits, wpr, H, up, dn, g, gpitch);
+    CUtensorMap tm_wide;
+    if ((rc = vsb_make_tmap_2d(&tm_wide, seed_bits, 4, (size_t)wpr, (size_t)H, (size_t)wpr * 4, EDT_CD_WARPS, 32))) return rc;
+    k_edt_coldist<<<dim3((wpr + EDT_CD_WARPS - 1) / EDT_CD_WARPS, (unsigned)nb), EDT_CD_WARPS * 32, 0, s>>>(tm_wide, wpr, H, up, dn, g, gpitch);
     if ((rc = vsb_check_launch("k_edt_coldist"))) return rc;
 
     const int Wa = (W + 15) & ~15; // row buffer: 2 Wa bytes of g + Wa bytes of A; at 16K five CTAs share an SM's shared memory
