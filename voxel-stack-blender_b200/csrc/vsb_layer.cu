@@ -73,6 +73,7 @@ struct LayerParams {
     int gen_grid;        // CTAs of the list-mode launch
     int *gen_list;       // XY: k_layer2 appends the tiles it leaves to the general kernel; k_layer then walks that list
     int *dense_list;     // XY: interior tiles with thousands of receding pixels, set aside for k_layer2_dense
+    int rcap;            // k_layer2: entries of the receding-pixel list (sm.glist = entries of the bilateral pixel list)
     int two_valued;      // k_layer2: a window holding only LUT1[0] / LUT1[255] with >= 3 taps equal to the centre keeps the centre
     // VSB_Z_ENHANCED: distances at the receding pixels, their component roots and the per-root maxima (vsb_ccl8_max)
     const float *enh_dist; size_t enh_dpitch; const int32_t *enh_labels; const uint32_t *enh_cmax;
@@ -741,11 +742,13 @@ static int launch_layer_v(LayerParams &p, const BilTapsL *taps, size_t smem, cud
 
 // binary fast path: k_layer2 over all tiles (it lists the tiles it does not take), then k_layer over that list
 template <int ZMODE, int METRIC>
-static int launch_layer2(LayerParams &p, const BilTapsL *taps, size_t smem2, size_t smem, int *gen_list, cudaStream_t s)
+static int launch_layer2(LayerParams &p, LayerParams &pd, const BilTapsL *taps, size_t smem2, size_t smem2d, size_t smem, int *gen_list,
+                         cudaStream_t s)
 {
     static int n_sms = 0; // per instantiation
     if (n_sms == 0) {
         VSB_CUDA(cudaFuncSetAttribute(k_layer2<ZMODE, METRIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        VSB_CUDA(cudaFuncSetAttribute(k_layer2<ZMODE, METRIC>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         VSB_CUDA(cudaFuncSetAttribute(k_layer2_dense<ZMODE, METRIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
         int dev = 0, sms = 0;
         VSB_CUDA(cudaGetDevice(&dev));
@@ -753,8 +756,8 @@ static int launch_layer2(LayerParams &p, const BilTapsL *taps, size_t smem2, siz
         n_sms = sms > 0 ? sms : 148;
     }
     // two lists in the scratch: the general kernel's, and behind it the dense launch's
-    p.gen_list = gen_list;
-    p.dense_list = gen_list + 1 + p.ntiles;
+    p.gen_list = pd.gen_list = gen_list;
+    p.dense_list = pd.dense_list = gen_list + 1 + p.ntiles;
     VSB_CUDA(cudaMemsetAsync(p.gen_list, 0, sizeof(int), s));
     VSB_CUDA(cudaMemsetAsync(p.dense_list, 0, sizeof(int), s));
     dim3 grid(p.tiles_x, p.tiles_y);
@@ -763,7 +766,7 @@ static int launch_layer2(LayerParams &p, const BilTapsL *taps, size_t smem2, siz
     if (rc) return rc;
     p.gen_grid = p.ntiles < 2 * n_sms ? p.ntiles : 2 * n_sms;
     if (ZL_SEARCHES(ZMODE)) {
-        k_layer2_dense<ZMODE, METRIC><<<p.ntiles < 3 * n_sms ? p.ntiles : 3 * n_sms, VSB_THREADS, smem2, s>>>(p, taps);
+        k_layer2_dense<ZMODE, METRIC><<<p.ntiles < 3 * n_sms ? p.ntiles : 3 * n_sms, VSB_THREADS, smem2d, s>>>(pd, taps);
         if ((rc = vsb_check_launch("k_layer2_dense"))) return rc;
     }
     return launch_layer_v<ZMODE, METRIC, true>(p, taps, smem, s);
@@ -913,15 +916,20 @@ static int layer_launch(const uint8_t *in, size_t in_pitch, int W, int H, const 
         p2.sm.s1 = (int)o2; o2 += up16((size_t)RH * RG_W);
         p2.sm.s2 = (int)o2; o2 += up16((size_t)RH * RG_W);
         p2.sm.bits = (int)o2; o2 += searching ? up16((size_t)(RH + 2 * p.z.reach) * LBW * 4) : 16;
-        p2.sm.list = (int)o2; p2.sm.glist = 4480; // 34 x 130 bilateral pixels at most, 1024 Gaussian words, 46 x 142 receding pixels
-        o2 += (size_t)(4480 + 1024 + 6656) * 2;
-        const size_t smem2 = o2;
+        // lists of the first launch: 3072 bilateral pixels, 1024 Gaussian words, 2560 receding pixels (denser tiles are set aside
+        // or handed to the general kernel) -- four CTAs fit an SM; the dense launch gets room for the largest case (34 x 130,
+        // 46 x 142), which is also the space of its row-distance table
+        p2.sm.list = (int)o2;
+        LayerParams p2d = p2;
+        p2.sm.glist = 3072; p2.rcap = searching ? L2_DENSE_MIN : 6656; // (modes without search set nothing aside)
+        p2d.sm.glist = 4480; p2d.rcap = 6656;
+        const size_t smem2 = o2 + (size_t)(p2.sm.glist + 1024 + p2.rcap) * 2, smem2d = o2 + (size_t)(p2d.sm.glist + 1024 + p2d.rcap) * 2;
         int rc2;
         switch (mode) {
-        case VSB_Z_FIXED: rc2 = ex ? launch_layer2<VSB_Z_FIXED, 1>(p2, taps_dev, smem2, smem, general_tiles, s) : launch_layer2<VSB_Z_FIXED, 0>(p2, taps_dev, smem2, smem, general_tiles, s); break;
-        case VSB_Z_WEIGHTED: rc2 = ex ? launch_layer2<VSB_Z_WEIGHTED, 1>(p2, taps_dev, smem2, smem, general_tiles, s) : launch_layer2<VSB_Z_WEIGHTED, 0>(p2, taps_dev, smem2, smem, general_tiles, s); break;
-        case VSB_Z_CONST: rc2 = launch_layer2<VSB_Z_CONST, 0>(p2, taps_dev, smem2, smem, general_tiles, s); break;
-        default: rc2 = launch_layer2<VSB_Z_ENHANCED, 0>(p2, taps_dev, smem2, smem, general_tiles, s); break;
+        case VSB_Z_FIXED: rc2 = ex ? launch_layer2<VSB_Z_FIXED, 1>(p2, p2d, taps_dev, smem2, smem2d, smem, general_tiles, s) : launch_layer2<VSB_Z_FIXED, 0>(p2, p2d, taps_dev, smem2, smem2d, smem, general_tiles, s); break;
+        case VSB_Z_WEIGHTED: rc2 = ex ? launch_layer2<VSB_Z_WEIGHTED, 1>(p2, p2d, taps_dev, smem2, smem2d, smem, general_tiles, s) : launch_layer2<VSB_Z_WEIGHTED, 0>(p2, p2d, taps_dev, smem2, smem2d, smem, general_tiles, s); break;
+        case VSB_Z_CONST: rc2 = launch_layer2<VSB_Z_CONST, 0>(p2, p2d, taps_dev, smem2, smem2d, smem, general_tiles, s); break;
+        default: rc2 = launch_layer2<VSB_Z_ENHANCED, 0>(p2, p2d, taps_dev, smem2, smem2d, smem, general_tiles, s); break;
         }
         return rc2;
     }

@@ -222,9 +222,10 @@ __device__ __forceinline__ void layer2_tile(const LayerParams &p, const BilTapsL
                 safe = (sl & sr) | (su & sd) | ((sl | sr) & (su | sd));
             }
             s_pl[6][rr][k] = safe;
-            if (rc) { // receding pixels of this word -> list
+            if (rc) { // receding pixels of this word -> list (a tile holding more than the list does is handed on below)
                 uint32_t rw = rc;
                 int base = atomicAdd(&s_rcnt, __popc(rw));
+                if (base + __popc(rw) > p.rcap) rw = 0u;
                 while (rw) {
                     const int bq = __ffs(rw) - 1;
                     rw &= rw - 1;
@@ -251,6 +252,10 @@ __device__ __forceinline__ void layer2_tile(const LayerParams &p, const BilTapsL
     bool use_h = false;
     if (!DENSE && any_rec && searching && !border && s_rcnt >= L2_DENSE_MIN) { // set aside for the dense launch
         if (t == 0) p.dense_list[1 + atomicAdd(&p.dense_list[0], 1)] = ty * p.tiles_x + tx;
+        return;
+    }
+    if (any_rec && s_rcnt > p.rcap) { // more receding pixels than the list holds (border tiles, modes without search): general kernel
+        if (t == 0) p.gen_list[1 + atomicAdd(&p.gen_list[0], 1)] = ty * p.tiles_x + tx;
         return;
     }
     if (DENSE && any_rec && searching && s_rcnt >= L2_DENSE_MIN) {
@@ -451,6 +456,7 @@ __device__ __forceinline__ void layer2_tile(const LayerParams &p, const BilTapsL
                     nb &= span_mask(k, max(32 - hg, img_lo), min(160 + hg, img_hi));
                     if (nb) {
                         int base = atomicAdd(&s_cnt, __popc(nb));
+                        if (base + __popc(nb) > p.sm.glist) nb = 0u; // list full: the tile goes to the general kernel below
                         while (nb) {
                             const int bq = __ffs(nb) - 1;
                             nb &= nb - 1;
@@ -477,6 +483,10 @@ __device__ __forceinline__ void layer2_tile(const LayerParams &p, const BilTapsL
         }
     }
     __syncthreads();
+    if (hb > 0 && s_cnt > p.sm.glist) { // more bilateral pixels than the list holds: the general kernel takes the tile
+        if (t == 0) p.gen_list[1 + atomicAdd(&p.gen_list[0], 1)] = ty * p.tiles_x + tx;
+        return;
+    }
 
     if (any_rec && !use_h) receding_listed();
 
@@ -555,7 +565,7 @@ __device__ __forceinline__ void layer2_tile(const LayerParams &p, const BilTapsL
 }
 
 template <int ZMODE, int METRIC>
-__global__ void __launch_bounds__(VSB_THREADS, 3) k_layer2(const __grid_constant__ LayerParams p, const BilTapsL *__restrict__ taps)
+__global__ void __launch_bounds__(VSB_THREADS, 4) k_layer2(const __grid_constant__ LayerParams p, const BilTapsL *__restrict__ taps)
 {
     layer2_tile<ZMODE, METRIC, false>(p, taps, (int)blockIdx.x, (int)blockIdx.y);
 }
