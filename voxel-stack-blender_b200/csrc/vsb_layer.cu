@@ -921,7 +921,7 @@ static int layer_launch(const uint8_t *in, size_t in_pitch, int W, int H, const 
         // 46 x 142), which is also the space of its row-distance table
         p2.sm.list = (int)o2;
         LayerParams p2d = p2;
-        p2.sm.glist = 3072; p2.rcap = searching ? L2_DENSE_MIN : 6656; // (modes without search set nothing aside)
+        p2.sm.glist = 3072; p2.rcap = L2_DENSE_MIN; // (modes without search set nothing aside: their fuller tiles take the general kernel)
         p2d.sm.glist = 4480; p2d.rcap = 6656;
         const size_t smem2 = o2 + (size_t)(p2.sm.glist + 1024 + p2.rcap) * 2, smem2d = o2 + (size_t)(p2d.sm.glist + 1024 + p2d.rcap) * 2;
         int rc2;
