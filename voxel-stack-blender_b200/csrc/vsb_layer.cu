@@ -275,7 +275,7 @@ __device__ __forceinline__ uint32_t gauss_word_ry(const uint8_t (*S)[RG_W], int 
     } while (0)
 
 template <int ZMODE, int METRIC, bool XY>
-__global__ void __launch_bounds__(VSB_THREADS, XY ? VSB_LAYER_CTAS_XY : 6) k_layer(const __grid_constant__ LayerParams p,
+__global__ void __launch_bounds__(VSB_THREADS, XY ? VSB_LAYER_CTAS_XY : 7) k_layer(const __grid_constant__ LayerParams p,
                                                        const BilTapsL *__restrict__ taps)
 {
     // work list of the patch launch: CTAs beyond the number of listed tiles leave before any set-up
@@ -894,12 +894,14 @@ static int layer_launch(const uint8_t *in, size_t in_pitch, int W, int H, const 
     const bool searching = mode != VSB_Z_NONE && mode != VSB_Z_CONST && mode != VSB_Z_ENHANCED;
     size_t off = 0;
     p.sm.T = (int)off; off += up16((searching && zp->metric == VSB_METRIC_CHAMFER5) ? (size_t)n1 * n1 * 4 : 16);
-    p.sm.s1 = (int)off; off += up16((size_t)RH * RG_W);
+    // (the patch launch stages no pixels: it only needs the table, the window and the receding-pixel list -- the smaller its
+    //  footprint, the more of its CTAs sit beside the pack pass of the next layer)
+    p.sm.s1 = (int)off; off += sparse ? 16 : up16((size_t)RH * RG_W);
     p.sm.bits = (int)off; off += searching ? up16((size_t)(RH + 2 * p.z.reach) * LBW * 4) : 16;
-    const size_t s2bytes = up16((size_t)RH * RG_W);
+    const size_t s2bytes = sparse ? 16 : up16((size_t)RH * RG_W);
     p.sm.s2 = (int)off; off += s2bytes;
     const size_t rlist = (mode != VSB_Z_NONE) ? (size_t)RH * (VSB_TW + 2 * p.halo) * 2 : 0; // overlays [s2 | list]
-    const size_t lmin = (size_t)(GL_OFF + 1100) * 2;
+    const size_t lmin = sparse ? 16 : (size_t)(GL_OFF + 1100) * 2;
     p.sm.list = (int)off; off += up16(rlist > s2bytes + lmin ? rlist - s2bytes : lmin);
     const size_t smem = off;
     cudaStream_t s = (cudaStream_t)stream;
