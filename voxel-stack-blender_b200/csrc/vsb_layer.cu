@@ -918,14 +918,15 @@ static int layer_launch(const uint8_t *in, size_t in_pitch, int W, int H, const 
         p2.sm.s1 = (int)o2; o2 += up16((size_t)RH * RG_W);
         p2.sm.s2 = (int)o2; o2 += up16((size_t)RH * RG_W);
         p2.sm.bits = (int)o2; o2 += searching ? up16((size_t)(RH + 2 * p.z.reach) * LBW * 4) : 16;
-        // lists of the first launch: 3072 bilateral pixels, 1024 Gaussian words, 2560 receding pixels (denser tiles are set aside
-        // or handed to the general kernel) -- four CTAs fit an SM; the dense launch gets room for the largest case (34 x 130,
-        // 46 x 142), which is also the space of its row-distance table
+        // the list arena (receding pixels | bilateral pixels ... | 1024 Gaussian words).  First launch: 7424 entries -- tiles
+        // with more than 2560 receding pixels are set aside or handed to the general kernel, which leaves room for at least
+        // 3840 bilateral pixels (all 34 x 130 of them once fewer than 1980 recede) -- four CTAs fit an SM at F = 40.  The dense
+        // launch gets the largest case (46 x 142 receding, 34 x 130 bilateral), which is also the space of its table.
         p2.sm.list = (int)o2;
         LayerParams p2d = p2;
-        p2.sm.glist = 3072; p2.rcap = L2_DENSE_MIN; // (modes without search set nothing aside: their fuller tiles take the general kernel)
-        p2d.sm.glist = 4480; p2d.rcap = 6656;
-        const size_t smem2 = o2 + (size_t)(p2.sm.glist + 1024 + p2.rcap) * 2, smem2d = o2 + (size_t)(p2d.sm.glist + 1024 + p2d.rcap) * 2;
+        p2.sm.glist = 7424 - 1024; p2.rcap = L2_DENSE_MIN; // (modes without search set nothing aside: their fuller tiles take the general kernel)
+        p2d.sm.glist = 6656 + 4480; p2d.rcap = 6656;
+        const size_t smem2 = o2 + (size_t)(p2.sm.glist + 1024) * 2, smem2d = o2 + (size_t)(p2d.sm.glist + 1024) * 2;
         int rc2;
         switch (mode) {
         case VSB_Z_FIXED: rc2 = ex ? launch_layer2<VSB_Z_FIXED, 1>(p2, p2d, taps_dev, smem2, smem2d, smem, general_tiles, s) : launch_layer2<VSB_Z_FIXED, 0>(p2, p2d, taps_dev, smem2, smem2d, smem, general_tiles, s); break;

@@ -64,10 +64,11 @@ __device__ __forceinline__ void layer2_tile(const LayerParams &p, const BilTapsL
     uint8_t (*s1)[RG_W] = (uint8_t (*)[RG_W])(dsm + p.sm.s1);
     uint8_t (*s2buf)[RG_W] = (uint8_t (*)[RG_W])(dsm + p.sm.s2);
     uint32_t (*s_bits)[LBW] = (uint32_t (*)[LBW])(dsm + p.sm.bits);
-    uint16_t *s_list = (uint16_t *)(dsm + p.sm.list);   // bilateral pixel list; Gaussian word list behind it
-    uint16_t *s_glist = s_list + p.sm.glist;
-    uint16_t *s_rlist = s_glist + 1024;                  // receding pixel list
-    uint8_t *s_h = (uint8_t *)s_list;                    // dense tiles: row-distance table [column][L2_HS], in the space of the lists
+    // one arena for the three lists: receding pixels from its start (at most p.rcap), the bilateral pixel list right behind
+    // them (its room is what the receding pixels leave), the 1024 Gaussian words at its end (offset p.sm.glist)
+    uint16_t *s_rlist = (uint16_t *)(dsm + p.sm.list);
+    uint16_t *s_glist = s_rlist + p.sm.glist;
+    uint8_t *s_h = (uint8_t *)s_rlist;                   // dense tiles: row-distance table [column][L2_HS], in the space of the lists
     __shared__ uint32_t s_c[RG_ROWS_MAX][8], s_r[RG_ROWS_MAX][8];      // region words: current mask, receding mask
     __shared__ uint32_t s_pl[L2_PLANES][RG_ROWS_MAX][8];
     __shared__ uint32_t s_rowany[(LB_ROWS_MAX + 31) / 32];
@@ -243,6 +244,10 @@ __device__ __forceinline__ void layer2_tile(const LayerParams &p, const BilTapsL
         }
     }
     __syncthreads();
+
+    const int n_listed_rec = any_rec ? s_rcnt : 0;
+    uint16_t *s_list = s_rlist + n_listed_rec;           // bilateral pixel list
+    const int bcap = p.sm.glist - n_listed_rec;
 
     // ---- dense tiles (hundreds of receding pixels: wide rims, and whole tiles right after a raft ends): the per-pixel row walk
     //      probes the same window rows over and over, and most of them hold no white pixel.  List the non-empty window rows, take
@@ -456,7 +461,7 @@ __device__ __forceinline__ void layer2_tile(const LayerParams &p, const BilTapsL
                     nb &= span_mask(k, max(32 - hg, img_lo), min(160 + hg, img_hi));
                     if (nb) {
                         int base = atomicAdd(&s_cnt, __popc(nb));
-                        if (base + __popc(nb) > p.sm.glist) nb = 0u; // list full: the tile goes to the general kernel below
+                        if (base + __popc(nb) > bcap) nb = 0u; // arena full: the tile goes to the general kernel below
                         while (nb) {
                             const int bq = __ffs(nb) - 1;
                             nb &= nb - 1;
@@ -483,7 +488,7 @@ __device__ __forceinline__ void layer2_tile(const LayerParams &p, const BilTapsL
         }
     }
     __syncthreads();
-    if (hb > 0 && s_cnt > p.sm.glist) { // more bilateral pixels than the list holds: the general kernel takes the tile
+    if (hb > 0 && s_cnt > bcap) { // more bilateral pixels than the arena has room for: the general kernel takes the tile
         if (t == 0) p.gen_list[1 + atomicAdd(&p.gen_list[0], 1)] = ty * p.tiles_x + tx;
         return;
     }
