@@ -758,8 +758,7 @@ static int launch_layer2(LayerParams &p, LayerParams &pd, const BilTapsL *taps, 
     // two lists in the scratch: the general kernel's, and behind it the dense launch's
     p.gen_list = pd.gen_list = gen_list;
     p.dense_list = pd.dense_list = gen_list + 1 + p.ntiles;
-    VSB_CUDA(cudaMemsetAsync(p.gen_list, 0, sizeof(int), s));
-    VSB_CUDA(cudaMemsetAsync(p.dense_list, 0, sizeof(int), s));
+    VSB_CUDA(cudaMemsetAsync(p.gen_list, 0, (size_t)(2 + p.ntiles) * sizeof(int), s)); // both counters with one node (93 KB at 16K)
     dim3 grid(p.tiles_x, p.tiles_y);
     k_layer2<ZMODE, METRIC><<<grid, VSB_THREADS, smem2, s>>>(p, taps);
     int rc = vsb_check_launch("k_layer2");
