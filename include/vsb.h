@@ -281,7 +281,7 @@ int vsb_layer_fused_enhanced(const uint8_t *in, size_t in_pitch, int W, int H, c
                              const uint8_t *lut1_dev, const vsb_xy_fused *xy /* host, may be NULL */,
                              const uint8_t *lut2_dev, uint8_t *out, size_t out_pitch,
                              const uint16_t *cur_flags /* NULL, or the layer's tile flags */,
-                             int *general_tiles /* NULL, or int[2 * (1 + tiles)] scratch: see vsb_layer_fused */,
+                             int *general_tiles /* NULL, or int[3 * (1 + tiles)] scratch: see vsb_layer_fused */,
                              vsb_stream_t stream);
 
 /* LUT-only pipelines (no XY filter): one pass over the gray layer writes the packed mask AND lut[gray] (the final
@@ -312,7 +312,7 @@ int vsb_layer_fused(const uint8_t *in, size_t in_pitch, int W, int H, const uint
                     const uint16_t *const *prior_flags, int wpr, const vsb_zparams *params, const float *T_dev,
                     const uint8_t *lut1_dev, const vsb_xy_fused *xy /* host, may be NULL */,
                     const uint8_t *lut2_dev, uint8_t *out, size_t out_pitch,
-                    int *general_tiles /* NULL, or int[2 * (1 + tiles)] device scratch.  With it and cur_flags, tiles whose
+                    int *general_tiles /* NULL, or int[3 * (1 + tiles)] device scratch.  With it and cur_flags, tiles whose
                                           3x3 tile neighbourhood is strictly binary (flag bit 0x200) run in k_layer2, which
                                           derives everything from the packed masks and never reads `in`; the other
                                           tiles are listed here and taken by the general kernel */,

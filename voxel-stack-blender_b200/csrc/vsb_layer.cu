@@ -73,6 +73,7 @@ struct LayerParams {
     int gen_grid;        // CTAs of the list-mode launch
     int *gen_list;       // XY: k_layer2 appends the tiles it leaves to the general kernel; k_layer then walks that list
     int *dense_list;     // XY: interior tiles with thousands of receding pixels, set aside for k_layer2_dense
+    uint16_t *tile_class; // k_layer2: per tile, from k_layer2_classify
     int rcap;            // k_layer2: entries of the receding-pixel list (sm.glist = entries of the bilateral pixel list)
     int two_valued;      // k_layer2: a window holding only LUT1[0] / LUT1[255] with >= 3 taps equal to the centre keeps the centre
     // VSB_Z_ENHANCED: distances at the receding pixels, their component roots and the per-root maxima (vsb_ccl8_max)
@@ -759,10 +760,13 @@ static int launch_layer2(LayerParams &p, LayerParams &pd, const BilTapsL *taps, 
     p.gen_list = pd.gen_list = gen_list;
     p.dense_list = pd.dense_list = gen_list + 1 + p.ntiles;
     VSB_CUDA(cudaMemsetAsync(p.gen_list, 0, (size_t)(2 + p.ntiles) * sizeof(int), s)); // both counters with one node (93 KB at 16K)
+    p.tile_class = pd.tile_class = (uint16_t *)(gen_list + 2 * (1 + p.ntiles));
+    k_layer2_classify<<<(p.ntiles + 255) / 256, 256, 0, s>>>(p);
+    int rc = vsb_check_launch("k_layer2_classify");
+    if (rc) return rc;
     dim3 grid(p.tiles_x, p.tiles_y);
     k_layer2<ZMODE, METRIC><<<grid, VSB_THREADS, smem2, s>>>(p, taps);
-    int rc = vsb_check_launch("k_layer2");
-    if (rc) return rc;
+    if ((rc = vsb_check_launch("k_layer2"))) return rc;
     p.gen_grid = p.ntiles < 2 * n_sms ? p.ntiles : 2 * n_sms;
     if (ZL_SEARCHES(ZMODE)) {
         k_layer2_dense<ZMODE, METRIC><<<p.ntiles < 3 * n_sms ? p.ntiles : 3 * n_sms, VSB_THREADS, smem2d, s>>>(pd, taps);

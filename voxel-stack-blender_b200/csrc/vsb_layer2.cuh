@@ -75,7 +75,7 @@ __device__ __forceinline__ void layer2_tile(const LayerParams &p, const BilTapsL
     __shared__ float s_cw2[512];
     __shared__ __align__(4) uint8_t s_lut1[256];
     __shared__ __align__(4) uint8_t s_lut2[256];
-    __shared__ int s_cnt, s_gcnt, s_rcnt, s_state, s_decision, s_nact;
+    __shared__ int s_cnt, s_gcnt, s_rcnt, s_state, s_nact;
     __shared__ uint8_t s_act[LB_ROWS_MAX + 4], s_lo[RG_ROWS_MAX], s_hi[RG_ROWS_MAX], s_mid[RG_ROWS_MAX]; // dense tiles: non-empty window rows, and per region row the ones in reach
 
     const int t = threadIdx.x, lane = t & 31;
@@ -91,40 +91,24 @@ __device__ __forceinline__ void layer2_tile(const LayerParams &p, const BilTapsL
     const int oy = y0 + r, ox = x0 + c * 16;
     const int nvalid = (oy < H) ? max(0, min(16, W - ox)) : 0;
 
-    // ---- 1. tile flags of the 3x3 neighbourhood --------------------------------------------------------------------------
-    if (t < 32) {
-        bool all_bin = true, same = true, pri_black = true;
-        uint32_t f0 = 0;
-        if (lane < 9) {
-            const int ny = min(max(ty + lane / 3 - 1, 0), p.tiles_y - 1), nx = min(max(tx + lane % 3 - 1, 0), p.tiles_x - 1);
-            const uint32_t f = p.cur_flags[ny * p.tiles_x + nx];
-            f0 = f;
-            all_bin = (f & FLAG_BINARY) != 0u;
-            for (int j = 0; j < np; ++j) {
-                const uint16_t *pf = p.prior_flags[j];
-                const uint32_t g = pf ? pf[ny * p.tiles_x + nx] : FLAG_MIXED;
-                pri_black = pri_black && !(g & FLAG_MIXED) && (g & 0xFFu) <= 127u;
-            }
+    // ---- 1. the tile's class (k_layer2_classify, from the tile flags of the 3x3 neighbourhood): constant tiles are written and
+    //         left at once -- no table staging, no barrier -- and non-binary ones were listed for the general kernel
+    const uint32_t cls = p.tile_class[ty * p.tiles_x + tx]; // the same word for every thread of the CTA
+    if ((cls & 3u) == 1u) return;
+    if (cls & 2u) {
+        if (nvalid > 0) {
+            const uint32_t cv = (cls >> 8) * 0x01010101u;
+            uint8_t *dst = p.out + (size_t)oy * p.opitch + ox;
+            const uint4 o = make_uint4(cv, cv, cv, cv);
+            if (nvalid == 16 && p.aligned) vsb_st16_stream(dst, o);
+            else vsb_st_bytes(dst, o, nvalid);
         }
-        const uint32_t fc = __shfl_sync(0xffffffffu, f0, 4); // the tile itself
-        if (lane < 9) same = (f0 == fc) && !(f0 & FLAG_MIXED);
-        all_bin = __all_sync(0xffffffffu, all_bin);
-        same = __all_sync(0xffffffffu, same);
-        pri_black = __all_sync(0xffffffffu, pri_black);
-        int dec = 0; // 0 = work, 1 = not binary -> general kernel, 2 = constant output
-        if (!all_bin) dec = 1;
-        else if (same && ((fc & 0xFFu) > 127u || pri_black || np == 0)) dec = 2 | (int)((fc & 0xFFu) << 8);
-        if (lane == 0) {
-            s_decision = dec;
-            s_cnt = 0; s_gcnt = 0; s_rcnt = 0; s_state = 0;
-            if (dec == 1 && !DENSE) p.gen_list[1 + atomicAdd(&p.gen_list[0], 1)] = ty * p.tiles_x + tx;
-        }
+        return;
     }
+    if (t == 0) { s_cnt = 0; s_gcnt = 0; s_rcnt = 0; s_state = 0; }
     if (t < 64 && p.lut1) ((uint32_t *)s_lut1)[t] = ((const uint32_t *)p.lut1)[t];
     if (t >= 64 && t < 128 && p.lut2) ((uint32_t *)s_lut2)[t - 64] = ((const uint32_t *)p.lut2)[t - 64];
     __syncthreads();
-    const int dec = s_decision;
-    if (dec == 1) return;
     const uint32_t k0b = p.lut1 ? s_lut1[0] : 0u, k1b = p.lut1 ? s_lut1[255] : 255u;
     const uint32_t K0 = k0b * 0x01010101u, K1 = k1b * 0x01010101u;
     auto constant_out = [&](uint32_t s1val) {
@@ -136,7 +120,6 @@ __device__ __forceinline__ void layer2_tile(const LayerParams &p, const BilTapsL
             else vsb_st_bytes(dst, o, nvalid);
         }
     };
-    if (dec & 2) { constant_out(((dec >> 8) & 0xFF) > 127 ? k1b : k0b); return; }
 
     // ---- 2. region mask words --------------------------------------------------------------------------------------------
     const int wx0 = (x0 >> 5) - 1;               // word column of region word 0
@@ -567,6 +550,41 @@ __device__ __forceinline__ void layer2_tile(const LayerParams &p, const BilTapsL
         if (nvalid == 16 && p.aligned) vsb_st16_stream(dst, o);
         else vsb_st_bytes(dst, o, nvalid);
     }
+}
+
+// One thread per tile: the decision every CTA of k_layer2 used to derive from 9 + 9 N tile flags behind a barrier.
+//   class & 3: 0 = work, 1 = a neighbour is not strictly binary -> listed for the general kernel, 2 = constant output;
+//   class >> 8: that constant (LUT2[LUT1[0 or 255]]).  A tile is constant when its 3x3 neighbourhood is one uniform value and
+//   nothing can recede there (the value is white, or every prior's neighbourhood is uniformly black).
+__global__ void __launch_bounds__(256) k_layer2_classify(const __grid_constant__ LayerParams p)
+{
+    const int tile = blockIdx.x * 256 + threadIdx.x;
+    if (tile >= p.ntiles) return;
+    const int ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
+    const int np = p.z.n_priors;
+    bool all_bin = true, same = true, pri_black = true;
+    const uint32_t fc = p.cur_flags[tile];
+    for (int q = 0; q < 9; ++q) {
+        const int ny = min(max(ty + q / 3 - 1, 0), p.tiles_y - 1), nx = min(max(tx + q % 3 - 1, 0), p.tiles_x - 1);
+        const int fi = ny * p.tiles_x + nx;
+        const uint32_t f = p.cur_flags[fi];
+        all_bin = all_bin && (f & FLAG_BINARY) != 0u;
+        same = same && f == fc && !(f & FLAG_MIXED);
+        for (int j = 0; j < np; ++j) {
+            const uint16_t *pf = p.prior_flags[j];
+            const uint32_t g = pf ? pf[fi] : FLAG_MIXED;
+            pri_black = pri_black && !(g & FLAG_MIXED) && (g & 0xFFu) <= 127u;
+        }
+    }
+    uint32_t cls = 0u;
+    if (!all_bin) {
+        cls = 1u;
+        p.gen_list[1 + atomicAdd(&p.gen_list[0], 1)] = tile;
+    } else if (same && ((fc & 0xFFu) > 127u || pri_black || np == 0)) {
+        const uint32_t s1val = (fc & 0xFFu) > 127u ? (p.lut1 ? p.lut1[255] : 255u) : (p.lut1 ? p.lut1[0] : 0u);
+        cls = 2u | ((p.lut2 ? (uint32_t)p.lut2[s1val] : s1val) << 8);
+    }
+    p.tile_class[tile] = (uint16_t)cls;
 }
 
 template <int ZMODE, int METRIC>

@@ -65,7 +65,7 @@ struct vsb_stack {
     uint8_t *lut2_dev;
     std::vector<uint16_t *> flag_ring;
     int *rec_tiles[2];     // LUT-only chains: work list of the patch kernel (1 + tiles ints), per lane
-    int *gen_tiles[2];     // XY chains: tiles k_layer2 leaves to the general kernel / to its dense launch (2 x (1 + tiles) ints), per lane
+    int *gen_tiles[2];     // XY chains: tiles k_layer2 leaves to the general kernel / to its dense launch (3 x (1 + tiles) ints: two lists and the tile classes), per lane
     // environment switches, read once at creation
     bool env_no_patch, env_no_fused_enh, env_tile_flags, env_no_overlap;
     // optional per-stage CUDA-event profiling (bench.py roofline leg)
@@ -321,7 +321,7 @@ extern "C" int vsb_stack_create(int W, int H, int n_priors, const vsb_zparams *z
         for (auto &p : s->flag_ring) STACK_CUDA(cudaMalloc((void **)&p, ntiles * sizeof(uint16_t)));
         for (int i = 0; i < 2; ++i) {
             STACK_CUDA(cudaMalloc((void **)&s->rec_tiles[i], (ntiles + 1) * sizeof(int)));
-            STACK_CUDA(cudaMalloc((void **)&s->gen_tiles[i], 2 * (ntiles + 1) * sizeof(int)));
+            STACK_CUDA(cudaMalloc((void **)&s->gen_tiles[i], 3 * (ntiles + 1) * sizeof(int)));
         }
         if (s->fx.has_bilateral) { // may a two-valued window be taken as the identity?  (values after the leading LUT)
             const int v0 = have_lead ? lead[0] : 0, v1 = have_lead ? lead[255] : 255;
