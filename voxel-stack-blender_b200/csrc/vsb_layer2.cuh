@@ -152,12 +152,6 @@ __device__ __forceinline__ void layer2_tile(const LayerParams &p, const BilTapsL
     }
     code = __reduce_or_sync(0xffffffffu, code);
     if (lane == 0 && code) atomicOr(&s_state, (int)code);
-    if (searching && METRIC == VSB_METRIC_CHAMFER5) { // the chamfer table rides along with the first round trip
-        const int nT = (R + 1) * (R + 1);
-        const int nfull = ((((size_t)p.T) & 15) == 0) ? (nT >> 2) : 0;
-        for (int i = t; i < nfull; i += VSB_THREADS) ((float4 *)s_T)[i] = ((const float4 *)p.T)[i];
-        for (int i = 4 * nfull + t; i < nT; i += VSB_THREADS) s_T[i] = p.T[i];
-    }
     if (hb > 0) {
         const float cwt = taps->cw[t];
         s_cw2[255 + t] = cwt; s_cw2[255 - t] = cwt;
@@ -166,6 +160,12 @@ __device__ __forceinline__ void layer2_tile(const LayerParams &p, const BilTapsL
     const int state = s_state;
     const bool any_rec = (state & 1) != 0;
     if (!any_rec && (state & 6) != 6) { constant_out((state & 2) ? k1b : k0b); return; } // one value, nothing recedes
+    if (any_rec && searching && METRIC == VSB_METRIC_CHAMFER5) { // the chamfer table: only tiles with receding pixels read it
+        const int nT = (R + 1) * (R + 1);                       // (first use is two barriers away)
+        const int nfull = ((((size_t)p.T) & 15) == 0) ? (nT >> 2) : 0;
+        for (int i = t; i < nfull; i += VSB_THREADS) ((float4 *)s_T)[i] = ((const float4 *)p.T)[i];
+        for (int i = 4 * nfull + t; i < nT; i += VSB_THREADS) s_T[i] = p.T[i];
+    }
 
     // out-of-image columns (left / right border tiles): mirrored bits, one thread per region row
     if (border && t < RH && ((x0 - Hh < 0) || (x0 + VSB_TW + Hh > W))) {
