@@ -75,7 +75,8 @@ __device__ __forceinline__ void layer2_tile(const LayerParams &p, const BilTapsL
     __shared__ float s_cw2[512];
     __shared__ __align__(4) uint8_t s_lut1[256];
     __shared__ __align__(4) uint8_t s_lut2[256];
-    __shared__ int s_cnt, s_gcnt, s_rcnt, s_state, s_nact;
+    __shared__ int s_cnt, s_gcnt, s_rcnt, s_nact;
+    __shared__ __align__(16) uint32_t s_wcode[VSB_THREADS / 32]; // per warp: receding / white / black seen in the region
     __shared__ uint8_t s_act[LB_ROWS_MAX + 4], s_lo[RG_ROWS_MAX], s_hi[RG_ROWS_MAX], s_mid[RG_ROWS_MAX]; // dense tiles: non-empty window rows, and per region row the ones in reach
 
     const int t = threadIdx.x, lane = t & 31;
@@ -105,12 +106,11 @@ __device__ __forceinline__ void layer2_tile(const LayerParams &p, const BilTapsL
         }
         return;
     }
-    if (t == 0) { s_cnt = 0; s_gcnt = 0; s_rcnt = 0; s_state = 0; }
+    // (no barrier here: the two LUTs, the counters and the region words all become visible at the barrier that ends step 2)
+    if (t == 0) { s_cnt = 0; s_gcnt = 0; s_rcnt = 0; }
     if (t < 64 && p.lut1) ((uint32_t *)s_lut1)[t] = ((const uint32_t *)p.lut1)[t];
     if (t >= 64 && t < 128 && p.lut2) ((uint32_t *)s_lut2)[t - 64] = ((const uint32_t *)p.lut2)[t - 64];
-    __syncthreads();
-    const uint32_t k0b = p.lut1 ? s_lut1[0] : 0u, k1b = p.lut1 ? s_lut1[255] : 255u;
-    const uint32_t K0 = k0b * 0x01010101u, K1 = k1b * 0x01010101u;
+    uint32_t k0b = 0u, k1b = 255u, K0 = 0u, K1 = 0xFFFFFFFFu; // LUT1[0], LUT1[255] (set after the barrier)
     auto constant_out = [&](uint32_t s1val) {
         if (nvalid > 0) {
             const uint32_t cv = (p.lut2 ? (uint32_t)s_lut2[s1val] : s1val) * 0x01010101u;
@@ -151,13 +151,16 @@ __device__ __forceinline__ void layer2_tile(const LayerParams &p, const BilTapsL
         }
     }
     code = __reduce_or_sync(0xffffffffu, code);
-    if (lane == 0 && code) atomicOr(&s_state, (int)code);
+    if (lane == 0) s_wcode[t >> 5] = code;
     if (hb > 0) {
         const float cwt = taps->cw[t];
         s_cw2[255 + t] = cwt; s_cw2[255 - t] = cwt;
     }
     __syncthreads();
-    const int state = s_state;
+    if (p.lut1) { k0b = s_lut1[0]; k1b = s_lut1[255]; }
+    K0 = k0b * 0x01010101u; K1 = k1b * 0x01010101u;
+    const uint4 wc0 = *(const uint4 *)&s_wcode[0], wc1 = *(const uint4 *)&s_wcode[4];
+    const int state = (int)(wc0.x | wc0.y | wc0.z | wc0.w | wc1.x | wc1.y | wc1.z | wc1.w);
     const bool any_rec = (state & 1) != 0;
     if (!any_rec && (state & 6) != 6) { constant_out((state & 2) ? k1b : k0b); return; } // one value, nothing recedes
     if (any_rec && searching && METRIC == VSB_METRIC_CHAMFER5) { // the chamfer table: only tiles with receding pixels read it
