@@ -141,7 +141,11 @@ __device__ __forceinline__ void layer2_tile(const LayerParams &p, const BilTapsL
                 const size_t o = (size_t)y * wpr + wx;
                 cw = p.cur[o];
                 uint32_t acc = 0;
-                for (int j = 0; j < np; ++j) acc |= p.prior[j][o];
+                for (int j = 0; j < np; j += 4) { // four independent requests per trip
+                    const uint32_t a0 = p.prior[j][o], a1 = j + 1 < np ? p.prior[j + 1][o] : 0u;
+                    const uint32_t a2 = j + 2 < np ? p.prior[j + 2][o] : 0u, a3 = j + 3 < np ? p.prior[j + 3][o] : 0u;
+                    acc |= a0 | a1 | a2 | a3;
+                }
                 rw = acc & ~cw & span_mask(k, max(32 - Hh, img_lo), min(160 + Hh, img_hi));
             }
             s_c[rr][k] = cw;
