@@ -748,8 +748,10 @@ static int launch_layer2(LayerParams &p, LayerParams &pd, const BilTapsL *taps, 
 {
     static int n_sms = 0; // per instantiation
     if (n_sms == 0) {
-        VSB_CUDA(cudaFuncSetAttribute(k_layer2<ZMODE, METRIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-        VSB_CUDA(cudaFuncSetAttribute(k_layer2<ZMODE, METRIC>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        VSB_CUDA(cudaFuncSetAttribute(k_layer2<ZMODE, METRIC, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        VSB_CUDA(cudaFuncSetAttribute(k_layer2<ZMODE, METRIC, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        VSB_CUDA(cudaFuncSetAttribute(k_layer2<ZMODE, METRIC, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        VSB_CUDA(cudaFuncSetAttribute(k_layer2<ZMODE, METRIC, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         VSB_CUDA(cudaFuncSetAttribute(k_layer2_dense<ZMODE, METRIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
         int dev = 0, sms = 0;
         VSB_CUDA(cudaGetDevice(&dev));
@@ -765,7 +767,10 @@ static int launch_layer2(LayerParams &p, LayerParams &pd, const BilTapsL *taps, 
     int rc = vsb_check_launch("k_layer2_classify");
     if (rc) return rc;
     dim3 grid(p.tiles_x, p.tiles_y);
-    k_layer2<ZMODE, METRIC><<<grid, VSB_THREADS, smem2, s>>>(p, taps);
+    // the XY chain of Preset-Double-LUT (bilateral d = 7, Gaussian 3 x 3) has its own instantiation with the window sizes
+    // as constants
+    if (p.hb == 3 && p.ntaps == 29 && p.nkx == 3 && p.nky == 3 && p.halo == 4) k_layer2<ZMODE, METRIC, 1><<<grid, VSB_THREADS, smem2, s>>>(p, taps);
+    else k_layer2<ZMODE, METRIC, 0><<<grid, VSB_THREADS, smem2, s>>>(p, taps);
     if ((rc = vsb_check_launch("k_layer2"))) return rc;
     p.gen_grid = p.ntiles < 2 * n_sms ? p.ntiles : 2 * n_sms;
     if (ZL_SEARCHES(ZMODE)) {
