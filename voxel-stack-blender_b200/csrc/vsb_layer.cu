@@ -742,23 +742,41 @@ static int launch_layer_v(LayerParams &p, const BilTapsL *taps, size_t smem, cud
 }
 
 // binary fast path: k_layer2 over all tiles (it lists the tiles it does not take), then k_layer over that list
+template <int ZMODE, int METRIC, int SHAPE>
+static int launch_layer2_s(LayerParams &p, LayerParams &pd, const BilTapsL *taps, size_t smem2, size_t smem2d, int n_sms, cudaStream_t s)
+{
+    static bool configured = false; // per instantiation
+    if (!configured) {
+        VSB_CUDA(cudaFuncSetAttribute(k_layer2<ZMODE, METRIC, SHAPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        VSB_CUDA(cudaFuncSetAttribute(k_layer2<ZMODE, METRIC, SHAPE>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        VSB_CUDA(cudaFuncSetAttribute(k_layer2_dense<ZMODE, METRIC, SHAPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        configured = true;
+    }
+    dim3 grid(p.tiles_x, p.tiles_y);
+    k_layer2<ZMODE, METRIC, SHAPE><<<grid, VSB_THREADS, smem2, s>>>(p, taps);
+    int rc = vsb_check_launch("k_layer2");
+    if (rc) return rc;
+    if (ZL_SEARCHES(ZMODE)) {
+        k_layer2_dense<ZMODE, METRIC, SHAPE><<<p.ntiles < 3 * n_sms ? p.ntiles : 3 * n_sms, VSB_THREADS, smem2d, s>>>(pd, taps);
+        if ((rc = vsb_check_launch("k_layer2_dense"))) return rc;
+    }
+    return VSB_OK;
+}
+
+// binary fast path: k_layer2_classify, k_layer2 over all tiles (it lists the tiles it does not take), k_layer2_dense over the
+// tiles set aside, then k_layer over the general list
 template <int ZMODE, int METRIC>
 static int launch_layer2(LayerParams &p, LayerParams &pd, const BilTapsL *taps, size_t smem2, size_t smem2d, size_t smem, int *gen_list,
                          cudaStream_t s)
 {
-    static int n_sms = 0; // per instantiation
+    static int n_sms = 0;
     if (n_sms == 0) {
-        VSB_CUDA(cudaFuncSetAttribute(k_layer2<ZMODE, METRIC, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-        VSB_CUDA(cudaFuncSetAttribute(k_layer2<ZMODE, METRIC, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        VSB_CUDA(cudaFuncSetAttribute(k_layer2<ZMODE, METRIC, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-        VSB_CUDA(cudaFuncSetAttribute(k_layer2<ZMODE, METRIC, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        VSB_CUDA(cudaFuncSetAttribute(k_layer2_dense<ZMODE, METRIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
         int dev = 0, sms = 0;
         VSB_CUDA(cudaGetDevice(&dev));
         VSB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         n_sms = sms > 0 ? sms : 148;
     }
-    // two lists in the scratch: the general kernel's, and behind it the dense launch's
+    // two lists in the scratch: the general kernel's, and behind it the dense launch's; then the tile classes
     p.gen_list = pd.gen_list = gen_list;
     p.dense_list = pd.dense_list = gen_list + 1 + p.ntiles;
     VSB_CUDA(cudaMemsetAsync(p.gen_list, 0, (size_t)(2 + p.ntiles) * sizeof(int), s)); // both counters with one node (93 KB at 16K)
@@ -766,17 +784,14 @@ static int launch_layer2(LayerParams &p, LayerParams &pd, const BilTapsL *taps, 
     k_layer2_classify<<<(p.ntiles + 255) / 256, 256, 0, s>>>(p);
     int rc = vsb_check_launch("k_layer2_classify");
     if (rc) return rc;
-    dim3 grid(p.tiles_x, p.tiles_y);
-    // the XY chain of Preset-Double-LUT (bilateral d = 7, Gaussian 3 x 3) has its own instantiation with the window sizes
-    // as constants
-    if (p.hb == 3 && p.ntaps == 29 && p.nkx == 3 && p.nky == 3 && p.halo == 4) k_layer2<ZMODE, METRIC, 1><<<grid, VSB_THREADS, smem2, s>>>(p, taps);
-    else k_layer2<ZMODE, METRIC, 0><<<grid, VSB_THREADS, smem2, s>>>(p, taps);
-    if ((rc = vsb_check_launch("k_layer2"))) return rc;
+    // the window sizes of the two XY chains BASELINE names are compile-time constants in their own instantiations
+    // (Preset-Double-LUT: bilateral d = 7 + Gaussian 3 x 3; config 3: bilateral d = 7 alone); any other chain takes SHAPE 0
+    const bool bil7 = p.hb == 3 && p.ntaps == 29;
+    if (bil7 && p.nkx == 3 && p.nky == 3 && p.halo == 4) rc = launch_layer2_s<ZMODE, METRIC, 1>(p, pd, taps, smem2, smem2d, n_sms, s);
+    else if (bil7 && p.nkx == 0 && p.nky == 0 && p.halo == 3) rc = launch_layer2_s<ZMODE, METRIC, 2>(p, pd, taps, smem2, smem2d, n_sms, s);
+    else rc = launch_layer2_s<ZMODE, METRIC, 0>(p, pd, taps, smem2, smem2d, n_sms, s);
+    if (rc) return rc;
     p.gen_grid = p.ntiles < 2 * n_sms ? p.ntiles : 2 * n_sms;
-    if (ZL_SEARCHES(ZMODE)) {
-        k_layer2_dense<ZMODE, METRIC><<<p.ntiles < 3 * n_sms ? p.ntiles : 3 * n_sms, VSB_THREADS, smem2d, s>>>(pd, taps);
-        if ((rc = vsb_check_launch("k_layer2_dense"))) return rc;
-    }
     return launch_layer_v<ZMODE, METRIC, true>(p, taps, smem, s);
 }
 

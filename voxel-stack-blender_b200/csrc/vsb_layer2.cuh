@@ -57,7 +57,7 @@ __device__ __forceinline__ uint32_t expand4(uint32_t nib, uint32_t K0, uint32_t 
 // one tile.  DENSE: the instantiation of the second launch, which holds the row-distance-table path for the tiles the first one
 // sets aside (interior tiles with thousands of receding pixels) -- kept out of the first launch's code
 // SHAPE 1: the XY chain of Preset-Double-LUT (bilateral d = 7: radius 3, 29 taps; Gaussian 3 x 3) as compile-time constants, so the
-// window loops unroll; SHAPE 0: any fused chain, from the parameters
+// window loops unroll; SHAPE 2: the d = 7 bilateral alone (BASELINE config 3); SHAPE 0: any fused chain, from the parameters
 template <int ZMODE, int METRIC, bool DENSE, int SHAPE>
 __device__ __forceinline__ void layer2_tile(const LayerParams &p, const BilTapsL *__restrict__ taps, const int tx, const int ty)
 {
@@ -85,9 +85,9 @@ __device__ __forceinline__ void layer2_tile(const LayerParams &p, const BilTapsL
     const int W = p.W, H = p.H, wpr = p.wpr;
     const int np = p.z.n_priors;
     const int r = t >> 3, c = t & 7;
-    const int Hh = SHAPE == 1 ? 4 : p.halo, hb = SHAPE == 1 ? 3 : p.hb;
-    const int rx = SHAPE == 1 ? 1 : p.nkx >> 1, ry = SHAPE == 1 ? 1 : p.nky >> 1, hg = max(rx, ry);
-    const bool gauss = SHAPE == 1 ? true : p.nkx > 0;
+    const int Hh = SHAPE == 1 ? 4 : (SHAPE == 2 ? 3 : p.halo), hb = SHAPE != 0 ? 3 : p.hb;
+    const int rx = SHAPE == 1 ? 1 : (SHAPE == 2 ? 0 : p.nkx >> 1), ry = SHAPE == 1 ? 1 : (SHAPE == 2 ? 0 : p.nky >> 1), hg = max(rx, ry);
+    const bool gauss = SHAPE == 1 ? true : (SHAPE == 2 ? false : p.nkx > 0);
     const int RH = VSB_TH + 2 * Hh;
     const int R = p.z.reach;
     const int x0 = tx * VSB_TW, y0 = ty * VSB_TH;
@@ -494,7 +494,7 @@ __device__ __forceinline__ void layer2_tile(const LayerParams &p, const BilTapsL
     if (hb > 0) {
         const int total = s_cnt;
         if (total > 0) {
-            const int ntaps = SHAPE == 1 ? 29 : p.ntaps;
+            const int ntaps = SHAPE != 0 ? 29 : p.ntaps;
             for (int i = t; i < total; i += VSB_THREADS) {
                 const int codev = s_list[i];
                 const int rr = codev >> 8, rc = codev & 255;
@@ -603,14 +603,14 @@ __global__ void __launch_bounds__(VSB_THREADS, 4) k_layer2(const __grid_constant
 }
 
 // the tiles set aside by k_layer2: a few CTAs per SM stride over the list (empty on ordinary layers)
-template <int ZMODE, int METRIC>
+template <int ZMODE, int METRIC, int SHAPE>
 __global__ void __launch_bounds__(VSB_THREADS, 3) k_layer2_dense(const __grid_constant__ LayerParams p, const BilTapsL *__restrict__ taps)
 {
     const int n = p.dense_list[0];
     for (int li = (int)blockIdx.x; li < n; li += (int)gridDim.x) {
         const int tile = p.dense_list[1 + li];
         const int ty = tile / p.tiles_x;
-        layer2_tile<ZMODE, METRIC, true, 0>(p, taps, tile - ty * p.tiles_x, ty);
+        layer2_tile<ZMODE, METRIC, true, SHAPE>(p, taps, tile - ty * p.tiles_x, ty);
         __syncthreads(); // the next tile re-initialises the shared state
     }
 }
