@@ -6,6 +6,7 @@ import collections, csv, json, os, re, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag, bench_json, ref_json, launches_csv = sys.argv[1:5]
 reps = sys.argv[5:]
+traffic_reps = [r for r in reps if "cliff" not in os.path.basename(r)]  # (the cliff capture is a different layer)
 P = os.path.join(ROOT, "profiles")
 os.makedirs(P, exist_ok=True)
 
@@ -67,13 +68,14 @@ for rep in reps:
         out.append(e)
         def mb(k):
             v = float(d[k].replace(",", "")); return v * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[u[k]]
-        traffic[short(d["Kernel Name"])].append(mb("dram__bytes_read.sum") + mb("dram__bytes_write.sum"))
+        if rep in traffic_reps:
+            traffic[short(d["Kernel Name"])].append(mb("dram__bytes_read.sum") + mb("dram__bytes_write.sum"))
 if out:
     json.dump(out, open(os.path.join(P, f"{tag}_ncu_full_summary.json"), "w"), indent=1)
     per = {k: round(sum(v) / len(v), -4) for k, v in traffic.items()}
     t = {"per_kernel": per,
          # the bench's stage names: bytes per layer of all the launches the stage makes
-         "layer_fused": sum(v for k, v in per.items() if k.startswith("k_layer2") or (k.startswith("k_layer<") and k.endswith(", 1>"))),
+         "layer_fused": sum(v for k, v in per.items() if (k.startswith("k_layer2") and "<4," not in k) or (k.startswith("k_layer<") and k.endswith(", 1>"))),
          "layer_patch_lut_only": sum(v for k, v in per.items() if k.startswith("k_layer<") and k.endswith(", 0>")),
          "pack_flags_lut_only": sum(v for k, v in per.items() if k.startswith("k_pack_tma<1>")),
          "pack_flags": sum(v for k, v in per.items() if k.startswith("k_pack_tma<0>") or k.startswith("k_pack_tma<(bool)0>")),

@@ -571,20 +571,31 @@ __global__ void __launch_bounds__(256) k_layer2_classify(const __grid_constant__
     if (tile >= p.ntiles) return;
     const int ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
     const int np = p.z.n_priors;
-    bool all_bin = true, same = true, pri_black = true;
-    const uint32_t fc = p.cur_flags[tile];
+    // 9 + 9 N independent requests: the flags are combined with bitwise operators so that no load waits for a branch
+    int fi[9];
+#pragma unroll
     for (int q = 0; q < 9; ++q) {
         const int ny = min(max(ty + q / 3 - 1, 0), p.tiles_y - 1), nx = min(max(tx + q % 3 - 1, 0), p.tiles_x - 1);
-        const int fi = ny * p.tiles_x + nx;
-        const uint32_t f = p.cur_flags[fi];
-        all_bin = all_bin && (f & FLAG_BINARY) != 0u;
-        same = same && f == fc && !(f & FLAG_MIXED);
-        for (int j = 0; j < np; ++j) {
-            const uint16_t *pf = p.prior_flags[j];
-            const uint32_t g = pf ? pf[fi] : FLAG_MIXED;
-            pri_black = pri_black && !(g & FLAG_MIXED) && (g & 0xFFu) <= 127u;
+        fi[q] = ny * p.tiles_x + nx;
+    }
+    const uint32_t fc = p.cur_flags[tile];
+    uint32_t bin_and = FLAG_BINARY, diff_or = 0u, pri_or = 0u;
+#pragma unroll
+    for (int q = 0; q < 9; ++q) {
+        const uint32_t f = p.cur_flags[fi[q]];
+        bin_and &= f;
+        diff_or |= (f ^ fc) | (f & FLAG_MIXED);
+    }
+    for (int j = 0; j < np; ++j) {
+        const uint16_t *pf = p.prior_flags[j];
+        if (!pf) { pri_or |= FLAG_MIXED; continue; }
+#pragma unroll
+        for (int q = 0; q < 9; ++q) {
+            const uint32_t g = pf[fi[q]];
+            pri_or |= (g & FLAG_MIXED) | ((g & 0xFFu) > 127u ? 1u : 0u); // mixed, or a uniform white tile
         }
     }
+    const bool all_bin = (bin_and & FLAG_BINARY) != 0u, same = diff_or == 0u, pri_black = pri_or == 0u;
     uint32_t cls = 0u;
     if (!all_bin) {
         cls = 1u;
