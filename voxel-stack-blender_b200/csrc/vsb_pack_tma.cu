@@ -107,15 +107,14 @@ __global__ void __launch_bounds__(PK_WARPS * 32) k_pack_tma(const __grid_constan
     // LUTOUT: lut[gray] is written back into the stage it was read from and leaves from there with a bulk tensor store;
     // the stage is refilled once that store has drained it, i.e. two tiles later -> S - 2 loads in flight per warp
 
-    auto issue = [&](int k) { // lane 0: tile k of this warp -> stage k % S
+    auto issue = [&](int k, int st) { // lane 0: tile k of this warp -> stage st = k % S
         const int tile = gw + k * nw;
         const int ty = (int)((unsigned)tile / (unsigned)p.tiles_x), tx = tile - ty * p.tiles_x;
-        const int st = k % S;
         vsb_mbar_expect_tx(&bar[st], PK_TILE_BYTES);
         vsb_tma_load_2d(ring + (size_t)st * PK_TILE_BYTES, &tm_in, tx * VSB_TW, ty * VSB_TH, &bar[st]);
     };
     if (lane == 0)
-        for (int k = 0; k < S && k < count; ++k) issue(k);
+        for (int k = 0; k < S && k < count; ++k) issue(k, k);
 
     // lane geometry: chunk c = lane & 7 of rows (lane >> 3) + 4 j, j = 0..7; after the pair exchange a lane owns the
     // mask words (row (lane >> 3) + 4 (2 m + (lane & 1)), word (lane & 7) >> 1), m = 0..3
@@ -162,17 +161,18 @@ __global__ void __launch_bounds__(PK_WARPS * 32) k_pack_tma(const __grid_constan
         gate_flag_next = load_gate(1);
     }
 
+    int st = 0;          // k % S and (k / S) & 1, kept incrementally
+    uint32_t phase = 0u;
     for (int k = 0; k < count; ++k) {
         const int tile = gw + k * nw;
         const int x0 = tx * VSB_TW, y0 = ty * VSB_TH;
         int ty1 = ty + dty, tx1 = tx + dtx; // the warp's next tile
         if (tx1 >= p.tiles_x) { tx1 -= p.tiles_x; ++ty1; }
-        const int st = k % S;
         if (LUTOUT && lane == 0 && k >= 2 && k - 2 + S < count) { // the store of tile k-2 has drained its stage: refill it
             vsb_tma_wait_read<1>();
-            issue(k - 2 + S);
+            issue(k - 2 + S, st >= 2 ? st - 2 : st - 2 + S);
         }
-        vsb_mbar_wait(&bar[st], (uint32_t)((k / S) & 1));
+        vsb_mbar_wait(&bar[st], phase);
         uint8_t *src = ring + (size_t)st * PK_TILE_BYTES;
         uint4 v[8];
 #pragma unroll
@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(PK_WARPS * 32) k_pack_tma(const __grid_constan
         if (!LUTOUT) {
             // the stage has been consumed (every value above depends on the loads): refill it
             __syncwarp();
-            if (lane == 0 && k + S < count) issue(k + S);
+            if (lane == 0 && k + S < count) issue(k + S, st);
         } else {
             // ---- lut[gray], in place, then out through the tensor store ---------------------------------------------------
             if (binary) { // every byte is 0 or 255: select between lut[0] and lut[255] by the sign mask, no look-ups
@@ -278,6 +278,7 @@ __global__ void __launch_bounds__(PK_WARPS * 32) k_pack_tma(const __grid_constan
             gate_flag_next = load_gate(k + 2);
         }
         ty = ty1; tx = tx1;
+        if (++st == S) { st = 0; phase ^= 1u; }
     }
     if (LUTOUT && lane == 0) vsb_tma_wait_all<0>();
 }
