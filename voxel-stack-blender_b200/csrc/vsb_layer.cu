@@ -280,7 +280,7 @@ __global__ void __launch_bounds__(VSB_THREADS, XY ? VSB_LAYER_CTAS_XY : 7) k_lay
                                                        const BilTapsL *__restrict__ taps)
 {
     // work list of the patch launch: CTAs beyond the number of listed tiles leave before any set-up
-    if (!XY && p.rec_list && (int)(blockIdx.y * gridDim.x + blockIdx.x) >= p.rec_list[0]) return;
+    if (!XY && p.rec_list && (int)blockIdx.x >= p.rec_list[0]) return;
     extern __shared__ __align__(16) uint8_t dsm[];
     float *s_T = (float *)(dsm + p.sm.T);
     uint8_t (*s1)[RG_W] = (uint8_t (*)[RG_W])(dsm + p.sm.s1);      // stage 1; later the Gaussian output
@@ -316,16 +316,15 @@ __global__ void __launch_bounds__(VSB_THREADS, XY ? VSB_LAYER_CTAS_XY : 7) k_lay
 
     // gen_list (XY launches that follow k_layer2): a 1-D grid of CTAs strides over the listed tiles -- the tiles whose
     // region is not strictly binary; the list is empty for the input the reference asks for
-    const int *glist = XY ? p.gen_list : nullptr;
+    // rec_list (the patch launch of LUT-only chains) is walked the same way, by a grid of a quarter of the tiles: when up to a
+    // quarter of the tiles is listed every CTA takes one tile and none starts in vain; beyond that some take a second one
+    const int *glist = XY ? p.gen_list : p.rec_list;
     const int n_listed = glist ? glist[0] : 1;
     for (int li = glist ? (int)blockIdx.x : 0; li < n_listed; li += glist ? (int)gridDim.x : 1) {
         int tile = (int)(blockIdx.y * gridDim.x + blockIdx.x);
         int wl_tx = (int)blockIdx.x, wl_ty = (int)blockIdx.y;
         if (glist) {
             tile = glist[1 + li];
-            wl_tx = tile % p.tiles_x; wl_ty = tile / p.tiles_x;
-        } else if (!XY && p.rec_list) { // work list of the patch launch: CTA i takes the i-th listed tile
-            tile = p.rec_list[1 + tile];
             wl_tx = tile % p.tiles_x; wl_ty = tile / p.tiles_x;
         }
         const int tx = wl_tx, ty = wl_ty; // 2-D grid: no division
@@ -737,6 +736,7 @@ static int launch_layer_v(LayerParams &p, const BilTapsL *taps, size_t smem, cud
     }
     dim3 grid(p.tiles_x, p.tiles_y);
     if (XY && p.gen_list) grid = dim3(p.gen_grid, 1);
+    if (!XY && p.rec_list) grid = dim3(p.gen_grid, 1);
     k_layer<ZMODE, METRIC, XY><<<grid, VSB_THREADS, smem, s>>>(p, taps);
     return vsb_check_launch("k_layer");
 }
@@ -909,6 +909,11 @@ static int layer_launch(const uint8_t *in, size_t in_pitch, int W, int H, const 
     p.ntiles = p.tiles_x * p.tiles_y;
     p.sparse = sparse;
     p.rec_list = sparse ? rec_list : nullptr;
+    if (p.rec_list) { // CTAs of the list-walking patch launch
+        static const int div_env = getenv("VSB_PATCH_GRID_DIV") ? atoi(getenv("VSB_PATCH_GRID_DIV")) : 0;
+        const int dv = div_env > 0 ? div_env : 4;
+        p.gen_grid = (p.ntiles + dv - 1) / dv;
+    }
     const BilTapsL *taps_dev = nullptr;
     if (p.hb > 0) { const int rc = taps_on_device(taps, &taps_dev); if (rc) return rc; }
     const int RH = VSB_TH + 2 * p.halo;
