@@ -28,18 +28,19 @@ if os.path.exists(launches_csv):
     kn, mv, mu = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
     agg = collections.OrderedDict()
     with open(os.path.join(P, f"{tag}_launches.csv"), "w") as fh:
-        fh.write("# ncu --metrics gpu__time_duration.sum --clock-control none, python bench.py --steps 1 --warmup 1 --batch 4 --resident 12 --no-e2e --no-cpu-baseline (extras on)\n")
+        fh.write("# ncu --metrics gpu__time_duration.sum --clock-control none, python bench.py --steps 1 --warmup 1 --batch 4 --resident 12 --no-e2e --no-cpu-baseline --no-extras (the headline step only)\n")
         fh.write("id,kernel,duration_us\n")
         for r in rows:
             v = float(r[mv].replace(",", "")) * {"ns": 1e-3, "us": 1.0, "ms": 1e3}.get(r[mu], 1.0)
             fh.write(f"{r[0]},{short(r[kn])},{v:.3f}\n")
             agg.setdefault(short(r[kn]), []).append(v)
-    tot = sum(sum(v) for k, v in agg.items() if "synth" not in k)
+    setup = lambda k: "synth" in k or k.startswith("at::")   # stack rasteriser / torch fills: not part of a step
+    tot = sum(sum(v) for k, v in agg.items() if not setup(k))
     with open(os.path.join(P, f"{tag}_launches_summary.csv"), "w") as fh:
         fh.write("# ncu launch list (gpu__time_duration.sum, --clock-control none; cold-cache serialised launches: compare SHARES)\n")
         fh.write("kernel,launches,mean_us,share_of_all_listed_kernels\n")
         for k, v in agg.items():
-            fh.write(f"{k},{len(v)},{sum(v)/len(v):.2f},{(sum(v)/tot if 'synth' not in k else 0):.4f}\n")
+            fh.write(f"{k.replace(',', ';')},{len(v)},{sum(v)/len(v):.2f},{(sum(v)/tot if not setup(k) else 0):.4f}\n")
 
 # ---- ncu --set full summaries --------------------------------------------------------------------------------------
 keep = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
