@@ -135,12 +135,18 @@ __device__ __forceinline__ void layer2_tile(const LayerParams &p, const BilTapsL
         if (i < RH * L2W) {
             const int rr = i / L2W, k = i - rr * L2W;
             int y = y0 - Hh + rr;
-            const bool row_in = y >= 0 && y < H;
-            if (!row_in) y = vsb_reflect101(y, H); // BORDER_REFLECT_101 rows: the mirrored row's bits
-            const int wx = wx0 + k;
+            uint32_t rm; // the region's columns in this word
+            bool word_in = true;
+            if (!border) { // interior tile: the region is span bits 32 - Hh .. 159 + Hh, every row and word exists
+                rm = k == 0 ? (Hh ? 0xFFFFFFFFu << (32 - Hh) : 0u) : (k == L2W - 1 ? (1u << Hh) - 1u : 0xFFFFFFFFu);
+            } else {
+                if (y < 0 || y >= H) y = vsb_reflect101(y, H); // BORDER_REFLECT_101 rows: the mirrored row's bits
+                word_in = wx0 + k >= 0 && wx0 + k < wpr;
+                rm = span_mask(k, max(32 - Hh, img_lo), min(160 + Hh, img_hi));
+            }
             uint32_t cw = 0, rw = 0;
-            if (wx >= 0 && wx < wpr) {
-                const size_t o = (size_t)y * wpr + wx;
+            if (word_in) {
+                const size_t o = (size_t)y * wpr + (wx0 + k);
                 cw = p.cur[o];
                 uint32_t acc = 0;
                 for (int j = 0; j < np; j += 4) { // four independent requests per trip
@@ -148,11 +154,10 @@ __device__ __forceinline__ void layer2_tile(const LayerParams &p, const BilTapsL
                     const uint32_t a2 = j + 2 < np ? p.prior[j + 2][o] : 0u, a3 = j + 3 < np ? p.prior[j + 3][o] : 0u;
                     acc |= a0 | a1 | a2 | a3;
                 }
-                rw = acc & ~cw & span_mask(k, max(32 - Hh, img_lo), min(160 + Hh, img_hi));
+                rw = acc & ~cw & rm;
             }
             s_c[rr][k] = cw;
             s_r[rr][k] = rw;
-            const uint32_t rm = span_mask(k, max(32 - Hh, img_lo), min(160 + Hh, img_hi));
             code |= (rw ? 1u : 0u) | ((cw & rm) ? 2u : 0u) | ((~cw & rm) ? 4u : 0u);
         }
     }
