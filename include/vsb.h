@@ -307,6 +307,11 @@ int vsb_layer_patch(const uint8_t *in, size_t in_pitch, int W, int H, const uint
  * 0, 0) and clear, 0 = disable */
 int vsb_layer_stats(int op, unsigned long long *out8);
 
+/* test hook of vsb_layer_fused's mask-only fast path: size of the per-tile list arena (entries; 0 = default 7424) and of the
+ * receding-pixel list (0 = default 2560).  Smaller values send ordinary tiles down the routes that only unusually full tiles
+ * take (general kernel for tiles fuller than the arena or -- at image borders -- than the list); results must not change. */
+int vsb_layer_fast_path_limits(int arena_entries, int receding_entries);
+
 int vsb_layer_fused(const uint8_t *in, size_t in_pitch, int W, int H, const uint32_t *cur_bits,
                     const uint32_t *const *prior_bits, const uint16_t *cur_flags,
                     const uint16_t *const *prior_flags, int wpr, const vsb_zparams *params, const float *T_dev,

@@ -853,3 +853,30 @@ def test_stack_engine_random_configs_vs_oracle(E, seed):
     for zi, (a, b) in enumerate(zip(got, want)):
         assert a.shape == b.shape, (seed, zi, a.shape, b.shape, d)
         assert np.array_equal(a, b), (seed, zi, int((a != b).sum()), d)
+
+
+def test_fast_path_routes_for_full_tiles(E):
+    """The mask-only layer kernel hands tiles that are fuller than its shared-memory lists to other routes (the general kernel;
+    the dense launch).  With the lists shrunk through the test hook, ordinary tiles take those routes too: same layers, bit for
+    bit, as with the default sizes and as the oracle -- fixed and weighted fades, both metrics, over a raft cliff."""
+    import vsb_native as N
+    from config import Config
+    W, H, L = 640, 400, 7
+    layers = small_stack(W=W, H=H, L=L, seed=23, raft=True, n_blobs=10)
+    lib = N.load()
+    for mode, F, metric in (("fixed_fade", 40.0, "chamfer5"), ("weighted_stack", 14.0, "chamfer5"), ("fixed_fade", 12.0, "exact")):
+        base = {"blending_mode": mode, "receding_layers": 3, "use_fixed_fade_receding": True, "fixed_fade_distance_receding": F,
+                "manual_weights": [5, 3, 1], "fade_distances_receding": [14.0, 9.0, 5.0],
+                "xy_blend_pipeline": FUSED_CHAINS["lut_bil7_g3_lut"]}
+        want = O.run_stack(layers, dict(base, metric=metric))
+        cfg = Config.from_dict(dict(base, distance_metric=metric))
+        try:
+            for arena, rec in ((0, 0), (1024 + 256, 64), (2048, 700)):
+                N.check(lib.vsb_layer_fast_path_limits(arena, rec), "vsb_layer_fast_path_limits")
+                eng = engine_for_metric(E, cfg, W, H, metric)
+                got = [eng.process(g) for g in layers]
+                eng.close()
+                for zi, (a, b) in enumerate(zip(got, want)):
+                    assert np.array_equal(a, b), (mode, metric, arena, rec, zi, int((a != b).sum()))
+        finally:
+            N.check(lib.vsb_layer_fast_path_limits(0, 0), "vsb_layer_fast_path_limits")

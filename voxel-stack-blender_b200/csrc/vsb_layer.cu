@@ -829,6 +829,16 @@ static int taps_on_device(const BilTapsL &h, const BilTapsL **out)
 static unsigned long long *g_layer_stats = nullptr;
 // debugging aid: device counters [uniform tiles, worked tiles, tiles with receding pixels, receding pixels,
 // bilateral pixels, Gaussian words]; enabled by vsb_layer_stats(1), read-and-cleared by vsb_layer_stats(2)
+static int g_l2_arena = 0, g_l2_rcap = 0; // vsb_layer_fast_path_limits (0 = defaults)
+extern "C" int vsb_layer_fast_path_limits(int arena_entries, int receding_entries)
+{
+    VSB_REQUIRE(arena_entries == 0 || (arena_entries >= 1024 + 256 && arena_entries <= 7424), "vsb_layer_fast_path_limits: arena of %d entries", arena_entries);
+    VSB_REQUIRE(receding_entries >= 0 && receding_entries <= L2_DENSE_MIN, "vsb_layer_fast_path_limits: list of %d entries", receding_entries);
+    g_l2_arena = arena_entries;
+    g_l2_rcap = receding_entries;
+    return VSB_OK;
+}
+
 extern "C" int vsb_layer_stats(int op, unsigned long long *out8)
 {
     if (op == 1) {
@@ -952,7 +962,8 @@ static int layer_launch(const uint8_t *in, size_t in_pitch, int W, int H, const 
         // launch gets the largest case (46 x 142 receding, 34 x 130 bilateral), which is also the space of its table.
         p2.sm.list = (int)o2;
         LayerParams p2d = p2;
-        p2.sm.glist = 7424 - 1024; p2.rcap = L2_DENSE_MIN; // (modes without search set nothing aside: their fuller tiles take the general kernel)
+        p2.sm.glist = (g_l2_arena ? g_l2_arena : 7424) - 1024; p2.rcap = g_l2_rcap ? g_l2_rcap : L2_DENSE_MIN;
+        if (p2.rcap > p2.sm.glist) p2.rcap = p2.sm.glist; // (modes without search set nothing aside: their fuller tiles take the general kernel)
         p2d.sm.glist = 6656 + 4480; p2d.rcap = 6656;
         const size_t smem2 = o2 + (size_t)(p2.sm.glist + 1024) * 2, smem2d = o2 + (size_t)(p2d.sm.glist + 1024) * 2;
         int rc2;

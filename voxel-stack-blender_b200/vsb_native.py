@@ -113,6 +113,7 @@ _SIGS = {
                                          c_void_p, c_void_p, c_void_p]),
     "vsb_bilateral_two_valued_min_same": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int]),
     "vsb_layer_stats": (c_int, [c_int, c_void_p]),
+    "vsb_layer_fast_path_limits": (c_int, [c_int, c_int]),
     "vsb_layer_fused": (c_int, [c_void_p, c_size_t, c_int, c_int, c_void_p, POINTER(c_void_p), c_void_p, POINTER(c_void_p),
                                 c_int, POINTER(ZParams), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p,
                                 c_void_p]),
