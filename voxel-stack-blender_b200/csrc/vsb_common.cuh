@@ -33,6 +33,18 @@ int vsb_check_launch(const char *what);
         }                                                                                          \
     } while (0)
 
+// Function attributes (opt-in shared memory, carve-out) belong to the device the call runs on: a process that drives several
+// devices (config.devices: one engine thread per GPU) has to set them once on each.  `seen` is a per-call-site flag array.
+#define VSB_MAX_DEVICES 32
+static inline bool vsb_first_on_device(bool (&seen)[VSB_MAX_DEVICES])
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= VSB_MAX_DEVICES) return true;
+    if (seen[dev]) return false;
+    seen[dev] = true;
+    return true;
+}
+
 static inline bool vsb_aligned16(const void *p, size_t pitch)
 {
     return (((uintptr_t)p) & 15u) == 0 && (pitch & 15u) == 0;

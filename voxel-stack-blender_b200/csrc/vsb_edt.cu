@@ -348,11 +348,10 @@ extern "C" int vsb_edt_exact(const uint32_t *seed_bits, int wpr, int W, int H, v
 
     const int Wa = (W + 15) & ~15; // row buffer: 2 Wa bytes of g + Wa bytes of A; at 16K five CTAs share an SM's shared memory
     const size_t smem = (size_t)Wa * 3;
-    static bool configured = false;
-    if (!configured) {
+    static bool seen[VSB_MAX_DEVICES] = {false};
+    if (vsb_first_on_device(seen)) {
         VSB_CUDA(cudaFuncSetAttribute(k_edt_rowdc, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         VSB_CUDA(cudaFuncSetAttribute(k_edt_rowdc, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        configured = true;
     }
     VSB_REQUIRE(smem <= 200 * 1024, "vsb_edt_exact: a row of %d pixels does not fit the row kernel's shared memory", W);
     int top_log2 = 0; // levels S = 2^top_log2 .. 2 (the largest power of two below W), none for W <= 2; S = 1 always runs

@@ -729,10 +729,9 @@ __global__ void __launch_bounds__(VSB_THREADS, XY ? VSB_LAYER_CTAS_XY : 7) k_lay
 template <int ZMODE, int METRIC, bool XY>
 static int launch_layer_v(LayerParams &p, const BilTapsL *taps, size_t smem, cudaStream_t s)
 {
-    static bool configured = false; // per instantiation
-    if (!configured) {
+    static bool seen[VSB_MAX_DEVICES] = {false}; // per instantiation and device
+    if (vsb_first_on_device(seen)) {
         VSB_CUDA(cudaFuncSetAttribute(k_layer<ZMODE, METRIC, XY>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-        configured = true;
     }
     dim3 grid(p.tiles_x, p.tiles_y);
     if (XY && p.gen_list) grid = dim3(p.gen_grid, 1);
@@ -745,12 +744,11 @@ static int launch_layer_v(LayerParams &p, const BilTapsL *taps, size_t smem, cud
 template <int ZMODE, int METRIC, int SHAPE>
 static int launch_layer2_s(LayerParams &p, LayerParams &pd, const BilTapsL *taps, size_t smem2, size_t smem2d, int n_sms, cudaStream_t s)
 {
-    static bool configured = false; // per instantiation
-    if (!configured) {
+    static bool seen[VSB_MAX_DEVICES] = {false}; // per instantiation and device
+    if (vsb_first_on_device(seen)) {
         VSB_CUDA(cudaFuncSetAttribute(k_layer2<ZMODE, METRIC, SHAPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
         VSB_CUDA(cudaFuncSetAttribute(k_layer2<ZMODE, METRIC, SHAPE>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         VSB_CUDA(cudaFuncSetAttribute(k_layer2_dense<ZMODE, METRIC, SHAPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-        configured = true;
     }
     dim3 grid(p.tiles_x, p.tiles_y);
     k_layer2<ZMODE, METRIC, SHAPE><<<grid, VSB_THREADS, smem2, s>>>(p, taps);

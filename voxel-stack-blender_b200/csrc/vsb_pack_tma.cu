@@ -298,6 +298,9 @@ int vsb_pack_tma_launch(const uint8_t *gray, size_t pitch, int W, int H, uint32_
         stages_env = e ? atoi(e) : 0;
         e = getenv("VSB_PACK_CTAS");
         ctas_env = e ? atoi(e) : 0;
+    }
+    static bool seen[VSB_MAX_DEVICES] = {false};
+    if (vsb_first_on_device(seen)) {
         VSB_CUDA(cudaFuncSetAttribute(k_pack_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         VSB_CUDA(cudaFuncSetAttribute(k_pack_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     }
