@@ -880,3 +880,30 @@ def test_fast_path_routes_for_full_tiles(E):
                     assert np.array_equal(a, b), (mode, metric, arena, rec, zi, int((a != b).sum()))
         finally:
             N.check(lib.vsb_layer_fast_path_limits(0, 0), "vsb_layer_fast_path_limits")
+
+
+def test_pipeline_thread_z_sharded_over_devices(E, slices, ref_stack, lut_file, tmp_path):
+    """config.devices = [0, 1]: ProcessingPipelineThread.run() splits the stack into two contiguous slabs, one engine thread per
+    GPU with a halo of mask-only layers -- same files, same pixels as the reference's single run.  With one GPU in the box the
+    two slabs run on device 0 (two engines in one process), which checks the slab / halo logic all the same."""
+    import cv2
+    import processing_pipeline as pp
+    t = E.torch()
+    src, dst = tmp_path / "in", tmp_path / "out"
+    src.mkdir(); dst.mkdir()
+    os.chdir(tmp_path)
+    zs = list(range(6, 26))
+    for zi in zs:
+        cv2.imwrite(str(src / f"layer{zi:03d}.png"), slices[zi])
+    cfg = stack_cfg("preset", lut_file)
+    cfg.input_folder, cfg.output_folder, cfg.start_index, cfg.stop_index = str(src), str(dst), 0, None
+    cfg.devices = [0, 1] if t.cuda.device_count() >= 2 else [0, 0]
+    th = pp.ProcessingPipelineThread(cfg, max_workers=3)
+    errors, finished = [], []
+    th.error_signal.connect(errors.append); th.finished_signal.connect(lambda: finished.append(1))
+    th.run()
+    assert not errors and finished == [1] and not th.error_occurred, errors
+    assert sorted(os.listdir(dst)) == [f"layer{zi:03d}.png" for zi in zs]
+    for zi in zs[4:]:                                          # from the first layer whose whole window lies inside the run
+        out = cv2.imread(str(dst / f"layer{zi:03d}.png"), cv2.IMREAD_GRAYSCALE)
+        assert sha(out) == str(ref_stack["preset_sha1"][zi]), zi
