@@ -207,6 +207,55 @@ def test_file_ordering_rules(tmp_path):
     assert pp.list_layer_files(str(tmp_path), 2, 9) == ["layer2.png", "slice_0003.tif"]
 
 
+def test_roi_tracker_equals_scalar_oracle_tracker():
+    """ROITracker (vectorised, candidate-pair score matrix) against the oracle's scalar restatement of
+    roi_tracker.py:3-109 on a drifting population of boxes: contained boxes (score 1.0), splits, births and deaths,
+    zero-area boxes, one box spanning the plate.  Ids, classes and list order per layer are identical."""
+    import roi_tracker
+    import vsb_oracle_roi as R
+    from config import Config, RoiParameters
+    rng = np.random.default_rng(11)
+    for a, b in [((0, 0, 10, 10), (5, 5, 10, 10)), ((0, 0, 0, 5), (0, 0, 3, 3)), ((2, 2, 4, 4), (0, 0, 20, 20)), ((0, 0, 3, 3), (3, 0, 3, 3))]:
+        assert roi_tracker.calculate_iou(a, b) == R.overlap_over_min(a, b)
+    for n, m, big in [(0, 4, 0), (4, 0, 0), (1, 1, 0), (120, 150, 0), (150, 120, 2)]:
+        def boxes(k):
+            out = [(int(rng.integers(0, 900)), int(rng.integers(0, 700)), int(rng.integers(0, 60)), int(rng.integers(0, 60))) for _ in range(k)]
+            for i in range(min(big, k)):
+                out[i] = (0, 0, 960, 760)
+            return out
+        c, q = boxes(n), boxes(m)
+        want = np.array([[roi_tracker.calculate_iou(x, y) for y in q] for x in c]).reshape(n, m)
+        assert np.array_equal(roi_tracker._score_matrix(c, q), want)
+
+    rp = dict(min_size=1, enable_raft_support_handling=True, raft_layer_count=3, raft_min_size=900, support_max_size=400,
+              support_max_layer=30, support_max_growth=1.5)
+    cfg = Config()
+    cfg.roi_params = RoiParameters(**rp)
+    mine, theirs = roi_tracker.ROITracker(), R.Tracker()
+    pop = [[int(rng.integers(0, 900)), int(rng.integers(0, 700)), int(rng.integers(4, 50)), int(rng.integers(4, 50))] for _ in range(90)]
+    for z in range(12):
+        nxt = []
+        for x, y, w, h in pop:
+            if rng.random() < 0.05:
+                continue                                                  # dies
+            x, y = x + int(rng.integers(-3, 4)), y + int(rng.integers(-3, 4))
+            w, h = max(1, w + int(rng.integers(-2, 5))), max(1, h + int(rng.integers(-2, 5)))
+            nxt.append([x, y, w, h])
+            if rng.random() < 0.08:
+                nxt.append([x + 1, y + 1, max(1, w // 2), max(1, h // 2)])   # a contained sibling: scores 1.0 twice
+        for _ in range(int(rng.integers(0, 6))):
+            nxt.append([int(rng.integers(0, 900)), int(rng.integers(0, 700)), int(rng.integers(4, 50)), int(rng.integers(4, 50))])
+        if z == 5:
+            nxt.append([0, 0, 960, 760])
+        pop = nxt
+        order = rng.permutation(len(pop))
+        raw = [{"label": i + 1, "area": int(pop[k][2] * pop[k][3] * 0.7) + 1, "bbox": tuple(pop[k])} for i, k in enumerate(order)]
+        got = mine.update_and_classify([dict(r) for r in raw], z, cfg)
+        want = theirs.update([dict(r) for r in raw], z, rp)
+        assert [(r["id"], r["classification"], r["bbox"]) for r in got] == [(r["id"], r["classification"], r["bbox"]) for r in want], z
+    assert mine.next_roi_id == theirs.next_id
+
+
 def test_zshard_plan():
     import vsb_engine as E
     plan = E.zshard_plan(2000, 8, 4)

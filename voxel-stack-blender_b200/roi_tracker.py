@@ -21,19 +21,36 @@ def calculate_iou(boxA, boxB):
 
 def _score_matrix(cur_boxes, prev_boxes):
     """calculate_iou for every (current, previous) pair at once: the same integer intersections and the same
-    float64 division as the scalar function, so the matrix equals the reference's element for element (a stack with
-    thousands of supports makes this millions of pairs per layer)."""
+    float64 division as the scalar function, so the matrix equals the reference's element for element.  A stack
+    with thousands of supports makes this millions of pairs per layer, nearly all of them disjoint (score 0), so
+    only the pairs whose x-extents overlap are evaluated: previous boxes sorted by left edge, one binary search
+    per current box for the run of candidates."""
     n, m = len(cur_boxes), len(prev_boxes)
+    out = np.zeros((n, m))
     if n == 0 or m == 0:
-        return np.zeros((n, m))
+        return out
     c = np.asarray(cur_boxes, np.int64).reshape(n, 4)
     q = np.asarray(prev_boxes, np.int64).reshape(m, 4)
-    iw = np.minimum((c[:, 0] + c[:, 2])[:, None], (q[:, 0] + q[:, 2])[None, :]) - np.maximum(c[:, 0][:, None], q[:, 0][None, :])
-    ih = np.minimum((c[:, 1] + c[:, 3])[:, None], (q[:, 1] + q[:, 3])[None, :]) - np.maximum(c[:, 1][:, None], q[:, 1][None, :])
+    order = np.argsort(q[:, 0], kind="stable")
+    q_left = q[order, 0]
+    # a previous box can only reach over c's left edge if it starts within max(width) of it, and has to start
+    # before c's right edge; everything outside that run has a non-positive x overlap, i.e. score 0
+    lo = np.searchsorted(q_left, c[:, 0] - max(int(q[:, 2].max()), 0), side="right")
+    hi = np.searchsorted(q_left, c[:, 0] + c[:, 2], side="left")
+    cnt = np.maximum(hi - lo, 0)
+    total = int(cnt.sum())
+    if total == 0:
+        return out
+    ci = np.repeat(np.arange(n), cnt)
+    pj = order[np.repeat(lo, cnt) + (np.arange(total) - np.repeat(np.cumsum(cnt) - cnt, cnt))]
+    a, b = c[ci], q[pj]
+    iw = np.minimum(a[:, 0] + a[:, 2], b[:, 0] + b[:, 2]) - np.maximum(a[:, 0], b[:, 0])
+    ih = np.minimum(a[:, 1] + a[:, 3], b[:, 1] + b[:, 3]) - np.maximum(a[:, 1], b[:, 1])
     inter = np.maximum(iw, 0) * np.maximum(ih, 0)
-    smaller = np.minimum((c[:, 2] * c[:, 3])[:, None], (q[:, 2] * q[:, 3])[None, :])
-    out = np.zeros((n, m))
-    np.divide(inter, smaller.astype(np.float64), out=out, where=smaller != 0)
+    smaller = np.minimum(a[:, 2] * a[:, 3], b[:, 2] * b[:, 3])
+    val = np.zeros(total)
+    np.divide(inter, smaller.astype(np.float64), out=val, where=smaller != 0)
+    out[ci, pj] = val
     return out
 
 
@@ -73,12 +90,17 @@ class ROITracker:
         prev_ids = list(self.previous_rois)
         scores = _score_matrix([r["bbox"] for r in current_rois_raw], [self.previous_rois[i]["bbox"] for i in prev_ids])
 
-        # greedy one-to-one assignment, best score first; equal scores keep their flattened (row-major) order
+        # greedy one-to-one assignment, best score first: the reference's argsort of the negated matrix (same call on
+        # the same values, so ties come out in the order its sort leaves them); negated in place, the matrix is 8 bytes
+        # per pair
+        neg = np.negative(scores, out=scores)
         assigned, taken = {}, set()
-        for flat in np.argsort(-scores, axis=None):
-            ci, pj = divmod(int(flat), scores.shape[1]) if scores.shape[1] else (0, 0)
-            if scores.size == 0 or scores[ci, pj] < self.MATCH_THRESHOLD:
-                break
+        width = neg.shape[1]
+        order = np.argsort(neg, axis=None) if neg.size else np.zeros(0, np.int64)
+        # scores at or above the threshold come first; stop at the first one below it
+        n_hits = int(np.count_nonzero(neg <= -self.MATCH_THRESHOLD))
+        for flat in order[:n_hits].tolist():
+            ci, pj = divmod(flat, width)
             pid = prev_ids[pj]
             if ci in assigned or pid in taken:
                 continue

@@ -71,7 +71,14 @@ class DevImage:
         return d
 
     def numpy(self) -> np.ndarray:
-        return self.t[:, : self.W].contiguous().cpu().numpy()
+        t = torch()
+        if self.H * self.W < (1 << 22):
+            return self.t[:, : self.W].contiguous().cpu().numpy()
+        # large layers: into page-locked memory (blocks come from torch's caching host allocator, so only the first
+        # layer of a size pays for the registration); a pageable copy of a 16K layer runs at a tenth of the link
+        host = t.empty((self.H, self.W), dtype=t.uint8, pin_memory=True)
+        host.copy_(self.t[:, : self.W])
+        return host.numpy()
 
 
 class DevBits:
@@ -386,17 +393,20 @@ class Components:
 
     def rois(self, min_size: int, with_masks: bool = False) -> List[dict]:
         """identify_rois' list (processing_core.py:82-103): label, area, bbox, centroid (+ mask on request)."""
-        out = []
         cid_host = self.cid.cpu().numpy() if with_masks else None
-        for rank, c in enumerate(self.order):
-            st = self.stats[c]
-            if st["area"] >= min_size:
-                r = {"label": rank + 1, "area": int(st["area"]),
-                     "bbox": (int(st["x0"]), int(st["y0"]), int(st["x1"] - st["x0"] + 1), int(st["y1"] - st["y0"] + 1)),
-                     "centroid": np.array([st["sum_x"] / st["area"], st["sum_y"] / st["area"]]), "component": int(c)}
-                if with_masks:
-                    r["mask"] = (cid_host == c + 1).astype(np.uint8) * 255
-                out.append(r)
+        st = self.stats[self.order]                      # the library's label order
+        keep = np.nonzero(st["area"] >= min_size)[0]
+        st = st[keep]
+        area = st["area"].astype(np.int64)
+        cx, cy = st["sum_x"] / area, st["sum_y"] / area   # uint64 / int64 -> float64, as the per-ROI division did
+        cols = (keep.tolist(), self.order[keep].tolist(), area.tolist(), st["x0"].tolist(), st["y0"].tolist(),
+                (st["x1"] - st["x0"] + 1).tolist(), (st["y1"] - st["y0"] + 1).tolist(), cx.tolist(), cy.tolist())
+        out = []
+        for rank, c, a, x0, y0, w, h, mx, my in zip(*cols):
+            r = {"label": rank + 1, "area": a, "bbox": (x0, y0, w, h), "centroid": np.array([mx, my]), "component": c}
+            if with_masks:
+                r["mask"] = (cid_host == c + 1).astype(np.uint8) * 255
+            out.append(r)
         return out
 
 
