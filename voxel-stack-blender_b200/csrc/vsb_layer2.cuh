@@ -79,7 +79,7 @@ __device__ __forceinline__ void layer2_tile(const LayerParams &p, const BilTapsL
     __shared__ __align__(4) uint8_t s_lut2[256];
     __shared__ int s_cnt, s_gcnt, s_rcnt, s_nact;
     __shared__ __align__(16) uint32_t s_wcode[VSB_THREADS / 32]; // per warp: receding / white / black seen in the region
-    __shared__ uint8_t s_act[LB_ROWS_MAX + 4], s_lo[RG_ROWS_MAX], s_hi[RG_ROWS_MAX], s_mid[RG_ROWS_MAX]; // dense tiles: non-empty window rows, and per region row the ones in reach
+    __shared__ __align__(4) uint8_t s_act[LB_ROWS_MAX + 4], s_lo[RG_ROWS_MAX], s_hi[RG_ROWS_MAX], s_mid[RG_ROWS_MAX]; // dense tiles: non-empty window rows, and per region row the ones in reach
 
     const int t = threadIdx.x, lane = t & 31;
     const int W = p.W, H = p.H, wpr = p.wpr;
@@ -349,45 +349,58 @@ __device__ __forceinline__ void layer2_tile(const LayerParams &p, const BilTapsL
             const int hr0 = rr + R;
             const uint8_t *hp = s_h + min(max(rc - L2_HC0, 0), L2_HCOLS - 1) * L2_HS;
             // the listed rows in groups of four (one 32-bit read of the table each), outwards from the pixel's own row, first
-            // upwards then downwards; a SIMD byte compare picks the rows that hold a white pixel closer than the best distance
-            // so far, and a direction ends once no lane can do better than the group's smallest |dy|
+            // upwards then downwards.  Every metric here grows with |dy| for a fixed |dx| and is >= max(|dx|, |dy|), so a row can
+            // only improve a lane's best if its white pixel is closer IN X than the best distance so far, than that of every
+            // nearer row of the same direction, and than the pixel's own row: one byte compare against that bound picks the
+            // candidates of a group, the rows any lane still wants are evaluated by all lanes in step (|dy| is warp-uniform),
+            // and a direction ends once no lane can do better than the group's smallest |dy|
             float best = mine ? 3.0e38f : 0.0f;
             int best2 = mine ? 0x7fffffff : 0;
-            uint32_t thr4 = (uint32_t)R * 0x01010101u; // per byte: dx <= thr can still improve this lane's best
             const int lo = s_lo[rr], hi = s_hi[rr], mid = s_mid[rr];
-            auto group = [&](const int g4) { // rows g4 .. g4 + 3 of the list
+            const int dx0 = mid > lo && (int)s_act[mid - 1] == hr0 ? (int)hp[mid - 1] : R + 1; // the pixel's own row, if listed
+            int dxmin = R + 1;
+            int thr = mine ? R : -1; // dx <= thr can still improve this lane's best; < 0: nothing can
+            uint32_t thrb = (uint32_t)R * 0x01010101u | 0x80808080u;
+            auto bound = [&]() {
+                const int reach = METRIC == VSB_METRIC_CHAMFER5 ? (int)best : (best2 == 0x7fffffff ? R : (int)__fsqrt_ru((float)best2));
+                thr = min(min(R, reach), dxmin - 1);
+                thrb = (uint32_t)max(thr, 0) * 0x01010101u | 0x80808080u;
+            };
+            auto group = [&](const int g4, const uint32_t a4, const bool up) { // rows g4 .. g4 + 3 of the list (a4: their window rows)
+                // table bytes are 0..64, or 255 for padding: per byte, bit 7 of (thr | 0x80) - (dx & 0x7f) is set iff dx <= thr
                 const uint32_t w4 = *(const uint32_t *)(hp + g4);
-                uint32_t hit = mine ? __vcmpleu4(w4, thr4) : 0u;
-                while (hit) {
-                    const int q = (__ffs(hit) - 1) >> 3;
-                    hit &= ~(0xFFu << (8 * q));
-                    const int dx = (w4 >> (8 * q)) & 255, kk = abs((int)s_act[g4 + q] - hr0);
-                    if (kk <= R) {
-                        if (METRIC == VSB_METRIC_CHAMFER5) {
-                            const int M = max(kk, dx);
-                            if ((float)M < best) {
-                                best = fminf(best, s_T[M * n1 + min(kk, dx)]);
-                                thr4 = (uint32_t)min(R, (int)best) * 0x01010101u; // dx > floor(best) gives T >= dx > best... never better
-                            }
-                        } else {
-                            const int c2 = kk * kk + dx * dx;
-                            if (c2 < best2) {
-                                best2 = c2;
-                                thr4 = (uint32_t)min(R, (int)__fsqrt_ru((float)c2)) * 0x01010101u;
-                            }
-                        }
+                const uint32_t hit = thr >= 0 ? ((thrb - (w4 & 0x7f7f7f7fu)) & 0x80808080u) : 0u;
+                const uint32_t any = __reduce_or_sync(0xffffffffu, hit);
+                if (any == 0u) return;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if (!(any & (0x80u << (8 * q))) || (up ? g4 + q >= mid : g4 + q < mid)) continue; // warp-uniform
+                    const int kk = abs((int)((a4 >> (8 * q)) & 255u) - hr0);
+                    if (kk > R) continue;
+                    if (hit & (0x80u << (8 * q))) {
+                        const int dx = (w4 >> (8 * q)) & 255;
+                        if (METRIC == VSB_METRIC_CHAMFER5) best = fminf(best, s_T[max(kk, dx) * n1 + min(kk, dx)]);
+                        else best2 = min(best2, kk * kk + dx * dx);
+                        dxmin = min(dxmin, dx);
                     }
                 }
+                bound();
             };
             for (int g4 = (mid - 1) & ~3; g4 >= (lo & ~3) && mid > lo; g4 -= 4) { // upwards: the group's nearest row is its last
-                const int kmin = max(hr0 - (int)s_act[min(g4 + 3, mid - 1)], 0);
-                if (METRIC == VSB_METRIC_CHAMFER5 ? __all_sync(0xffffffffu, best <= (float)kmin) : __all_sync(0xffffffffu, best2 <= kmin * kmin)) break;
-                group(g4);
+                const uint32_t a4 = *(const uint32_t *)(s_act + g4);
+                const int kmin = max(hr0 - (int)((a4 >> (8 * (min(g4 + 3, mid - 1) - g4))) & 255u), 0);
+                if (__all_sync(0xffffffffu, thr < 0 || (METRIC == VSB_METRIC_CHAMFER5 ? best <= (float)kmin : best2 <= kmin * kmin))) break;
+                group(g4, a4, true);
             }
-            for (int g4 = mid & ~3; g4 < hi; g4 += 4) {                           // downwards: its first
-                const int kmin = max((int)s_act[max(g4, mid)] - hr0, 0);
-                if (METRIC == VSB_METRIC_CHAMFER5 ? __all_sync(0xffffffffu, best <= (float)kmin) : __all_sync(0xffffffffu, best2 <= kmin * kmin)) break;
-                group(g4);
+            if (mine) { // downwards: of the rows above, only the pixel's own carries over
+                dxmin = dx0;
+                bound();
+            }
+            for (int g4 = mid & ~3; g4 < hi; g4 += 4) {                           // its first
+                const uint32_t a4 = *(const uint32_t *)(s_act + g4);
+                const int kmin = max((int)((a4 >> (8 * (max(g4, mid) - g4))) & 255u) - hr0, 0);
+                if (__all_sync(0xffffffffu, thr < 0 || (METRIC == VSB_METRIC_CHAMFER5 ? best <= (float)kmin : best2 <= kmin * kmin))) break;
+                group(g4, a4, false);
             }
             bool graded = false;
             if (mine) {
