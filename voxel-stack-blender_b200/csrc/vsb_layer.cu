@@ -74,6 +74,8 @@ struct LayerParams {
     int *gen_list;       // XY: k_layer2 appends the tiles it leaves to the general kernel; k_layer then walks that list
     int *dense_list;     // XY: interior tiles with thousands of receding pixels, set aside for k_layer2_dense
     uint16_t *tile_class; // k_layer2: per tile, from k_layer2_classify
+    int dense_from;      // k_layer2: receding pixels from which a tile takes the dense launch's row-distance table
+    int route_dense;     // k_layer2_classify: all-receding interior tiles go straight to the dense launch (modes that search)
     int rcap;            // k_layer2: entries of the receding-pixel list (sm.glist = entries of the bilateral pixel list)
     int two_valued;      // k_layer2: a window holding only LUT1[0] / LUT1[255] with >= 3 taps equal to the centre keeps the centre
     // VSB_Z_ENHANCED: distances at the receding pixels, their component roots and the per-root maxima (vsb_ccl8_max)
@@ -779,6 +781,8 @@ static int launch_layer2(LayerParams &p, LayerParams &pd, const BilTapsL *taps, 
     p.dense_list = pd.dense_list = gen_list + 1 + p.ntiles;
     VSB_CUDA(cudaMemsetAsync(p.gen_list, 0, (size_t)(2 + p.ntiles) * sizeof(int), s)); // both counters with one node (93 KB at 16K)
     p.tile_class = pd.tile_class = (uint16_t *)(gen_list + 2 * (1 + p.ntiles));
+    p.route_dense = pd.route_dense = ZL_SEARCHES(ZMODE) ? 1 : 0;
+    { static int df = -1; if (df < 0) { const char *e = getenv("VSB_DENSE_FROM"); df = e ? atoi(e) : L2_DENSE_MIN; } p.dense_from = pd.dense_from = df; }
     k_layer2_classify<<<(p.ntiles + 255) / 256, 256, 0, s>>>(p);
     int rc = vsb_check_launch("k_layer2_classify");
     if (rc) return rc;
@@ -950,7 +954,7 @@ static int layer_launch(const uint8_t *in, size_t in_pitch, int W, int H, const 
         p.two_valued = (xy && p.hb >= 1 && xy->two_valued_min_same >= 1 && xy->two_valued_min_same <= 3) ? 1 : 0;
         LayerParams p2 = p; // same carve for T / s1 / s2 / bits, then the three lists
         size_t o2 = 0;
-        p2.sm.T = (int)o2; o2 += up16((searching && zp->metric == VSB_METRIC_CHAMFER5) ? (size_t)n1 * n1 * 4 : 16);
+        p2.sm.T = (int)o2; o2 += up16((searching && zp->metric == VSB_METRIC_CHAMFER5) ? (size_t)n1 * (n1 + 1) * 4 : 16); // (dense launch: odd row stride)
         p2.sm.s1 = (int)o2; o2 += up16((size_t)RH * RG_W);
         p2.sm.s2 = (int)o2; o2 += up16((size_t)RH * RG_W);
         p2.sm.bits = (int)o2; o2 += searching ? up16((size_t)(RH + 2 * p.z.reach) * LBW * 4) : 16;

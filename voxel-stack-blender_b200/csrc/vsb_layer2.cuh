@@ -24,6 +24,7 @@
 #define L2_HC0 9
 #define EDT_FAR (1 << 20)
 #define L2_HS 164                    // bytes per table column (the listed rows side by side; 41 words: conflict-free across columns)
+#define L2_DV 8                      // dense tiles: region rows per lane in the table search
 #define L2_DENSE_ROWS 164            // 142 x 164 bytes fit the space of the three lists (4480 + 1024 + 6656 entries)
 
 // bits [lo, hi) of the 192-bit region span that fall into word k
@@ -90,6 +91,7 @@ __device__ __forceinline__ void layer2_tile(const LayerParams &p, const BilTapsL
     const bool gauss = SHAPE == 1 ? true : (SHAPE == 2 ? false : p.nkx > 0);
     const int RH = VSB_TH + 2 * Hh;
     const int R = p.z.reach;
+    const int TS = DENSE ? ((R + 1) | 1) : R + 1; // floats per row of the staged chamfer table
     const int x0 = tx * VSB_TW, y0 = ty * VSB_TH;
     const int oy = y0 + r, ox = x0 + c * 16;
     const int nvalid = (oy < H) ? max(0, min(16, W - ox)) : 0;
@@ -98,7 +100,9 @@ __device__ __forceinline__ void layer2_tile(const LayerParams &p, const BilTapsL
     //         left at once -- no table staging, no barrier -- and non-binary ones were listed for the general kernel
     const uint32_t cls = p.tile_class[ty * p.tiles_x + tx]; // the same word for every thread of the CTA
     if ((cls & 3u) == 1u) return;
-    if (cls & 2u) {
+    if ((cls & 3u) == 3u) { // listed for the dense launch by the pre-pass
+        if (!DENSE) return;
+    } else if (cls & 2u) {
         if (nvalid > 0) {
             const uint32_t cv = (cls >> 8) * 0x01010101u;
             uint8_t *dst = p.out + (size_t)oy * p.opitch + ox;
@@ -128,7 +132,7 @@ __device__ __forceinline__ void layer2_tile(const LayerParams &p, const BilTapsL
     const int img_lo = 32 - x0, img_hi = W - x0 + 32; // image columns in span coordinates
     const bool border = (x0 - Hh < 0) || (x0 + VSB_TW + Hh > W) || (y0 - Hh < 0) || (y0 + VSB_TH + Hh > H);
     const bool searching = ZL_SEARCHES(ZMODE);
-    uint32_t code = 0;
+    uint32_t code = 0, nrec = 0;
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
         const int i = t + u * VSB_THREADS;
@@ -159,9 +163,11 @@ __device__ __forceinline__ void layer2_tile(const LayerParams &p, const BilTapsL
             s_c[rr][k] = cw;
             s_r[rr][k] = rw;
             code |= (rw ? 1u : 0u) | ((cw & rm) ? 2u : 0u) | ((~cw & rm) ? 4u : 0u);
+            if (!DENSE && searching) nrec += __popc(rw);
         }
     }
     code = __reduce_or_sync(0xffffffffu, code);
+    if (!DENSE && searching) code |= __reduce_add_sync(0xffffffffu, nrec) << 3; // + the warp's receding pixels (at most 2048)
     if (lane == 0) s_wcode[t >> 5] = code;
     if (hb > 0) {
         const float cwt = taps->cw[t];
@@ -171,14 +177,25 @@ __device__ __forceinline__ void layer2_tile(const LayerParams &p, const BilTapsL
     if (p.lut1) { k0b = s_lut1[0]; k1b = s_lut1[255]; }
     K0 = k0b * 0x01010101u; K1 = k1b * 0x01010101u;
     const uint4 wc0 = *(const uint4 *)&s_wcode[0], wc1 = *(const uint4 *)&s_wcode[4];
-    const int state = (int)(wc0.x | wc0.y | wc0.z | wc0.w | wc1.x | wc1.y | wc1.z | wc1.w);
+    const int state = (int)((wc0.x | wc0.y | wc0.z | wc0.w | wc1.x | wc1.y | wc1.z | wc1.w) & 7u);
     const bool any_rec = (state & 1) != 0;
     if (!any_rec && (state & 6) != 6) { constant_out((state & 2) ? k1b : k0b); return; } // one value, nothing recedes
+    // dense tiles (thousands of receding pixels: whole tiles right after a raft ends) are set aside for the second launch
+    // before anything is staged for them
+    if (!DENSE && searching && !border &&
+        (int)((wc0.x >> 3) + (wc0.y >> 3) + (wc0.z >> 3) + (wc0.w >> 3) + (wc1.x >> 3) + (wc1.y >> 3) + (wc1.z >> 3) + (wc1.w >> 3)) >= p.dense_from) {
+        if (t == 0) p.dense_list[1 + atomicAdd(&p.dense_list[0], 1)] = ty * p.tiles_x + tx;
+        return;
+    }
     if (any_rec && searching && METRIC == VSB_METRIC_CHAMFER5) { // the chamfer table: only tiles with receding pixels read it
         const int nT = (R + 1) * (R + 1);                       // (first use is two barriers away)
-        const int nfull = ((((size_t)p.T) & 15) == 0) ? (nT >> 2) : 0;
-        for (int i = t; i < nfull; i += VSB_THREADS) ((float4 *)s_T)[i] = ((const float4 *)p.T)[i];
-        for (int i = 4 * nfull + t; i < nT; i += VSB_THREADS) s_T[i] = p.T[i];
+        if (DENSE) { // rows an odd number of floats apart: the lanes of the table search read T[dx][k] with one k and 32 dx
+            for (int i = t; i < nT; i += VSB_THREADS) { const int r = i / (R + 1); s_T[r * TS + (i - r * (R + 1))] = p.T[i]; }
+        } else {
+            const int nfull = ((((size_t)p.T) & 15) == 0) ? (nT >> 2) : 0;
+            for (int i = t; i < nfull; i += VSB_THREADS) ((float4 *)s_T)[i] = ((const float4 *)p.T)[i];
+            for (int i = 4 * nfull + t; i < nT; i += VSB_THREADS) s_T[i] = p.T[i];
+        }
     }
 
     // out-of-image columns (left / right border tiles): mirrored bits, one thread per region row
@@ -252,15 +269,11 @@ __device__ __forceinline__ void layer2_tile(const LayerParams &p, const BilTapsL
     //      let the pixels read them four rows at a time.  The table borrows the space of the three lists (the receding pixels are
     //      then taken from the mask words), so this runs BEFORE the filter lists are built.
     bool use_h = false;
-    if (!DENSE && any_rec && searching && !border && s_rcnt >= L2_DENSE_MIN) { // set aside for the dense launch
-        if (t == 0) p.dense_list[1 + atomicAdd(&p.dense_list[0], 1)] = ty * p.tiles_x + tx;
-        return;
-    }
     if (any_rec && s_rcnt > p.rcap) { // more receding pixels than the list holds (border tiles, modes without search): general kernel
         if (t == 0) p.gen_list[1 + atomicAdd(&p.gen_list[0], 1)] = ty * p.tiles_x + tx;
         return;
     }
-    if (DENSE && any_rec && searching && s_rcnt >= L2_DENSE_MIN) {
+    if (DENSE && any_rec && searching && s_rcnt >= p.dense_from) {
         const int brows = RH + 2 * R;
         stage_rowany_rows<LBW>(s_rowany, s_bits, brows);
         __syncthreads();
@@ -338,79 +351,116 @@ __device__ __forceinline__ void layer2_tile(const LayerParams &p, const BilTapsL
         s2buf[rr][rc] = v;
         return v;
     };
-    if (DENSE && use_h) { // dense, interior tile: a warp per mask word, a lane per pixel, distances from the table
-        const int n1 = R + 1;
-        for (int item = t >> 5; item < RH * L2W; item += VSB_THREADS / 32) {
-            const int rr = item / L2W, k = item - rr * L2W;
-            const uint32_t rw = s_r[rr][k];
-            if (rw == 0u) continue; // warp-uniform
-            const bool mine = (rw >> lane) & 1u;
+    if (DENSE && use_h) { // dense, interior tile: a warp per mask word and block of L2_DV region rows, a lane per pixel COLUMN
+        // A lane owns the L2_DV pixels of its column in the block.  They share the column's table bytes (the nearest white
+        // pixel of a listed row lies equally far in x from all of them) and differ only in |dy|, which is warp-uniform: a
+        // listed row costs one byte compare for the block and, where it is wanted, one table read per pixel.  Every metric
+        // here grows with |dy| for a fixed |dx| and is >= max(|dx|, |dy|), so a row can only improve one of the lane's
+        // pixels if its white pixel is closer in x than the largest of their best distances so far, and than that of every
+        // listed row that is nearer to ALL of them: the nearer rows on the same side of the block, and -- from L2_DV rows away
+        // -- the rows inside the block.  Order: the rows inside the block, then upwards, then downwards, in groups of four
+        // (one 32-bit read of the table each); a direction ends once no lane can do better than the group's smallest |dy|.
+        const int nblk = (RH + L2_DV - 1) / L2_DV;
+        for (int item = t >> 5; item < nblk * L2W; item += VSB_THREADS / 32) {
+            const int blk = item / L2W, k = item - blk * L2W;
+            const int rr0 = blk * L2_DV, nv = min(L2_DV, RH - rr0);
+            uint32_t mine = 0u, anyrow = 0u; // bit j: pixel (rr0 + j, this lane's column) is receding
+#pragma unroll
+            for (int j = 0; j < L2_DV; ++j) {
+                if (j < nv) {
+                    const uint32_t rw = s_r[rr0 + j][k];
+                    anyrow |= rw;
+                    mine |= ((rw >> lane) & 1u) << j;
+                }
+            }
+            if (anyrow == 0u) continue; // warp-uniform
             const int rc = 32 * k + lane - 16;
-            const int hr0 = rr + R;
+            const int hr0 = rr0 + R, hr1 = hr0 + nv - 1; // window rows of the block's first and last pixel row
             const uint8_t *hp = s_h + min(max(rc - L2_HC0, 0), L2_HCOLS - 1) * L2_HS;
-            // the listed rows in groups of four (one 32-bit read of the table each), outwards from the pixel's own row, first
-            // upwards then downwards.  Every metric here grows with |dy| for a fixed |dx| and is >= max(|dx|, |dy|), so a row can
-            // only improve a lane's best if its white pixel is closer IN X than the best distance so far, than that of every
-            // nearer row of the same direction, and than the pixel's own row: one byte compare against that bound picks the
-            // candidates of a group, the rows any lane still wants are evaluated by all lanes in step (|dy| is warp-uniform),
-            // and a direction ends once no lane can do better than the group's smallest |dy|
-            float best = mine ? 3.0e38f : 0.0f;
-            int best2 = mine ? 0x7fffffff : 0;
-            const int lo = s_lo[rr], hi = s_hi[rr], mid = s_mid[rr];
-            const int dx0 = mid > lo && (int)s_act[mid - 1] == hr0 ? (int)hp[mid - 1] : R + 1; // the pixel's own row, if listed
-            int dxmin = R + 1;
-            int thr = mine ? R : -1; // dx <= thr can still improve this lane's best; < 0: nothing can
+            float best[L2_DV]; // chamfer: the distance; exact metric: its square (integers below 2^24, exact in float)
+#pragma unroll
+            for (int j = 0; j < L2_DV; ++j) best[j] = (mine >> j) & 1u ? 3.0e38f : 0.0f;
+            const int lo = s_lo[rr0], hi = s_hi[rr0 + nv - 1];
+            int i0 = s_mid[rr0];
+            if (i0 > lo && (int)s_act[i0 - 1] == hr0) --i0; // [i0, i1): the listed rows inside the block
+            const int i1 = max((int)s_mid[rr0 + nv - 1], i0);
+            int dx_in = R + 1, dx_side = R + 1; // smallest |dx| among the rows inside the block / on the current side of it
+            int thr = mine ? R : -1;            // dx <= thr can still improve one of this lane's pixels; < 0: nothing can
             uint32_t thrb = (uint32_t)R * 0x01010101u | 0x80808080u;
-            auto bound = [&]() {
-                const int reach = METRIC == VSB_METRIC_CHAMFER5 ? (int)best : (best2 == 0x7fffffff ? R : (int)__fsqrt_ru((float)best2));
-                thr = min(min(R, reach), dxmin - 1);
+            auto bound = [&](const int dxdom) {
+                float bm = best[0];
+#pragma unroll
+                for (int j = 1; j < L2_DV; ++j) bm = fmaxf(bm, best[j]);
+                const int reach = METRIC == VSB_METRIC_CHAMFER5 ? (int)bm : (bm >= 1.0e30f ? R : (int)__fsqrt_ru(bm));
+                thr = mine ? min(min(R, reach), dxdom - 1) : -1;
                 thrb = (uint32_t)max(thr, 0) * 0x01010101u | 0x80808080u;
+                return bm;
             };
-            auto group = [&](const int g4, const uint32_t a4, const bool up) { // rows g4 .. g4 + 3 of the list (a4: their window rows)
+            // rows g4 .. g4 + 3 of the list, those with index in [ia, ib); a4: their window rows.  Returns the smallest |dx| taken.
+            auto group = [&](const int g4, const int ia, const int ib) {
                 // table bytes are 0..64, or 255 for padding: per byte, bit 7 of (thr | 0x80) - (dx & 0x7f) is set iff dx <= thr
                 const uint32_t w4 = *(const uint32_t *)(hp + g4);
                 const uint32_t hit = thr >= 0 ? ((thrb - (w4 & 0x7f7f7f7fu)) & 0x80808080u) : 0u;
                 const uint32_t any = __reduce_or_sync(0xffffffffu, hit);
-                if (any == 0u) return;
+                int dmin = R + 1;
+                if (any == 0u) return dmin;
+                const uint32_t a4 = *(const uint32_t *)(s_act + g4);
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    if (!(any & (0x80u << (8 * q))) || (up ? g4 + q >= mid : g4 + q < mid)) continue; // warp-uniform
-                    const int kk = abs((int)((a4 >> (8 * q)) & 255u) - hr0);
-                    if (kk > R) continue;
+                    if (!(any & (0x80u << (8 * q))) || g4 + q < ia || g4 + q >= ib) continue; // warp-uniform
+                    const int d0 = (int)((a4 >> (8 * q)) & 255u) - hr0;                        // row - first pixel row
                     if (hit & (0x80u << (8 * q))) {
                         const int dx = (w4 >> (8 * q)) & 255;
-                        if (METRIC == VSB_METRIC_CHAMFER5) best = fminf(best, s_T[max(kk, dx) * n1 + min(kk, dx)]);
-                        else best2 = min(best2, kk * kk + dx * dx);
-                        dxmin = min(dxmin, dx);
+                        dmin = min(dmin, dx);
+                        if (METRIC == VSB_METRIC_CHAMFER5) {
+                            const float *Tr = s_T + dx * TS; // the table is symmetric: T[dx][|dy|]
+#pragma unroll
+                            for (int j = 0; j < L2_DV; ++j) {
+                                const int kk = abs(d0 - j);
+                                if (kk <= R) best[j] = fminf(best[j], Tr[kk]);
+                            }
+                        } else {
+                            const float dx2 = (float)(dx * dx);
+#pragma unroll
+                            for (int j = 0; j < L2_DV; ++j) {
+                                const int kk = abs(d0 - j);
+                                if (kk <= R) best[j] = fminf(best[j], dx2 + (float)(kk * kk));
+                            }
+                        }
                     }
                 }
-                bound();
+                return dmin;
             };
-            for (int g4 = (mid - 1) & ~3; g4 >= (lo & ~3) && mid > lo; g4 -= 4) { // upwards: the group's nearest row is its last
-                const uint32_t a4 = *(const uint32_t *)(s_act + g4);
-                const int kmin = max(hr0 - (int)((a4 >> (8 * (min(g4 + 3, mid - 1) - g4))) & 255u), 0);
-                if (__all_sync(0xffffffffu, thr < 0 || (METRIC == VSB_METRIC_CHAMFER5 ? best <= (float)kmin : best2 <= kmin * kmin))) break;
-                group(g4, a4, true);
+            for (int g4 = i0 & ~3; g4 < i1; g4 += 4) dx_in = min(dx_in, group(g4, i0, i1)); // inside: every row, no order
+            float bm = bound(R + 1);
+            for (int g4 = (i0 - 1) & ~3; g4 >= (lo & ~3) && i0 > lo; g4 -= 4) { // upwards: the group's nearest row is its last
+                const int kmin = hr0 - (int)s_act[min(g4 + 3, i0 - 1)];
+                if (__all_sync(0xffffffffu, thr < 0 || (METRIC == VSB_METRIC_CHAMFER5 ? bm <= (float)kmin : bm <= (float)(kmin * kmin)))) break;
+                dx_side = min(dx_side, group(g4, lo, i0));
+                bm = bound(kmin >= L2_DV ? min(dx_side, dx_in) : dx_side); // (the NEXT group is at least as far as this one)
             }
-            if (mine) { // downwards: of the rows above, only the pixel's own carries over
-                dxmin = dx0;
-                bound();
-            }
-            for (int g4 = mid & ~3; g4 < hi; g4 += 4) {                           // its first
-                const uint32_t a4 = *(const uint32_t *)(s_act + g4);
-                const int kmin = max((int)((a4 >> (8 * (max(g4, mid) - g4))) & 255u) - hr0, 0);
-                if (__all_sync(0xffffffffu, thr < 0 || (METRIC == VSB_METRIC_CHAMFER5 ? best <= (float)kmin : best2 <= kmin * kmin))) break;
-                group(g4, a4, false);
-            }
-            bool graded = false;
-            if (mine) {
-                if (METRIC != VSB_METRIC_CHAMFER5) best = best2 == 0x7fffffff ? 3.0e38f : __fsqrt_rn((float)best2);
-                graded = fade_pixel(rr, rc, best) != (uint8_t)k0b;
+            dx_side = R + 1;
+            bm = bound(R + 1);
+            for (int g4 = i1 & ~3; g4 < hi; g4 += 4) {                          // downwards: its first
+                const int kmin = (int)s_act[max(g4, i1)] - hr1;
+                if (__all_sync(0xffffffffu, thr < 0 || (METRIC == VSB_METRIC_CHAMFER5 ? bm <= (float)kmin : bm <= (float)(kmin * kmin)))) break;
+                dx_side = min(dx_side, group(g4, i1, hi));
+                bm = bound(kmin >= L2_DV ? min(dx_side, dx_in) : dx_side);
             }
             // a receding pixel whose value came out as black's (beyond the fade distance) IS a black pixel for the filters:
             // only the others keep their mark, so the bypass planes below see a plain two-valued region there
-            const uint32_t nw = __ballot_sync(0xffffffffu, graded);
-            if (lane == 0) s_r[rr][k] = nw;
+#pragma unroll
+            for (int j = 0; j < L2_DV; ++j) {
+                if (j < nv) {
+                    bool graded = false;
+                    if ((mine >> j) & 1u) {
+                        const float d = METRIC == VSB_METRIC_CHAMFER5 ? best[j] : (best[j] >= 1.0e30f ? 3.0e38f : __fsqrt_rn(best[j]));
+                        graded = fade_pixel(rr0 + j, rc, d) != (uint8_t)k0b;
+                    }
+                    const uint32_t nw = __ballot_sync(0xffffffffu, graded);
+                    if (lane == 0) s_r[rr0 + j][k] = nw;
+                }
+            }
         }
         __syncthreads();
 #pragma unroll
@@ -433,7 +483,7 @@ __device__ __forceinline__ void layer2_tile(const LayerParams &p, const BilTapsL
             const int x = x0 - 16 + rc, y = y0 - Hh + rr;
             if (y < 0 || y >= H || x < 0 || x >= W) continue; // mirrored positions are filled in below
             float best = 0.0f;
-            if (ZL_SEARCHES(ZMODE)) best = tile_search<METRIC, LBW, false>(s_bits, s_rowany, s_T, R, rr + R, rc + 80);
+            if (ZL_SEARCHES(ZMODE)) best = tile_search<METRIC, LBW, false>(s_bits, s_rowany, s_T, R, rr + R, rc + 80, TS);
             fade_pixel(rr, rc, best);
         }
         __syncthreads();
@@ -598,6 +648,7 @@ __global__ void __launch_bounds__(256) k_layer2_classify(const __grid_constant__
     }
     const uint32_t fc = p.cur_flags[tile];
     uint32_t bin_and = FLAG_BINARY, diff_or = 0u, pri_or = 0u;
+    bool own_white = false; // some prior layer's tile is uniformly white
 #pragma unroll
     for (int q = 0; q < 9; ++q) {
         const uint32_t f = p.cur_flags[fi[q]];
@@ -611,6 +662,7 @@ __global__ void __launch_bounds__(256) k_layer2_classify(const __grid_constant__
         for (int q = 0; q < 9; ++q) {
             const uint32_t g = pf[fi[q]];
             pri_or |= (g & FLAG_MIXED) | ((g & 0xFFu) > 127u ? 1u : 0u); // mixed, or a uniform white tile
+            if (q == 4) own_white |= !(g & FLAG_MIXED) && (g & 0xFFu) > 127u;
         }
     }
     const bool all_bin = (bin_and & FLAG_BINARY) != 0u, same = diff_or == 0u, pri_black = pri_or == 0u;
@@ -621,6 +673,12 @@ __global__ void __launch_bounds__(256) k_layer2_classify(const __grid_constant__
     } else if (same && ((fc & 0xFFu) > 127u || pri_black || np == 0)) {
         const uint32_t s1val = (fc & 0xFFu) > 127u ? (p.lut1 ? p.lut1[255] : 255u) : (p.lut1 ? p.lut1[0] : 0u);
         cls = 2u | ((p.lut2 ? (uint32_t)p.lut2[s1val] : s1val) << 8);
+    } else if (p.route_dense && own_white && !(fc & FLAG_MIXED) && (fc & 0xFFu) <= 127u && tx > 0 && tx < p.tiles_x - 1 &&
+               ty > 0 && ty < p.tiles_y - 1 && (tx + 2) * VSB_TW <= p.W && (ty + 2) * VSB_TH <= p.H) {
+        // a black tile over a white one, away from the image border: every pixel recedes (right after a raft ends, most of
+        // the plate) -- straight to the dense launch, k_layer2 does not stage it first to find that out
+        cls = 3u;
+        p.dense_list[1 + atomicAdd(&p.dense_list[0], 1)] = tile;
     }
     p.tile_class[tile] = (uint16_t)cls;
 }

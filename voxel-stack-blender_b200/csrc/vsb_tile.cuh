@@ -81,12 +81,12 @@ __device__ __forceinline__ void stage_rowany_rows(uint32_t *s_rowany, const uint
 // distance from staged-row position (hr0, px) to the nearest set bit of the staged mask, either metric;
 // returns a value >= 3e38 when nothing lies within reach R.  T monotone in |dx| per row => the nearest
 // set bit of each row is that row's minimum; rows are visited outwards while |dy| < best.
-// TRI: the table is stored as its lower triangle, entry (M, m) at M*(M+1)/2 + m
+// TRI: the table is stored as its lower triangle, entry (M, m) at M*(M+1)/2 + m; `stride`: floats per table row if not R + 1
 template <int METRIC, int RW, bool TRI = false>
 __device__ __forceinline__ float tile_search(const uint32_t (*s_cur)[RW], const uint32_t *s_rowany, const float *s_T,
-                                             int R, int hr0, int px)
+                                             int R, int hr0, int px, int stride = 0)
 {
-    const int n1 = R + 1;
+    const int n1 = stride ? stride : R + 1; // floats per table row
     if (METRIC == VSB_METRIC_CHAMFER5) {
         float best = 3.0e38f;
         {
