@@ -858,7 +858,7 @@ def test_stack_engine_random_configs_vs_oracle(E, seed):
 def test_fast_path_routes_for_full_tiles(E):
     """The mask-only layer kernel hands tiles that are fuller than its shared-memory lists to other routes (the general kernel;
     the dense launch).  With the lists shrunk through the test hook, ordinary tiles take those routes too: same layers, bit for
-    bit, as with the default sizes and as the oracle -- fixed and weighted fades, both metrics, over a raft cliff."""
+    bit, as with the default sizes and as the oracle -- fixed and weighted fades, both metrics, tiles under a raft."""
     import vsb_native as N
     from config import Config
     W, H, L = 640, 400, 7
@@ -880,6 +880,28 @@ def test_fast_path_routes_for_full_tiles(E):
                     assert np.array_equal(a, b), (mode, metric, arena, rec, zi, int((a != b).sum()))
         finally:
             N.check(lib.vsb_layer_fast_path_limits(0, 0), "vsb_layer_fast_path_limits")
+
+
+@pytest.mark.parametrize("chain", ["lut_bil7_g3_lut", "bil9", "bil7_g5"])
+@pytest.mark.parametrize("mode,F,metric", [("fixed_fade", 5.0, "chamfer5"), ("fixed_fade", 9.0, "exact"), ("fixed_fade", 27.5, "chamfer5"),
+                                           ("fixed_fade", 40.0, "exact"), ("weighted_stack", 33.0, "chamfer5"), ("fixed_fade", 63.0, "chamfer5")])
+def test_dense_tiles_after_raft(E, chain, mode, F, metric):
+    """The layers right after a raft ends: whole tiles recede and take the dense launch (row-distance table, column blocks of
+    eight region rows per lane).  Reaches below, at and above the block height, both metrics, region heights that are and are
+    not a multiple of the block (halo 4, 4 and 5 rows), supports dense enough that most window rows are listed."""
+    from config import Config
+    W, H = 896, 448
+    layers = small_stack(W=W, H=H, L=15, seed=31, raft=True, n_blobs=30)[9:]   # z = 9..14: the raft is gone from z = 12
+    assert layers[2].mean() > 1.5 * layers[3].mean()
+    base = {"blending_mode": mode, "receding_layers": 3, "use_fixed_fade_receding": True, "fixed_fade_distance_receding": F,
+            "manual_weights": [4, 2, 1], "fade_distances_receding": [F, max(1.0, F - 9.0), max(1.0, F / 3)],
+            "xy_blend_pipeline": FUSED_CHAINS[chain]}
+    want = O.run_stack(layers, dict(base, metric=metric))
+    eng = engine_for_metric(E, Config.from_dict(dict(base, distance_metric=metric)), W, H, metric)
+    got = [eng.process(g) for g in layers]
+    eng.close()
+    for zi, (a, b) in enumerate(zip(got, want)):
+        assert np.array_equal(a, b), (chain, mode, F, metric, zi, int((a != b).sum()))
 
 
 def test_pipeline_thread_z_sharded_over_devices(E, slices, ref_stack, lut_file, tmp_path):
