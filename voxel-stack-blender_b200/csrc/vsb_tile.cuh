@@ -52,7 +52,28 @@ template <int RW>
 __device__ __forceinline__ void stage_mask_rows(uint32_t (*s_cur)[RW], const uint32_t *__restrict__ bits, int wpr,
                                                 int H, int wbase, int ystart, int nrows)
 {
-    for (int i = threadIdx.x; i < nrows * RW; i += VSB_THREADS) {
+    const int total = nrows * RW;
+    if (ystart >= 0 && ystart + nrows <= H && wbase >= 0 && wbase + RW <= wpr) { // inside the image: no checks, four requests in flight
+        const uint32_t *__restrict__ src = bits + (size_t)ystart * wpr + wbase;
+        uint32_t *dst = &s_cur[0][0];
+        int i = threadIdx.x;
+        for (; i + 3 * VSB_THREADS < total; i += 4 * VSB_THREADS) {
+            uint32_t v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int j = i + u * VSB_THREADS, hr = j / RW;
+                v[u] = src[hr * wpr + (j - hr * RW)];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) dst[i + u * VSB_THREADS] = v[u];
+        }
+        for (; i < total; i += VSB_THREADS) {
+            const int hr = i / RW;
+            dst[i] = src[hr * wpr + (i - hr * RW)];
+        }
+        return;
+    }
+    for (int i = threadIdx.x; i < total; i += VSB_THREADS) {
         const int hr = i / RW, hw = i - hr * RW;
         const int yy = ystart + hr, wx = wbase + hw;
         uint32_t v = 0;
