@@ -381,7 +381,8 @@ def main():
         eng.profile(False)
         eng.close()
         tbl, _ = stage_table(stages, alg)
-        return {"workload": WORKLOAD_TEXT.get(name, name), "layers_timed": n_timed, "ms_per_layer": round(ms, 5),
+        return {"workload": WORKLOAD_TEXT.get(name, name), "layers_timed": n_timed,
+                "slab_layers": [first + n_fill, first + n_fill + n_timed - 1], "ms_per_layer": round(ms, 5),
                 "layers_per_s_per_gpu": round(1000.0 / ms, 1), "hbm_gbs_algorithmic": round(alg / (ms * 1e-3) / 1e9, 1),
                 "frac_of_measured_peak": round(alg / (ms * 1e-3) / 1e9 / peak, 4),
                 "stage_ms": {k: v["ms_per_layer"] for k, v in tbl.items()},
@@ -630,10 +631,12 @@ def main():
                 extras[name] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
             torch.cuda.empty_cache()
         nfill, ntime = 8, min(L - 8, 96)
+        # the blocks time the layers the headline's timed region starts with (the slab's layers after the warm-up steps)
+        blk0 = max(0, min(Wm * B - nfill, L - nfill - ntime))
         if main_wl != "zlut":
-            guarded("zblend_lut_only", lambda: run_block("zlut", workload_dict("zlut", lut_path), stack, 0, nfill, ntime, W, H))
+            guarded("zblend_lut_only", lambda: run_block("zlut", workload_dict("zlut", lut_path), stack, blk0, nfill, ntime, W, H))
         if main_wl != "cfg3" and (W, H) == (W16, H16):
-            guarded("cfg3", lambda: run_block("cfg3", workload_dict("cfg3", lut_path), stack, 0, nfill, min(ntime, 32), W, H))
+            guarded("cfg3", lambda: run_block("cfg3", workload_dict("cfg3", lut_path), stack, blk0, nfill, min(ntime, 32), W, H))
         if main_wl == "preset" and (W, H) == (W16, H16):
             def cliff():
                 # the raft (60 % of the plate) ends at z = 12: layers 12..15 see it recede all at once over the dense
