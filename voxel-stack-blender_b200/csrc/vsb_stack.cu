@@ -67,7 +67,7 @@ struct vsb_stack {
     int *rec_tiles[2];     // LUT-only chains: work list of the patch kernel (1 + tiles ints), per lane
     int *gen_tiles[2];     // XY chains: tiles k_layer2 leaves to the general kernel / to its dense launch (3 x (1 + tiles) ints: two lists and the tile classes), per lane
     // environment switches, read once at creation
-    bool env_no_patch, env_no_fused_enh, env_tile_flags, env_no_overlap;
+    bool env_no_patch, env_no_fused_enh, env_no_overlap;
     // optional per-stage CUDA-event profiling (bench.py roofline leg)
     bool prof_on;
     struct ProfRec { int stage; int launches; cudaEvent_t a, b; };
@@ -186,7 +186,6 @@ extern "C" int vsb_stack_create(int W, int H, int n_priors, const vsb_zparams *z
     s->overlap_ok = false;
     s->env_no_patch = getenv("VSB_NO_PATCH") != nullptr;
     s->env_no_fused_enh = getenv("VSB_NO_FUSED_ENHANCED") != nullptr;
-    s->env_tile_flags = getenv("VSB_TILE_FLAGS") != nullptr;
     s->env_no_overlap = getenv("VSB_NO_OVERLAP") != nullptr;
     for (int i = 0; i < STACK_SLOTS; ++i) {
         s->ev_h2d[i] = s->ev_comp[i] = s->ev_d2h[i] = nullptr;
