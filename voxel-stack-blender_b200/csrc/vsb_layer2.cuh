@@ -24,6 +24,8 @@
 #define L2_HC0 9
 #define EDT_FAR (1 << 20)
 #define L2_HS 164                    // bytes per table column (the listed rows side by side; 41 words: conflict-free across columns)
+#define L2_CLIFF_TILES 2048          // dense tiles in a layer from which the lower threshold applies
+#define L2_DENSE_MIN_CLIFF 1024      // ... that threshold
 #define L2_DV 8                      // dense tiles: region rows per lane in the table search
 #define L2_DENSE_ROWS 164            // 142 x 164 bytes fit the space of the three lists (4480 + 1024 + 6656 entries)
 
@@ -79,6 +81,7 @@ __device__ __forceinline__ void layer2_tile(const LayerParams &p, const BilTapsL
     __shared__ __align__(4) uint8_t s_lut1[256];
     __shared__ __align__(4) uint8_t s_lut2[256];
     __shared__ int s_cnt, s_gcnt, s_rcnt, s_nact;
+    __shared__ int s_aside;
     __shared__ __align__(16) uint32_t s_wcode[VSB_THREADS / 32]; // per warp: receding / white / black seen in the region
     __shared__ __align__(4) uint8_t s_act[LB_ROWS_MAX + 4], s_lo[RG_ROWS_MAX], s_hi[RG_ROWS_MAX], s_mid[RG_ROWS_MAX]; // dense tiles: non-empty window rows, and per region row the ones in reach
 
@@ -182,10 +185,20 @@ __device__ __forceinline__ void layer2_tile(const LayerParams &p, const BilTapsL
     if (!any_rec && (state & 6) != 6) { constant_out((state & 2) ? k1b : k0b); return; } // one value, nothing recedes
     // dense tiles (thousands of receding pixels: whole tiles right after a raft ends) are set aside for the second launch
     // before anything is staged for them
-    if (!DENSE && searching && !border &&
-        (int)((wc0.x >> 3) + (wc0.y >> 3) + (wc0.z >> 3) + (wc0.w >> 3) + (wc1.x >> 3) + (wc1.y >> 3) + (wc1.z >> 3) + (wc1.w >> 3)) >= p.dense_from) {
-        if (t == 0) p.dense_list[1 + atomicAdd(&p.dense_list[0], 1)] = ty * p.tiles_x + tx;
-        return;
+    if (!DENSE && searching && !border) {
+        const int nrec_region = (int)((wc0.x >> 3) + (wc0.y >> 3) + (wc0.z >> 3) + (wc0.w >> 3) + (wc1.x >> 3) + (wc1.y >> 3) + (wc1.z >> 3) + (wc1.w >> 3));
+        bool aside = nrec_region >= p.dense_from;
+        // half-full tiles: only in a layer that sends thousands of tiles to the dense launch anyway (the pre-pass's count plus the
+        // ones set aside so far -- right after a raft ended), where that launch takes them better than the lists do
+        if (!aside && nrec_region >= L2_DENSE_MIN_CLIFF) { // (the count moves while the kernel runs: one thread reads it for the CTA)
+            if (t == 0) s_aside = __ldcg(&p.dense_list[0]) >= L2_CLIFF_TILES;
+            __syncthreads();
+            aside = s_aside != 0;
+        }
+        if (aside) {
+            if (t == 0) p.dense_list[1 + atomicAdd(&p.dense_list[0], 1)] = ty * p.tiles_x + tx;
+            return;
+        }
     }
     if (any_rec && searching && METRIC == VSB_METRIC_CHAMFER5) { // the chamfer table: only tiles with receding pixels read it
         const int nT = (R + 1) * (R + 1);                       // (first use is two barriers away)
@@ -273,7 +286,7 @@ __device__ __forceinline__ void layer2_tile(const LayerParams &p, const BilTapsL
         if (t == 0) p.gen_list[1 + atomicAdd(&p.gen_list[0], 1)] = ty * p.tiles_x + tx;
         return;
     }
-    if (DENSE && any_rec && searching && s_rcnt >= p.dense_from) {
+    if (DENSE && any_rec && searching && s_rcnt >= min(p.dense_from, L2_DENSE_MIN_CLIFF)) {
         const int brows = RH + 2 * R;
         stage_rowany_rows<LBW>(s_rowany, s_bits, brows);
         __syncthreads();
