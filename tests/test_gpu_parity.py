@@ -887,8 +887,8 @@ def test_fast_path_routes_for_full_tiles(E):
                                            ("fixed_fade", 40.0, "exact"), ("weighted_stack", 33.0, "chamfer5"), ("fixed_fade", 63.0, "chamfer5")])
 def test_dense_tiles_after_raft(E, chain, mode, F, metric):
     """The layers right after a raft ends: whole tiles recede and take the dense launch (row-distance table, column blocks of
-    eight region rows per lane).  Reaches below, at and above the block height, both metrics, region heights that are and are
-    not a multiple of the block (halo 4, 4 and 5 rows), supports dense enough that most window rows are listed."""
+    ten region rows per lane).  Reaches below, at and above the block height, both metrics, region heights that are and are
+    not a multiple of the block (40, 40 and 42 rows), supports dense enough that most window rows are listed."""
     from config import Config
     W, H = 896, 448
     layers = small_stack(W=W, H=H, L=15, seed=31, raft=True, n_blobs=30)[9:]   # z = 9..14: the raft is gone from z = 12

@@ -26,7 +26,7 @@
 #define L2_HS 164                    // bytes per table column (the listed rows side by side; 41 words: conflict-free across columns)
 #define L2_CLIFF_TILES 2048          // dense tiles in a layer from which the lower threshold applies
 #define L2_DENSE_MIN_CLIFF 1024      // ... that threshold
-#define L2_DV 8                      // dense tiles: region rows per lane in the table search
+#define L2_DV 10                     // dense tiles: region rows per lane in the table search
 #define L2_DENSE_ROWS 164            // 142 x 164 bytes fit the space of the three lists (4480 + 1024 + 6656 entries)
 
 // bits [lo, hi) of the 192-bit region span that fall into word k
