@@ -279,8 +279,9 @@ __device__ __forceinline__ void layer2_tile(const LayerParams &p, const BilTapsL
     // ---- dense tiles (hundreds of receding pixels: wide rims, and whole tiles right after a raft ends): the per-pixel row walk
     //      probes the same window rows over and over, and most of them hold no white pixel.  List the non-empty window rows, take
     //      the nearest-white distance of every (column, listed row) once -- one byte each, rows of a column side by side -- and
-    //      let the pixels read them four rows at a time.  The table borrows the space of the three lists (the receding pixels are
-    //      then taken from the mask words), so this runs BEFORE the filter lists are built.
+    //      let a lane per column read them four rows at a time for a block of L2_DV pixels (step 4).  The table borrows the space
+    //      of the three lists (the receding pixels are then taken from the mask words), so this runs BEFORE the filter lists are
+    //      built.  Only the second launch (DENSE) holds this path; the first one set such tiles aside after its first barrier.
     bool use_h = false;
     if (any_rec && s_rcnt > p.rcap) { // more receding pixels than the list holds (border tiles, modes without search): general kernel
         if (t == 0) p.gen_list[1 + atomicAdd(&p.gen_list[0], 1)] = ty * p.tiles_x + tx;
