@@ -253,6 +253,7 @@ def test_roi_tracker_equals_scalar_oracle_tracker():
         got = mine.update_and_classify([dict(r) for r in raw], z, cfg)
         want = theirs.update([dict(r) for r in raw], z, rp)
         assert [(r["id"], r["classification"], r["bbox"]) for r in got] == [(r["id"], r["classification"], r["bbox"]) for r in want], z
+        assert not np.any(mine._neg.view(np.uint64) != np.float64(-0.0).view(np.uint64))   # the scratch matrix is left clear
     assert mine.next_roi_id == theirs.next_id
 
 

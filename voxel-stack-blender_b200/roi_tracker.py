@@ -19,16 +19,15 @@ def calculate_iou(boxA, boxB):
     return inter / float(smaller) if smaller != 0 else 0.0
 
 
-def _score_matrix(cur_boxes, prev_boxes):
-    """calculate_iou for every (current, previous) pair at once: the same integer intersections and the same
-    float64 division as the scalar function, so the matrix equals the reference's element for element.  A stack
-    with thousands of supports makes this millions of pairs per layer, nearly all of them disjoint (score 0), so
-    only the pairs whose x-extents overlap are evaluated: previous boxes sorted by left edge, one binary search
-    per current box for the run of candidates."""
+def _score_pairs(cur_boxes, prev_boxes):
+    """The pairs (current index, previous index) whose boxes overlap in x, and calculate_iou of each: the same integer
+    intersections and the same float64 division as the scalar function.  A stack with thousands of supports makes
+    millions of pairs per layer, nearly all of them disjoint (score 0); every pair that is NOT returned scores 0.
+    Previous boxes sorted by left edge, one binary search per current box for the run of candidates."""
     n, m = len(cur_boxes), len(prev_boxes)
-    out = np.zeros((n, m))
+    none = np.zeros(0, np.int64)
     if n == 0 or m == 0:
-        return out
+        return none, none, np.zeros(0)
     c = np.asarray(cur_boxes, np.int64).reshape(n, 4)
     q = np.asarray(prev_boxes, np.int64).reshape(m, 4)
     order = np.argsort(q[:, 0], kind="stable")
@@ -40,7 +39,7 @@ def _score_matrix(cur_boxes, prev_boxes):
     cnt = np.maximum(hi - lo, 0)
     total = int(cnt.sum())
     if total == 0:
-        return out
+        return none, none, np.zeros(0)
     ci = np.repeat(np.arange(n), cnt)
     pj = order[np.repeat(lo, cnt) + (np.arange(total) - np.repeat(np.cumsum(cnt) - cnt, cnt))]
     a, b = c[ci], q[pj]
@@ -50,6 +49,13 @@ def _score_matrix(cur_boxes, prev_boxes):
     smaller = np.minimum(a[:, 2] * a[:, 3], b[:, 2] * b[:, 3])
     val = np.zeros(total)
     np.divide(inter, smaller.astype(np.float64), out=val, where=smaller != 0)
+    return ci, pj, val
+
+
+def _score_matrix(cur_boxes, prev_boxes):
+    """calculate_iou for every (current, previous) pair as the reference's dense matrix, element for element."""
+    out = np.zeros((len(cur_boxes), len(prev_boxes)))
+    ci, pj, val = _score_pairs(cur_boxes, prev_boxes)
     out[ci, pj] = val
     return out
 
@@ -62,6 +68,7 @@ class ROITracker:
     def __init__(self):
         self.next_roi_id = 0
         self.previous_rois = {}
+        self._neg = np.full(0, -0.0)   # scratch of update_and_classify
 
     def _classify_new_roi(self, roi, layer_index, config):
         rp = config.roi_params
@@ -88,17 +95,25 @@ class ROITracker:
             return list(tracked.values())
 
         prev_ids = list(self.previous_rois)
-        scores = _score_matrix([r["bbox"] for r in current_rois_raw], [self.previous_rois[i]["bbox"] for i in prev_ids])
+        n, width = len(current_rois_raw), len(prev_ids)
+        pair_c, pair_p, score = _score_pairs([r["bbox"] for r in current_rois_raw],
+                                             [self.previous_rois[i]["bbox"] for i in prev_ids])
 
-        # greedy one-to-one assignment, best score first: the reference's argsort of the negated matrix (same call on
-        # the same values, so ties come out in the order its sort leaves them); negated in place, the matrix is 8 bytes
-        # per pair
-        neg = np.negative(scores, out=scores)
+        # greedy one-to-one assignment, best score first: the reference's own call -- argsort of the negated dense matrix,
+        # so that tied scores (identical boxes score 1.0 by the hundred) come out in the order its sort leaves them.  The
+        # matrix (8 bytes per pair, nearly all of them -0.0) lives in a buffer that stays -0.0 between layers: only the
+        # candidate pairs are written, and cleared again afterwards.
+        if self._neg.size < n * width:
+            self._neg = np.full(n * width, -0.0)
+        neg = self._neg[: n * width].reshape(n, width)
         assigned, taken = {}, set()
-        width = neg.shape[1]
-        order = np.argsort(neg, axis=None) if neg.size else np.zeros(0, np.int64)
-        # scores at or above the threshold come first; stop at the first one below it
-        n_hits = int(np.count_nonzero(neg <= -self.MATCH_THRESHOLD))
+        try:
+            neg[pair_c, pair_p] = -score
+            order = np.argsort(neg, axis=None) if neg.size else np.zeros(0, np.int64)
+        finally:
+            neg[pair_c, pair_p] = -0.0
+        # scores at or above the threshold come first; the reference stops at the first one below it
+        n_hits = int(np.count_nonzero(score >= self.MATCH_THRESHOLD))
         for flat in order[:n_hits].tolist():
             ci, pj = divmod(flat, width)
             pid = prev_ids[pj]
