@@ -103,8 +103,8 @@ class ROITracker:
         # so that tied scores (identical boxes score 1.0 by the hundred) come out in the order its sort leaves them.  The
         # matrix (8 bytes per pair, nearly all of them -0.0) lives in a buffer that stays -0.0 between layers: only the
         # candidate pairs are written, and cleared again afterwards.
-        if self._neg.size < n * width:
-            self._neg = np.full(n * width, -0.0)
+        if self._neg.size < n * width:             # with headroom: the ROI count drifts from layer to layer
+            self._neg = np.full(n * width + (n * width >> 2), -0.0)
         neg = self._neg[: n * width].reshape(n, width)
         assigned, taken = {}, set()
         try:
